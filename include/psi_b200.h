@@ -1,0 +1,174 @@
+/*
+ * psi_b200.h — C ABI of the B200-native BatchedFHEPIE server evaluation.
+ *
+ * This is the drop-in boundary for ONE hot path of SAP/nested-hashing-psi:
+ *   BatchedFHEHIPPIE::run()          src/Common/Crypto/PrivateIndexedEqualityCheck/BatchedFHEHIPPIE.cpp:88-129
+ * and for the data the path consumes:
+ *   BatchedFHEHIPPIE ctor            BatchedFHEHIPPIE.cpp:9-86   (plaintext DB + random masks)
+ *   setIndex / setMinusCompareElement BatchedFHEHIPPIE.hpp:40-48 (the encrypted query)
+ *   getResultList                    BatchedFHEHIPPIE.hpp:35-38  (b result ciphertexts)
+ *
+ * The reference performs every homomorphic operation through OpenFHE
+ * (cryptoContext->EvalMult / EvalAdd, BatchedFHEHIPPIE.cpp:108,112,113,116,123,126).
+ * This library replaces exactly those calls with sm_100a kernels.  All entry
+ * points are extern "C", take plain pointers and sizes, return an int status
+ * (0 = ok) and never throw across the ABI.  Host buffers are owned by the
+ * caller, device buffers by the library.  There is no CPU fallback: every
+ * compute entry point fails with PSI_ERR_NO_DEVICE when no CUDA device exists.
+ *
+ * Layouts (u64 = uint64_t, all residues canonical in [0, q_l)):
+ *   poly        [L][N]              limb-major, N contiguous
+ *   ciphertext  [2][L][N]           (c0, c1), Format::EVALUATION (negacyclic NTT,
+ *                                   natural-order input -> bit-reversed output,
+ *                                   psi = minimal primitive 2N-th root mod q_l)
+ *   plaintext   [L][N]              EVALUATION
+ *   index       [K][E][2][L][N]     indexMatrix[hf][pos]         (BatchedFHEHIPPIE.hpp:25)
+ *   minus       [2][L][N]           minusCompareElement          (BatchedFHEHIPPIE.hpp:26)
+ *   pt DB       [K][b][E][L][N]     vectorizedHCT[hf][bin][pos]  (BatchedFHEHIPPIE.hpp:23)
+ *   masks       [b][L][N]           preCalcRandomMask[bin]       (BatchedFHEHIPPIE.hpp:27)
+ *   results     [b][2][L][N]        resultList[bin]              (BatchedFHEHIPPIE.hpp:24)
+ *   relin key   [L][L][N] x 2       BV digit i, limb k; "b" then "a" vector
+ */
+#ifndef PSI_B200_H
+#define PSI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSI_MAX_LIMBS 8
+
+enum psi_status {
+    PSI_OK = 0,
+    PSI_ERR_INVALID = 1,   /* bad argument (mirrors std::invalid_argument in the reference) */
+    PSI_ERR_NO_DEVICE = 2, /* CUDA device / driver missing: the product has no CPU path */
+    PSI_ERR_CUDA = 3,      /* a CUDA call failed; see psi_last_error() */
+    PSI_ERR_STATE = 4      /* call order violated (e.g. run before query_set) */
+};
+
+/* OpenFHE MultiplicationTechnique / KeySwitchTechnique of the BFV context. */
+enum { PSI_MULT_HPS = 0, PSI_MULT_HPSPOVERQ = 1 };
+enum { PSI_KS_BV = 0 };
+
+/*
+ * Everything the device needs to know about the BFV-RNS context.  When linked
+ * next to a real OpenFHE the adapter fills this from CryptoParametersBFVRNS
+ * getters (INTEGRATION.md lists each getter), so the double tables are
+ * bit-identical to the host library's; psi_params_generate() builds the same
+ * tables from (N, t, depth) for stand-alone use.
+ * q = moduli of Q (ciphertext basis), p = moduli of the auxiliary basis P used
+ * by EvalMult(ct,ct); S = Q*P.
+ */
+typedef struct psi_params {
+    uint32_t N;              /* ring dimension, power of two, 1024..16384 */
+    uint32_t L;              /* sizeQ */
+    uint32_t Lp;             /* sizeP */
+    uint32_t mult_technique; /* PSI_MULT_* */
+    uint32_t ks_technique;   /* PSI_KS_*  (BV, digit size 0) */
+    uint32_t reserved;
+    uint64_t t;              /* plaintext modulus, t = 1 mod 2N */
+    uint64_t q[PSI_MAX_LIMBS];
+    uint64_t p[PSI_MAX_LIMBS];
+    uint64_t psi_q[PSI_MAX_LIMBS]; /* primitive 2N-th root of unity mod q_i */
+    uint64_t psi_p[PSI_MAX_LIMBS];
+    uint64_t psi_t;                /* primitive 2N-th root mod t (packed encoding) */
+
+    /* DCRTPoly::ExpandCRTBasis (exact Q -> P, first operand of EvalMult) */
+    uint64_t QHatInvModq[PSI_MAX_LIMBS];               /* [(Q/q_i)^-1]_{q_i} */
+    uint64_t QHatModp[PSI_MAX_LIMBS][PSI_MAX_LIMBS];   /* [j][i] = (Q/q_i) mod p_j */
+    uint64_t alphaQModp[PSI_MAX_LIMBS + 1][PSI_MAX_LIMBS]; /* [a][j] = a*Q mod p_j */
+    double qInv[PSI_MAX_LIMBS];                        /* 1.0 / (double) q_i */
+
+    /* DCRTPoly::FastExpandCRTBasisPloverQ (second operand, HPSPOVERQ) */
+    uint64_t negPQHatInvModq[PSI_MAX_LIMBS];           /* [-P (Q/q_i)^-1]_{q_i} */
+    uint64_t qInvModp[PSI_MAX_LIMBS][PSI_MAX_LIMBS];   /* [i][j] = q_i^-1 mod p_j */
+    uint64_t PHatInvModp[PSI_MAX_LIMBS];               /* [(P/p_j)^-1]_{p_j} */
+    uint64_t PHatModq[PSI_MAX_LIMBS][PSI_MAX_LIMBS];   /* [i][j] = (P/p_j) mod q_i */
+    uint64_t alphaPModq[PSI_MAX_LIMBS + 1][PSI_MAX_LIMBS]; /* [a][i] = a*P mod q_i */
+    double pInv[PSI_MAX_LIMBS];                        /* 1.0 / (double) p_j */
+
+    /* DCRTPoly::ScaleAndRound by t/P with output basis Q (HPSPOVERQ) */
+    uint64_t tQSHatInvModsDivsModq[PSI_MAX_LIMBS][PSI_MAX_LIMBS + 1]; /* [j][i<Lp], [j][Lp] */
+    double tQSHatInvModsDivsFrac[PSI_MAX_LIMBS];
+} psi_params;
+
+typedef struct psi_ctx psi_ctx; /* opaque, one per device */
+
+/* Stand-alone context parameters, restating OpenFHE's BFVrns parameter
+ * generation (client side: BatchedFHEPSIClient.cpp:22-78 picks t, depth, ring
+ * dimension).  L_override = 0 derives sizeQ from the noise estimate. */
+int psi_params_generate(uint32_t N, uint64_t t, uint32_t mult_depth, uint32_t L_override,
+                        psi_params* out);
+
+/* Replaces the server's context deserialisation result as far as run() needs it
+ * (BatchedFHEPSIServer.cpp:28). */
+int psi_ctx_create(const psi_params* p, int device, psi_ctx** out);
+int psi_ctx_destroy(psi_ctx* ctx);
+
+/* Replaces cryptoContext->DeserializeEvalMultKey (BatchedFHEPSIServer.cpp:49) as
+ * consumed by EvalMult(ct,ct) (BatchedFHEHIPPIE.cpp:123).  evk_b, evk_a:
+ * [L][L][N] u64 each, EVALUATION. */
+int psi_set_relin_key(psi_ctx* ctx, const uint64_t* evk_b, const uint64_t* evk_a);
+
+/* Replaces the ctor's vectorizedHCT / preCalcRandomMask members
+ * (BatchedFHEHIPPIE.cpp:37-82) with already encoded EVALUATION limbs. */
+int psi_db_load_limbs(psi_ctx* ctx, uint32_t K, uint32_t b, uint32_t E, const uint64_t* pt_limbs,
+                      const uint64_t* mask_limbs);
+
+/* Same members, from raw slot values: performs MakePackedPlaintext
+ * (BatchedFHEHIPPIE.cpp:68,81) plus the first-use SetFormat(EVALUATION) on the
+ * device.  slots: [K][b][E][nslots] int64, mask_slots: [b][nslots] int64,
+ * |v| < t; nslots <= N, remaining slots are zero. */
+int psi_db_encode_slots(psi_ctx* ctx, uint32_t K, uint32_t b, uint32_t E, uint32_t nslots,
+                        const int64_t* slots, const int64_t* mask_slots);
+
+/* Copies the encoded DB back (tests / caching): pt [K][b][E][L][N], mask [b][L][N]. */
+int psi_db_get_limbs(psi_ctx* ctx, uint64_t* pt_limbs, uint64_t* mask_limbs);
+
+/* setIndex + setMinusCompareElement (BatchedFHEHIPPIE.hpp:40-48): asynchronous
+ * H2D on `stream` (a cudaStream_t, NULL = legacy default stream). */
+int psi_query_set(psi_ctx* ctx, const uint64_t* idx, const uint64_t* minus, void* stream);
+
+/* BatchedFHEHIPPIE::run (BatchedFHEHIPPIE.cpp:88-129): enqueues all kernels on
+ * `stream`; does not synchronise. */
+int psi_run(psi_ctx* ctx, void* stream);
+
+/* getResultList (BatchedFHEHIPPIE.hpp:35-38): asynchronous D2H of [b][2][L][N]
+ * on `stream`; the caller synchronises the stream before reading `out`. */
+int psi_result_get(psi_ctx* ctx, uint64_t* out, void* stream);
+
+int psi_stream_sync(void* stream);
+
+/* Number of kernels one psi_run() launches for the loaded DB (bench.py's
+ * gpu_launches claim is computed from this). */
+int psi_run_launch_count(psi_ctx* ctx, uint32_t* out);
+
+/* Device pointer of the result buffer (multi-GPU gather over NCCL works on
+ * device memory). */
+int psi_result_device_ptr(psi_ctx* ctx, void** out, size_t* bytes);
+
+/* Kernel-level entry points used by the parity tests (each one kernel family):
+ *  psi_debug_ntt:      in-place forward (inverse=0) / inverse NTT of n_polys
+ *                      limb-polys; modulus index m: 0..L-1 = q, L..L+Lp-1 = p,
+ *                      L+Lp = t.  data: [n_polys][N] host, moduli: [n_polys].
+ *  psi_debug_mul_ctct: one EvalMult(ct,ct)+relinearise on host ciphertexts
+ *                      ([2][L][N] each) -> out [2][L][N]. */
+int psi_debug_ntt(psi_ctx* ctx, uint64_t* data, const uint32_t* moduli, uint32_t n_polys,
+                  int inverse);
+int psi_debug_mul_ctct(psi_ctx* ctx, const uint64_t* ct1, const uint64_t* ct2, uint64_t* out);
+
+/* Integer-pipe peak micro-benchmark (the IMAD roofline
+ * denominator is measured, not assumed).  Returns 32x32->64 multiply-adds per
+ * second over the whole chip. */
+int psi_bench_imad_peak(int device, double* mads_per_second);
+
+const char* psi_last_error(void);
+const char* psi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSI_B200_H */

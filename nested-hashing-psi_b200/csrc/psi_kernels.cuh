@@ -1,0 +1,74 @@
+// Kernel launch interface between psi_api.cu (C ABI, orchestration) and the kernel TUs.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "modarith.cuh"
+#include "psi_b200.h"
+
+namespace psi {
+
+constexpr int kMaxMods = 2 * PSI_MAX_LIMBS + 1;
+
+// Device-resident copy of psi_params plus derived constants (Shoup companions, relin lifts).
+struct DevTables {
+    uint32_t N, logN, L, Lp;
+    u64 t;
+    u64 QHatInvModq[PSI_MAX_LIMBS], QHatInvModq_s[PSI_MAX_LIMBS];
+    u64 QHatModp[PSI_MAX_LIMBS][PSI_MAX_LIMBS];
+    u64 alphaQModp[PSI_MAX_LIMBS + 1][PSI_MAX_LIMBS];
+    double qInv[PSI_MAX_LIMBS];
+    u64 negPQHatInvModq[PSI_MAX_LIMBS], negPQHatInvModq_s[PSI_MAX_LIMBS];
+    u64 qInvModp[PSI_MAX_LIMBS][PSI_MAX_LIMBS];
+    u64 PHatInvModp[PSI_MAX_LIMBS], PHatInvModp_s[PSI_MAX_LIMBS];
+    u64 PHatModq[PSI_MAX_LIMBS][PSI_MAX_LIMBS];
+    u64 alphaPModq[PSI_MAX_LIMBS + 1][PSI_MAX_LIMBS];
+    double pInv[PSI_MAX_LIMBS];
+    u64 tQS[PSI_MAX_LIMBS][PSI_MAX_LIMBS + 1];
+    double tQSfrac[PSI_MAX_LIMBS];
+    u64 qModq[PSI_MAX_LIMBS][PSI_MAX_LIMBS];  // [i][k] = q_i mod q_k (BV digit lift)
+    ModDev mods[kMaxMods];                    // 0..L-1: q, L..L+Lp-1: p, L+Lp: t
+};
+
+// What every launcher needs: device tables + the host copy of the dimensions + the stream.
+struct KCtx {
+    const DevTables* tab;
+    uint32_t N, logN, L, Lp;
+    cudaStream_t s;
+};
+
+// Batched negacyclic NTT over `n_polys` limb-polynomials of N coefficients.
+//   poly i: group g = i / G, limb l = i % G
+//   src = src_base + g*src_gs + l*src_ls,  dst = dst_base + g*dst_gs + l*N   (element strides)
+//   modulus index = mod_base + (l % mod_period)
+struct NttBatch {
+    const u64* src;
+    u64* dst;
+    uint32_t n_polys, G;
+    size_t src_gs, src_ls, dst_gs;
+    uint32_t mod_base, mod_period;
+};
+cudaError_t launch_ntt(const KCtx& k, const NttBatch& b, bool inverse);
+
+// Phase 1: acc[hf][bin] = sum_pos idx[hf][pos] (.) pt[hf][bin][pos] + minus
+cudaError_t launch_mac(const KCtx& k, uint32_t K, uint32_t b, uint32_t E, const u64* pt, const u64* idx,
+                       const u64* minus, u64* acc);
+
+// EvalMult(ct,ct) building blocks, all batched over B ciphertexts (see psi_api.cu for the sequence)
+cudaError_t launch_expand_q_to_p(const KCtx& k, uint32_t groups, const u64* coef, u64* ext);
+cudaError_t launch_fast_expand_poverq(const KCtx& k, uint32_t groups, const u64* coef, u64* ext);
+cudaError_t launch_tensor(const KCtx& k, uint32_t B, const u64* e1, const u64* e2, u64* ten);
+cudaError_t launch_scale_round(const KCtx& k, uint32_t groups, const u64* ten, u64* res);
+cudaError_t launch_relin_digits(const KCtx& k, uint32_t B, const u64* res, u64* dig);
+cudaError_t launch_relin_accum(const KCtx& k, uint32_t B, const u64* res_eval, const u64* dig, const u64* evk_b,
+                               const u64* evk_a, const u64* mask /*nullable*/, u64* out);
+cudaError_t launch_mul_ctpt(const KCtx& k, uint32_t B, const u64* ct, const u64* pt, u64* out);
+
+// Packed encoding front end: slot values -> CRT-ordered residues mod t
+cudaError_t launch_slots_to_crt(const KCtx& k, uint32_t n_pt, uint32_t nslots, const long long* slots,
+                                const uint32_t* to_crt, u64* out);
+
+cudaError_t imad_peak(int device, double* mads_per_second);
+
+}  // namespace psi

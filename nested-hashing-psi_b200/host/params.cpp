@@ -1,0 +1,196 @@
+// psi_params_generate — stand-alone BFV-RNS context tables for the B200 BatchedFHEPIE path.
+//
+// In the reference the context is created by the CLIENT through OpenFHE
+// (/root/reference/src/Client/FHE/BatchedFHEPSIClient.cpp:22-78: plaintext modulus by bit size,
+// depth by eachCuckooTableSize, ring dimension 16384, HEStd_128_classic, library defaults for
+// everything else) and reaches the server serialised (BatchedFHEPSIServer.cpp:21-54).  When this
+// library is linked next to OpenFHE the adapter copies the tables out of CryptoParametersBFVRNS
+// (INTEGRATION.md); this file builds the same tables from (N, t, depth) so the path also runs
+// without OpenFHE.  OpenFHE 1.0.x defaults as recalled: 60-bit moduli, largest primes below 2^60
+// congruent to 1 mod 2N in descending order, minimal primitive roots, HPSPOVERQ with
+// |P| = |Q| limbs continuing below Q, BV key switching with digit size 0.
+//
+// All tables are residues of products/inverses modulo one word-sized prime, so no multi-precision
+// arithmetic is needed (the exact big-integer definitions live in oracle/params_ref.py and
+// tests/test_params.py compares the two generators table by table).
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "psi_b200.h"
+#include "psi_host_internal.hpp"
+
+namespace psi {
+
+typedef unsigned __int128 u128;
+
+static inline uint64_t mulmod(uint64_t a, uint64_t b, uint64_t m) { return (uint64_t)(((u128)a * b) % m); }
+
+static uint64_t powmod(uint64_t a, uint64_t e, uint64_t m) {
+    uint64_t r = 1 % m;
+    a %= m;
+    for (; e; e >>= 1) {
+        if (e & 1) r = mulmod(r, a, m);
+        a = mulmod(a, a, m);
+    }
+    return r;
+}
+
+static inline uint64_t invmod_prime(uint64_t a, uint64_t p) { return powmod(a % p, p - 2, p); }
+
+bool is_prime_u64(uint64_t n) {
+    static const uint64_t bases[] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37};
+    if (n < 2) return false;
+    for (uint64_t b : bases) {
+        if (n % b == 0) return n == b;
+    }
+    uint64_t d = n - 1;
+    int s = 0;
+    while ((d & 1) == 0) {
+        d >>= 1;
+        ++s;
+    }
+    for (uint64_t a : bases) {
+        uint64_t x = powmod(a, d, n);
+        if (x == 1 || x == n - 1) continue;
+        bool composite = true;
+        for (int r = 1; r < s; ++r) {
+            x = mulmod(x, x, n);
+            if (x == n - 1) {
+                composite = false;
+                break;
+            }
+        }
+        if (composite) return false;
+    }
+    return true;
+}
+
+// first prime >= 2^bits that is 1 mod m, then step down: the largest such prime below it
+static uint64_t first_prime(unsigned bits, uint64_t m) {
+    uint64_t x = 1ull << bits;
+    uint64_t r = x % m;
+    uint64_t q = r ? x + (m - r) + 1 : x + 1;
+    while (!is_prime_u64(q)) q += m;
+    return q;
+}
+static uint64_t previous_prime(uint64_t q, uint64_t m) {
+    do {
+        q -= m;
+    } while (!is_prime_u64(q));
+    return q;
+}
+
+// minimum primitive m-th root of unity modulo prime q (m a power of two dividing q-1)
+uint64_t min_primitive_root(uint64_t m, uint64_t q) {
+    uint64_t r = 0;
+    for (uint64_t x = 2;; ++x) {
+        r = powmod(x, (q - 1) / m, q);
+        if (powmod(r, m / 2, q) == q - 1) break;
+    }
+    uint64_t r2 = mulmod(r, r, q), best = r, cur = r;
+    for (uint64_t i = 1; i < m / 2; ++i) {
+        cur = mulmod(cur, r2, q);
+        if (cur < best) best = cur;
+    }
+    return best;
+}
+
+// sizeQ from the BFVrns noise estimate (EvalMult-only branch, BV digit size 0), 60-bit moduli
+static uint32_t derive_size_q(uint32_t N, uint64_t t, uint32_t depth) {
+    const double dcrt_bits = 60.0, sigma = 3.19, alpha = 36.0;
+    const double p = (double)t, Berr = sigma * std::sqrt(alpha), Bkey = 1.0;
+    const double delta = 2.0 * std::sqrt((double)N);
+    const double Vnorm = Berr * (1.0 + 2.0 * delta * Bkey);
+    const double w = std::pow(2.0, dcrt_bits);
+    const double C1 = delta * delta * p * Bkey;
+    auto logq_bfv = [&](double logq_prev) {
+        double noise_ks = delta * (std::floor(logq_prev / (std::log(2.0) * dcrt_bits)) + 1) * w * Berr;
+        double C2 = delta * delta * Bkey * Bkey / 2.0 + noise_ks;
+        return std::log(4 * p) + (depth - 1) * std::log(C1) + std::log(C1 * Vnorm + depth * C2);
+    };
+    double logq = logq_bfv(6.0 * std::log(10.0));
+    logq = logq_bfv(logq);
+    return (uint32_t)std::ceil((std::ceil(logq / std::log(2.0)) + 1.0) / dcrt_bits);
+}
+
+int generate_params(uint32_t N, uint64_t t, uint32_t depth, uint32_t L_override, psi_params* out) {
+    if (!out) return PSI_ERR_INVALID;
+    if (N < 8 || (N & (N - 1)) != 0 || N > 65536) return set_error(PSI_ERR_INVALID, "ring dimension must be a power of two");
+    const uint64_t m = 2ull * N;
+    if (t < 2 || (t - 1) % m != 0 || !is_prime_u64(t))
+        return set_error(PSI_ERR_INVALID, "plaintext modulus must be a prime congruent to 1 mod 2N");
+    uint32_t L = L_override ? L_override : derive_size_q(N, t, depth ? depth : 1);
+    if (L < 1 || L > PSI_MAX_LIMBS) return set_error(PSI_ERR_INVALID, "sizeQ out of range (1..PSI_MAX_LIMBS)");
+    std::memset(out, 0, sizeof(*out));
+    const uint32_t Lp = L;
+    out->N = N;
+    out->L = L;
+    out->Lp = Lp;
+    out->mult_technique = PSI_MULT_HPSPOVERQ;
+    out->ks_technique = PSI_KS_BV;
+    out->t = t;
+    uint64_t* q = out->q;
+    uint64_t* p = out->p;
+    q[0] = previous_prime(first_prime(60, m), m);
+    for (uint32_t i = 1; i < L; ++i) q[i] = previous_prime(q[i - 1], m);
+    p[0] = previous_prime(q[L - 1], m);
+    for (uint32_t j = 1; j < Lp; ++j) p[j] = previous_prime(p[j - 1], m);
+    for (uint32_t i = 0; i < L; ++i) out->psi_q[i] = min_primitive_root(m, q[i]);
+    for (uint32_t j = 0; j < Lp; ++j) out->psi_p[j] = min_primitive_root(m, p[j]);
+    out->psi_t = min_primitive_root(m, t);
+
+    auto prod_mod = [](const uint64_t* v, uint32_t n, int skip, uint64_t mod) {
+        uint64_t r = 1 % mod;
+        for (uint32_t i = 0; i < n; ++i)
+            if ((int)i != skip) r = mulmod(r, v[i] % mod, mod);
+        return r;
+    };
+    for (uint32_t i = 0; i < L; ++i) {
+        uint64_t qhat = prod_mod(q, L, (int)i, q[i]);            // (Q/q_i) mod q_i
+        out->QHatInvModq[i] = invmod_prime(qhat, q[i]);
+        out->qInv[i] = 1.0 / (double)q[i];
+        uint64_t Pmodqi = prod_mod(p, Lp, -1, q[i]);
+        out->negPQHatInvModq[i] = (q[i] - mulmod(Pmodqi, out->QHatInvModq[i], q[i])) % q[i];
+        for (uint32_t j = 0; j < Lp; ++j) {
+            out->qInvModp[i][j] = invmod_prime(q[i], p[j]);
+            out->PHatModq[i][j] = prod_mod(p, Lp, (int)j, q[i]); // (P/p_j) mod q_i
+        }
+    }
+    for (uint32_t j = 0; j < Lp; ++j) {
+        uint64_t phat = prod_mod(p, Lp, (int)j, p[j]);
+        out->PHatInvModp[j] = invmod_prime(phat, p[j]);
+        out->pInv[j] = 1.0 / (double)p[j];
+        for (uint32_t i = 0; i < L; ++i) out->QHatModp[j][i] = prod_mod(q, L, (int)i, p[j]);
+        uint64_t Qmodpj = prod_mod(q, L, -1, p[j]);
+        for (uint32_t a = 0; a <= L; ++a) out->alphaQModp[a][j] = mulmod(a, Qmodpj, p[j]);
+    }
+    for (uint32_t i = 0; i < L; ++i) {
+        uint64_t Pmodqi = prod_mod(p, Lp, -1, q[i]);
+        for (uint32_t a = 0; a <= Lp; ++a) out->alphaPModq[a][i] = mulmod(a, Pmodqi, q[i]);
+    }
+    // ScaleAndRound by t/P, output Q.  With S = Q*P and c_i = t*Q*[(S/p_i)^-1]_{p_i}:
+    //   frac_i = (c_i mod p_i)/p_i,   floor(c_i/p_i) = -(c_i mod p_i) * p_i^-1  (mod q_j)   [c_i = 0 mod q_j]
+    for (uint32_t i = 0; i < Lp; ++i) {
+        uint64_t shat = mulmod(prod_mod(q, L, -1, p[i]), prod_mod(p, Lp, (int)i, p[i]), p[i]); // (S/p_i) mod p_i
+        uint64_t inv = invmod_prime(shat, p[i]);
+        uint64_t rem = mulmod(mulmod(t % p[i], prod_mod(q, L, -1, p[i]), p[i]), inv, p[i]);
+        out->tQSHatInvModsDivsFrac[i] = (double)rem / (double)p[i];
+        for (uint32_t j = 0; j < L; ++j) {
+            uint64_t v = mulmod(rem % q[j], invmod_prime(p[i], q[j]), q[j]);
+            out->tQSHatInvModsDivsModq[j][i] = (q[j] - v) % q[j];
+        }
+    }
+    for (uint32_t j = 0; j < L; ++j) {
+        uint64_t qhat = prod_mod(q, L, (int)j, q[j]);                       // (Q/q_j) mod q_j
+        uint64_t shat = mulmod(qhat, prod_mod(p, Lp, -1, q[j]), q[j]);      // (S/q_j) mod q_j
+        out->tQSHatInvModsDivsModq[j][Lp] = mulmod(mulmod(t % q[j], qhat, q[j]), invmod_prime(shat, q[j]), q[j]);
+    }
+    return PSI_OK;
+}
+
+}  // namespace psi
+
+extern "C" int psi_params_generate(uint32_t N, uint64_t t, uint32_t mult_depth, uint32_t L_override, psi_params* out) {
+    return psi::generate_params(N, t, mult_depth, L_override, out);
+}

@@ -1,0 +1,173 @@
+"""
+ORACLE (test infrastructure) — ctypes/numpy binding of oracle/libpsi_oracle.so.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this.  See oracle/psi_oracle.c for the reference line map and the "parity unpinned"
+statement.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from .params_ref import PsiParams
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libpsi_oracle.so")
+    src = os.path.join(_HERE, "psi_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libpsi_oracle.so")
+        if not os.path.exists(so):
+            build()
+        L = ctypes.CDLL(so)
+        L.orc_create.restype = ctypes.c_void_p
+        L.orc_create.argtypes = [ctypes.POINTER(PsiParams)]
+        L.orc_destroy.argtypes = [ctypes.c_void_p]
+        L.orc_ntt.argtypes = [ctypes.c_void_p, _u64p, ctypes.c_int, ctypes.c_int]
+        L.orc_pack.argtypes = [ctypes.c_void_p, _i64p, ctypes.c_int, _u64p]
+        L.orc_unpack.argtypes = [ctypes.c_void_p, _u64p, _i64p]
+        L.orc_encode.argtypes = [ctypes.c_void_p, _i64p, ctypes.c_int, _u64p]
+        L.orc_keygen.argtypes = [ctypes.c_void_p, ctypes.c_uint64, _u64p, _u64p, _u64p]
+        L.orc_encrypt_sk.argtypes = [ctypes.c_void_p, _u64p, _i64p, ctypes.c_int, ctypes.c_uint64, _u64p]
+        L.orc_decrypt.argtypes = [ctypes.c_void_p, _u64p, _u64p, ctypes.c_int, _i64p,
+                                  ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)]
+        L.orc_mac_bin.argtypes = [ctypes.c_void_p, ctypes.c_int, _u64p, _u64p, _u64p, _u64p]
+        L.orc_mul_ctpt.argtypes = [ctypes.c_void_p, _u64p, _u64p, _u64p]
+        L.orc_mul_ctct.argtypes = [ctypes.c_void_p, _u64p, _u64p, _u64p, _u64p, _u64p]
+        L.orc_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _u64p, _u64p, _u64p,
+                              _u64p, _u64p, _u64p, _u64p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.orc_max_threads.restype = ctypes.c_int
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_u64p)
+
+
+def _pi(a):
+    assert a.dtype == np.int64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_i64p)
+
+
+class Oracle:
+    """CPU restatement of the BFV-RNS context + the BatchedFHEPIE server evaluation."""
+
+    def __init__(self, params_struct):
+        self.params = params_struct
+        self.N, self.L, self.Lp, self.t = params_struct.N, params_struct.L, params_struct.Lp, params_struct.t
+        self._h = lib().orc_create(ctypes.byref(params_struct))
+        assert self._h
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().orc_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # -- transforms ---------------------------------------------------------------
+    def ntt(self, poly, mod_index, inverse=False):
+        out = np.ascontiguousarray(poly, dtype=np.uint64).copy()
+        lib().orc_ntt(self._h, _p(out), mod_index, 1 if inverse else 0)
+        return out
+
+    def pack(self, slots):
+        slots = np.ascontiguousarray(slots, dtype=np.int64)
+        out = np.empty(self.N, dtype=np.uint64)
+        rc = lib().orc_pack(self._h, _pi(slots), len(slots), _p(out))
+        if rc:
+            raise ValueError("slot value out of range of the plaintext modulus")
+        return out
+
+    def unpack(self, coeff):
+        out = np.empty(self.N, dtype=np.int64)
+        lib().orc_unpack(self._h, _p(np.ascontiguousarray(coeff, dtype=np.uint64)), _pi(out))
+        return out
+
+    def encode(self, slots):
+        """MakePackedPlaintext + SetFormat(EVALUATION): [L][N]."""
+        slots = np.ascontiguousarray(slots, dtype=np.int64)
+        out = np.empty((self.L, self.N), dtype=np.uint64)
+        rc = lib().orc_encode(self._h, _pi(slots), len(slots), _p(out))
+        if rc:
+            raise ValueError("slot value out of range of the plaintext modulus")
+        return out
+
+    # -- client side --------------------------------------------------------------
+    def keygen(self, seed):
+        sk = np.empty((self.L, self.N), dtype=np.uint64)
+        evk_b = np.empty((self.L, self.L, self.N), dtype=np.uint64)
+        evk_a = np.empty((self.L, self.L, self.N), dtype=np.uint64)
+        lib().orc_keygen(self._h, seed, _p(sk), _p(evk_b), _p(evk_a))
+        return sk, evk_b, evk_a
+
+    def encrypt(self, sk, slots, seed):
+        slots = np.ascontiguousarray(slots, dtype=np.int64)
+        ct = np.empty((2, self.L, self.N), dtype=np.uint64)
+        rc = lib().orc_encrypt_sk(self._h, _p(sk), _pi(slots), len(slots), seed, _p(ct))
+        if rc:
+            raise ValueError("slot value out of range of the plaintext modulus")
+        return ct
+
+    def decrypt(self, sk, ct):
+        """-> (slots[N] centred int64, ambiguous roundings, noise budget bits)."""
+        ct = np.ascontiguousarray(ct, dtype=np.uint64)
+        out = np.empty(self.N, dtype=np.int64)
+        amb = ctypes.c_int(0)
+        nb = ctypes.c_double(0)
+        lib().orc_decrypt(self._h, _p(sk), _p(ct), ct.shape[0], _pi(out), ctypes.byref(amb), ctypes.byref(nb))
+        return out, amb.value, nb.value
+
+    # -- server side --------------------------------------------------------------
+    def mac_bin(self, idx, pt, minus):
+        """idx [E][2][L][N], pt [E][L][N], minus [2][L][N] -> [2][L][N]."""
+        E = idx.shape[0]
+        out = np.empty((2, self.L, self.N), dtype=np.uint64)
+        lib().orc_mac_bin(self._h, E, _p(np.ascontiguousarray(idx)), _p(np.ascontiguousarray(pt)),
+                          _p(np.ascontiguousarray(minus)), _p(out))
+        return out
+
+    def mul_ctpt(self, ct, pt):
+        out = np.empty((2, self.L, self.N), dtype=np.uint64)
+        lib().orc_mul_ctpt(self._h, _p(np.ascontiguousarray(ct)), _p(np.ascontiguousarray(pt)), _p(out))
+        return out
+
+    def mul_ctct(self, ct1, ct2, evk_b, evk_a):
+        out = np.empty((2, self.L, self.N), dtype=np.uint64)
+        lib().orc_mul_ctct(self._h, _p(np.ascontiguousarray(ct1)), _p(np.ascontiguousarray(ct2)),
+                           _p(evk_b), _p(evk_a), _p(out))
+        return out
+
+    def run(self, pt, mask, idx, minus, evk_b, evk_a, bin_begin=0, bin_end=None, nthreads=1, out=None):
+        """BatchedFHEHIPPIE::run.  pt [K][b][E][L][N], mask [b][L][N], idx [K][E][2][L][N],
+        minus [2][L][N] -> [b][2][L][N] (only bins bin_begin..bin_end-1 are written)."""
+        K, b, E = pt.shape[0], pt.shape[1], pt.shape[2]
+        if bin_end is None:
+            bin_end = b
+        if out is None:
+            out = np.zeros((b, 2, self.L, self.N), dtype=np.uint64)
+        lib().orc_run(self._h, K, b, E, _p(pt), _p(mask), _p(idx), _p(minus), _p(evk_b), _p(evk_a), _p(out),
+                      bin_begin, bin_end, nthreads)
+        return out
+
+
+def max_threads():
+    return lib().orc_max_threads()
