@@ -136,6 +136,15 @@ int psi_query_set(psi_ctx* ctx, const uint64_t* idx, const uint64_t* minus, void
  * `stream`; does not synchronise. */
 int psi_run(psi_ctx* ctx, void* stream);
 
+/* The two halves of run(), separately launchable so that each kernel family can be timed with CUDA
+ * events and profiled on its own (bench.py roofline):
+ *   PSI_PHASE_INNER_PRODUCT  BatchedFHEHIPPIE.cpp:101-116  (ct x pt multiply-accumulate + minus)
+ *   PSI_PHASE_MULTIPLY_MASK  BatchedFHEHIPPIE.cpp:119-127  (ct x ct + relinearise, mask)
+ * psi_run(ctx, s) == psi_run_phases(ctx, PSI_PHASE_ALL, s).  Phase 2 alone reuses the inner
+ * products of the previous phase-1 launch. */
+enum { PSI_PHASE_INNER_PRODUCT = 1, PSI_PHASE_MULTIPLY_MASK = 2, PSI_PHASE_ALL = 3 };
+int psi_run_phases(psi_ctx* ctx, uint32_t phases, void* stream);
+
 /* getResultList (BatchedFHEHIPPIE.hpp:35-38): asynchronous D2H of [b][2][L][N]
  * on `stream`; the caller synchronises the stream before reading `out`. */
 int psi_result_get(psi_ctx* ctx, uint64_t* out, void* stream);
@@ -164,6 +173,52 @@ int psi_debug_mul_ctct(psi_ctx* ctx, const uint64_t* ct1, const uint64_t* ct2, u
  * denominator is measured, not assumed).  Returns 32x32->64 multiply-adds per
  * second over the whole chip. */
 int psi_bench_imad_peak(int device, double* mads_per_second);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-side objects around the path (offline phase; nothing here is inside run()).
+ * They exist so that the PIE operator can be constructed exactly as the reference constructs it:
+ *   BatchedFHEHIPPIE(cryptoContext, pk, HierarchicalCuckooHashTable&)   BatchedFHEHIPPIE.cpp:9-86
+ * and so that tests / the bench can build the same inputs the reference's drivers build.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct psi_hct psi_hct; /* TabulationHashing + HierarchicalCuckooHashTable */
+typedef struct psi_pie psi_pie; /* BatchedFHEHIPPIE */
+
+/* HierarchicalCuckooHashTable ctor (HierarchicalCuckooHashTable.cpp:16-53) over
+ * TabulationHashing(hash_seed, k + K) (TabulationHashing.cpp:16-36).  The reference seeds the
+ * eviction RNG of every inner table from std::random_device (CuckooHashTable.cpp:51-52);
+ * eviction_seed pins it. */
+int psi_hct_create(uint64_t hash_seed, uint32_t k, uint64_t e, uint32_t K, uint64_t E, uint64_t b, uint64_t stash,
+                   int simple_multi, int cuckoo_multi, uint64_t eviction_seed, psi_hct** out);
+/* insertAll (HierarchicalCuckooHashTable.cpp:55-73); a failed insertion reports PSI_ERR_STATE
+ * with the reference's message "(Blocked) Cuckoo hashing error" (CuckooHashTable.cpp:113). */
+int psi_hct_insert_all(psi_hct* h, const uint64_t* items, size_t n);
+/* cells: [k][e][K][b][E] = hierarchicalCuckooTable[outerHf][outerPos].cuckooTable[innerHf][bin][pos] */
+int psi_hct_get_cells(psi_hct* h, uint64_t* cells);
+int psi_hct_destroy(psi_hct* h);
+
+/* calculateHashIndex (HashUtils.cpp:34-37) for n items with TabulationHashing(hash_seed, n_hash_functions). */
+int psi_hash_index(uint64_t hash_seed, uint32_t n_hash_functions, const uint64_t* items, size_t n, uint32_t hf,
+                   uint32_t table_size, uint64_t* out);
+/* The client's own cuckoo table, k tables x e positions x 1 item (BatchedFHEPSIClient.cpp:97-99,109);
+ * cells: [k][e], 0 = empty. */
+int psi_client_table(uint64_t hash_seed, uint32_t k, uint64_t e, uint32_t K, const uint64_t* items, size_t n,
+                     uint64_t eviction_seed, uint64_t* cells);
+/* RandomDataInput (RandomDataInput.cpp:10-66): any output pointer may be NULL. */
+int psi_random_data_input(size_t server_size, size_t client_size, size_t intersection_size, uint64_t seed,
+                          uint64_t bit_size, uint64_t* server, uint64_t* client, uint64_t* intersection);
+
+/* BatchedFHEHIPPIE ctor: validates (stash, combined tables -> PSI_ERR_INVALID with the reference's
+ * messages), shuffles the bin rows of hct IN PLACE, transposes, encodes on the device. */
+int psi_pie_create(psi_ctx* ctx, const psi_params* params, psi_hct* hct, uint64_t shuffle_seed, uint64_t mask_seed,
+                   int keep_slots, psi_pie** out);
+int psi_pie_dims(psi_pie* p, uint32_t* K, uint32_t* b, uint32_t* E, uint32_t* nslots);
+/* slots [K][b][E][nslots], mask_slots [b][nslots]; needs keep_slots at creation. */
+int psi_pie_get_slots(psi_pie* p, int64_t* slots, int64_t* mask_slots);
+/* setIndex + setMinusCompareElement / run / getResultList (BatchedFHEHIPPIE.hpp:33-48), synchronous. */
+int psi_pie_set_query(psi_pie* p, const uint64_t* idx, const uint64_t* minus);
+int psi_pie_run(psi_pie* p);
+int psi_pie_get_result_list(psi_pie* p, uint64_t* out);
+int psi_pie_destroy(psi_pie* p);
 
 const char* psi_last_error(void);
 const char* psi_version(void);

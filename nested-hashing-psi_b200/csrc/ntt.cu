@@ -109,8 +109,8 @@ __global__ void __launch_bounds__(kNttThreads) k_ntt(const DevTables* __restrict
     const uint32_t N = 1u << logN;
     const uint32_t i = blockIdx.x;
     const uint32_t g = i / b.G, l = i % b.G;
-    const u64* __restrict__ src = b.src + (size_t)g * b.src_gs + (size_t)l * b.src_ls;
-    u64* __restrict__ dst = b.dst + (size_t)g * b.dst_gs + (size_t)l * N;
+    const u64* src = b.src + (size_t)g * b.src_gs + (size_t)l * b.src_ls;
+    u64* dst = b.dst + (size_t)g * b.dst_gs + (size_t)l * N;
     const ModDev& md = tab->mods[b.mod_base + (l % b.mod_period)];
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
 

@@ -1,0 +1,584 @@
+// C ABI (include/psi_b200.h) and kernel orchestration of the B200 BatchedFHEPIE server path.
+//
+// Replaces, behind plain pointers and sizes, what the reference does through OpenFHE objects:
+//   context / relin key        BatchedFHEPSIServer.cpp:21-54  (deserialised CryptoContext, EvalMultKey)
+//   plaintext DB + masks       BatchedFHEHIPPIE.cpp:37-82     (vectorizedHCT, preCalcRandomMask)
+//   query                      BatchedFHEHIPPIE.hpp:40-48     (setIndex, setMinusCompareElement)
+//   run()                      BatchedFHEHIPPIE.cpp:88-129
+//   getResultList()            BatchedFHEHIPPIE.hpp:35-38
+// There is no CPU path: every entry point that computes needs a CUDA device and says so.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "psi_b200.h"
+#include "psi_kernels.cuh"
+#include "../host/psi_host_internal.hpp"
+
+namespace psi {
+
+static thread_local std::string g_last_error;
+
+int set_error(int status, const std::string& msg) {
+    g_last_error = msg;
+    return status;
+}
+
+static int cuda_fail(cudaError_t e, const char* what) {
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInitializationError ||
+        e == cudaErrorSystemDriverMismatch || e == cudaErrorNotSupported)
+        return set_error(PSI_ERR_NO_DEVICE, std::string(what) + ": no usable CUDA device (" + cudaGetErrorString(e) +
+                                                "); this library has no CPU path");
+    return set_error(PSI_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CK(call)                                        \
+    do {                                                \
+        cudaError_t e__ = (call);                       \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+typedef unsigned __int128 u128h;
+
+static u64 h_mulmod(u64 a, u64 b, u64 q) { return (u64)(((u128h)a * b) % q); }
+static u64 h_powmod(u64 a, u64 e, u64 q) {
+    u64 r = 1;
+    a %= q;
+    for (; e; e >>= 1) {
+        if (e & 1) r = h_mulmod(r, a, q);
+        a = h_mulmod(a, a, q);
+    }
+    return r;
+}
+static u64 h_shoup(u64 w, u64 q) { return (u64)(((u128h)w << 64) / q); }
+static uint32_t h_bitrev(uint32_t x, int bits) {
+    uint32_t r = 0;
+    for (int i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
+    return r;
+}
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+}  // namespace psi
+
+using namespace psi;
+
+struct psi_ctx {
+    int device = 0;
+    psi_params P{};
+    uint32_t N = 0, logN = 0, L = 0, Lp = 0;
+    DevTables* d_tab = nullptr;
+    DevBuf<u64> twiddles;       // [(L+Lp+1)][4][N]
+    DevBuf<uint32_t> to_crt;    // packed-encoding permutation
+    DevBuf<u64> evk_b, evk_a;   // [L][L][N]
+    bool have_evk = false;
+    // database
+    uint32_t K = 0, b = 0, E = 0;
+    DevBuf<u64> pt, mask;
+    bool have_db = false;
+    // query
+    DevBuf<u64> idx, minus;
+    bool have_query = false;
+    // work
+    DevBuf<u64> acc, coef, e1, e2, ten, res, dig, prod, out;
+    bool ran = false;
+    uint32_t launches_per_run = 0;
+
+    KCtx k(cudaStream_t s) const { return KCtx{d_tab, N, logN, L, Lp, s}; }
+};
+
+namespace psi {
+
+static int ensure_device(psi_ctx* c) {
+    CK(cudaSetDevice(c->device));
+    return PSI_OK;
+}
+
+static int build_tables(psi_ctx* c) {
+    const psi_params& P = c->P;
+    const uint32_t N = c->N, L = c->L, Lp = c->Lp, nm = L + Lp + 1;
+    std::vector<u64> tw((size_t)nm * 4 * N);
+    DevTables T;
+    std::memset(&T, 0, sizeof(T));
+    T.N = N;
+    T.logN = c->logN;
+    T.L = L;
+    T.Lp = Lp;
+    T.t = P.t;
+    CK(c->twiddles.alloc(tw.size()));
+    for (uint32_t m = 0; m < nm; m++) {
+        const u64 q = m < L ? P.q[m] : (m < L + Lp ? P.p[m - L] : P.t);
+        const u64 psi_root = m < L ? P.psi_q[m] : (m < L + Lp ? P.psi_p[m - L] : P.psi_t);
+        if (q < 2 || q >= (1ull << 62)) return set_error(PSI_ERR_INVALID, "moduli must be below 2^62");
+        if (h_powmod(psi_root, N, q) != q - 1)
+            return set_error(PSI_ERR_INVALID, "psi is not a primitive 2N-th root of unity for one of the moduli");
+        u64* w = &tw[((size_t)m * 4 + 0) * N];
+        u64* ws = &tw[((size_t)m * 4 + 1) * N];
+        u64* iw = &tw[((size_t)m * 4 + 2) * N];
+        u64* iws = &tw[((size_t)m * 4 + 3) * N];
+        const u64 ipsi = h_powmod(psi_root, q - 2, q);
+        u64 pw = 1, ipw = 1;
+        for (uint32_t i = 0; i < N; i++) {
+            const uint32_t r = h_bitrev(i, (int)c->logN);
+            w[r] = pw;
+            iw[r] = ipw;
+            pw = h_mulmod(pw, psi_root, q);
+            ipw = h_mulmod(ipw, ipsi, q);
+        }
+        for (uint32_t i = 0; i < N; i++) {
+            ws[i] = h_shoup(w[i], q);
+            iws[i] = h_shoup(iw[i], q);
+        }
+        ModDev& md = T.mods[m];
+        md.q = q;
+        const u128h mu = (~(u128h)0) / q;
+        md.mu_hi = (u64)(mu >> 64);
+        md.mu_lo = (u64)mu;
+        md.ninv = h_powmod(N, q - 2, q);
+        md.ninv_s = h_shoup(md.ninv, q);
+        md.w = c->twiddles.p + ((size_t)m * 4 + 0) * N;
+        md.ws = c->twiddles.p + ((size_t)m * 4 + 1) * N;
+        md.iw = c->twiddles.p + ((size_t)m * 4 + 2) * N;
+        md.iws = c->twiddles.p + ((size_t)m * 4 + 3) * N;
+    }
+    CK(cudaMemcpy(c->twiddles.p, tw.data(), tw.size() * sizeof(u64), cudaMemcpyHostToDevice));
+    for (uint32_t i = 0; i < L; i++) {
+        T.QHatInvModq[i] = P.QHatInvModq[i];
+        T.QHatInvModq_s[i] = h_shoup(P.QHatInvModq[i], P.q[i]);
+        T.qInv[i] = P.qInv[i];
+        T.negPQHatInvModq[i] = P.negPQHatInvModq[i];
+        T.negPQHatInvModq_s[i] = h_shoup(P.negPQHatInvModq[i], P.q[i]);
+        for (uint32_t j = 0; j < Lp; j++) {
+            T.qInvModp[i][j] = P.qInvModp[i][j];
+            T.PHatModq[i][j] = P.PHatModq[i][j];
+        }
+        for (uint32_t j = 0; j <= Lp; j++) T.tQS[i][j] = P.tQSHatInvModsDivsModq[i][j];
+        for (uint32_t k = 0; k < L; k++) T.qModq[i][k] = P.q[i] % P.q[k];
+    }
+    for (uint32_t j = 0; j < Lp; j++) {
+        T.PHatInvModp[j] = P.PHatInvModp[j];
+        T.PHatInvModp_s[j] = h_shoup(P.PHatInvModp[j], P.p[j]);
+        T.pInv[j] = P.pInv[j];
+        T.tQSfrac[j] = P.tQSHatInvModsDivsFrac[j];
+        for (uint32_t i = 0; i < L; i++) T.QHatModp[j][i] = P.QHatModp[j][i];
+    }
+    for (uint32_t a = 0; a <= L; a++)
+        for (uint32_t j = 0; j < Lp; j++) T.alphaQModp[a][j] = P.alphaQModp[a][j];
+    for (uint32_t a = 0; a <= Lp; a++)
+        for (uint32_t i = 0; i < L; i++) T.alphaPModq[a][i] = P.alphaPModq[a][i];
+    CK(cudaMalloc(&c->d_tab, sizeof(DevTables)));
+    CK(cudaMemcpy(c->d_tab, &T, sizeof(T), cudaMemcpyHostToDevice));
+
+    // PackedEncoding slot permutation (OpenFHE PackedEncoding::SetParams_2n as restated in
+    // oracle/psi_oracle.c: slot i <-> exponent 5^i, slot i+N/2 <-> 3*5^i, bit-reversed transform order)
+    std::vector<uint32_t> perm(N);
+    const u64 m2 = 2ull * N;
+    u64 cur = 1;
+    for (uint32_t i = 0; i < N / 2; i++) {
+        perm[h_bitrev((uint32_t)((cur - 1) / 2), (int)c->logN)] = i;
+        const u64 cof = (cur * 3) % m2;
+        perm[h_bitrev((uint32_t)((cof - 1) / 2), (int)c->logN)] = i + N / 2;
+        cur = (cur * 5) % m2;
+    }
+    CK(c->to_crt.alloc(N));
+    CK(cudaMemcpy(c->to_crt.p, perm.data(), N * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return PSI_OK;
+}
+
+static int alloc_work(psi_ctx* c) {
+    const size_t N = c->N, L = c->L, LT = c->L + c->Lp, b = c->b, K = c->K;
+    CK(c->acc.alloc(K * b * 2 * L * N));
+    CK(c->out.alloc(b * 2 * L * N));
+    if (K > 1) {
+        CK(c->coef.alloc(b * 4 * L * N));
+        CK(c->e1.alloc(b * 2 * LT * N));
+        CK(c->e2.alloc(b * 2 * LT * N));
+        CK(c->ten.alloc(b * 3 * LT * N));
+        CK(c->res.alloc(b * 3 * L * N));
+        CK(c->dig.alloc(b * L * L * N));
+        if (K > 2) CK(c->prod.alloc(b * 2 * L * N));
+    }
+    return PSI_OK;
+}
+
+// One batched EvalMult(ct,ct) + relinearise over B ciphertext pairs (+ optional mask multiply).
+// a, bb: [B][2][L][N] EVALUATION (a = multipliedResult, bb = innerProductResult; the operand order of
+// BatchedFHEHIPPIE.cpp:123 matters); out: [B][2][L][N].
+static int mul_ctct_batch(psi_ctx* c, cudaStream_t s, uint32_t B, const u64* a, const u64* bb, const u64* mask,
+                          u64* out, uint32_t* launches) {
+    const KCtx k = c->k(s);
+    const uint32_t L = c->L, Lp = c->Lp, LT = L + Lp;
+    const size_t N = c->N;
+    uint32_t nl = 0;
+    u64* coef1 = c->coef.p;                         // [B*2][L][N]
+    u64* coef2 = c->coef.p + (size_t)B * 2 * L * N;  // [B*2][L][N]
+    // (1) both operands to COEFFICIENT
+    NttBatch nb{a, coef1, B * 2 * L, L, L * N, N, L * N, 0, L};
+    CK(launch_ntt(k, nb, true)); nl++;
+    nb = NttBatch{bb, coef2, B * 2 * L, L, L * N, N, L * N, 0, L};
+    CK(launch_ntt(k, nb, true)); nl++;
+    // (2) first operand: exact Q -> P extension; Q limbs stay as given (EVALUATION)
+    CK(launch_expand_q_to_p(k, B * 2, coef1, c->e1.p)); nl++;
+    nb = NttBatch{c->e1.p + (size_t)L * N, c->e1.p + (size_t)L * N, B * 2 * Lp, Lp, LT * N, N, LT * N, L, Lp};
+    CK(launch_ntt(k, nb, false)); nl++;
+    CK(cudaMemcpy2DAsync(c->e1.p, LT * N * sizeof(u64), a, L * N * sizeof(u64), L * N * sizeof(u64), (size_t)B * 2,
+                         cudaMemcpyDeviceToDevice, s));
+    // (3) second operand: P-over-Q fast extension, all limbs back to EVALUATION
+    CK(launch_fast_expand_poverq(k, B * 2, coef2, c->e2.p)); nl++;
+    nb = NttBatch{c->e2.p, c->e2.p, B * 2 * LT, LT, LT * N, N, LT * N, 0, LT};
+    CK(launch_ntt(k, nb, false)); nl++;
+    // (4) tensor, (5) COEFFICIENT, (6) scale by t/P and round into Q
+    CK(launch_tensor(k, B, c->e1.p, c->e2.p, c->ten.p)); nl++;
+    nb = NttBatch{c->ten.p, c->ten.p, B * 3 * LT, LT, LT * N, N, LT * N, 0, LT};
+    CK(launch_ntt(k, nb, true)); nl++;
+    CK(launch_scale_round(k, B * 3, c->ten.p, c->res.p)); nl++;
+    // (7) relinearise: digits of c2 (BV, digit size 0), everything to EVALUATION, accumulate
+    CK(launch_relin_digits(k, B, c->res.p, c->dig.p)); nl++;
+    nb = NttBatch{c->dig.p, c->dig.p, B * L * L, L, L * N, N, L * N, 0, L};
+    CK(launch_ntt(k, nb, false)); nl++;
+    // components 0 and 1 only: group = bin, 2L of its 3L limb-polys
+    nb = NttBatch{c->res.p, c->res.p, B * 2 * L, 2 * L, 3 * L * N, N, 3 * L * N, 0, L};
+    CK(launch_ntt(k, nb, false)); nl++;
+    CK(launch_relin_accum(k, B, c->res.p, c->dig.p, c->evk_b.p, c->evk_a.p, mask, out)); nl++;
+    if (launches) *launches += nl;
+    return PSI_OK;
+}
+
+}  // namespace psi
+
+extern "C" {
+
+const char* psi_last_error(void) { return g_last_error.c_str(); }
+const char* psi_version(void) { return "psi_b200 0.1 (sm_100a)"; }
+
+int psi_ctx_create(const psi_params* p, int device, psi_ctx** out) {
+    if (!p || !out) return set_error(PSI_ERR_INVALID, "null argument");
+    *out = nullptr;
+    const uint32_t N = p->N;
+    if (N < 8 || (N & (N - 1)) || N > 16384) return set_error(PSI_ERR_INVALID, "ring dimension must be a power of two in [8, 16384]");
+    if (p->L < 1 || p->L > PSI_MAX_LIMBS || p->Lp < 1 || p->Lp > PSI_MAX_LIMBS)
+        return set_error(PSI_ERR_INVALID, "sizeQ / sizeP out of range");
+    if (p->mult_technique != PSI_MULT_HPSPOVERQ)
+        return set_error(PSI_ERR_INVALID, "only MultiplicationTechnique HPSPOVERQ (the BFVrns default) is implemented");
+    if (p->ks_technique != PSI_KS_BV) return set_error(PSI_ERR_INVALID, "only BV key switching with digit size 0 is implemented");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    if (ndev == 0) return set_error(PSI_ERR_NO_DEVICE, "no CUDA device; this library has no CPU path");
+    if (device < 0 || device >= ndev) return set_error(PSI_ERR_INVALID, "device ordinal out of range");
+    psi_ctx* c = new (std::nothrow) psi_ctx();
+    if (!c) return set_error(PSI_ERR_INVALID, "out of host memory");
+    c->device = device;
+    c->P = *p;
+    c->N = N;
+    c->L = p->L;
+    c->Lp = p->Lp;
+    while ((1u << c->logN) < N) c->logN++;
+    int rc = ensure_device(c);
+    if (rc == PSI_OK) rc = build_tables(c);
+    if (rc != PSI_OK) {
+        psi_ctx_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return PSI_OK;
+}
+
+int psi_ctx_destroy(psi_ctx* c) {
+    if (!c) return PSI_OK;
+    cudaSetDevice(c->device);
+    if (c->d_tab) cudaFree(c->d_tab);
+    DevBuf<u64>* bufs[] = {&c->twiddles, &c->evk_b, &c->evk_a, &c->pt, &c->mask, &c->idx, &c->minus, &c->acc,
+                           &c->coef,     &c->e1,    &c->e2,    &c->ten, &c->res, &c->dig, &c->prod,  &c->out};
+    for (auto* b : bufs) b->release();
+    c->to_crt.release();
+    delete c;
+    return PSI_OK;
+}
+
+int psi_set_relin_key(psi_ctx* c, const uint64_t* evk_b, const uint64_t* evk_a) {
+    if (!c || !evk_b || !evk_a) return set_error(PSI_ERR_INVALID, "null argument");
+    int rc = ensure_device(c);
+    if (rc) return rc;
+    const size_t n = (size_t)c->L * c->L * c->N;
+    CK(c->evk_b.alloc(n));
+    CK(c->evk_a.alloc(n));
+    CK(cudaMemcpy(c->evk_b.p, evk_b, n * sizeof(u64), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->evk_a.p, evk_a, n * sizeof(u64), cudaMemcpyHostToDevice));
+    c->have_evk = true;
+    return PSI_OK;
+}
+
+static int db_dims(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E) {
+    if (K < 1 || b < 1 || E < 1) return set_error(PSI_ERR_INVALID, "K, b, E must be positive");
+    c->K = K;
+    c->b = b;
+    c->E = E;
+    c->have_db = false;
+    c->have_query = false;
+    c->ran = false;
+    const size_t LN = (size_t)c->L * c->N;
+    CK(c->pt.alloc((size_t)K * b * E * LN));
+    CK(c->mask.alloc((size_t)b * LN));
+    CK(c->idx.alloc((size_t)K * E * 2 * LN));
+    CK(c->minus.alloc(2 * LN));
+    return alloc_work(c);
+}
+
+int psi_db_load_limbs(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E, const uint64_t* pt_limbs,
+                      const uint64_t* mask_limbs) {
+    if (!c || !pt_limbs || !mask_limbs) return set_error(PSI_ERR_INVALID, "null argument");
+    int rc = ensure_device(c);
+    if (rc) return rc;
+    if ((rc = db_dims(c, K, b, E))) return rc;
+    const size_t LN = (size_t)c->L * c->N;
+    CK(cudaMemcpy(c->pt.p, pt_limbs, (size_t)K * b * E * LN * sizeof(u64), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->mask.p, mask_limbs, (size_t)b * LN * sizeof(u64), cudaMemcpyHostToDevice));
+    c->have_db = true;
+    return PSI_OK;
+}
+
+// MakePackedPlaintext + SetFormat(EVALUATION) for n_pt plaintexts, chunked so that the staging
+// buffers stay small next to the DB itself.
+static int encode_into(psi_ctx* c, size_t n_pt, uint32_t nslots, const int64_t* slots, u64* dst) {
+    const size_t N = c->N, L = c->L;
+    const size_t chunk = n_pt < 256 ? n_pt : 256;
+    DevBuf<long long> d_slots;
+    DevBuf<u64> d_crt;
+    CK(d_slots.alloc(chunk * nslots));
+    CK(d_crt.alloc(chunk * N));
+    const KCtx k = c->k(0);
+    int rc = PSI_OK;
+    for (size_t p0 = 0; p0 < n_pt && rc == PSI_OK; p0 += chunk) {
+        const uint32_t n = (uint32_t)((n_pt - p0) < chunk ? (n_pt - p0) : chunk);
+        cudaError_t e = cudaMemcpy(d_slots.p, slots + p0 * nslots, (size_t)n * nslots * sizeof(int64_t), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = launch_slots_to_crt(k, n, nslots, d_slots.p, c->to_crt.p, d_crt.p);
+        if (e == cudaSuccess) {
+            NttBatch nb{d_crt.p, d_crt.p, n, 1, N, 0, N, c->L + c->Lp, 1};
+            e = launch_ntt(k, nb, true);  // slots -> coefficients mod t
+        }
+        if (e == cudaSuccess) {
+            // residues in [0,t) are below every q_l: each limb is the same vector, then NTT mod q_l
+            NttBatch nb{d_crt.p, dst + p0 * L * N, n * (uint32_t)L, (uint32_t)L, N, 0, L * N, 0, (uint32_t)L};
+            e = launch_ntt(k, nb, false);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+        if (e != cudaSuccess) rc = cuda_fail(e, "psi_db_encode_slots");
+    }
+    d_slots.release();
+    d_crt.release();
+    return rc;
+}
+
+int psi_db_encode_slots(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E, uint32_t nslots, const int64_t* slots,
+                        const int64_t* mask_slots) {
+    if (!c || !slots || !mask_slots) return set_error(PSI_ERR_INVALID, "null argument");
+    if (nslots < 1 || nslots > c->N) return set_error(PSI_ERR_INVALID, "batch size must be in [1, N]");
+    // PackedEncoding::Encode rejects |v| >= t
+    const uint64_t t = c->P.t;
+    const size_t n_slots_total = (size_t)K * b * E * nslots, n_mask_total = (size_t)b * nslots;
+    for (size_t i = 0; i < n_slots_total; i++) {
+        const int64_t v = slots[i];
+        if ((uint64_t)(v < 0 ? -v : v) >= t) return set_error(PSI_ERR_INVALID, "slot value out of range of the plaintext modulus");
+    }
+    for (size_t i = 0; i < n_mask_total; i++) {
+        const int64_t v = mask_slots[i];
+        if ((uint64_t)(v < 0 ? -v : v) >= t) return set_error(PSI_ERR_INVALID, "mask value out of range of the plaintext modulus");
+    }
+    int rc = ensure_device(c);
+    if (rc) return rc;
+    if ((rc = db_dims(c, K, b, E))) return rc;
+    if ((rc = encode_into(c, (size_t)K * b * E, nslots, slots, c->pt.p))) return rc;
+    if ((rc = encode_into(c, b, nslots, mask_slots, c->mask.p))) return rc;
+    c->have_db = true;
+    return PSI_OK;
+}
+
+int psi_db_get_limbs(psi_ctx* c, uint64_t* pt_limbs, uint64_t* mask_limbs) {
+    if (!c) return set_error(PSI_ERR_INVALID, "null argument");
+    if (!c->have_db) return set_error(PSI_ERR_STATE, "no database loaded");
+    int rc = ensure_device(c);
+    if (rc) return rc;
+    const size_t LN = (size_t)c->L * c->N;
+    if (pt_limbs) CK(cudaMemcpy(pt_limbs, c->pt.p, (size_t)c->K * c->b * c->E * LN * sizeof(u64), cudaMemcpyDeviceToHost));
+    if (mask_limbs) CK(cudaMemcpy(mask_limbs, c->mask.p, (size_t)c->b * LN * sizeof(u64), cudaMemcpyDeviceToHost));
+    return PSI_OK;
+}
+
+int psi_query_set(psi_ctx* c, const uint64_t* idx, const uint64_t* minus, void* stream) {
+    if (!c || !idx || !minus) return set_error(PSI_ERR_INVALID, "null argument");
+    if (!c->have_db) return set_error(PSI_ERR_STATE, "load the database before the query (it fixes K and E)");
+    int rc = ensure_device(c);
+    if (rc) return rc;
+    const size_t LN = (size_t)c->L * c->N;
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(c->idx.p, idx, (size_t)c->K * c->E * 2 * LN * sizeof(u64), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->minus.p, minus, 2 * LN * sizeof(u64), cudaMemcpyHostToDevice, s));
+    c->have_query = true;
+    return PSI_OK;
+}
+
+int psi_run(psi_ctx* c, void* stream) { return psi_run_phases(c, PSI_PHASE_ALL, stream); }
+
+int psi_run_phases(psi_ctx* c, uint32_t phases, void* stream) {
+    if (!c) return set_error(PSI_ERR_INVALID, "null argument");
+    if (!(phases & PSI_PHASE_ALL)) return set_error(PSI_ERR_INVALID, "no phase selected");
+    if (!c->have_db || !c->have_query) return set_error(PSI_ERR_STATE, "run() needs a database and a query");
+    if (c->K > 1 && !c->have_evk) return set_error(PSI_ERR_STATE, "EvalMult(ct,ct) needs the relinearisation key");
+    int rc = ensure_device(c);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const KCtx k = c->k(s);
+    const size_t ct = (size_t)2 * c->L * c->N;
+    uint32_t nl = 0;
+    if (phases & PSI_PHASE_INNER_PRODUCT) {
+        CK(launch_mac(k, c->K, c->b, c->E, c->pt.p, c->idx.p, c->minus.p, c->acc.p)); nl++;
+    }
+    if (!(phases & PSI_PHASE_MULTIPLY_MASK)) {
+        c->launches_per_run = nl;
+        return PSI_OK;
+    }
+    if (c->K == 1) {
+        CK(launch_mul_ctpt(k, c->b, c->acc.p, c->mask.p, c->out.p)); nl++;
+    } else {
+        const u64* prod = c->acc.p;  // hf = 0
+        for (uint32_t hf = 1; hf < c->K; hf++) {
+            const bool last = hf + 1 == c->K;
+            u64* dst = last ? c->out.p : c->prod.p;
+            if ((rc = mul_ctct_batch(c, s, c->b, prod, c->acc.p + (size_t)hf * c->b * ct, last ? c->mask.p : nullptr,
+                                     dst, &nl)))
+                return rc;
+            prod = dst;
+        }
+    }
+    c->launches_per_run = nl;
+    c->ran = true;
+    return PSI_OK;
+}
+
+int psi_result_get(psi_ctx* c, uint64_t* out, void* stream) {
+    if (!c || !out) return set_error(PSI_ERR_INVALID, "null argument");
+    if (!c->ran) return set_error(PSI_ERR_STATE, "getResultList() before run()");
+    int rc = ensure_device(c);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, c->out.p, (size_t)c->b * 2 * c->L * c->N * sizeof(u64), cudaMemcpyDeviceToHost,
+                       (cudaStream_t)stream));
+    return PSI_OK;
+}
+
+int psi_stream_sync(void* stream) {
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return PSI_OK;
+}
+
+int psi_run_launch_count(psi_ctx* c, uint32_t* out) {
+    if (!c || !out) return set_error(PSI_ERR_INVALID, "null argument");
+    if (!c->ran) return set_error(PSI_ERR_STATE, "launch count is known after the first run()");
+    *out = c->launches_per_run;
+    return PSI_OK;
+}
+
+int psi_result_device_ptr(psi_ctx* c, void** out, size_t* bytes) {
+    if (!c || !out || !bytes) return set_error(PSI_ERR_INVALID, "null argument");
+    if (!c->have_db) return set_error(PSI_ERR_STATE, "no database loaded");
+    *out = c->out.p;
+    *bytes = (size_t)c->b * 2 * c->L * c->N * sizeof(u64);
+    return PSI_OK;
+}
+
+int psi_debug_ntt(psi_ctx* c, uint64_t* data, const uint32_t* moduli, uint32_t n_polys, int inverse) {
+    if (!c || !data || !moduli) return set_error(PSI_ERR_INVALID, "null argument");
+    int rc = ensure_device(c);
+    if (rc) return rc;
+    const size_t N = c->N;
+    DevBuf<u64> d;
+    CK(d.alloc((size_t)n_polys * N));
+    CK(cudaMemcpy(d.p, data, (size_t)n_polys * N * sizeof(u64), cudaMemcpyHostToDevice));
+    const KCtx k = c->k(0);
+    // group consecutive polys with the same modulus into one launch
+    uint32_t i = 0;
+    while (i < n_polys) {
+        if (moduli[i] > c->L + c->Lp) {
+            d.release();
+            return set_error(PSI_ERR_INVALID, "modulus index out of range");
+        }
+        uint32_t j = i;
+        while (j < n_polys && moduli[j] == moduli[i]) j++;
+        NttBatch nb{d.p + i * N, d.p + i * N, j - i, 1, N, 0, N, moduli[i], 1};
+        cudaError_t e = launch_ntt(k, nb, inverse != 0);
+        if (e != cudaSuccess) {
+            d.release();
+            return cuda_fail(e, "launch_ntt");
+        }
+        i = j;
+    }
+    cudaError_t e = cudaMemcpy(data, d.p, (size_t)n_polys * N * sizeof(u64), cudaMemcpyDeviceToHost);
+    d.release();
+    if (e != cudaSuccess) return cuda_fail(e, "psi_debug_ntt");
+    return PSI_OK;
+}
+
+int psi_debug_mul_ctct(psi_ctx* c, const uint64_t* ct1, const uint64_t* ct2, uint64_t* out) {
+    if (!c || !ct1 || !ct2 || !out) return set_error(PSI_ERR_INVALID, "null argument");
+    if (!c->have_evk) return set_error(PSI_ERR_STATE, "EvalMult(ct,ct) needs the relinearisation key");
+    int rc = ensure_device(c);
+    if (rc) return rc;
+    // borrow the work buffers with b = 1, K = 2
+    const uint32_t sK = c->K, sb = c->b, sE = c->E;
+    const bool sdb = c->have_db, sq = c->have_query, sr = c->ran;
+    if (!c->have_db) {
+        c->K = 2;
+        c->b = 1;
+        c->E = 1;
+        if ((rc = alloc_work(c))) return rc;
+    } else if (c->K < 2) {
+        return set_error(PSI_ERR_STATE, "debug ct x ct needs work buffers of a K >= 2 database (or no database)");
+    }
+    const size_t ct = (size_t)2 * c->L * c->N;
+    DevBuf<u64> in;
+    CK(in.alloc(3 * ct));
+    CK(cudaMemcpy(in.p, ct1, ct * sizeof(u64), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(in.p + ct, ct2, ct * sizeof(u64), cudaMemcpyHostToDevice));
+    rc = mul_ctct_batch(c, 0, 1, in.p, in.p + ct, nullptr, in.p + 2 * ct, nullptr);
+    if (rc == PSI_OK) {
+        cudaError_t e = cudaMemcpy(out, in.p + 2 * ct, ct * sizeof(u64), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "psi_debug_mul_ctct");
+    }
+    in.release();
+    c->K = sK;
+    c->b = sb;
+    c->E = sE;
+    c->have_db = sdb;
+    c->have_query = sq;
+    c->ran = sr;
+    return rc;
+}
+
+int psi_bench_imad_peak(int device, double* mads_per_second) {
+    if (!mads_per_second) return set_error(PSI_ERR_INVALID, "null argument");
+    cudaError_t e = imad_peak(device, mads_per_second);
+    if (e != cudaSuccess) return cuda_fail(e, "psi_bench_imad_peak");
+    return PSI_OK;
+}
+
+}  // extern "C"

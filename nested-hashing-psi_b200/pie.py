@@ -1,0 +1,360 @@
+"""Host-side mirror of the reference's objects around the batched FHE PIE, over the C ABI.
+
+    BatchedFHEHIPPIE(cryptoContext, pK, hct)   src/Common/Crypto/PrivateIndexedEqualityCheck/BatchedFHEHIPPIE.hpp:30-31
+      .setIndex(indexMatrix)                   :40-43   K x E ciphertexts
+      .setMinusCompareElement(ct)              :45-48
+      .run()                                   :33      BatchedFHEHIPPIE.cpp:88-129
+      .getResultList()                         :35-38   b ciphertexts
+    HierarchicalCuckooHashTable(hashfunction, eachSimpleTableSize, eachCuckooTableSize, serverStashSize,
+                                numberOfSimpleHashFunctions, numberOfCuckooHashFunctions, simpleMultiTable,
+                                cuckooMultiTable, maxItemsPerPosition)   src/Common/Hashing/HierarchicalCuckooHashTable.cpp:16-53
+    TabulationHashing(seed, numberOfHashfunctions)                      src/Common/Hashing/TabulationHashing.cpp:16-36
+    RandomDataInput(serverSetSize, clientSetSize, intersectionSetSize, seed, bitSize)  src/Common/DataInput/RandomDataInput.cpp:10-29
+
+Ciphertexts are numpy uint64 arrays [2][L][N] (the limbs DCRTPoly::GetElementAtIndex(l).GetValues()
+exposes), EVALUATION format.  Errors follow the reference: invalid arguments raise ValueError with the
+reference's message (std::invalid_argument there), cuckoo insertion failure raises RuntimeError.
+"""
+import ctypes
+
+import numpy as np
+
+from . import capi
+from .capi import PsiError, check, lib
+
+
+def _u64(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a, a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
+
+
+def _i64(a):
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    return a, a.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+
+
+def _raise_like_reference(err):
+    """std::invalid_argument -> ValueError, std::runtime_error (hashing) -> RuntimeError."""
+    if err.status == capi.PSI_ERR_INVALID:
+        raise ValueError(err.message) from None
+    raise err
+
+
+class PublicKey:
+    """Stored but never used by run() (BatchedFHEHIPPIE.hpp:22); kept for signature parity."""
+
+
+class CryptoContext:
+    """What the PIE needs of lbcrypto::CryptoContext<DCRTPoly>: the BFV-RNS parameter tables, the
+    relinearisation key (DeserializeEvalMultKey, BatchedFHEPSIServer.cpp:49) and the device evaluator."""
+
+    def __init__(self, params, device=0):
+        self.params = params
+        self.device = device
+        self.N, self.L, self.Lp, self.t = params.N, params.L, params.Lp, params.t
+        h = ctypes.c_void_p()
+        check(lib().psi_ctx_create(ctypes.byref(params), device, ctypes.byref(h)))
+        self._h = h
+
+    @classmethod
+    def generate(cls, N, t, depth, device=0, L=0):
+        return cls(capi.params_generate(N, t, depth, L), device)
+
+    def GetPlaintextModulus(self):
+        return self.t
+
+    def GetRingDimension(self):
+        return self.N
+
+    def InsertEvalMultKey(self, evk_b, evk_a):
+        (evk_b, pb), (evk_a, pa) = _u64(evk_b), _u64(evk_a)
+        assert evk_b.shape == (self.L, self.L, self.N) and evk_a.shape == evk_b.shape
+        check(lib().psi_set_relin_key(self._h, pb, pa))
+
+    # --- raw C-ABI level (the PIE class sits on top of these) ----------------------------------
+    def db_load_limbs(self, pt, mask):
+        (pt, pp), (mask, pm) = _u64(pt), _u64(mask)
+        K, b, E = pt.shape[:3]
+        assert pt.shape == (K, b, E, self.L, self.N) and mask.shape == (b, self.L, self.N)
+        check(lib().psi_db_load_limbs(self._h, K, b, E, pp, pm))
+        self._dims = (K, b, E)
+
+    def db_encode_slots(self, slots, mask_slots):
+        (slots, ps), (mask_slots, pm) = _i64(slots), _i64(mask_slots)
+        K, b, E, n = slots.shape
+        assert mask_slots.shape == (b, n)
+        try:
+            check(lib().psi_db_encode_slots(self._h, K, b, E, n, ps, pm))
+        except PsiError as e:
+            _raise_like_reference(e)
+        self._dims = (K, b, E)
+
+    def db_get_limbs(self):
+        K, b, E = self._dims
+        pt = np.empty((K, b, E, self.L, self.N), dtype=np.uint64)
+        mask = np.empty((b, self.L, self.N), dtype=np.uint64)
+        check(lib().psi_db_get_limbs(self._h, pt.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)),
+                                     mask.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
+        return pt, mask
+
+    def query_set(self, idx, minus, stream=None):
+        (idx, pi), (minus, pm) = _u64(idx), _u64(minus)
+        K, b, E = self._dims
+        assert idx.shape == (K, E, 2, self.L, self.N) and minus.shape == (2, self.L, self.N)
+        check(lib().psi_query_set(self._h, pi, pm, stream))
+        self._keep = (idx, minus)  # the copy is asynchronous: keep the host buffers alive
+
+    def query_set_ptr(self, idx_ptr, minus_ptr, stream=None):
+        """Same, from raw (pinned) host addresses."""
+        check(lib().psi_query_set(self._h, ctypes.cast(idx_ptr, ctypes.POINTER(ctypes.c_uint64)),
+                                  ctypes.cast(minus_ptr, ctypes.POINTER(ctypes.c_uint64)), stream))
+
+    def run(self, stream=None, phases=3):
+        """psi_run / psi_run_phases: 1 = inner products only, 2 = ct x ct + mask only, 3 = all."""
+        check(lib().psi_run_phases(self._h, phases, stream))
+
+    def result_get(self, out=None, stream=None, sync=True):
+        K, b, E = self._dims
+        if out is None:
+            out = np.empty((b, 2, self.L, self.N), dtype=np.uint64)
+        check(lib().psi_result_get(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), stream))
+        if sync:
+            check(lib().psi_stream_sync(stream))
+        return out
+
+    def result_get_ptr(self, out_ptr, stream=None):
+        check(lib().psi_result_get(self._h, ctypes.cast(out_ptr, ctypes.POINTER(ctypes.c_uint64)), stream))
+
+    def sync(self, stream=None):
+        check(lib().psi_stream_sync(stream))
+
+    def run_launch_count(self):
+        n = ctypes.c_uint32()
+        check(lib().psi_run_launch_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    def result_device_ptr(self):
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        check(lib().psi_result_device_ptr(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def debug_ntt(self, polys, moduli, inverse=False):
+        polys = np.array(polys, dtype=np.uint64, order="C", copy=True)
+        moduli = np.ascontiguousarray(moduli, dtype=np.uint32)
+        assert polys.ndim == 2 and polys.shape[1] == self.N and moduli.shape == (polys.shape[0],)
+        check(lib().psi_debug_ntt(self._h, polys.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)),
+                                  moduli.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), polys.shape[0],
+                                  1 if inverse else 0))
+        return polys
+
+    def debug_mul_ctct(self, ct1, ct2):
+        (ct1, p1), (ct2, p2) = _u64(ct1), _u64(ct2)
+        out = np.empty((2, self.L, self.N), dtype=np.uint64)
+        check(lib().psi_debug_mul_ctct(self._h, p1, p2, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().psi_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class TabulationHashing:
+    """TabulationHashing(seed, numberOfHashfunctions) — tables are derived inside the library from
+    (seed, count), so this object only carries the two numbers."""
+
+    def __init__(self, seed=342797434736, numberOfHashfunctions=3):
+        self.seed = int(seed)
+        self.numberOfHashfunctions = int(numberOfHashfunctions)
+
+
+def hash_index(hashfunction, items, hfInd, tableSize):
+    """calculateHashIndex (HashUtils.cpp:34-37), vectorised over items."""
+    (items, pi) = _u64(np.atleast_1d(items))
+    out = np.empty(items.shape[0], dtype=np.uint64)
+    check(lib().psi_hash_index(hashfunction.seed, hashfunction.numberOfHashfunctions, pi, items.shape[0], hfInd,
+                               tableSize, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
+    return out
+
+
+class HierarchicalCuckooHashTable:
+    def __init__(self, hashfunction, eachSimpleTableSize, eachCuckooTableSize, serverStashSize=0,
+                 numberOfSimpleHashFunctions=2, numberOfCuckooHashFunctions=2, simpleMultiTable=False,
+                 cuckooMultiTable=True, maxItemsPerPosition=1, evictionSeed=0x5EED):
+        if hashfunction.numberOfHashfunctions < numberOfSimpleHashFunctions + numberOfCuckooHashFunctions:
+            raise ValueError("hash function object provides too few hash functions")
+        self.hashfunction = hashfunction
+        self.k, self.e = numberOfSimpleHashFunctions, eachSimpleTableSize
+        self.K, self.E, self.b = numberOfCuckooHashFunctions, eachCuckooTableSize, maxItemsPerPosition
+        self.stash = serverStashSize
+        h = ctypes.c_void_p()
+        try:
+            check(lib().psi_hct_create(hashfunction.seed, self.k, self.e, self.K, self.E, self.b, serverStashSize,
+                                       int(simpleMultiTable), int(cuckooMultiTable), evictionSeed, ctypes.byref(h)))
+        except PsiError as e:
+            _raise_like_reference(e)
+        self._h = h
+
+    def insertAll(self, elements):
+        (elements, pe) = _u64(elements)
+        try:
+            check(lib().psi_hct_insert_all(self._h, pe, elements.shape[0]))
+        except PsiError as e:
+            if e.status == capi.PSI_ERR_STATE:
+                raise RuntimeError(e.message) from None
+            _raise_like_reference(e)
+
+    def cells(self):
+        """[k][e][K][b][E] — hierarchicalCuckooTable[outerHf][outerPos].cuckooTable[innerHf][bin][pos]."""
+        out = np.empty((self.k, self.e, self.K, self.b, self.E), dtype=np.uint64)
+        check(lib().psi_hct_get_cells(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
+        return out
+
+    def getServerStashSize(self):
+        return self.stash
+
+    def getEachBinSize(self):
+        return self.b
+
+    def getEachCuckooTableSize(self):
+        return self.E
+
+    def getNumberOfCuckooHashFunctions(self):
+        return self.K
+
+    def getNumberOfSimpleTables(self):
+        return self.k
+
+    def getEachSimpleTableSize(self):
+        return self.e
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().psi_hct_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def client_table(hashfunction, k, e, K, items, evictionSeed=0xC11E):
+    """The client's cuckoo table (BatchedFHEPSIClient.cpp:97-99,109): [k][e], 0 = empty."""
+    (items, pi) = _u64(items)
+    out = np.empty((k, e), dtype=np.uint64)
+    try:
+        check(lib().psi_client_table(hashfunction.seed, k, e, K, pi, items.shape[0], evictionSeed,
+                                     out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
+    except PsiError as err:
+        if err.status == capi.PSI_ERR_STATE:
+            raise RuntimeError(err.message) from None
+        _raise_like_reference(err)
+    return out
+
+
+class RandomDataInput:
+    def __init__(self, serverSetSize, clientSetSize, intersectionSetSize, setGenerationSeed=123456789, bitSize=32):
+        self.serverSet = np.empty(serverSetSize, dtype=np.uint64)
+        self.clientSet = np.empty(clientSetSize, dtype=np.uint64)
+        self.intersectionSet = np.empty(intersectionSetSize, dtype=np.uint64)
+        p = ctypes.POINTER(ctypes.c_uint64)
+        try:
+            check(lib().psi_random_data_input(serverSetSize, clientSetSize, intersectionSetSize, setGenerationSeed,
+                                              bitSize, self.serverSet.ctypes.data_as(p),
+                                              self.clientSet.ctypes.data_as(p), self.intersectionSet.ctypes.data_as(p)))
+        except PsiError as e:
+            _raise_like_reference(e)
+
+    def getServerSet(self):
+        return self.serverSet
+
+    def getClientSet(self):
+        return self.clientSet
+
+    def getIntersectionSet(self):
+        return self.intersectionSet
+
+
+class BatchedFHEHIPPIE:
+    """The reference's operator, same five entry points.  The constructor mutates `hct` (bin shuffle),
+    exactly as BatchedFHEHIPPIE.cpp:28-35 does."""
+
+    def __init__(self, cryptoContext, pK, hct, shuffleSeed=0x5EED0001, maskSeed=0x5EED0002, keepSlots=False):
+        self.cryptoContext = cryptoContext
+        self.pK = pK
+        h = ctypes.c_void_p()
+        try:
+            check(lib().psi_pie_create(cryptoContext._h, ctypes.byref(cryptoContext.params), hct._h, shuffleSeed,
+                                       maskSeed, int(keepSlots), ctypes.byref(h)))
+        except PsiError as e:
+            _raise_like_reference(e)
+        self._h = h
+        K, b, E, n = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        check(lib().psi_pie_dims(h, ctypes.byref(K), ctypes.byref(b), ctypes.byref(E), ctypes.byref(n)))
+        self.K, self.b, self.E, self.batchSize = K.value, b.value, E.value, n.value
+        cryptoContext._dims = (self.K, self.b, self.E)
+        self.indexMatrix = None
+        self.minusCompareElement = None
+        self._uploaded = False
+        self._resultList = None
+
+    def setIndex(self, indexMatrix):
+        """indexMatrix: K x E ciphertexts (nested lists of [2][L][N] arrays, or one [K][E][2][L][N] array)."""
+        self.indexMatrix = indexMatrix
+        self._uploaded = False
+
+    def setMinusCompareElement(self, minusCompareElement):
+        self.minusCompareElement = minusCompareElement
+        self._uploaded = False
+
+    def _upload(self):
+        if self._uploaded:
+            return
+        cc = self.cryptoContext
+        if self.indexMatrix is None or self.minusCompareElement is None:
+            raise ValueError("setIndex and setMinusCompareElement must be called before run()")
+        idx = np.ascontiguousarray(np.asarray(self.indexMatrix, dtype=np.uint64))
+        if idx.shape != (self.K, self.E, 2, cc.L, cc.N):
+            raise ValueError("indexMatrix must hold K x E ciphertexts of [2][L][N] limbs")
+        (idx, pi), (minus, pm) = _u64(idx), _u64(self.minusCompareElement)
+        if minus.shape != (2, cc.L, cc.N):
+            raise ValueError("minusCompareElement must be one ciphertext of [2][L][N] limbs")
+        try:
+            check(lib().psi_pie_set_query(self._h, pi, pm))
+        except PsiError as e:
+            _raise_like_reference(e)
+        self._uploaded = True
+
+    def run(self):
+        self._upload()
+        check(lib().psi_pie_run(self._h))
+        self._resultList = None
+
+    def getResultList(self):
+        if self._resultList is None:
+            cc = self.cryptoContext
+            out = np.empty((self.b, 2, cc.L, cc.N), dtype=np.uint64)
+            check(lib().psi_pie_get_result_list(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
+            self._resultList = out
+        return self._resultList
+
+    def slots(self):
+        """(slots [K][b][E][batch], mask slots [b][batch]) the constructor encoded; needs keepSlots."""
+        s = np.empty((self.K, self.b, self.E, self.batchSize), dtype=np.int64)
+        m = np.empty((self.b, self.batchSize), dtype=np.int64)
+        check(lib().psi_pie_get_slots(self._h, s.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                      m.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))))
+        return s, m
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().psi_pie_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

@@ -49,6 +49,8 @@ def lib():
         L.orc_mac_bin.argtypes = [ctypes.c_void_p, ctypes.c_int, _u64p, _u64p, _u64p, _u64p]
         L.orc_mul_ctpt.argtypes = [ctypes.c_void_p, _u64p, _u64p, _u64p]
         L.orc_mul_ctct.argtypes = [ctypes.c_void_p, _u64p, _u64p, _u64p, _u64p, _u64p]
+        L.orc_mul_core.argtypes = [ctypes.c_void_p, _u64p, _u64p, _u64p]
+        L.orc_relin.argtypes = [ctypes.c_void_p, _u64p, _u64p, _u64p, _u64p]
         L.orc_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _u64p, _u64p, _u64p,
                               _u64p, _u64p, _u64p, _u64p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.orc_max_threads.restype = ctypes.c_int
@@ -154,6 +156,17 @@ class Oracle:
         out = np.empty((2, self.L, self.N), dtype=np.uint64)
         lib().orc_mul_ctct(self._h, _p(np.ascontiguousarray(ct1)), _p(np.ascontiguousarray(ct2)),
                            _p(evk_b), _p(evk_a), _p(out))
+        return out
+
+    def mul_core(self, ct1, ct2):
+        """Tensor + scale-and-round only: [3][L][N], COEFFICIENT format, basis Q."""
+        out = np.empty((3, self.L, self.N), dtype=np.uint64)
+        lib().orc_mul_core(self._h, _p(np.ascontiguousarray(ct1)), _p(np.ascontiguousarray(ct2)), _p(out))
+        return out
+
+    def relin(self, res, evk_b, evk_a):
+        out = np.empty((2, self.L, self.N), dtype=np.uint64)
+        lib().orc_relin(self._h, _p(np.ascontiguousarray(res)), _p(evk_b), _p(evk_a), _p(out))
         return out
 
     def run(self, pt, mask, idx, minus, evk_b, evk_a, bin_begin=0, bin_end=None, nthreads=1, out=None):

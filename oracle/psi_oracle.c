@@ -532,7 +532,9 @@ static inline void switch_crt_basis_coeff(int nA, int nB, const u64* x, const u6
  * FastExpandCRTBasisPloverQ; the reference calls EvalMult(multipliedResult, innerProductResult)
  * (BatchedFHEHIPPIE.cpp:123) and that order is kept by orc_run.
  * ct1, ct2, out: [2][L][N] EVAL; evk_b, evk_a: [L][L][N] EVAL. */
-void orc_mul_ctct(const orc_ctx* c, const u64* ct1, const u64* ct2, const u64* evk_b, const u64* evk_a, u64* out) {
+/* Tensor + scale-and-round part of EvalMult(ct1, ct2) (no relinearisation).
+ * res: [3][L][N] COEFFICIENT, basis Q. */
+void orc_mul_core(const orc_ctx* c, const u64* ct1, const u64* ct2, u64* res) {
     const int N = c->N, L = c->L, Lp = c->Lp, LT = L + Lp;
     const psi_params* P = &c->P;
     size_t polyQ = (size_t)L * N, polyT = (size_t)LT * N;
@@ -540,7 +542,6 @@ void orc_mul_ctct(const orc_ctx* c, const u64* ct1, const u64* ct2, const u64* e
     u64* e2 = malloc(sizeof(u64) * 2 * polyT); /* ct2 in QP, EVAL */
     u64* tmp = malloc(sizeof(u64) * polyQ);
     u64* ten = malloc(sizeof(u64) * 3 * polyT);
-    u64* res = malloc(sizeof(u64) * 3 * polyQ); /* scaled result in Q, COEFFICIENT */
 
     for (int k = 0; k < 2; k++) {
         /* --- ct1: ExpandCRTBasis, Q limbs kept from the EVALUATION input */
@@ -613,8 +614,20 @@ void orc_mul_ctct(const orc_ctx* c, const u64* ct1, const u64* ct2, const u64* e
             }
         }
     }
-    /* --- relinearise: c0, c1 -> EVALUATION; c2 -> CRTDecompose (digit i = limb i, centred
-     * switch to every q_k, NTT) ; out = (c0 + sum_i d_i evk_b[i], c1 + sum_i d_i evk_a[i]) */
+    free(ten);
+    free(tmp);
+    free(e2);
+    free(e1);
+}
+
+/* RelinearizeCore + KeySwitchBV::KeySwitchCore (recalled): c0, c1 -> EVALUATION; c2 -> CRTDecompose
+ * (digit i = limb i, centred switch to every q_k, NTT); out = (c0 + sum_i d_i evk_b[i],
+ * c1 + sum_i d_i evk_a[i]).  res: [3][L][N] COEFFICIENT; out: [2][L][N] EVALUATION. */
+void orc_relin(const orc_ctx* c, const u64* res, const u64* evk_b, const u64* evk_a, u64* out) {
+    const int N = c->N, L = c->L;
+    const psi_params* P = &c->P;
+    size_t polyQ = (size_t)L * N;
+    u64* tmp = malloc(sizeof(u64) * polyQ);
     for (int k = 0; k < 2; k++) {
         memcpy(out + k * polyQ, res + k * polyQ, sizeof(u64) * polyQ);
         for (int l = 0; l < L; l++) ntt_fwd(out + k * polyQ + (size_t)l * N, &c->mq[l], N);
@@ -644,11 +657,14 @@ void orc_mul_ctct(const orc_ctx* c, const u64* ct1, const u64* ct2, const u64* e
             }
         }
     }
-    free(res);
-    free(ten);
     free(tmp);
-    free(e2);
-    free(e1);
+}
+
+void orc_mul_ctct(const orc_ctx* c, const u64* ct1, const u64* ct2, const u64* evk_b, const u64* evk_a, u64* out) {
+    u64* res = malloc(sizeof(u64) * 3 * (size_t)c->L * c->N); /* scaled result in Q, COEFFICIENT */
+    orc_mul_core(c, ct1, ct2, res);
+    orc_relin(c, res, evk_b, evk_a, out);
+    free(res);
 }
 
 /* BatchedFHEHIPPIE::run, BatchedFHEHIPPIE.cpp:88-129.

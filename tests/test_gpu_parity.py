@@ -1,0 +1,232 @@
+"""GPU parity tests proper (run on the B200 box: pytest -m gpu).  Every test calls the product through
+the C ABI (ctypes -> libpsi_b200.so) and compares with the ORACLE on the same seeded inputs.
+Bar: bit-exact (integer residues)."""
+import os
+
+import numpy as np
+import pytest
+
+import psi_b200 as P
+from oracle.oracle import Oracle
+from oracle.params_ref import RefParams
+
+import scenario as sc
+
+pytestmark = pytest.mark.gpu
+T32 = 4296540161
+T16 = 65537
+
+
+def ctx_and_oracle(N, L, t=T32):
+    params = RefParams(N, t, L=L).to_struct()
+    return P.CryptoContext(params), Oracle(params), params
+
+
+@pytest.mark.parametrize("N,L", [(16384, 4), (8192, 3), (4096, 2), (1024, 2), (256, 2), (64, 1)])
+def test_ntt_every_modulus(N, L):
+    """Forward / inverse negacyclic NTT for every modulus of the context (q_i, p_j, t)."""
+    t = T32 if (T32 - 1) % (2 * N) == 0 else T16
+    cc, o, params = ctx_and_oracle(N, L, t)
+    rng = np.random.default_rng(N)
+    nm = params.L + params.Lp + 1
+    mods = np.repeat(np.arange(nm, dtype=np.uint32), 3)
+    polys = np.empty((len(mods), N), dtype=np.uint64)
+    for i, m in enumerate(mods):
+        q = int(params.q[m]) if m < params.L else (int(params.p[m - params.L]) if m < nm - 1 else int(params.t))
+        polys[i] = rng.integers(0, q, N, dtype=np.uint64)
+        if i % 3 == 1:
+            polys[i, ::2] = q - 1      # extreme residues
+        if i % 3 == 2:
+            polys[i] = 0
+            polys[i, -1] = 1
+    fwd = cc.debug_ntt(polys, mods)
+    for i, m in enumerate(mods):
+        assert np.array_equal(fwd[i], o.ntt(polys[i], int(m))), "forward, modulus %d" % m
+    inv = cc.debug_ntt(polys, mods, inverse=True)
+    for i, m in enumerate(mods):
+        assert np.array_equal(inv[i], o.ntt(polys[i], int(m), inverse=True)), "inverse, modulus %d" % m
+    assert np.array_equal(cc.debug_ntt(fwd, mods, inverse=True), polys)
+
+
+@pytest.mark.parametrize("N,L", [(16384, 4), (8192, 3), (1024, 2), (256, 1)])
+def test_mul_ctct_relin(N, L):
+    """EvalMult(ct,ct) + relinearisation, random (worst-case: uniformly distributed) operands."""
+    cc, o, params = ctx_and_oracle(N, L)
+    rng = np.random.default_rng(7 * N + L)
+    sk, evk_b, evk_a = o.keygen(11)
+    cc.InsertEvalMultKey(evk_b, evk_a)
+    for trial in range(2):
+        ct1, ct2 = sc.random_ct(rng, params), sc.random_ct(rng, params)
+        if trial == 1:  # structured edge values
+            ct1[0, :, :8] = 0
+            ct2[1, :, :8] = 0
+            for l in range(L):
+                ct1[1, l, 8:16] = int(params.q[l]) - 1
+                ct2[0, l, 8:16] = int(params.q[l]) - 1
+        got = cc.debug_mul_ctct(ct1, ct2)
+        want = o.mul_ctct(ct1, ct2, evk_b, evk_a)
+        assert np.array_equal(got, want)
+    # operand order matters (the two operands are extended differently)
+    assert not np.array_equal(cc.debug_mul_ctct(ct2, ct1), want) or np.array_equal(ct1, ct2)
+
+
+def test_mul_ctct_real_ciphertexts_decrypt():
+    cc, o, params = ctx_and_oracle(2048, 3)
+    rng = np.random.default_rng(5)
+    sk, evk_b, evk_a = o.keygen(2)
+    cc.InsertEvalMultKey(evk_b, evk_a)
+    t = int(params.t)
+    m1 = rng.integers(-(t // 2), t // 2, params.N, dtype=np.int64)
+    m2 = rng.integers(-(t // 2), t // 2, params.N, dtype=np.int64)
+    ct1, ct2 = o.encrypt(sk, m1, 1), o.encrypt(sk, m2, 2)
+    got = cc.debug_mul_ctct(ct1, ct2)
+    assert np.array_equal(got, o.mul_ctct(ct1, ct2, evk_b, evk_a))
+    dec, amb, budget = o.decrypt(sk, got)
+    want = np.array([(int(x) * int(y)) % t for x, y in zip(m1, m2)], dtype=np.int64)
+    want = np.where(want > t // 2, want - t, want)
+    assert amb == 0 and np.array_equal(dec, want)
+
+
+CASES = [
+    # N, L, K, b, E   -- ragged / edge shapes the loops of run() must survive
+    (1024, 2, 2, 5, 7),
+    (1024, 2, 1, 3, 4),     # K = 1: no ct x ct at all, mask only
+    (1024, 2, 3, 2, 3),     # K = 3: two chained ct x ct (depth 2)
+    (256, 1, 2, 1, 1),      # single bin, single position, single limb
+    (2048, 3, 2, 9, 2),
+    (512, 2, 2, 2, 300),    # E > 128: the lazy 128-bit accumulator is folded mid-way
+    (8192, 3, 2, 4, 5),
+]
+
+
+@pytest.mark.parametrize("N,L,K,b,E", CASES)
+def test_run_random_limbs(N, L, K, b, E):
+    """run() on uniformly random limbs: database, masks, query, key — bit-exact result limbs."""
+    cc, o, params = ctx_and_oracle(N, L)
+    rng = np.random.default_rng(N + 31 * K + 7 * b + E)
+    sk, evk_b, evk_a = o.keygen(4)
+    cc.InsertEvalMultKey(evk_b, evk_a)
+    pt = sc.random_pt(rng, params, (K, b, E))
+    mask = sc.random_pt(rng, params, (b,))
+    idx = sc.random_ct(rng, params, (K, E))
+    minus = sc.random_ct(rng, params)
+    cc.db_load_limbs(pt, mask)
+    cc.query_set(idx, minus)
+    cc.run()
+    got = cc.result_get()
+    want = o.run(pt, mask, idx, minus, evk_b, evk_a, nthreads=8)
+    assert np.array_equal(got, want)
+    assert cc.run_launch_count() >= 1
+    # idempotent: a second run on the same query gives the same limbs
+    cc.run()
+    assert np.array_equal(cc.result_get(), want)
+
+
+def test_encode_slots_matches_oracle():
+    """MakePackedPlaintext + SetFormat(EVALUATION) on the device, incl. negative values, short
+    vectors (nslots < N) and the value range check."""
+    cc, o, params = ctx_and_oracle(2048, 2)
+    rng = np.random.default_rng(8)
+    t = int(params.t)
+    K, b, E, n = 2, 3, 4, 1500
+    slots = rng.integers(-(t - 1), t, (K, b, E, n), dtype=np.int64)
+    slots[0, 0, 0, :4] = [0, t - 1, -(t - 1), 1]
+    mask_slots = rng.integers(1, t, (b, n), dtype=np.int64)
+    cc.db_encode_slots(slots, mask_slots)
+    pt, mask = cc.db_get_limbs()
+    assert np.array_equal(pt, sc.encode_db(o, slots))
+    assert np.array_equal(mask, sc.encode_masks(o, mask_slots))
+    bad = slots.copy()
+    bad[1, 2, 3, 7] = t
+    with pytest.raises(ValueError):
+        cc.db_encode_slots(bad, mask_slots)
+
+
+def test_golden_small_case():
+    """Committed fixture (tests/golden/small_case.npz, written by make_golden.py)."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "small_case.npz"))
+    params = RefParams(256, T32, L=2).to_struct()
+    cc = P.CryptoContext(params)
+    cc.InsertEvalMultKey(z["evk_b"], z["evk_a"])
+    cc.db_encode_slots(z["slots"], z["mask_slots"])
+    pt, mask = cc.db_get_limbs()
+    assert np.array_equal(pt, z["pt"]) and np.array_equal(mask, z["mask"])
+    cc.query_set(z["idx"], z["minus"])
+    cc.run()
+    assert np.array_equal(cc.result_get(), z["out"])
+
+
+def test_pie_operator_end_to_end():
+    """The reference-shaped operator: HierarchicalCuckooHashTable -> BatchedFHEHIPPIE(ctx, pk, hct) ->
+    setIndex / setMinusCompareElement / run / getResultList; limbs equal the oracle's evaluation of the
+    same (shuffled) table, and the decrypted intersection equals the planted one."""
+    d = P.RandomDataInput(3000, 48, 25, 777, 32)
+    s = sc.table_scenario(2048, T32, 3, 2, 40, 2, 7, 9, d.serverSet, d.clientSet)
+    cc = P.CryptoContext(s.params)
+    cc.InsertEvalMultKey(s.evk_b, s.evk_a)
+    pie = P.BatchedFHEHIPPIE(cc, P.PublicKey(), s.hct, keepSlots=True)
+    slots, mask_slots = pie.slots()
+    # ctor semantics: slot s of plaintext (hf, bin, pos) is the (shuffled) cell of outer table s
+    cells = s.hct.cells()  # after the in-place shuffle
+    k, e, K, b, E = cells.shape
+    assert np.array_equal(slots, cells.reshape(k * e, K, b, E).transpose(1, 2, 3, 0).astype(np.int64))
+    assert mask_slots.min() >= 1 and mask_slots.max() < int(s.params.t)
+    pie.setIndex([[s.idx[hf, pos] for pos in range(E)] for hf in range(K)])
+    pie.setMinusCompareElement(s.minus)
+    pie.run()
+    got = pie.getResultList()
+    pt, mask = sc.encode_db(s.oracle, slots), sc.encode_masks(s.oracle, mask_slots)
+    want = s.oracle.run(pt, mask, s.idx, s.minus, s.evk_b, s.evk_a, nthreads=8)
+    assert np.array_equal(got, want)
+    dec, budget = sc.decrypt_results(s, got)
+    assert budget > 20
+    inter = np.sort(P.extract_intersection(s.client_cells, dec))
+    assert np.array_equal(inter, np.sort(d.intersectionSet))
+
+
+def test_reference_known_answer_on_gpu():
+    """tests/TestBatchedFHEPIE.cpp scenario through the GPU operator: "Matches" exactly twice."""
+    from test_oracle import reference_test_scenario
+    elems, client_elem = reference_test_scenario()
+    s = sc.table_scenario(8192, T32, None, 2, 1, 2, 10, 20, elems, [client_elem], hash_seed=12223222, depth=2)
+    o = s.oracle
+    s.idx_slots[:] = 0
+    for hf in range(2):
+        pos = int(P.hash_index(s.hash, [client_elem], 2 + hf, 10)[0])
+        s.idx_slots[hf, pos, :] = 1
+    s.minus_slots[:] = -int(client_elem)
+    for hf in range(2):
+        for pos in range(10):
+            s.idx[hf, pos] = o.encrypt(s.sk, s.idx_slots[hf, pos], 1000 + hf * 10 + pos)
+    s.minus = o.encrypt(s.sk, s.minus_slots, 999)
+    cc = P.CryptoContext(s.params)
+    cc.InsertEvalMultKey(s.evk_b, s.evk_a)
+    pie = P.BatchedFHEHIPPIE(cc, P.PublicKey(), s.hct)
+    pie.setIndex(s.idx)
+    pie.setMinusCompareElement(s.minus)
+    pie.run()
+    dec, budget = sc.decrypt_results(s, pie.getResultList())
+    assert int((dec[:, :2] == 0).sum()) == 2 and budget > 20
+
+
+def test_error_behaviour():
+    """Call-order and argument errors surface as exceptions, as the reference throws
+    (std::invalid_argument, BatchedFHEHIPPIE.cpp:13-21)."""
+    cc, o, params = ctx_and_oracle(256, 2)
+    rng = np.random.default_rng(1)
+    with pytest.raises(P.PsiError):
+        cc._dims = (2, 1, 1)
+        cc.query_set(sc.random_ct(rng, params, (2, 1)), sc.random_ct(rng, params))   # no database yet
+    pt = sc.random_pt(rng, params, (2, 1, 1))
+    cc.db_load_limbs(pt, sc.random_pt(rng, params, (1,)))
+    with pytest.raises(P.PsiError):
+        cc.run()                                                                       # no query
+    cc.query_set(sc.random_ct(rng, params, (2, 1)), sc.random_ct(rng, params))
+    with pytest.raises(P.PsiError):
+        cc.run()                                                                       # K = 2 needs the relin key
+    h = P.TabulationHashing(1, 4)
+    hct = P.HierarchicalCuckooHashTable(h, 4, 3, 2, 2, 2, True, True, 2)               # stash = 2
+    with pytest.raises(ValueError, match="stash"):
+        P.BatchedFHEHIPPIE(cc, P.PublicKey(), hct)
+    with pytest.raises(ValueError, match="combined"):
+        P.HierarchicalCuckooHashTable(h, 4, 3, 0, 2, 2, False, True, 2)
