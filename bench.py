@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — server-side BatchedFHEPIE evaluation throughput on B200 (BASELINE.json metric).
+
+A "step" is one client query evaluated against the whole resident server database: one pass of
+BatchedFHEHIPPIE::run() (reference: BatchedFHEHIPPIE.cpp:88-129, timed there as onlineComputation,
+BatchedFHEPSIServer.cpp:99-106).
+
+  value      server items matched / s, query and database already resident in HBM, CUDA-event time of
+             K run() calls on the launching stream, max over ranks
+  e2e        same metric through the reference-facing call sequence with HOST buffers: pinned-host
+             query -> psi_query_set (H2D) -> psi_run -> psi_result_get (D2H) [+ NCCL gather for N > 1]
+  roofline   the inner-product kernel (HBM-bound): algorithmic bytes / its own event-timed duration
+  cpu_baseline  the CPU oracle (restatement of the OpenFHE path; the real reference cannot be built
+             here) on the host cores, on a bounded sample of bins of the same workload
+
+python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload NAME] [--scaling weak|strong]
+Under torchrun one rank per GPU; rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+T32 = 4296540161  # --bitSize 32 (BatchedFHEPSIClient.cpp:29)
+
+# name -> nested-cuckoo parameters (Performance-Evaluation/Parameters1.txt rows; columns C S I k e b E)
+WORKLOADS = {
+    # "1024 16777216 513 2 4949 47 47"  (Parameters1.txt:17)  BASELINE configs[2]
+    "2^24_vs_2^10": dict(S=1 << 24, C=1 << 10, I=513, k=2, e=4949, K=2, b=47, E=47, N=16384, bits=32),
+    # "1024 1048576 513 2 4949 14 14"   (Parameters1.txt:11)  BASELINE configs[1]
+    "2^20_vs_2^10": dict(S=1 << 20, C=1 << 10, I=513, k=2, e=4949, K=2, b=14, E=14, N=16384, bits=32),
+    # reduced case for quick functional runs (not a BASELINE config)
+    "2^16_vs_2^8": dict(S=1 << 16, C=1 << 8, I=129, k=2, e=1900, K=2, b=8, E=8, N=16384, bits=32),
+}
+DEFAULT_WORKLOAD = "2^24_vs_2^10"
+METRIC = "server items matched/sec (BatchedFHEPIE run(), ms per client query in ms_per_step)"
+
+
+def phase1_bytes(L, N, K, b, E):
+    """plaintext DB read once + index cts read once + minus ct + accumulators written once."""
+    return 8 * L * N * (K * b * E + 2 * K * E + 2 + 2 * K * b)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--cpu-sample-bins", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--synthetic-db", action="store_true",
+                    help="random slot values instead of hashing a real server set (same shapes, same timing)")
+    return ap.parse_args()
+
+
+def random_limbs(rng, params, lead):
+    L, N = params.L, params.N
+    out = np.empty(tuple(lead) + (L, N), dtype=np.uint64)
+    for l in range(L):
+        out[..., l, :] = rng.integers(0, int(params.q[l]), size=tuple(lead) + (N,), dtype=np.uint64)
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi-equivalent sampling (NVML) of SM clock + clock-event reasons during the timed regions."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.active = [], set(), False
+        self.stop_flag = False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        while not self.stop_flag and self.nv is not None:
+            if self.active:
+                try:
+                    mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                    try:
+                        mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    self.samples.append(mhz)
+                    for bit, name in self.REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.005)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_oracle_rate(w, params, n_bins, steps, threads=None):
+    """Oracle (CPU restatement, oracle/psi_oracle.c) on `n_bins` bins of the workload with random limbs.
+    Returns (items_per_s, seconds_per_step, threads)."""
+    from oracle.oracle import Oracle, max_threads
+    o = Oracle(params)
+    threads = threads or max_threads()
+    rng = np.random.default_rng(99)
+    K, E = w["K"], w["E"]
+    n_bins = min(n_bins, w["b"])
+    pt = random_limbs(rng, params, (K, n_bins, E))
+    mask = random_limbs(rng, params, (n_bins,))
+    idx = random_limbs(rng, params, (K, E, 2))
+    minus = random_limbs(rng, params, (2,))
+    evk_b = random_limbs(rng, params, (params.L,))
+    evk_a = random_limbs(rng, params, (params.L,))
+    o.run(pt, mask, idx, minus, evk_b, evk_a, nthreads=threads)  # warm-up (page in, twiddles hot)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.run(pt, mask, idx, minus, evk_b, evk_a, nthreads=threads)
+    dt = (time.perf_counter() - t0) / steps
+    items = w["S"] * n_bins / w["b"]
+    return items / dt, dt, threads, n_bins
+
+
+def run_reference(args, w, rank):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  The real
+    reference (OpenFHE + libscapi + Boost 1.71) cannot be built in this image, so this is the oracle
+    PORT of it, all host threads, each step a bounded sample of bins of the same workload."""
+    if rank != 0:
+        return
+    import psi_b200 as P
+    params = P.params_generate(w["N"], T32, P.depth_for_E(w["E"]))
+    n_bins = min(w["b"], max(args.cpu_sample_bins, 8))
+    for _ in range(max(args.warmup - 1, 0)):
+        pass  # the oracle call below warms itself once; further warm-up adds nothing on the CPU
+    rate, dt, threads, n_bins = cpu_oracle_rate(w, params, n_bins, max(args.steps, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "items/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * w["b"] / n_bins,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args, w, params, 1),
+        "cpu_baseline": {"value": rate, "unit": "items/s", "cores": threads, "kind": "port",
+                         "sample": "%d of %d bins per step, warm plaintexts (already in EVALUATION form), "
+                                   "OpenMP over bins" % (n_bins, w["b"])},
+        "e2e": {"value": rate, "unit": "items/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, w, params, world):
+    return {"workload": "Server/Client BFV PIE %s: S=%d server items vs C=%d client items, nested cuckoo k=%d e=%d "
+                        "K=%d b=%d E=%d (Parameters1.txt), N=%d, sizeQ=%d x 60-bit, sizeP=%d, t=%d, HPSPOVERQ + BV"
+                        % (args.workload, w["S"], w["C"], w["k"], w["e"], w["K"], w["b"], w["E"], params.N, params.L,
+                           params.Lp, params.t),
+            "bins_per_gpu": w["b"] if args.scaling == "weak" else "%d/%d" % (w["b"], world),
+            "server_items_total": w["S"] * (world if args.scaling == "weak" else 1),
+            "sharding": "bins" if world > 1 else "none",
+            "l2_policy": "inputs larger than L2 (plaintext DB %.2f GB per GPU streams from HBM every step)"
+                         % (8.0 * params.L * params.N * w["K"] * w["b"] * w["E"] / 1e9)}
+
+
+def main():
+    args = parse()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, w, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import psi_b200 as P
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    params = P.params_generate(w["N"], T32, P.depth_for_E(w["E"]))
+    L, N, K, E = params.L, params.N, w["K"], w["E"]
+    cc = P.CryptoContext(params, device=local_rank)
+    rng = np.random.default_rng(1234 + rank)
+
+    # ---- offline phase: server set -> nested cuckoo table -> BatchedFHEHIPPIE ctor (GPU encode) ----------
+    t_off = time.perf_counter()
+    shard = P.ShardedPIE(w["b"], rank, world)
+    if args.scaling == "weak":
+        b_local = w["b"]          # every GPU holds a full block of b bins of an N-times larger server set
+    else:
+        b_local = shard.end - shard.begin
+    nslots = w["k"] * w["e"]
+    if args.synthetic_db:
+        slots = rng.integers(1, T32, (K, b_local, E, nslots), dtype=np.int64)
+        mask_slots = rng.integers(1, T32, (b_local, nslots), dtype=np.int64)
+        cc.db_encode_slots(slots, mask_slots)
+        del slots
+    else:
+        seed = 123456789 + (rank if args.scaling == "weak" else 0)      # itemSeed (CLI.cpp:67)
+        data = P.RandomDataInput(w["S"], w["C"], w["I"], seed, w["bits"])
+        hashf = P.TabulationHashing(987654321, w["k"] + K)               # hashSeed (CLI.cpp:68)
+        hct = P.HierarchicalCuckooHashTable(hashf, w["e"], E, 0, w["k"], K, True, True, w["b"])
+        hct.insertAll(data.serverSet)
+        if args.scaling == "weak" or world == 1:
+            pie = P.BatchedFHEHIPPIE(cc, P.PublicKey(), hct)             # shuffles, transposes, encodes on the GPU
+            del pie
+        else:
+            cells = hct.cells()
+            k_, e_ = cells.shape[:2]
+            slots = np.ascontiguousarray(cells.reshape(k_ * e_, K, w["b"], E).transpose(1, 2, 3, 0)[:, shard.begin:shard.end]).astype(np.int64)
+            mask_slots = np.random.default_rng(5).integers(1, T32, (w["b"], nslots), dtype=np.int64)[shard.begin:shard.end]
+            cc.db_encode_slots(slots, np.ascontiguousarray(mask_slots))
+            del cells, slots
+        del hct, data
+    cc._dims = (K, b_local, E)
+    offline_s = time.perf_counter() - t_off
+
+    # ---- the query: K*E + 1 ciphertexts.  Uniform residues (what BFV ciphertexts look like); the server's
+    # work does not depend on their content.  Held in PINNED host memory for the e2e leg.
+    ct_words = 2 * L * N
+    q_host = torch.empty((K * E + 1) * ct_words, dtype=torch.int64, pin_memory=True)
+    q_np = q_host.numpy().view(np.uint64)
+    q_np[:K * E * ct_words] = random_limbs(rng, params, (K, E, 2)).reshape(-1)
+    q_np[K * E * ct_words:] = random_limbs(rng, params, (2,)).reshape(-1)
+    idx_ptr = q_host.data_ptr()
+    minus_ptr = idx_ptr + K * E * ct_words * 8
+    r_host = torch.empty(b_local * ct_words, dtype=torch.int64, pin_memory=True)
+    cc.InsertEvalMultKey(random_limbs(rng, params, (L,)), random_limbs(rng, params, (L,)))
+
+    stream = torch.cuda.Stream()
+    sp = stream.cuda_stream
+    cc.query_set_ptr(idx_ptr, minus_ptr, sp)
+    cc.sync(sp)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """CUDA-event time (ms) of `steps` calls of fn on `stream`; barrier + synchronize both sides."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        return ms
+
+    # ---- warm-up, then the headline: K x run() with everything resident ------------------------------
+    for _ in range(max(args.warmup, 3)):
+        cc.run(sp)
+    cc.sync(sp)
+    launches_per_run = cc.run_launch_count()
+    sampler.active = True
+    ms_total = timed(lambda: cc.run(sp), args.steps)
+    ms_step = ms_total / args.steps
+    # per-phase (same stream, same residency): the roofline numerator/denominator come from these
+    ms_p1 = timed(lambda: cc.run(sp, phases=1), args.steps) / args.steps
+    ms_p2 = timed(lambda: cc.run(sp, phases=2), args.steps) / args.steps
+
+    # ---- e2e: host query in, host results out, every step ---------------------------------------------
+    res_dev = None
+    if world > 1:
+        res_dev = P.ShardedPIE.device_result_tensor(cc).view(b_local, ct_words)
+        gather_bufs = [torch.empty_like(res_dev) for _ in range(world)] if rank == 0 else None
+        R_host = torch.empty(world * b_local * ct_words, dtype=torch.int64, pin_memory=True) if rank == 0 else None
+
+    def e2e_step():
+        cc.query_set_ptr(idx_ptr, minus_ptr, sp)
+        cc.run(sp)
+        if world == 1:
+            cc.result_get_ptr(r_host.data_ptr(), sp)
+        else:
+            # the response gather: the only cross-GPU traffic (NCCL over NVLink), then one D2H on rank 0
+            with torch.cuda.stream(stream):
+                dist.gather(res_dev, gather_bufs, dst=0)
+                if rank == 0:
+                    for r in range(world):
+                        R_host[r * b_local * ct_words:(r + 1) * b_local * ct_words].copy_(gather_bufs[r].view(-1), non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    cc.sync(sp)
+    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    sampler.active = False
+    sampler.stop_flag = True
+
+    items_per_gpu = w["S"] if args.scaling == "weak" else w["S"] / world
+    total_items = items_per_gpu * world
+    value = total_items / (ms_step * 1e-3)
+    e2e_value = total_items / (ms_e2e * 1e-3)
+    h2d = (K * E + 1) * ct_words * 8
+    d2h = b_local * ct_words * 8 * (world if (world > 1) else 1)
+
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak_hbm, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        peak_hbm, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    bytes1 = phase1_bytes(L, N, K, b_local, E)
+    ach = bytes1 / (ms_p1 * 1e-3) / 1e9
+    roofline = {"kernel": "k_mac (inner product, phase 1)", "bound": "hbm", "achieved": ach, "peak": peak_hbm,
+                "unit": "GB/s", "frac": ach / peak_hbm, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes1, "launch_ms": ms_p1}
+    phases = {"inner_product_ms": ms_p1, "multiply_relin_mask_ms": ms_p2, "run_ms": ms_step,
+              "launches_per_run": launches_per_run}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        rate, dt, threads, nb = cpu_oracle_rate(w, params, args.cpu_sample_bins, 3)
+        cpu = {"value": rate, "unit": "items/s", "cores": threads, "kind": "port",
+               "sample": "%d of %d bins x 3 repetitions (%.1f s of CPU work), warm plaintexts, OpenMP over bins; "
+                         "port = oracle/psi_oracle.c, the real reference (OpenFHE) cannot be built in this image"
+                         % (nb, w["b"], time.perf_counter() - t0),
+               "ms_per_query_extrapolated": dt * 1e3 * w["b"] / nb}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "items/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": workload_config(args, w, params, world),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "items/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h,
+                    "path": "pinned host query -> psi_query_set -> psi_run -> psi_result_get -> pinned host"
+                            + (" (+ NCCL gather to rank 0)" if world > 1 else "")},
+            "gpu_launches": launches_per_run * args.steps,
+            "phases": phases, "clocks": sampler.summary(), "offline_build_s": offline_s,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -49,6 +49,10 @@ class CryptoContext:
     relinearisation key (DeserializeEvalMultKey, BatchedFHEPSIServer.cpp:49) and the device evaluator."""
 
     def __init__(self, params, device=0):
+        if not isinstance(params, capi.PsiParams):   # any byte-compatible mirror of struct psi_params
+            if ctypes.sizeof(params) != ctypes.sizeof(capi.PsiParams):
+                raise ValueError("params is not a struct psi_params")
+            params = capi.PsiParams.from_buffer_copy(bytes(params))
         self.params = params
         self.device = device
         self.N, self.L, self.Lp, self.t = params.N, params.L, params.Lp, params.t

@@ -72,6 +72,9 @@ class Oracle:
     """CPU restatement of the BFV-RNS context + the BatchedFHEPIE server evaluation."""
 
     def __init__(self, params_struct):
+        if not isinstance(params_struct, PsiParams):  # e.g. the product's own ctypes mirror
+            assert ctypes.sizeof(params_struct) == ctypes.sizeof(PsiParams)
+            params_struct = PsiParams.from_buffer_copy(bytes(params_struct))
         self.params = params_struct
         self.N, self.L, self.Lp, self.t = params_struct.N, params_struct.L, params_struct.Lp, params_struct.t
         self._h = lib().orc_create(ctypes.byref(params_struct))

@@ -185,7 +185,7 @@ def test_reference_known_answer_matches_twice():
     slots, mask_slots, pt, mask = sc.oracle_db(s)
     out = o.run(pt, mask, s.idx, s.minus, s.evk_b, s.evk_a, nthreads=4)
     dec, budget = sc.decrypt_results(s, out)
-    assert budget > 20
+    assert budget > 5
     matches = int((dec[:, :2] == 0).sum())
     assert matches == 2
     # every other value is a non-zero multiple produced by the mask
@@ -202,7 +202,7 @@ def test_small_protocol_intersection():
     dec, budget = sc.decrypt_results(s, out)
     got = np.sort(P.extract_intersection(s.client_cells, dec))
     assert np.array_equal(got, np.sort(d.intersectionSet))
-    assert budget > 20
+    assert budget > 5
 
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "oracle_digests.json")
