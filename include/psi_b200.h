@@ -173,6 +173,9 @@ int psi_debug_mul_ctct(psi_ctx* ctx, const uint64_t* ct1, const uint64_t* ct2, u
  * denominator is measured, not assumed).  Returns 32x32->64 multiply-adds per
  * second over the whole chip. */
 int psi_bench_imad_peak(int device, double* mads_per_second);
+/* kind 0: IMAD.WIDE.U32 per second (same as above); kind 1: 64-bit Harvey/Shoup lazy butterflies per
+ * second with operands in registers (the NTT's compute ceiling). */
+int psi_bench_pipe_peak(int device, int kind, double* per_second);
 
 /* ------------------------------------------------------------------------------------------
  * Host-side objects around the path (offline phase; nothing here is inside run()).

@@ -76,6 +76,7 @@ SYMBOLS = {
     "psi_debug_ntt": (_int, [_vp, _u64p, _u32p, _u32, _int]),
     "psi_debug_mul_ctct": (_int, [_vp, _u64p, _u64p, _u64p]),
     "psi_bench_imad_peak": (_int, [_int, ctypes.POINTER(ctypes.c_double)]),
+    "psi_bench_pipe_peak": (_int, [_int, _int, ctypes.POINTER(ctypes.c_double)]),
     "psi_hct_create": (_int, [_u64, _u32, _u64, _u32, _u64, _u64, _u64, _int, _int, _u64, _vpp]),
     "psi_hct_insert_all": (_int, [_vp, _u64p, _sz]),
     "psi_hct_get_cells": (_int, [_vp, _u64p]),

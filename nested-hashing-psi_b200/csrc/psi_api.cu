@@ -129,7 +129,7 @@ static int build_tables(psi_ctx* c) {
     for (uint32_t m = 0; m < nm; m++) {
         const u64 q = m < L ? P.q[m] : (m < L + Lp ? P.p[m - L] : P.t);
         const u64 psi_root = m < L ? P.psi_q[m] : (m < L + Lp ? P.psi_p[m - L] : P.psi_t);
-        if (q < 2 || q >= (1ull << 62)) return set_error(PSI_ERR_INVALID, "moduli must be below 2^62");
+        if (q < 2 || q >= (1ull << 60)) return set_error(PSI_ERR_INVALID, "moduli must be below 2^60 (OpenFHE's maximum for BFVrns)");
         if (h_powmod(psi_root, N, q) != q - 1)
             return set_error(PSI_ERR_INVALID, "psi is not a primitive 2N-th root of unity for one of the moduli");
         u64* w = &tw[((size_t)m * 4 + 0) * N];
@@ -354,6 +354,8 @@ int psi_db_load_limbs(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E, const uint
     const size_t LN = (size_t)c->L * c->N;
     CK(cudaMemcpy(c->pt.p, pt_limbs, (size_t)K * b * E * LN * sizeof(u64), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->mask.p, mask_limbs, (size_t)b * LN * sizeof(u64), cudaMemcpyHostToDevice));
+    CK(launch_split30(0, c->pt.p, (size_t)K * b * E * LN, true));
+    CK(cudaStreamSynchronize(0));
     c->have_db = true;
     return PSI_OK;
 }
@@ -410,6 +412,8 @@ int psi_db_encode_slots(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E, uint32_t
     if ((rc = db_dims(c, K, b, E))) return rc;
     if ((rc = encode_into(c, (size_t)K * b * E, nslots, slots, c->pt.p))) return rc;
     if ((rc = encode_into(c, b, nslots, mask_slots, c->mask.p))) return rc;
+    CK(launch_split30(0, c->pt.p, (size_t)K * b * E * (size_t)c->L * c->N, true));  // DB storage format
+    CK(cudaStreamSynchronize(0));
     c->have_db = true;
     return PSI_OK;
 }
@@ -420,7 +424,12 @@ int psi_db_get_limbs(psi_ctx* c, uint64_t* pt_limbs, uint64_t* mask_limbs) {
     int rc = ensure_device(c);
     if (rc) return rc;
     const size_t LN = (size_t)c->L * c->N;
-    if (pt_limbs) CK(cudaMemcpy(pt_limbs, c->pt.p, (size_t)c->K * c->b * c->E * LN * sizeof(u64), cudaMemcpyDeviceToHost));
+    if (pt_limbs) {
+        const size_t n = (size_t)c->K * c->b * c->E * LN;
+        CK(cudaMemcpy(pt_limbs, c->pt.p, n * sizeof(u64), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; i++)  // split-30 storage -> canonical residues
+            pt_limbs[i] = ((pt_limbs[i] >> 32) << 30) | (pt_limbs[i] & 0x3fffffffull);
+    }
     if (mask_limbs) CK(cudaMemcpy(mask_limbs, c->mask.p, (size_t)c->b * LN * sizeof(u64), cudaMemcpyDeviceToHost));
     return PSI_OK;
 }
@@ -434,6 +443,7 @@ int psi_query_set(psi_ctx* c, const uint64_t* idx, const uint64_t* minus, void* 
     cudaStream_t s = (cudaStream_t)stream;
     CK(cudaMemcpyAsync(c->idx.p, idx, (size_t)c->K * c->E * 2 * LN * sizeof(u64), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(c->minus.p, minus, 2 * LN * sizeof(u64), cudaMemcpyHostToDevice, s));
+    CK(launch_split30(s, c->idx.p, (size_t)c->K * c->E * 2 * LN, true));  // index cts -> split-30
     c->have_query = true;
     return PSI_OK;
 }
@@ -574,10 +584,13 @@ int psi_debug_mul_ctct(psi_ctx* c, const uint64_t* ct1, const uint64_t* ct2, uin
     return rc;
 }
 
-int psi_bench_imad_peak(int device, double* mads_per_second) {
-    if (!mads_per_second) return set_error(PSI_ERR_INVALID, "null argument");
-    cudaError_t e = imad_peak(device, mads_per_second);
-    if (e != cudaSuccess) return cuda_fail(e, "psi_bench_imad_peak");
+int psi_bench_imad_peak(int device, double* mads_per_second) { return psi_bench_pipe_peak(device, 0, mads_per_second); }
+
+int psi_bench_pipe_peak(int device, int kind, double* per_second) {
+    if (!per_second) return set_error(PSI_ERR_INVALID, "null argument");
+    if (kind < 0 || kind > 1) return set_error(PSI_ERR_INVALID, "unknown micro-benchmark kind");
+    cudaError_t e = pipe_peak(device, kind, per_second);
+    if (e != cudaSuccess) return cuda_fail(e, "psi_bench_pipe_peak");
     return PSI_OK;
 }
 

@@ -3,6 +3,8 @@
 // replaces; the CPU restatement it is checked against is oracle/psi_oracle.c.
 #include "psi_kernels.cuh"
 
+#include <type_traits>
+
 namespace psi {
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
@@ -17,58 +19,138 @@ __device__ __forceinline__ u64 ld_stream(const u64* p) {
 // ------------------------------------------------------------------------------------------
 // Phase 1 — the encrypted one-hot inner product.
 // Replaces the EvalMult(ct,pt) / EvalAdd loop and the EvalAdd of minusCompareElement
-// (/root/reference/.../BatchedFHEHIPPIE.cpp:101-116).  HBM-bound: every plaintext word is read
-// exactly once; BT bins share the two index-ciphertext words held in registers; the sum over pos
-// is accumulated lazily in 128 bits and reduced once (canonical residue == term-by-term ModMul/ModAdd).
+// (/root/reference/.../BatchedFHEHIPPIE.cpp:101-116).
+//
+// HBM-bound by construction: every plaintext word is read exactly once (streaming, L1 bypass).
+// To keep the integer pipe below the HBM time the products are formed WITHOUT carry chains:
+// the plaintext DB and the index ciphertexts are stored "split-30" (word = hi30:lo30 in the two
+// 32-bit halves, residues are < 2^60), so one 60x60-bit product is four IMAD.WIDE.U32 into three
+// 64-bit partial sums  ll += x0*y0,  mid += x0*y1 + x1*y0,  hh += x1*y1  (each product < 2^60, so
+// 8 positions fit before a fold).  Every 8 positions the partial sums are folded into a 128-bit
+// running total, which is reduced once at the end: the canonical residue of the same sum OpenFHE
+// forms term by term (ModMul / ModAdd), hence bit-identical.
+// A CTA covers 128 coefficients x (LANES bin-lanes x BT bins); the LANES threads of a coefficient
+// read the same index words, so those come from L1 after the first lane.
 // ------------------------------------------------------------------------------------------
-template <int BT>
-__global__ void __launch_bounds__(256) k_mac(const DevTables* __restrict__ tab, uint32_t N, uint32_t L, uint32_t b,
-                                             uint32_t E, const u64* __restrict__ pt, const u64* __restrict__ idx,
-                                             const u64* __restrict__ minus, u64* __restrict__ acc) {
-    const size_t LN = (size_t)L * N;
-    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= LN) return;
-    const uint32_t nbg = (b + BT - 1) / BT;
-    const uint32_t hf = blockIdx.y / nbg;
-    const uint32_t bin0 = (blockIdx.y % nbg) * BT;
-    const ModDev& md = tab->mods[c / N];
-    const u64 q = md.q, mu_hi = md.mu_hi, mu_lo = md.mu_lo;
+__device__ __forceinline__ uint2 ld_stream_v2(const u64* p) {
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ u64 madw(uint32_t a, uint32_t b, u64 c) {
+    u64 d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ void fold30(u64& hi, u64& lo, u64 ll, u64 mid, u64 hh) {
+    // (hi:lo) += ll + mid * 2^30 + hh * 2^60
+    u128 t = (u128)ll + ((u128)mid << 30) + ((u128)hh << 60);
+    t += ((u128)hi << 64) | lo;
+    lo = (u64)t;
+    hi = (u64)(t >> 64);
+}
 
-    u64 lo0[BT], hi0[BT], lo1[BT], hi1[BT];
+constexpr int kMacCoeffs = 128;  // coefficients per CTA
+
+template <int BT, int LANES>
+__global__ void __launch_bounds__(kMacCoeffs* LANES)
+    k_mac(const DevTables* __restrict__ tab, uint32_t N, uint32_t L, uint32_t b, uint32_t E,
+          const u64* __restrict__ pt, const u64* __restrict__ idx, const u64* __restrict__ minus,
+          u64* __restrict__ acc) {
+    const size_t LN = (size_t)L * N;
+    const size_t c = (size_t)blockIdx.x * kMacCoeffs + (threadIdx.x & (kMacCoeffs - 1));
+    const uint32_t lane = threadIdx.x / kMacCoeffs;
+    const uint32_t nbb = (b + BT * LANES - 1) / (BT * LANES);
+    const uint32_t hf = blockIdx.y / nbb;
+    const uint32_t bin0 = (blockIdx.y % nbb) * (BT * LANES) + lane * BT;
+    if (c >= LN || bin0 >= b) return;
+    const int nb = (int)min((uint32_t)BT, b - bin0);
+
+    u64 ll[BT][2], mid[BT][2], hh[BT][2], tlo[BT][2], thi[BT][2];
 #pragma unroll
-    for (int j = 0; j < BT; j++) lo0[j] = hi0[j] = lo1[j] = hi1[j] = 0;
+    for (int j = 0; j < BT; j++)
+#pragma unroll
+        for (int k = 0; k < 2; k++) ll[j][k] = mid[j][k] = hh[j][k] = tlo[j][k] = thi[j][k] = 0;
 
     const u64* ip = idx + (size_t)hf * E * 2 * LN + c;
     const size_t bin_stride = (size_t)E * LN;
-    const u64* pp = pt + ((size_t)hf * b + bin0) * bin_stride + c;
-    for (uint32_t pos = 0; pos < E; pos++) {
-        const u64 i0 = ip[0], i1 = ip[LN];
-        ip += 2 * LN;
+    // bins past the end of a ragged last block alias bin0 (loaded, accumulated, never stored):
+    // keeps the inner loop free of branches so that the loads of a whole sub-block are in flight together
+    const u64* pp[BT];
 #pragma unroll
-        for (int j = 0; j < BT; j++) {
-            if (bin0 + j < b) {
-                const u64 pv = ld_stream(pp + (size_t)j * bin_stride);
-                mac128(hi0[j], lo0[j], i0, pv);
-                mac128(hi1[j], lo1[j], i1, pv);
-            }
+    for (int j = 0; j < BT; j++) pp[j] = pt + ((size_t)hf * b + bin0 + (j < nb ? j : 0)) * bin_stride + c;
+
+    constexpr int U = 4;  // positions per software-pipelined sub-block
+    auto sub_block = [&](auto n_tag) {
+        constexpr int n = decltype(n_tag)::value;
+        uint2 i0[n], i1[n], y[n][BT];
+#pragma unroll
+        for (int p = 0; p < n; p++) {
+            i0[p] = __ldg(reinterpret_cast<const uint2*>(ip + (size_t)p * 2 * LN));
+            i1[p] = __ldg(reinterpret_cast<const uint2*>(ip + (size_t)p * 2 * LN + LN));
+#pragma unroll
+            for (int j = 0; j < BT; j++) y[p][j] = ld_stream_v2(pp[j] + (size_t)p * LN);
         }
-        pp += LN;
-        if ((pos & 127u) == 127u) {  // keep the lazy sum below 2^128 for any E
+#pragma unroll
+        for (int p = 0; p < n; p++)
 #pragma unroll
             for (int j = 0; j < BT; j++) {
-                lo0[j] = barrett128(hi0[j], lo0[j], q, mu_hi, mu_lo);
-                lo1[j] = barrett128(hi1[j], lo1[j], q, mu_hi, mu_lo);
-                hi0[j] = hi1[j] = 0;
+                ll[j][0] = madw(i0[p].x, y[p][j].x, ll[j][0]);
+                mid[j][0] = madw(i0[p].x, y[p][j].y, mid[j][0]);
+                mid[j][0] = madw(i0[p].y, y[p][j].x, mid[j][0]);
+                hh[j][0] = madw(i0[p].y, y[p][j].y, hh[j][0]);
+                ll[j][1] = madw(i1[p].x, y[p][j].x, ll[j][1]);
+                mid[j][1] = madw(i1[p].x, y[p][j].y, mid[j][1]);
+                mid[j][1] = madw(i1[p].y, y[p][j].x, mid[j][1]);
+                hh[j][1] = madw(i1[p].y, y[p][j].y, hh[j][1]);
             }
+        ip += (size_t)n * 2 * LN;
+#pragma unroll
+        for (int j = 0; j < BT; j++) pp[j] += (size_t)n * LN;
+    };
+    auto fold_all = [&]() {
+#pragma unroll
+        for (int j = 0; j < BT; j++)
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                fold30(thi[j][k], tlo[j][k], ll[j][k], mid[j][k], hh[j][k]);
+                ll[j][k] = mid[j][k] = hh[j][k] = 0;
+            }
+    };
+
+    uint32_t folds = 0;
+    uint32_t pos = 0;
+    for (; pos + 2 * U <= E; pos += 2 * U) {  // 8 positions between folds: every partial sum stays < 2^64
+        sub_block(std::integral_constant<int, U>());
+        sub_block(std::integral_constant<int, U>());
+        fold_all();
+        if (++folds == 16) {  // 128 positions: keep the running total below 2^128 for any E
+            folds = 0;
+            const ModDev& mdr = tab->mods[c / N];
+#pragma unroll
+            for (int j = 0; j < BT; j++)
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    tlo[j][k] = barrett128(thi[j][k], tlo[j][k], mdr.q, mdr.mu_hi, mdr.mu_lo);
+                    thi[j][k] = 0;
+                }
         }
     }
+    if (pos + U <= E) {
+        sub_block(std::integral_constant<int, U>());
+        pos += U;
+    }
+    for (; pos < E; pos++) sub_block(std::integral_constant<int, 1>());
+    fold_all();
+    const ModDev& md = tab->mods[c / N];
+    const u64 q = md.q, mu_hi = md.mu_hi, mu_lo = md.mu_lo;
     const u64 m0 = minus[c], m1 = minus[LN + c];
 #pragma unroll
     for (int j = 0; j < BT; j++) {
-        if (bin0 + j < b) {
+        if (j < nb) {
             u64* o = acc + (((size_t)hf * b + bin0 + j) * 2) * LN + c;
-            o[0] = addmod(barrett128(hi0[j], lo0[j], q, mu_hi, mu_lo), m0, q);
-            o[LN] = addmod(barrett128(hi1[j], lo1[j], q, mu_hi, mu_lo), m1, q);
+            o[0] = addmod(barrett128(thi[j][0], tlo[j][0], q, mu_hi, mu_lo), m0, q);
+            o[LN] = addmod(barrett128(thi[j][1], tlo[j][1], q, mu_hi, mu_lo), m1, q);
         }
     }
 }
@@ -76,9 +158,22 @@ __global__ void __launch_bounds__(256) k_mac(const DevTables* __restrict__ tab, 
 cudaError_t launch_mac(const KCtx& k, uint32_t K, uint32_t b, uint32_t E, const u64* pt, const u64* idx,
                        const u64* minus, u64* acc) {
     const size_t LN = (size_t)k.L * k.N;
-    constexpr int BT = 4;
-    dim3 grid(cdiv(LN, 256), K * ((b + BT - 1) / BT));
-    k_mac<BT><<<grid, 256, 0, k.s>>>(k.tab, k.N, k.L, b, E, pt, idx, minus, acc);
+    constexpr int BT = 2, LANES = 4;
+    dim3 grid(cdiv(LN, kMacCoeffs), K * ((b + BT * LANES - 1) / (BT * LANES)));
+    k_mac<BT, LANES><<<grid, kMacCoeffs * LANES, 0, k.s>>>(k.tab, k.N, k.L, b, E, pt, idx, minus, acc);
+    return cudaGetLastError();
+}
+
+// canonical residue < 2^60  <->  split-30 word (hi30 in the upper 32 bits, lo30 in the lower)
+__global__ void __launch_bounds__(256) k_split30(u64* __restrict__ data, size_t n, int to_split) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 v = data[i];
+    data[i] = to_split ? (((v >> 30) << 32) | (v & 0x3fffffffull)) : (((v >> 32) << 30) | (v & 0x3fffffffull));
+}
+cudaError_t launch_split30(cudaStream_t s, u64* data, size_t n, bool to_split) {
+    if (n == 0) return cudaSuccess;
+    k_split30<<<cdiv(n, 256), 256, 0, s>>>(data, n, to_split ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -352,8 +447,10 @@ cudaError_t launch_slots_to_crt(const KCtx& k, uint32_t n_pt, uint32_t nslots, c
 }
 
 // ------------------------------------------------------------------------------------------
-// Integer-pipe peak: independent 32x32+64 multiply-add chains (IMAD.WIDE), the instruction the
-// NTT butterflies and the lazy MACs are made of.  Denominator of the integer roofline.
+// Integer-pipe micro-benchmarks: the denominators of the integer roofline are MEASURED, not assumed.
+//   kind 0: IMAD.WIDE.U32 (32x32 + 64 -> 64), the instruction the lazy inner product is made of
+//   kind 1: Harvey/Shoup lazy butterflies on 64-bit residues, the unit of work of the NTT
+// Independent dependency chains per thread, no memory traffic.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_imad_peak(u64* out, uint32_t iters, uint32_t seed) {
     uint32_t a = threadIdx.x * 2654435761u + seed, b = blockIdx.x * 40503u + 12345u;
@@ -374,22 +471,48 @@ __global__ void __launch_bounds__(256) k_imad_peak(u64* out, uint32_t iters, uin
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
 }
 
-cudaError_t imad_peak(int device, double* mads_per_second) {
+__global__ void __launch_bounds__(256) k_butterfly_peak(u64* out, uint32_t iters, u64 q, u64 w, u64 ws) {
+    const u64 q2 = 2 * q;
+    u64 x[4], y[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        x[k] = (threadIdx.x * 2654435761ull + k * 977 + blockIdx.x) % q;
+        y[k] = (threadIdx.x * 40503ull + k * 131 + 7 * blockIdx.x) % q;
+    }
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            u64 u = x[k];
+            if (u >= q2) u -= q2;
+            const u64 v = mul_shoup_lazy(y[k], w, ws, q);
+            x[k] = u + v;
+            y[k] = u - v + q2;
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x[0] ^ x[1] ^ x[2] ^ x[3] ^ y[0] ^ y[1] ^ y[2] ^ y[3];
+}
+
+cudaError_t pipe_peak(int device, int kind, double* per_second) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return e;
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return e;
     const unsigned blocks = prop.multiProcessorCount * 8, threads = 256;
-    const uint32_t iters = 4096;
+    const uint32_t iters = kind == 0 ? 4096 : 2048;
     u64* out = nullptr;
     if ((e = cudaMalloc(&out, (size_t)blocks * threads * sizeof(u64))) != cudaSuccess) return e;
     cudaEvent_t t0, t1;
     cudaEventCreate(&t0);
     cudaEventCreate(&t1);
     float best = 1e30f;
+    const u64 q = 1152921504606748673ull, w = 123456789123456789ull % q;
+    const u64 ws = (u64)(((unsigned __int128)w << 64) / q);
     for (int rep = 0; rep < 5; rep++) {
         cudaEventRecord(t0);
-        k_imad_peak<<<blocks, threads>>>(out, iters, rep);
+        if (kind == 0)
+            k_imad_peak<<<blocks, threads>>>(out, iters, rep);
+        else
+            k_butterfly_peak<<<blocks, threads>>>(out, iters, q, w, ws);
         cudaEventRecord(t1);
         if ((e = cudaEventSynchronize(t1)) != cudaSuccess) break;
         float ms = 0;
@@ -400,7 +523,8 @@ cudaError_t imad_peak(int device, double* mads_per_second) {
     cudaEventDestroy(t1);
     cudaFree(out);
     if (e != cudaSuccess) return e;
-    *mads_per_second = (double)blocks * threads * iters * 64.0 / (best * 1e-3);
+    const double per_thread = kind == 0 ? (double)iters * 64.0 : (double)iters * 4.0;
+    *per_second = (double)blocks * threads * per_thread / (best * 1e-3);
     return cudaSuccess;
 }
 

@@ -52,6 +52,8 @@ struct NttBatch {
 cudaError_t launch_ntt(const KCtx& k, const NttBatch& b, bool inverse);
 
 // Phase 1: acc[hf][bin] = sum_pos idx[hf][pos] (.) pt[hf][bin][pos] + minus
+// pt and idx are in split-30 storage format (launch_split30), minus and acc canonical.
+cudaError_t launch_split30(cudaStream_t s, u64* data, size_t n, bool to_split);
 cudaError_t launch_mac(const KCtx& k, uint32_t K, uint32_t b, uint32_t E, const u64* pt, const u64* idx,
                        const u64* minus, u64* acc);
 
@@ -69,6 +71,6 @@ cudaError_t launch_mul_ctpt(const KCtx& k, uint32_t B, const u64* ct, const u64*
 cudaError_t launch_slots_to_crt(const KCtx& k, uint32_t n_pt, uint32_t nslots, const long long* slots,
                                 const uint32_t* to_crt, u64* out);
 
-cudaError_t imad_peak(int device, double* mads_per_second);
+cudaError_t pipe_peak(int device, int kind, double* per_second);
 
 }  // namespace psi
