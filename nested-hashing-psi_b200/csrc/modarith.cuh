@@ -17,6 +17,8 @@ struct ModDev {
     const u64* ws;     // floor(w * 2^64 / q)
     const u64* iw;     // psi^-bitrev(i)           (inverse, Gentleman-Sande)
     const u64* iws;
+    const ulonglong2* ftw;  // {w, ws} interleaved: one 16-byte load per twiddle (fused kernels)
+    const ulonglong2* itw;  // {iw, iws}
 };
 
 __device__ __forceinline__ u64 mulhi64(u64 a, u64 b) { return __umul64hi(a, b); }
@@ -59,6 +61,97 @@ __device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q) {
     return r >= q ? r - q : r;
 }
 __device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
+
+// ---- hand-scheduled variants for the NTT inner loop -------------------------------------------
+// The integer pipe (IMAD on the fma pipe, 64 lanes/clk/SM measured) is the NTT's roofline, so the
+// butterfly is written to spend exactly 10 multiply issues and as few ALU issues as possible.
+__device__ __forceinline__ u64 madw32(uint32_t a, uint32_t b, u64 c) {
+    u64 d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t lo32(u64 x) { return (uint32_t)x; }
+__device__ __forceinline__ uint32_t hi32(u64 x) { return (uint32_t)(x >> 32); }
+
+// floor(x * y / 2^64) with four IMAD.WIDE and one 64-bit add
+__device__ __forceinline__ u64 mulhi64_4(u64 x, u64 y) {
+    const uint32_t x0 = lo32(x), x1 = hi32(x), y0 = lo32(y), y1 = hi32(y);
+    const u64 p00 = madw32(x0, y0, 0);
+    const u64 t = madw32(x0, y1, (u64)hi32(p00));
+    const u64 t2 = madw32(x1, y0, (u64)lo32(t));
+    return madw32(x1, y1, (u64)hi32(t)) + (u64)hi32(t2);
+}
+// x * w - floor(x * ws / 2^64) * q  (mod 2^64), in [0, 2q) for any x < 2^64; nq = 2^64 - q.
+// Low 64 bits of x*w + h*nq: two IMAD.WIDE for the low words, four 32-bit IMADs into the high word.
+__device__ __forceinline__ u64 mul_shoup_lazy_nq(u64 x, u64 w, u64 ws, u64 nq) {
+    const u64 h = mulhi64_4(x, ws);
+    const uint32_t x0 = lo32(x), x1 = hi32(x), w0 = lo32(w), w1 = hi32(w);
+    const uint32_t h0 = lo32(h), h1 = hi32(h), n0 = lo32(nq), n1 = hi32(nq);
+    u64 r = madw32(x0, w0, 0);
+    r = madw32(h0, n0, r);
+    uint32_t top = hi32(r);
+    top += x0 * w1;
+    top += x1 * w0;
+    top += h0 * n1;
+    top += h1 * n0;
+    return ((u64)top << 32) | lo32(r);
+}
+// Approximate lazy correction: subtracts q2 only when the HIGH WORD already proves x >= q2, so it can
+// never underflow; afterwards x < q2 + 2^32.  One 32-bit compare + a predicated 64-bit subtract.
+__device__ __forceinline__ u64 lazy_sub_hi(u64 x, u64 q2) {
+    if (hi32(x) > hi32(q2)) x -= q2;
+    return x;
+}
+
+// Whole forward (Cooley-Tukey, Harvey lazy) butterfly in one PTX block: x' = x~ + v, y' = x~ - v + 2q with
+// x~ = lazy_sub_hi(x), v = y * w mod q in [0, 2q).  Everything on 32-bit halves so that ptxas sees the
+// carry chains explicitly.
+__device__ __forceinline__ void ct_butterfly_asm(u64& x, u64& y, u64 w, u64 ws, u64 q2, u64 nq) {
+    asm("{\n\t"
+        ".reg .u32 x0,x1,y0,y1,w0,w1,s0,s1,a0,a1,n0,n1,h0,h1,t0,t1,b0,b1,v0,v1,u0,u1,z;\n\t"
+        ".reg .u64 p,t,t2,h,r;\n\t"
+        ".reg .pred pg;\n\t"
+        "mov.b64 {x0,x1}, %0;\n\t"
+        "mov.b64 {y0,y1}, %1;\n\t"
+        "mov.b64 {w0,w1}, %2;\n\t"
+        "mov.b64 {s0,s1}, %3;\n\t"
+        "mov.b64 {a0,a1}, %4;\n\t"
+        "mov.b64 {n0,n1}, %5;\n\t"
+        "mov.u32 z, 0;\n\t"
+        "setp.gt.u32 pg, x1, a1;\n\t"
+        "@pg sub.cc.u32 x0, x0, a0;\n\t"
+        "@pg subc.u32 x1, x1, a1;\n\t"
+        "mul.hi.u32 t1, y0, s0;\n\t"
+        "mov.b64 t, {t1, z};\n\t"
+        "mad.wide.u32 t, y0, s1, t;\n\t"
+        "mov.b64 {t0,t1}, t;\n\t"
+        "mov.b64 t2, {t0, z};\n\t"
+        "mad.wide.u32 t2, y1, s0, t2;\n\t"
+        "mov.b64 {b0,b1}, t2;\n\t"
+        "mov.b64 h, {t1, z};\n\t"
+        "mad.wide.u32 h, y1, s1, h;\n\t"
+        "mov.b64 {h0,h1}, h;\n\t"
+        "add.cc.u32 h0, h0, b1;\n\t"
+        "addc.u32 h1, h1, 0;\n\t"
+        "mul.wide.u32 r, y0, w0;\n\t"
+        "mad.wide.u32 r, h0, n0, r;\n\t"
+        "mov.b64 {v0,v1}, r;\n\t"
+        "mad.lo.u32 v1, y0, w1, v1;\n\t"
+        "mad.lo.u32 v1, y1, w0, v1;\n\t"
+        "mad.lo.u32 v1, h0, n1, v1;\n\t"
+        "mad.lo.u32 v1, h1, n0, v1;\n\t"
+        "add.cc.u32 u0, x0, v0;\n\t"
+        "addc.u32 u1, x1, v1;\n\t"
+        "sub.cc.u32 t0, x0, v0;\n\t"
+        "subc.u32 t1, x1, v1;\n\t"
+        "add.cc.u32 t0, t0, a0;\n\t"
+        "addc.u32 t1, t1, a1;\n\t"
+        "mov.b64 %0, {u0,u1};\n\t"
+        "mov.b64 %1, {t0,t1};\n\t"
+        "}"
+        : "+l"(x), "+l"(y)
+        : "l"(w), "l"(ws), "l"(q2), "l"(nq));
+}
 
 // 128-bit multiply-accumulate: (hi:lo) += a * b
 __device__ __forceinline__ void mac128(u64& hi, u64& lo, u64 a, u64 b) {

@@ -89,6 +89,7 @@ struct psi_ctx {
     uint32_t N = 0, logN = 0, L = 0, Lp = 0;
     DevTables* d_tab = nullptr;
     DevBuf<u64> twiddles;       // [(L+Lp+1)][4][N]
+    DevBuf<u64> twiddles2;      // [(L+Lp+1)][2][N][2]: {w, ws} and {iw, iws} interleaved
     DevBuf<uint32_t> to_crt;    // packed-encoding permutation
     DevBuf<u64> evk_b, evk_a;   // [L][L][N]
     bool have_evk = false;
@@ -126,6 +127,8 @@ static int build_tables(psi_ctx* c) {
     T.Lp = Lp;
     T.t = P.t;
     CK(c->twiddles.alloc(tw.size()));
+    CK(c->twiddles2.alloc(tw.size()));
+    std::vector<u64> tw2(tw.size());
     for (uint32_t m = 0; m < nm; m++) {
         const u64 q = m < L ? P.q[m] : (m < L + Lp ? P.p[m - L] : P.t);
         const u64 psi_root = m < L ? P.psi_q[m] : (m < L + Lp ? P.psi_p[m - L] : P.psi_t);
@@ -160,7 +163,18 @@ static int build_tables(psi_ctx* c) {
         md.ws = c->twiddles.p + ((size_t)m * 4 + 1) * N;
         md.iw = c->twiddles.p + ((size_t)m * 4 + 2) * N;
         md.iws = c->twiddles.p + ((size_t)m * 4 + 3) * N;
+        u64* f2 = &tw2[((size_t)m * 2 + 0) * 2 * N];
+        u64* i2 = &tw2[((size_t)m * 2 + 1) * 2 * N];
+        for (uint32_t i = 0; i < N; i++) {
+            f2[2 * i] = w[i];
+            f2[2 * i + 1] = ws[i];
+            i2[2 * i] = iw[i];
+            i2[2 * i + 1] = iws[i];
+        }
+        md.ftw = reinterpret_cast<const ulonglong2*>(c->twiddles2.p + ((size_t)m * 2 + 0) * 2 * N);
+        md.itw = reinterpret_cast<const ulonglong2*>(c->twiddles2.p + ((size_t)m * 2 + 1) * 2 * N);
     }
+    CK(cudaMemcpy(c->twiddles2.p, tw2.data(), tw2.size() * sizeof(u64), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->twiddles.p, tw.data(), tw.size() * sizeof(u64), cudaMemcpyHostToDevice));
     for (uint32_t i = 0; i < L; i++) {
         T.QHatInvModq[i] = P.QHatInvModq[i];
@@ -174,6 +188,10 @@ static int build_tables(psi_ctx* c) {
         }
         for (uint32_t j = 0; j <= Lp; j++) T.tQS[i][j] = P.tQSHatInvModsDivsModq[i][j];
         for (uint32_t k = 0; k < L; k++) T.qModq[i][k] = P.q[i] % P.q[k];
+        T.QHatInvNinv[i] = h_mulmod(P.QHatInvModq[i], T.mods[i].ninv, P.q[i]);
+        T.QHatInvNinv_s[i] = h_shoup(T.QHatInvNinv[i], P.q[i]);
+        T.negPQHatInvNinv[i] = h_mulmod(P.negPQHatInvModq[i], T.mods[i].ninv, P.q[i]);
+        T.negPQHatInvNinv_s[i] = h_shoup(T.negPQHatInvNinv[i], P.q[i]);
     }
     for (uint32_t j = 0; j < Lp; j++) {
         T.PHatInvModp[j] = P.PHatInvModp[j];
@@ -230,6 +248,12 @@ static int mul_ctct_batch(psi_ctx* c, cudaStream_t s, uint32_t B, const u64* a, 
     const uint32_t L = c->L, Lp = c->Lp, LT = L + Lp;
     const size_t N = c->N;
     uint32_t nl = 0;
+    if (fused_mul_supported(k)) {
+        CK(launch_fused_mul(k, B, a, bb, c->coef.p, c->coef.p + (size_t)B * 2 * L * N, c->e1.p, c->e2.p, c->ten.p,
+                            c->res.p, c->dig.p, c->evk_b.p, c->evk_a.p, mask, out));
+        if (launches) *launches += 5;
+        return PSI_OK;
+    }
     u64* coef1 = c->coef.p;                         // [B*2][L][N]
     u64* coef2 = c->coef.p + (size_t)B * 2 * L * N;  // [B*2][L][N]
     // (1) both operands to COEFFICIENT
@@ -308,7 +332,7 @@ int psi_ctx_destroy(psi_ctx* c) {
     if (!c) return PSI_OK;
     cudaSetDevice(c->device);
     if (c->d_tab) cudaFree(c->d_tab);
-    DevBuf<u64>* bufs[] = {&c->twiddles, &c->evk_b, &c->evk_a, &c->pt, &c->mask, &c->idx, &c->minus, &c->acc,
+    DevBuf<u64>* bufs[] = {&c->twiddles, &c->twiddles2, &c->evk_b, &c->evk_a, &c->pt, &c->mask, &c->idx, &c->minus, &c->acc,
                            &c->coef,     &c->e1,    &c->e2,    &c->ten, &c->res, &c->dig, &c->prod,  &c->out};
     for (auto* b : bufs) b->release();
     c->to_crt.release();
@@ -588,7 +612,7 @@ int psi_bench_imad_peak(int device, double* mads_per_second) { return psi_bench_
 
 int psi_bench_pipe_peak(int device, int kind, double* per_second) {
     if (!per_second) return set_error(PSI_ERR_INVALID, "null argument");
-    if (kind < 0 || kind > 1) return set_error(PSI_ERR_INVALID, "unknown micro-benchmark kind");
+    if (kind < 0 || kind > 3) return set_error(PSI_ERR_INVALID, "unknown micro-benchmark kind");
     cudaError_t e = pipe_peak(device, kind, per_second);
     if (e != cudaSuccess) return cuda_fail(e, "psi_bench_pipe_peak");
     return PSI_OK;

@@ -492,6 +492,49 @@ __global__ void __launch_bounds__(256) k_butterfly_peak(u64* out, uint32_t iters
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x[0] ^ x[1] ^ x[2] ^ x[3] ^ y[0] ^ y[1] ^ y[2] ^ y[3];
 }
 
+// kind 2: the hand-scheduled butterfly (mul_shoup_lazy_nq + approximate lazy correction) with
+// per-thread twiddles, as the fused NTT kernels use it
+__global__ void __launch_bounds__(256) k_butterfly2_peak(u64* out, uint32_t iters, u64 q, u64 w_in, u64 ws_in) {
+    const u64 q2 = 2 * q, nq = 0 - q;
+    u64 x[4], y[4];
+    // per-thread twiddle so that nothing lands on the uniform datapath
+    const u64 w = (w_in + threadIdx.x) % q;
+    const u64 ws = (u64)(((unsigned __int128)w << 64) / q);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        x[k] = (threadIdx.x * 2654435761ull + k * 977 + blockIdx.x) % q;
+        y[k] = (threadIdx.x * 40503ull + k * 131 + 7 * blockIdx.x) % q;
+    }
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const u64 u = lazy_sub_hi(x[k], q2);
+            const u64 v = mul_shoup_lazy_nq(y[k], w, ws, nq);
+            x[k] = u + v;
+            y[k] = u - v + q2;
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x[0] ^ x[1] ^ x[2] ^ x[3] ^ y[0] ^ y[1] ^ y[2] ^ y[3];
+}
+
+// kind 3: the same butterfly as one explicit PTX block
+__global__ void __launch_bounds__(256) k_butterfly3_peak(u64* out, uint32_t iters, u64 q, u64 w_in, u64 ws_in) {
+    const u64 q2 = 2 * q, nq = 0 - q;
+    u64 x[4], y[4];
+    const u64 w = (w_in + threadIdx.x) % q;
+    const u64 ws = (u64)(((unsigned __int128)w << 64) / q);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        x[k] = (threadIdx.x * 2654435761ull + k * 977 + blockIdx.x) % q;
+        y[k] = (threadIdx.x * 40503ull + k * 131 + 7 * blockIdx.x) % q;
+    }
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) ct_butterfly_asm(x[k], y[k], w, ws, q2, nq);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x[0] ^ x[1] ^ x[2] ^ x[3] ^ y[0] ^ y[1] ^ y[2] ^ y[3];
+}
+
 cudaError_t pipe_peak(int device, int kind, double* per_second) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return e;
@@ -511,8 +554,12 @@ cudaError_t pipe_peak(int device, int kind, double* per_second) {
         cudaEventRecord(t0);
         if (kind == 0)
             k_imad_peak<<<blocks, threads>>>(out, iters, rep);
-        else
+        else if (kind == 1)
             k_butterfly_peak<<<blocks, threads>>>(out, iters, q, w, ws);
+        else if (kind == 2)
+            k_butterfly2_peak<<<blocks, threads>>>(out, iters, q, w, ws);
+        else
+            k_butterfly3_peak<<<blocks, threads>>>(out, iters, q, w, ws);
         cudaEventRecord(t1);
         if ((e = cudaEventSynchronize(t1)) != cudaSuccess) break;
         float ms = 0;

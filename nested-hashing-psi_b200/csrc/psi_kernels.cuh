@@ -28,6 +28,9 @@ struct DevTables {
     u64 tQS[PSI_MAX_LIMBS][PSI_MAX_LIMBS + 1];
     double tQSfrac[PSI_MAX_LIMBS];
     u64 qModq[PSI_MAX_LIMBS][PSI_MAX_LIMBS];  // [i][k] = q_i mod q_k (BV digit lift)
+    // N^-1 of the inverse NTT folded into the first constant of the two basis extensions
+    u64 QHatInvNinv[PSI_MAX_LIMBS], QHatInvNinv_s[PSI_MAX_LIMBS];
+    u64 negPQHatInvNinv[PSI_MAX_LIMBS], negPQHatInvNinv_s[PSI_MAX_LIMBS];
     ModDev mods[kMaxMods];                    // 0..L-1: q, L..L+Lp-1: p, L+Lp: t
 };
 
@@ -65,6 +68,12 @@ cudaError_t launch_scale_round(const KCtx& k, uint32_t groups, const u64* ten, u
 cudaError_t launch_relin_digits(const KCtx& k, uint32_t B, const u64* res, u64* dig);
 cudaError_t launch_relin_accum(const KCtx& k, uint32_t B, const u64* res_eval, const u64* dig, const u64* evk_b,
                                const u64* evk_a, const u64* mask /*nullable*/, u64* out);
+// Fused EvalMult(ct,ct) + relinearise (+ mask), fused_mul.cu.  a, b: [B][2][L][N] EVALUATION; scratch:
+// ha, hb [B][2][L][N], e1p [B][2][Lp][N], e2h [B][2][LT][N], th [B][3][LT][N], rh [B][2][L][N], dh [B][L][L][N].
+bool fused_mul_supported(const KCtx& k);
+cudaError_t launch_fused_mul(const KCtx& k, uint32_t B, const u64* a, const u64* b, u64* ha, u64* hb, u64* e1p,
+                             u64* e2h, u64* th, u64* rh, u64* dh, const u64* evk_b, const u64* evk_a, const u64* mask,
+                             u64* out);
 cudaError_t launch_mul_ctpt(const KCtx& k, uint32_t B, const u64* ct, const u64* pt, u64* out);
 
 // Packed encoding front end: slot values -> CRT-ordered residues mod t
