@@ -26,10 +26,11 @@
 
 namespace psi {
 
-constexpr uint32_t kLogCols = 7;    // row length 2^7 coefficients
-constexpr uint32_t kRowTileLog = 3; // 8 rows per row tile
-constexpr uint32_t kColTileLog = 3; // 8 columns per column tile
-constexpr uint32_t kGroup = 64;     // threads cooperating on one shared-memory array
+constexpr uint32_t kLogCols = 7;     // row length 2^7 coefficients
+constexpr uint32_t kRowTileLog = 3;  // 8 rows per row tile
+constexpr uint32_t kColTileLog = 3;  // 8 columns per column tile
+constexpr uint32_t kGroup = 64;      // threads cooperating on one shared-memory array
+constexpr uint32_t kColGroups = 4;   // groups per CTA in the column kernels (arrays are dealt round-robin)
 
 // padded shared-memory slot: one pad word per 16 coefficients keeps both the strided gathers and the
 // 16-contiguous-per-thread pattern of the last radix pass off a single bank group
@@ -53,286 +54,280 @@ __device__ __forceinline__ void gs_bf(u64& x, u64& y, const ulonglong2 tw, u64 q
     y = mul_shoup_lazy_nq(d, tw.x, tw.y, nq);
 }
 
-// Radix-2^R Cooley-Tukey pass over local stages [sig0, sig0 + R) of a local array of 2^m coefficients.
-// Global twiddle index of local stage sig, local group g:  2^(sig + delta) + (tile_base >> (m - sig)) + g
-template <int R>
-__device__ __forceinline__ void fwd_pass(u64* __restrict__ sm, const ulonglong2* __restrict__ tw, uint32_t m, uint32_t sig0,
-                                         uint32_t delta, uint32_t tile_base, u64 q, uint32_t tid) {
-    const uint32_t tl = (1u << m) >> (sig0 + R);
-    const u64 q2 = 2 * q, nq = 0 - q;
-    for (uint32_t blk = tid; blk < ((1u << m) >> R); blk += kGroup) {
-        const uint32_t off = blk & (tl - 1), grp = blk / tl;
-        const uint32_t base = (grp << (m - sig0)) + off;
-        u64 v[1 << R];
+// One stage (local stage sig0 + r) of a radix-2^R register pass.  All loop bounds are template constants
+// so that every index into v[] is a compile-time constant (the array must stay in registers).
+template <int R, int r, bool INV>
+__device__ __forceinline__ void reg_stage(u64 (&v)[1 << R], const ulonglong2* __restrict__ tw, uint32_t w0, u64 q2, u64 nq) {
+    constexpr int half = 1 << (R - 1 - r);
 #pragma unroll
-        for (int k = 0; k < (1 << R); k++) v[k] = sm[sl(base + k * tl)];
+    for (int j = 0; j < (1 << r); j++) {
+        const ulonglong2 t = __ldg(tw + w0 + j);
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int half = 1 << (R - 1 - r);
-            const uint32_t w0 = (1u << (sig0 + r + delta)) + (tile_base >> (m - sig0 - r)) + (grp << r);
-#pragma unroll
-            for (int j = 0; j < (1 << r); j++) {
-                const ulonglong2 t = __ldg(tw + w0 + j);
-#pragma unroll
-                for (int i = 0; i < half; i++) ct_bf(v[j * 2 * half + i], v[j * 2 * half + i + half], t, q2, nq);
-            }
+        for (int i = 0; i < half; i++) {
+            if (INV)
+                gs_bf(v[j * 2 * half + i], v[j * 2 * half + i + half], t, q2, nq);
+            else
+                ct_bf(v[j * 2 * half + i], v[j * 2 * half + i + half], t, q2, nq);
         }
-#pragma unroll
-        for (int k = 0; k < (1 << R); k++) sm[sl(base + k * tl)] = v[k];
     }
 }
-template <int R>
-__device__ __forceinline__ void inv_pass(u64* __restrict__ sm, const ulonglong2* __restrict__ tw, uint32_t m, uint32_t sig0,
-                                         uint32_t delta, uint32_t tile_base, u64 q, uint32_t tid) {
-    const uint32_t tl = (1u << m) >> (sig0 + R);
+template <int R, int rr, bool INV>
+struct RegStages {
+    static __device__ __forceinline__ void run(u64 (&v)[1 << R], const ulonglong2* __restrict__ tw, uint32_t m, uint32_t sig0,
+                                               uint32_t delta, uint32_t tile_base, uint32_t grp, u64 q2, u64 nq) {
+        constexpr int r = INV ? R - 1 - rr : rr;
+        const uint32_t w0 = (1u << (sig0 + r + delta)) + (tile_base >> (m - sig0 - r)) + (grp << r);
+        reg_stage<R, r, INV>(v, tw, w0, q2, nq);
+        RegStages<R, rr + 1, INV>::run(v, tw, m, sig0, delta, tile_base, grp, q2, nq);
+    }
+};
+template <int R, bool INV>
+struct RegStages<R, R, INV> {
+    static __device__ __forceinline__ void run(u64 (&)[1 << R], const ulonglong2* __restrict__, uint32_t, uint32_t, uint32_t,
+                                               uint32_t, uint32_t, u64, u64) {}
+};
+
+// Radix-2^R pass over local stages [sig0, sig0 + R) of a local array of 2^m coefficients.
+// Global twiddle index of local stage sig, local group g:  2^(sig + delta) + (tile_base >> (m - sig)) + g
+template <int R, bool INV>
+__device__ __forceinline__ void radix_pass(u64* __restrict__ sm, const ulonglong2* __restrict__ tw, uint32_t m,
+                                           uint32_t sig0, uint32_t delta, uint32_t tile_base, u64 q, uint32_t tid) {
+    const uint32_t lt = m - sig0 - R;  // log2 of the stride between a thread's coefficients
     const u64 q2 = 2 * q, nq = 0 - q;
     for (uint32_t blk = tid; blk < ((1u << m) >> R); blk += kGroup) {
-        const uint32_t off = blk & (tl - 1), grp = blk / tl;
+        const uint32_t off = blk & ((1u << lt) - 1), grp = blk >> lt;
         const uint32_t base = (grp << (m - sig0)) + off;
         u64 v[1 << R];
 #pragma unroll
-        for (int k = 0; k < (1 << R); k++) v[k] = sm[sl(base + k * tl)];
+        for (int k = 0; k < (1 << R); k++) v[k] = sm[sl(base + (k << lt))];
+        RegStages<R, 0, INV>::run(v, tw, m, sig0, delta, tile_base, grp, q2, nq);
 #pragma unroll
-        for (int r = R - 1; r >= 0; r--) {
-            const int half = 1 << (R - 1 - r);
-            const uint32_t w0 = (1u << (sig0 + r + delta)) + (tile_base >> (m - sig0 - r)) + (grp << r);
-#pragma unroll
-            for (int j = 0; j < (1 << r); j++) {
-                const ulonglong2 t = __ldg(tw + w0 + j);
-#pragma unroll
-                for (int i = 0; i < half; i++) gs_bf(v[j * 2 * half + i], v[j * 2 * half + i + half], t, q2, nq);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < (1 << R); k++) sm[sl(base + k * tl)] = v[k];
+        for (int k = 0; k < (1 << R); k++) sm[sl(base + (k << lt))] = v[k];
     }
 }
 
 // how many stages the next register pass takes when `rem` remain: 7 -> 4+3, 6 -> 3+3, 5 -> 3+2
 __device__ __forceinline__ uint32_t pass_width(uint32_t rem) { return (rem >= 7 || rem == 4) ? 4 : (rem >= 3 ? 3 : rem); }
 
-// Forward stages [lo, hi) in ascending order.  `active` = this thread's group owns an array; all
-// threads of the CTA must call (CTA-wide barriers between register passes).
-__device__ __forceinline__ void fwd_range(bool active, u64* sm, const ulonglong2* tw, uint32_t m, uint32_t lo, uint32_t hi,
-                                          uint32_t delta, uint32_t tile_base, u64 q, uint32_t tid) {
-    uint32_t s = lo;
-    while (s < hi) {
-        const uint32_t w = pass_width(hi - s);
-        if (active) {
-            if (w == 4) fwd_pass<4>(sm, tw, m, s, delta, tile_base, q, tid);
-            else if (w == 3) fwd_pass<3>(sm, tw, m, s, delta, tile_base, q, tid);
-            else if (w == 2) fwd_pass<2>(sm, tw, m, s, delta, tile_base, q, tid);
-            else fwd_pass<1>(sm, tw, m, s, delta, tile_base, q, tid);
-        }
-        s += w;
-        __syncthreads();
-    }
+template <bool INV>
+__device__ __forceinline__ void one_pass(uint32_t w, uint32_t s, u64* sm, const ulonglong2* tw, uint32_t m, uint32_t delta,
+                                         uint32_t tile_base, u64 q, uint32_t tid) {
+    if (w == 4) radix_pass<4, INV>(sm, tw, m, s, delta, tile_base, q, tid);
+    else if (w == 3) radix_pass<3, INV>(sm, tw, m, s, delta, tile_base, q, tid);
+    else if (w == 2) radix_pass<2, INV>(sm, tw, m, s, delta, tile_base, q, tid);
+    else radix_pass<1, INV>(sm, tw, m, s, delta, tile_base, q, tid);
 }
-// Inverse stages [lo, hi) in descending order.
-__device__ __forceinline__ void inv_range(bool active, u64* sm, const ulonglong2* tw, uint32_t m, uint32_t lo, uint32_t hi,
-                                          uint32_t delta, uint32_t tile_base, u64 q, uint32_t tid) {
-    uint32_t s = hi;
-    while (s > lo) {
-        const uint32_t w = pass_width(s - lo);
-        if (active) {
-            if (w == 4) inv_pass<4>(sm, tw, m, s - 4, delta, tile_base, q, tid);
-            else if (w == 3) inv_pass<3>(sm, tw, m, s - 3, delta, tile_base, q, tid);
-            else if (w == 2) inv_pass<2>(sm, tw, m, s - 2, delta, tile_base, q, tid);
-            else inv_pass<1>(sm, tw, m, s - 1, delta, tile_base, q, tid);
+
+// Stages [lo, hi) of n_arr arrays (ascending for the forward, descending for the inverse transform).
+// Array `a` lives at smem + a * stride and uses modulus index mod_of(a); group g of ng handles arrays
+// g, g + ng, ...  Every thread of the CTA must call (CTA-wide barrier after each register pass).
+template <bool INV, typename ModOf>
+__device__ __forceinline__ void transform(const DevTables* __restrict__ tab, u64* smem, uint32_t stride, uint32_t n_arr,
+                                          ModOf mod_of, uint32_t g, uint32_t ng, uint32_t m, uint32_t lo, uint32_t hi,
+                                          uint32_t delta, uint32_t tile_base, uint32_t tid) {
+    uint32_t rem = hi - lo;
+    uint32_t s = INV ? hi : lo;
+    while (rem) {
+        const uint32_t w = pass_width(rem);
+        const uint32_t s0 = INV ? s - w : s;
+        for (uint32_t a = g; a < n_arr; a += ng) {
+            const ModDev& md = tab->mods[mod_of(a)];
+            one_pass<INV>(w, s0, smem + a * stride, INV ? md.itw : md.ftw, m, delta, tile_base, md.q, tid);
         }
-        s -= w;
+        s = INV ? s - w : s + w;
+        rem -= w;
         __syncthreads();
     }
 }
 
-// a mod q for a < 16q (alpha of ScaleAndRound is below sizeP * 2^60 and q is above 2^59... any q > a/16):
-// four compare-subtract steps instead of a 64-bit division
-__device__ __forceinline__ u64 reduce_lt16q(u64 a, u64 q) {
-    if (a >= 8 * q) a -= 8 * q;
-    if (a >= 4 * q) a -= 4 * q;
-    if (a >= 2 * q) a -= 2 * q;
-    if (a >= q) a -= q;
+// ---- small modular helpers ----------------------------------------------------------------------
+// canonical residue of a < 2^K * q by K exact compare-subtract steps
+template <int K>
+__device__ __forceinline__ u64 reduce_pow2q(u64 a, u64 q) {
+#pragma unroll
+    for (int k = K - 1; k >= 0; k--) {
+        const u64 kq = q << k;
+        if (a >= kq) a -= kq;
+    }
     return a;
 }
+__device__ __forceinline__ u64 shoup_lazy(u64 x, u64 c, u64 cs, u64 q) { return mul_shoup_lazy_nq(x, c, cs, 0 - q); }
+__device__ __forceinline__ u64 shoup_canon(u64 x, u64 c, u64 cs, u64 q) {
+    const u64 r = shoup_lazy(x, c, cs, q);
+    return r >= q ? r - q : r;
+}
 
-// ---- tile movers -------------------------------------------------------------------------------
-// row tile: 2^(7+kRowTileLog) contiguous coefficients starting at poly + tile_base
+// ---- tile movers (16-byte global accesses) ------------------------------------------------------
+// row tile: 2^(7+kRowTileLog) contiguous coefficients
 __device__ __forceinline__ void load_rows(u64* sm, const u64* __restrict__ poly_tile, uint32_t tid) {
-    const uint32_t M = 1u << (kLogCols + kRowTileLog);
-    for (uint32_t j = tid; j < M; j += kGroup) sm[sl(j)] = poly_tile[j];
+    const uint32_t M2 = 1u << (kLogCols + kRowTileLog - 1);
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(poly_tile);
+#pragma unroll 4
+    for (uint32_t j = tid; j < M2; j += kGroup) {
+        const ulonglong2 v = src[j];
+        sm[sl(2 * j)] = v.x;
+        sm[sl(2 * j) + 1] = v.y;
+    }
 }
 __device__ __forceinline__ void store_rows(const u64* sm, u64* __restrict__ poly_tile, uint32_t tid) {
-    const uint32_t M = 1u << (kLogCols + kRowTileLog);
-    for (uint32_t j = tid; j < M; j += kGroup) poly_tile[j] = sm[sl(j)];
+    const uint32_t M2 = 1u << (kLogCols + kRowTileLog - 1);
+    ulonglong2* dst = reinterpret_cast<ulonglong2*>(poly_tile);
+#pragma unroll 4
+    for (uint32_t j = tid; j < M2; j += kGroup) dst[j] = make_ulonglong2(sm[sl(2 * j)], sm[sl(2 * j) + 1]);
 }
 // column tile: local j = r * 8 + cc  <->  global n = r * 128 + c0 + cc
 __device__ __forceinline__ void load_cols(u64* sm, const u64* __restrict__ poly, uint32_t logR, uint32_t c0, uint32_t tid) {
-    const uint32_t M = 1u << (logR + kColTileLog);
-    for (uint32_t j = tid; j < M; j += kGroup)
-        sm[sl(j)] = poly[((j >> kColTileLog) << kLogCols) + c0 + (j & ((1u << kColTileLog) - 1))];
+    const uint32_t M2 = 1u << (logR + kColTileLog - 1);
+#pragma unroll 4
+    for (uint32_t j = tid; j < M2; j += kGroup) {
+        const uint32_t e = 2 * j;
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(
+            poly + ((e >> kColTileLog) << kLogCols) + c0 + (e & ((1u << kColTileLog) - 1)));
+        sm[sl(e)] = v.x;
+        sm[sl(e) + 1] = v.y;
+    }
 }
 __device__ __forceinline__ void store_cols(const u64* sm, u64* __restrict__ poly, uint32_t logR, uint32_t c0, uint32_t tid) {
-    const uint32_t M = 1u << (logR + kColTileLog);
-    for (uint32_t j = tid; j < M; j += kGroup)
-        poly[((j >> kColTileLog) << kLogCols) + c0 + (j & ((1u << kColTileLog) - 1))] = sm[sl(j)];
+    const uint32_t M2 = 1u << (logR + kColTileLog - 1);
+#pragma unroll 4
+    for (uint32_t j = tid; j < M2; j += kGroup) {
+        const uint32_t e = 2 * j;
+        *reinterpret_cast<ulonglong2*>(poly + ((e >> kColTileLog) << kLogCols) + c0 + (e & ((1u << kColTileLog) - 1))) =
+            make_ulonglong2(sm[sl(e)], sm[sl(e) + 1]);
+    }
 }
 
 // ---- (1) rows, inverse: both operands, all 4L limb-polys of a bin --------------------------------
 // grid (R/8, L, B), 4 groups: a.c0, a.c1, b.c0, b.c1 of limb blockIdx.y
-__global__ void __launch_bounds__(4 * kGroup) k_rows_inv(const DevTables* __restrict__ tab, uint32_t logN,
-                                                         const u64* __restrict__ a, const u64* __restrict__ b,
-                                                         u64* __restrict__ ha, u64* __restrict__ hb) {
-    extern __shared__ u64 smem[];
+__global__ void __launch_bounds__(4 * kGroup, 3) k_rows_inv(const DevTables* __restrict__ tab, uint32_t logN,
+                                                            const u64* __restrict__ a, const u64* __restrict__ b,
+                                                            u64* __restrict__ ha, u64* __restrict__ hb) {
+    extern __shared__ __align__(16) u64 smem[];
     const uint32_t N = 1u << logN, L = tab->L;
-    const uint32_t m = kLogCols + kRowTileLog, M = 1u << m;
+    const uint32_t m = kLogCols + kRowTileLog, M = 1u << m, P = padded(M);
     const uint32_t g = threadIdx.x / kGroup, tid = threadIdx.x % kGroup;
     const uint32_t l = blockIdx.y, tile_base = blockIdx.x * M;
     const size_t bin = blockIdx.z;
     const size_t off = ((bin * 2 + (g & 1)) * L + l) * N + tile_base;
-    const u64* src = (g < 2 ? a : b) + off;
-    u64* dst = (g < 2 ? ha : hb) + off;
-    u64* sm = smem + g * padded(M);
-    const ModDev& md = tab->mods[l];
-    load_rows(sm, src, tid);
+    load_rows(smem + g * P, (g < 2 ? a : b) + off, tid);
     __syncthreads();
-    inv_range(true, sm, md.itw, m, kRowTileLog, m, logN - m, tile_base, md.q, tid);
-    store_rows(sm, dst, tid);
+    transform<true>(tab, smem, P, 4, [l](uint32_t) { return l; }, g, 4, m, kRowTileLog, m, logN - m, tile_base, tid);
+    store_rows(smem + g * P, (g < 2 ? ha : hb) + off, tid);
 }
 
 // ---- (2) columns: inverse, basis extension, forward -----------------------------------------------
-// grid (128/8, 4 = operand*2 + component, B); LT groups.
+// grid (128/8, 4 = operand*2 + component, B); kColGroups groups.
 //   operand 0 (multipliedResult):  DCRTPoly::ExpandCRTBasis            -> e1p [B][2][Lp][N]
 //   operand 1 (innerProductResult): DCRTPoly::FastExpandCRTBasisPloverQ -> e2h [B][2][LT][N]
-__global__ void __launch_bounds__(PSI_MAX_LIMBS * kGroup) k_cols_extend(const DevTables* __restrict__ tab,
-                                                                           uint32_t logN, const u64* __restrict__ ha,
-                                                                           const u64* __restrict__ hb,
-                                                                           u64* __restrict__ e1p, u64* __restrict__ e2h) {
-    extern __shared__ u64 smem[];
-    const uint32_t N = 1u << logN, L = tab->L, Lp = tab->Lp, LT = L + Lp;
-    const uint32_t logR = logN - kLogCols, m = logR + kColTileLog, M = 1u << m;
+// All modular sums are formed as sums of lazy Shoup products (< 2q each, at most 8 terms < 2^64) and
+// reduced once: the canonical residue, identical to the 128-bit Barrett form of the reference.
+template <int L, int LP>
+__global__ void __launch_bounds__(kColGroups* kGroup, 2)
+    k_cols_extend(const DevTables* __restrict__ tab, uint32_t logN, const u64* __restrict__ ha, const u64* __restrict__ hb,
+                  u64* __restrict__ e1p, u64* __restrict__ e2h) {
+    extern __shared__ __align__(16) u64 smem[];
+    constexpr int LT = L + LP;
+    const uint32_t N = 1u << logN;
+    const uint32_t logR = logN - kLogCols, m = logR + kColTileLog, M = 1u << m, P = padded(M);
     const uint32_t g = threadIdx.x / kGroup, tid = threadIdx.x % kGroup;
     const uint32_t c0 = blockIdx.x << kColTileLog;
     const uint32_t operand = blockIdx.y >> 1, comp = blockIdx.y & 1;
     const size_t bin = blockIdx.z;
-    const uint32_t P = padded(M);
-    u64* sm = smem + g * P;
 
     // column-inverse of the L input limbs
     const u64* src = (operand ? hb : ha) + ((bin * 2 + comp) * L) * (size_t)N;
-    const bool in_active = g < L;
-    if (in_active) load_cols(sm, src + (size_t)g * N, logR, c0, tid);
+    for (uint32_t a = g; a < L; a += kColGroups) load_cols(smem + a * P, src + (size_t)a * N, logR, c0, tid);
     __syncthreads();
-    inv_range(in_active, sm, tab->mods[in_active ? g : 0].itw, m, 0, logR, 0, 0, tab->mods[in_active ? g : 0].q, tid);
+    transform<true>(tab, smem, P, L, [](uint32_t a) { return a; }, g, kColGroups, m, 0, logR, 0, 0, tid);
 
     // coefficient-wise extension; N^-1 of the inverse transform is folded into the first constant
     for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) {
-        u64 y[PSI_MAX_LIMBS];
+        u64 y[L];
         if (operand == 0) {
             double nu = 0.5;
 #pragma unroll
-            for (int i = 0; i < PSI_MAX_LIMBS; i++)
-                if (i < (int)L) {
-                    y[i] = mul_shoup(smem[i * P + sl(j)], tab->QHatInvNinv[i], tab->QHatInvNinv_s[i], tab->mods[i].q);
-                    nu = __dadd_rn(nu, __dmul_rn(__ull2double_rn(y[i]), tab->qInv[i]));
-                }
+            for (int i = 0; i < L; i++) {
+                y[i] = shoup_canon(smem[i * P + sl(j)], tab->QHatInvNinv[i], tab->QHatInvNinv_s[i], tab->mods[i].q);
+                nu = __dadd_rn(nu, __dmul_rn(__ull2double_rn(y[i]), tab->qInv[i]));
+            }
             const unsigned alpha = (unsigned)nu;
 #pragma unroll
-            for (int jj = 0; jj < PSI_MAX_LIMBS; jj++)
-                if (jj < (int)Lp) {
-                    const ModDev& mb = tab->mods[L + jj];
-                    u64 hi = 0, lo = 0;
+            for (int jj = 0; jj < LP; jj++) {
+                const u64 p = tab->mods[L + jj].q;
+                u64 acc = 0;
 #pragma unroll
-                    for (int i = 0; i < PSI_MAX_LIMBS; i++)
-                        if (i < (int)L) mac128(hi, lo, y[i], tab->QHatModp[jj][i]);
-                    const u64 v = barrett128(hi, lo, mb.q, mb.mu_hi, mb.mu_lo);
-                    smem[jj * P + sl(j)] = submod(v, tab->alphaQModp[alpha][jj], mb.q);
-                }
+                for (int i = 0; i < L; i++) acc += shoup_lazy(y[i], tab->QHatModp[jj][i], tab->QHatModp_s[jj][i], p);
+                const u64 v = reduce_pow2q<4>(acc, p);
+                smem[jj * P + sl(j)] = submod(v, tab->alphaQModp[alpha][jj], p);
+            }
         } else {
-            u64 pp[PSI_MAX_LIMBS];
+            u64 pp[LP], z[LP];
 #pragma unroll
-            for (int i = 0; i < PSI_MAX_LIMBS; i++)
-                if (i < (int)L)
-                    y[i] = mul_shoup(smem[i * P + sl(j)], tab->negPQHatInvNinv[i], tab->negPQHatInvNinv_s[i], tab->mods[i].q);
+            for (int i = 0; i < L; i++)
+                y[i] = shoup_canon(smem[i * P + sl(j)], tab->negPQHatInvNinv[i], tab->negPQHatInvNinv_s[i], tab->mods[i].q);
             double nu = 0.5;
 #pragma unroll
-            for (int jj = 0; jj < PSI_MAX_LIMBS; jj++)
-                if (jj < (int)Lp) {
-                    const ModDev& mp = tab->mods[L + jj];
-                    u64 hi = 0, lo = 0;
+            for (int jj = 0; jj < LP; jj++) {
+                const u64 p = tab->mods[L + jj].q;
+                u64 acc = 0;
 #pragma unroll
-                    for (int i = 0; i < PSI_MAX_LIMBS; i++)
-                        if (i < (int)L) mac128(hi, lo, y[i], tab->qInvModp[i][jj]);
-                    pp[jj] = barrett128(hi, lo, mp.q, mp.mu_hi, mp.mu_lo);
-                }
-            // exact P -> Q (DCRTPoly::SwitchCRTBasis)
-            u64 z[PSI_MAX_LIMBS];
-#pragma unroll
-            for (int jj = 0; jj < PSI_MAX_LIMBS; jj++)
-                if (jj < (int)Lp) {
-                    z[jj] = mul_shoup(pp[jj], tab->PHatInvModp[jj], tab->PHatInvModp_s[jj], tab->mods[L + jj].q);
-                    nu = __dadd_rn(nu, __dmul_rn(__ull2double_rn(z[jj]), tab->pInv[jj]));
-                }
+                for (int i = 0; i < L; i++) acc += shoup_lazy(y[i], tab->qInvModp[i][jj], tab->qInvModp_s[i][jj], p);
+                pp[jj] = reduce_pow2q<4>(acc, p);
+                // exact P -> Q (DCRTPoly::SwitchCRTBasis)
+                z[jj] = shoup_canon(pp[jj], tab->PHatInvModp[jj], tab->PHatInvModp_s[jj], p);
+                nu = __dadd_rn(nu, __dmul_rn(__ull2double_rn(z[jj]), tab->pInv[jj]));
+            }
             const unsigned alpha = (unsigned)nu;
 #pragma unroll
-            for (int i = 0; i < PSI_MAX_LIMBS; i++)
-                if (i < (int)L) {
-                    const ModDev& mq = tab->mods[i];
-                    u64 hi = 0, lo = 0;
+            for (int i = 0; i < L; i++) {
+                const u64 q = tab->mods[i].q;
+                u64 acc = 0;
 #pragma unroll
-                    for (int jj = 0; jj < PSI_MAX_LIMBS; jj++)
-                        if (jj < (int)Lp) mac128(hi, lo, z[jj], tab->PHatModq[i][jj]);
-                    const u64 v = barrett128(hi, lo, mq.q, mq.mu_hi, mq.mu_lo);
-                    smem[i * P + sl(j)] = submod(v, tab->alphaPModq[alpha][i], mq.q);
-                }
+                for (int jj = 0; jj < LP; jj++) acc += shoup_lazy(z[jj], tab->PHatModq[i][jj], tab->PHatModq_s[i][jj], q);
+                const u64 v = reduce_pow2q<4>(acc, q);
+                smem[i * P + sl(j)] = submod(v, tab->alphaPModq[alpha][i], q);
+            }
 #pragma unroll
-            for (int jj = 0; jj < PSI_MAX_LIMBS; jj++)
-                if (jj < (int)Lp) smem[(L + jj) * P + sl(j)] = pp[jj];
+            for (int jj = 0; jj < LP; jj++) smem[(L + jj) * P + sl(j)] = pp[jj];
         }
     }
     __syncthreads();
 
     // column-forward of the produced limbs
-    const uint32_t n_out = operand ? LT : Lp;
-    const uint32_t mod_out = operand ? g : L + g;  // array g holds modulus index mod_out
-    const bool out_active = g < n_out;
-    const ModDev& mo = tab->mods[out_active ? mod_out : 0];
-    fwd_range(out_active, sm, mo.ftw, m, 0, logR, 0, 0, mo.q, tid);
-    if (out_active) {
-        u64* dst = operand ? e2h + ((bin * 2 + comp) * LT + g) * (size_t)N : e1p + ((bin * 2 + comp) * Lp + g) * (size_t)N;
-        store_cols(sm, dst, logR, c0, tid);
+    const uint32_t n_out = operand ? LT : LP;
+    const uint32_t mod0 = operand ? 0 : L;
+    transform<false>(tab, smem, P, n_out, [mod0](uint32_t a) { return mod0 + a; }, g, kColGroups, m, 0, logR, 0, 0, tid);
+    for (uint32_t a = g; a < n_out; a += kColGroups) {
+        u64* dst = operand ? e2h + ((bin * 2 + comp) * LT + a) * (size_t)N : e1p + ((bin * 2 + comp) * LP + a) * (size_t)N;
+        store_cols(smem + a * P, dst, logR, c0, tid);
     }
 }
 
 // ---- (3) rows: forward, tensor, inverse -----------------------------------------------------------
 // grid (R/8, LT, B), 4 groups (a0, a1, b0, b1 of limb blockIdx.y); a: [B][2][L][N] EVALUATION (Q limbs
 // are used as given), e1p/e2h from (2); th: [B][3][LT][N] row-inverse halves
-__global__ void __launch_bounds__(4 * kGroup) k_rows_tensor(const DevTables* __restrict__ tab, uint32_t logN,
-                                                            const u64* __restrict__ a, const u64* __restrict__ e1p,
-                                                            const u64* __restrict__ e2h, u64* __restrict__ th) {
-    extern __shared__ u64 smem[];
+__global__ void __launch_bounds__(4 * kGroup, 3) k_rows_tensor(const DevTables* __restrict__ tab, uint32_t logN,
+                                                               const u64* __restrict__ a, const u64* __restrict__ e1p,
+                                                               const u64* __restrict__ e2h, u64* __restrict__ th) {
+    extern __shared__ __align__(16) u64 smem[];
     const uint32_t N = 1u << logN, L = tab->L, Lp = tab->Lp, LT = L + Lp;
     const uint32_t m = kLogCols + kRowTileLog, M = 1u << m, P = padded(M);
     const uint32_t g = threadIdx.x / kGroup, tid = threadIdx.x % kGroup;
     const uint32_t l = blockIdx.y, tile_base = blockIdx.x * M;
     const size_t bin = blockIdx.z;
     const ModDev& md = tab->mods[l];
-    u64* sm = smem + g * P;
     const uint32_t comp = g & 1;
-    bool transform = true;
     const u64* src;
-    if (g < 2) {
-        if (l < L) {
-            src = a + ((bin * 2 + comp) * L + l) * (size_t)N;
-            transform = false;
-        } else {
-            src = e1p + ((bin * 2 + comp) * Lp + (l - L)) * (size_t)N;
-        }
-    } else {
+    if (g < 2)
+        src = l < L ? a + ((bin * 2 + comp) * L + l) * (size_t)N : e1p + ((bin * 2 + comp) * Lp + (l - L)) * (size_t)N;
+    else
         src = e2h + ((bin * 2 + comp) * LT + l) * (size_t)N;
-    }
-    load_rows(sm, src + tile_base, tid);
+    load_rows(smem + g * P, src + tile_base, tid);
     __syncthreads();
-    fwd_range(transform, sm, md.ftw, m, kRowTileLog, m, logN - m, tile_base, md.q, tid);
+    // the Q limbs of the first operand are already in EVALUATION form: arrays 0, 1 are skipped for l < L
+    const uint32_t first = l < L ? 2 : 0;
+    transform<false>(tab, smem + first * P, P, 4 - first, [l](uint32_t) { return l; }, g >= first ? g - first : 4, 4 - first,
+                     m, kRowTileLog, m, logN - m, tile_base, tid);
 
     for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) {
         const u64 a0 = smem[sl(j)], a1 = smem[P + sl(j)], b0 = smem[2 * P + sl(j)], b1 = smem[3 * P + sl(j)];
@@ -344,77 +339,67 @@ __global__ void __launch_bounds__(4 * kGroup) k_rows_tensor(const DevTables* __r
         smem[2 * P + sl(j)] = barrett128(mulhi64(a1, b1), a1 * b1, md.q, md.mu_hi, md.mu_lo);
     }
     __syncthreads();
-    inv_range(g < 3, sm, md.itw, m, kRowTileLog, m, logN - m, tile_base, md.q, tid);
-    if (g < 3) store_rows(sm, th + ((bin * 3 + g) * LT + l) * (size_t)N + tile_base, tid);
+    transform<true>(tab, smem, P, 3, [l](uint32_t) { return l; }, g, 4, m, kRowTileLog, m, logN - m, tile_base, tid);
+    if (g < 3) store_rows(smem + g * P, th + ((bin * 3 + g) * LT + l) * (size_t)N + tile_base, tid);
 }
 
 // ---- (4) columns: inverse, scale-and-round, digit lift, forward -----------------------------------
-// grid (128/8, 3, B), LT groups.  th: [B][3][LT][N]; rh: [B][2][L][N] (column-forward halves of c0, c1);
-// dh: [B][L][L][N] (column-forward halves of the BV digits of c2)
-__global__ void __launch_bounds__(PSI_MAX_LIMBS * kGroup) k_cols_scale(const DevTables* __restrict__ tab,
-                                                                          uint32_t logN, const u64* __restrict__ th,
-                                                                          u64* __restrict__ rh, u64* __restrict__ dh) {
-    extern __shared__ u64 smem[];
-    const uint32_t N = 1u << logN, L = tab->L, Lp = tab->Lp, LT = L + Lp;
+// grid (128/8, 3, B), kColGroups groups.  th: [B][3][LT][N]; rh: [B][2][L][N] (column-forward halves of
+// c0, c1); dh: [B][L][L][N] (column-forward halves of the BV digits of c2)
+template <int L, int LP>
+__global__ void __launch_bounds__(kColGroups* kGroup, 2)
+    k_cols_scale(const DevTables* __restrict__ tab, uint32_t logN, const u64* __restrict__ th, u64* __restrict__ rh,
+                 u64* __restrict__ dh) {
+    extern __shared__ __align__(16) u64 smem[];
+    constexpr int LT = L + LP;
+    const uint32_t N = 1u << logN;
     const uint32_t logR = logN - kLogCols, m = logR + kColTileLog, M = 1u << m, P = padded(M);
     const uint32_t g = threadIdx.x / kGroup, tid = threadIdx.x % kGroup;
     const uint32_t c0 = blockIdx.x << kColTileLog, comp = blockIdx.y;
     const size_t bin = blockIdx.z;
-    u64* sm = smem + g * P;
-    const bool in_active = g < LT;
-    const ModDev& mi = tab->mods[in_active ? g : 0];
-    if (in_active) load_cols(sm, th + ((bin * 3 + comp) * LT + g) * (size_t)N, logR, c0, tid);
+    for (uint32_t a = g; a < LT; a += kColGroups)
+        load_cols(smem + a * P, th + ((bin * 3 + comp) * LT + a) * (size_t)N, logR, c0, tid);
     __syncthreads();
-    inv_range(in_active, sm, mi.itw, m, 0, logR, 0, 0, mi.q, tid);
+    transform<true>(tab, smem, P, LT, [](uint32_t a) { return a; }, g, kColGroups, m, 0, logR, 0, 0, tid);
 
     // DCRTPoly::ScaleAndRound (t/P, output basis Q) on canonical coefficients
     for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) {
-        u64 xp[PSI_MAX_LIMBS], xq[PSI_MAX_LIMBS];
+        u64 xp[LP];
         double nu = 0.5;
 #pragma unroll
-        for (int i = 0; i < PSI_MAX_LIMBS; i++)
-            if (i < (int)Lp) {
-                const ModDev& mp = tab->mods[L + i];
-                xp[i] = mul_shoup(smem[(L + i) * P + sl(j)], mp.ninv, mp.ninv_s, mp.q);
-                nu = __dadd_rn(nu, __dmul_rn(tab->tQSfrac[i], __ull2double_rn(xp[i])));
-            }
+        for (int i = 0; i < LP; i++) {
+            const ModDev& mp = tab->mods[L + i];
+            xp[i] = shoup_canon(smem[(L + i) * P + sl(j)], mp.ninv, mp.ninv_s, mp.q);
+            nu = __dadd_rn(nu, __dmul_rn(tab->tQSfrac[i], __ull2double_rn(xp[i])));
+        }
+        const u64 alpha = __double2ull_rz(nu);  // < LP * 2^60
 #pragma unroll
-        for (int l = 0; l < PSI_MAX_LIMBS; l++)
-            if (l < (int)L) {
-                const ModDev& mq = tab->mods[l];
-                xq[l] = mul_shoup(smem[l * P + sl(j)], mq.ninv, mq.ninv_s, mq.q);
-            }
-        const u64 alpha = __double2ull_rz(nu);
+        for (int l = 0; l < L; l++) {
+            const ModDev& mq = tab->mods[l];
+            const u64 q = mq.q;
+            const u64 xq = shoup_canon(smem[l * P + sl(j)], mq.ninv, mq.ninv_s, q);
+            u64 acc = shoup_lazy(xq, tab->tQS[l][LP], tab->tQS_s[l][LP], q);
 #pragma unroll
-        for (int l = 0; l < PSI_MAX_LIMBS; l++)
-            if (l < (int)L) {
-                const ModDev& mq = tab->mods[l];
-                u64 hi = 0, lo = 0;
-#pragma unroll
-                for (int i = 0; i < PSI_MAX_LIMBS; i++)
-                    if (i < (int)Lp) mac128(hi, lo, xp[i], tab->tQS[l][i]);
-                mac128(hi, lo, xq[l], tab->tQS[l][Lp]);
-                const u64 v = barrett128(hi, lo, mq.q, mq.mu_hi, mq.mu_lo);
-                smem[l * P + sl(j)] = addmod(v, reduce_lt16q(alpha, mq.q), mq.q);
-            }
+            for (int i = 0; i < LP; i++) acc += shoup_lazy(xp[i], tab->tQS[l][i], tab->tQS_s[l][i], q);
+            // acc < 2 (LP + 1) q, alpha < 16 q: reduce both, add
+            smem[l * P + sl(j)] = addmod(reduce_pow2q<4>(acc, q), alpha < (q << 4) ? reduce_pow2q<4>(alpha, q) : alpha % q, q);
+        }
     }
     __syncthreads();
 
     if (comp < 2) {
-        const bool act = g < L;
-        const ModDev& mo = tab->mods[act ? g : 0];
-        fwd_range(act, sm, mo.ftw, m, 0, logR, 0, 0, mo.q, tid);
-        if (act) store_cols(sm, rh + ((bin * 2 + comp) * L + g) * (size_t)N, logR, c0, tid);
+        transform<false>(tab, smem, P, L, [](uint32_t a) { return a; }, g, kColGroups, m, 0, logR, 0, 0, tid);
+        for (uint32_t a = g; a < L; a += kColGroups)
+            store_cols(smem + a * P, rh + ((bin * 2 + comp) * L + a) * (size_t)N, logR, c0, tid);
         return;
     }
     // DCRTPoly::CRTDecompose (BV, digit size 0): digit i = limb i of c2 switched to every q_k with the
     // centred lift of NativeVector::SwitchModulus; arrays L..2L-1 hold the L limbs of the current digit
-    const bool act = g >= L && g < 2 * L;
-    const uint32_t kk = act ? g - L : 0;
-    const ModDev& mo = tab->mods[kk];
     for (uint32_t i = 0; i < L; i++) {
-        if (act) {
-            const u64 qi = tab->mods[i].q, qk = mo.q, half = (qi - 1) >> 1, qiq = tab->qModq[i][kk];
+        const u64 qi = tab->mods[i].q, half = (qi - 1) >> 1;
+        for (uint32_t kk = g; kk < L; kk += kColGroups) {
+            const u64 qk = tab->mods[kk].q, qiq = tab->qModq[i][kk];
+            u64* dst = smem + (L + kk) * P;
             for (uint32_t j = tid; j < M; j += kGroup) {
                 const u64 v = smem[i * P + sl(j)];
                 u64 r = v;
@@ -422,12 +407,13 @@ __global__ void __launch_bounds__(PSI_MAX_LIMBS * kGroup) k_cols_scale(const Dev
                     r = (v < qk) ? v : ((v - qk < qk) ? v - qk : v % qk);
                     if (v > half) r = submod(r, qiq, qk);
                 }
-                sm[sl(j)] = r;
+                dst[sl(j)] = r;
             }
         }
         __syncthreads();
-        fwd_range(act, sm, mo.ftw, m, 0, logR, 0, 0, mo.q, tid);
-        if (act) store_cols(sm, dh + ((bin * L + i) * L + kk) * (size_t)N, logR, c0, tid);
+        transform<false>(tab, smem + L * P, P, L, [](uint32_t a) { return a; }, g, kColGroups, m, 0, logR, 0, 0, tid);
+        for (uint32_t kk = g; kk < L; kk += kColGroups)
+            store_cols(smem + (L + kk) * P, dh + ((bin * L + i) * L + kk) * (size_t)N, logR, c0, tid);
         __syncthreads();
     }
 }
@@ -441,18 +427,17 @@ __global__ void __launch_bounds__((2 + PSI_MAX_LIMBS) * kGroup) k_rows_relin(con
                                                                             const u64* __restrict__ evk_a,
                                                                             const u64* __restrict__ mask,
                                                                             u64* __restrict__ out) {
-    extern __shared__ u64 smem[];
+    extern __shared__ __align__(16) u64 smem[];
     const uint32_t N = 1u << logN, L = tab->L;
     const uint32_t m = kLogCols + kRowTileLog, M = 1u << m, P = padded(M);
     const uint32_t g = threadIdx.x / kGroup, tid = threadIdx.x % kGroup;
     const uint32_t kk = blockIdx.y, tile_base = blockIdx.x * M;
     const size_t bin = blockIdx.z;
     const ModDev& md = tab->mods[kk];
-    u64* sm = smem + g * P;
     const u64* src = g < 2 ? rh + ((bin * 2 + g) * L + kk) * (size_t)N : dh + ((bin * L + (g - 2)) * L + kk) * (size_t)N;
-    load_rows(sm, src + tile_base, tid);
+    load_rows(smem + g * P, src + tile_base, tid);
     __syncthreads();
-    fwd_range(true, sm, md.ftw, m, kRowTileLog, m, logN - m, tile_base, md.q, tid);
+    transform<false>(tab, smem, P, 2 + L, [kk](uint32_t) { return kk; }, g, 2 + L, m, kRowTileLog, m, logN - m, tile_base, tid);
 
     const size_t LN = (size_t)L * N;
     for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) {
@@ -478,30 +463,60 @@ __global__ void __launch_bounds__((2 + PSI_MAX_LIMBS) * kGroup) k_rows_relin(con
 }
 
 // ---- launcher --------------------------------------------------------------------------------------
-// column kernels run one 64-thread group per limb of Q*P: at most PSI_MAX_LIMBS groups (512 threads)
-bool fused_mul_supported(const KCtx& k) { return k.logN >= kLogCols + kRowTileLog && k.L + k.Lp <= PSI_MAX_LIMBS; }
+// The column kernels are instantiated for the limb counts BFVrns produces for this path (sizeQ 1..4,
+// sizeP = sizeQ or sizeQ + 1); anything else takes the unfused kernels.
+bool fused_mul_supported(const KCtx& k) {
+    return k.logN >= kLogCols + kRowTileLog && k.L >= 1 && k.L <= 4 && (k.Lp == k.L || k.Lp == k.L + 1) && k.L + k.Lp <= 8;
+}
+
+template <int L, int LP>
+static cudaError_t launch_cols(const KCtx& k, uint32_t B, const u64* ha, const u64* hb, u64* e1p, u64* e2h, const u64* th,
+                               u64* rh, u64* dh, int which) {
+    const uint32_t logR = k.logN - kLogCols, col_tiles = (1u << kLogCols) >> kColTileLog;
+    const size_t smem = (size_t)(L + LP) * padded(1u << (logR + kColTileLog)) * sizeof(u64);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e;
+        if ((e = cudaFuncSetAttribute(k_cols_extend<L, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_cols_scale<L, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (which == 0)
+        k_cols_extend<L, LP><<<dim3(col_tiles, 4, B), kColGroups * kGroup, smem, k.s>>>(k.tab, k.logN, ha, hb, e1p, e2h);
+    else
+        k_cols_scale<L, LP><<<dim3(col_tiles, 3, B), kColGroups * kGroup, smem, k.s>>>(k.tab, k.logN, th, rh, dh);
+    return cudaGetLastError();
+}
+
+static cudaError_t dispatch_cols(const KCtx& k, uint32_t B, const u64* ha, const u64* hb, u64* e1p, u64* e2h, const u64* th,
+                                 u64* rh, u64* dh, int which) {
+#define PSI_COLS_CASE(l, lp) \
+    if (k.L == l && k.Lp == lp) return launch_cols<l, lp>(k, B, ha, hb, e1p, e2h, th, rh, dh, which);
+    PSI_COLS_CASE(1, 1) PSI_COLS_CASE(1, 2) PSI_COLS_CASE(2, 2) PSI_COLS_CASE(2, 3)
+    PSI_COLS_CASE(3, 3) PSI_COLS_CASE(3, 4) PSI_COLS_CASE(4, 4)
+#undef PSI_COLS_CASE
+    return cudaErrorInvalidValue;
+}
 
 cudaError_t launch_fused_mul(const KCtx& k, uint32_t B, const u64* a, const u64* b, u64* ha, u64* hb, u64* e1p,
                              u64* e2h, u64* th, u64* rh, u64* dh, const u64* evk_b, const u64* evk_a, const u64* mask,
                              u64* out) {
     if (B == 0) return cudaSuccess;
-    const uint32_t L = k.L, Lp = k.Lp, LT = L + Lp;
+    const uint32_t L = k.L, LT = k.L + k.Lp;
     const uint32_t logR = k.logN - kLogCols;
-    const uint32_t row_tiles = (1u << logR) >> kRowTileLog, col_tiles = (1u << kLogCols) >> kColTileLog;
+    const uint32_t row_tiles = (1u << logR) >> kRowTileLog;
     const size_t row_arr = padded(1u << (kLogCols + kRowTileLog)) * sizeof(u64);
-    const size_t col_arr = padded(1u << (logR + kColTileLog)) * sizeof(u64);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e;
-        if ((e = cudaFuncSetAttribute(k_cols_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(k_cols_scale, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(k_rows_relin, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_rows_relin, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
         attr_set = true;
     }
+    cudaError_t e;
     k_rows_inv<<<dim3(row_tiles, L, B), 4 * kGroup, 4 * row_arr, k.s>>>(k.tab, k.logN, a, b, ha, hb);
-    k_cols_extend<<<dim3(col_tiles, 4, B), LT * kGroup, LT * col_arr, k.s>>>(k.tab, k.logN, ha, hb, e1p, e2h);
+    if ((e = dispatch_cols(k, B, ha, hb, e1p, e2h, nullptr, nullptr, nullptr, 0)) != cudaSuccess) return e;
     k_rows_tensor<<<dim3(row_tiles, LT, B), 4 * kGroup, 4 * row_arr, k.s>>>(k.tab, k.logN, a, e1p, e2h, th);
-    k_cols_scale<<<dim3(col_tiles, 3, B), LT * kGroup, LT * col_arr, k.s>>>(k.tab, k.logN, th, rh, dh);
+    if ((e = dispatch_cols(k, B, nullptr, nullptr, nullptr, nullptr, th, rh, dh, 1)) != cudaSuccess) return e;
     k_rows_relin<<<dim3(row_tiles, L, B), (2 + L) * kGroup, (2 + L) * row_arr, k.s>>>(k.tab, k.logN, rh, dh, evk_b,
                                                                                        evk_a, mask, out);
     return cudaGetLastError();

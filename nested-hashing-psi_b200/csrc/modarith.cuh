@@ -99,8 +99,16 @@ __device__ __forceinline__ u64 mul_shoup_lazy_nq(u64 x, u64 w, u64 ws, u64 nq) {
 // Approximate lazy correction: subtracts q2 only when the HIGH WORD already proves x >= q2, so it can
 // never underflow; afterwards x < q2 + 2^32.  One 32-bit compare + a predicated 64-bit subtract.
 __device__ __forceinline__ u64 lazy_sub_hi(u64 x, u64 q2) {
-    if (hi32(x) > hi32(q2)) x -= q2;
-    return x;
+    uint32_t xl = lo32(x), xh = hi32(x);
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.gt.u32 p, %1, %3;\n\t"
+        "@p sub.cc.u32 %0, %0, %2;\n\t"
+        "@p subc.u32 %1, %1, %3;\n\t"
+        "}"
+        : "+r"(xl), "+r"(xh)
+        : "r"(lo32(q2)), "r"(hi32(q2)));
+    return ((u64)xh << 32) | xl;
 }
 
 // Whole forward (Cooley-Tukey, Harvey lazy) butterfly in one PTX block: x' = x~ + v, y' = x~ - v + 2q with

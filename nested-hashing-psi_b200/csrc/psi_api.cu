@@ -184,9 +184,14 @@ static int build_tables(psi_ctx* c) {
         T.negPQHatInvModq_s[i] = h_shoup(P.negPQHatInvModq[i], P.q[i]);
         for (uint32_t j = 0; j < Lp; j++) {
             T.qInvModp[i][j] = P.qInvModp[i][j];
+            T.qInvModp_s[i][j] = h_shoup(P.qInvModp[i][j], P.p[j]);
             T.PHatModq[i][j] = P.PHatModq[i][j];
+            T.PHatModq_s[i][j] = h_shoup(P.PHatModq[i][j], P.q[i]);
         }
-        for (uint32_t j = 0; j <= Lp; j++) T.tQS[i][j] = P.tQSHatInvModsDivsModq[i][j];
+        for (uint32_t j = 0; j <= Lp; j++) {
+            T.tQS[i][j] = P.tQSHatInvModsDivsModq[i][j];
+            T.tQS_s[i][j] = h_shoup(P.tQSHatInvModsDivsModq[i][j], P.q[i]);
+        }
         for (uint32_t k = 0; k < L; k++) T.qModq[i][k] = P.q[i] % P.q[k];
         T.QHatInvNinv[i] = h_mulmod(P.QHatInvModq[i], T.mods[i].ninv, P.q[i]);
         T.QHatInvNinv_s[i] = h_shoup(T.QHatInvNinv[i], P.q[i]);
@@ -198,7 +203,10 @@ static int build_tables(psi_ctx* c) {
         T.PHatInvModp_s[j] = h_shoup(P.PHatInvModp[j], P.p[j]);
         T.pInv[j] = P.pInv[j];
         T.tQSfrac[j] = P.tQSHatInvModsDivsFrac[j];
-        for (uint32_t i = 0; i < L; i++) T.QHatModp[j][i] = P.QHatModp[j][i];
+        for (uint32_t i = 0; i < L; i++) {
+            T.QHatModp[j][i] = P.QHatModp[j][i];
+            T.QHatModp_s[j][i] = h_shoup(P.QHatModp[j][i], P.p[j]);
+        }
     }
     for (uint32_t a = 0; a <= L; a++)
         for (uint32_t j = 0; j < Lp; j++) T.alphaQModp[a][j] = P.alphaQModp[a][j];

@@ -31,6 +31,11 @@ struct DevTables {
     // N^-1 of the inverse NTT folded into the first constant of the two basis extensions
     u64 QHatInvNinv[PSI_MAX_LIMBS], QHatInvNinv_s[PSI_MAX_LIMBS];
     u64 negPQHatInvNinv[PSI_MAX_LIMBS], negPQHatInvNinv_s[PSI_MAX_LIMBS];
+    // Shoup companions floor(c * 2^64 / modulus) of the conversion matrices (fused kernels)
+    u64 QHatModp_s[PSI_MAX_LIMBS][PSI_MAX_LIMBS];
+    u64 qInvModp_s[PSI_MAX_LIMBS][PSI_MAX_LIMBS];
+    u64 PHatModq_s[PSI_MAX_LIMBS][PSI_MAX_LIMBS];
+    u64 tQS_s[PSI_MAX_LIMBS][PSI_MAX_LIMBS + 1];
     ModDev mods[kMaxMods];                    // 0..L-1: q, L..L+Lp-1: p, L+Lp: t
 };
 
