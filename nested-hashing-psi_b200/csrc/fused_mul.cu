@@ -329,14 +329,20 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_tensor(const DevTables* 
     transform<false>(tab, smem + first * P, P, 4 - first, [l](uint32_t) { return l; }, g >= first ? g - first : 4, 4 - first,
                      m, kRowTileLog, m, logN - m, tile_base, tid);
 
+    // Tensor product with ONE Montgomery reduction per output: the factor R^-1 it leaves is undone for
+    // free by k_cols_scale, whose N^-1 constant is N^-1 * R.  Operands are brought below 2q + 2^32 first
+    // so that every 128-bit sum stays below q * 2^64; outputs are in [0, 2q), which the inverse row pass
+    // accepts as is.
+    const u64 q = md.q, q2 = 2 * q, qinv = md.qinv;
     for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) {
-        const u64 a0 = smem[sl(j)], a1 = smem[P + sl(j)], b0 = smem[2 * P + sl(j)], b1 = smem[3 * P + sl(j)];
-        smem[sl(j)] = barrett128(mulhi64(a0, b0), a0 * b0, md.q, md.mu_hi, md.mu_lo);
+        const u64 a0 = lazy_sub_hi(smem[sl(j)], q2), a1 = lazy_sub_hi(smem[P + sl(j)], q2);
+        const u64 b0 = lazy_sub_hi(smem[2 * P + sl(j)], q2), b1 = lazy_sub_hi(smem[3 * P + sl(j)], q2);
+        smem[sl(j)] = mont_redc_lazy(mulhi64(a0, b0), a0 * b0, q, qinv);
         u64 hi = 0, lo = 0;
         mac128(hi, lo, a0, b1);
         mac128(hi, lo, a1, b0);
-        smem[P + sl(j)] = barrett128(hi, lo, md.q, md.mu_hi, md.mu_lo);
-        smem[2 * P + sl(j)] = barrett128(mulhi64(a1, b1), a1 * b1, md.q, md.mu_hi, md.mu_lo);
+        smem[P + sl(j)] = mont_redc_lazy(hi, lo, q, qinv);
+        smem[2 * P + sl(j)] = mont_redc_lazy(mulhi64(a1, b1), a1 * b1, q, qinv);
     }
     __syncthreads();
     transform<true>(tab, smem, P, 3, [l](uint32_t) { return l; }, g, 4, m, kRowTileLog, m, logN - m, tile_base, tid);
@@ -369,7 +375,7 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 2)
 #pragma unroll
         for (int i = 0; i < LP; i++) {
             const ModDev& mp = tab->mods[L + i];
-            xp[i] = shoup_canon(smem[(L + i) * P + sl(j)], mp.ninv, mp.ninv_s, mp.q);
+            xp[i] = shoup_canon(smem[(L + i) * P + sl(j)], mp.ninvR, mp.ninvR_s, mp.q);
             nu = __dadd_rn(nu, __dmul_rn(tab->tQSfrac[i], __ull2double_rn(xp[i])));
         }
         const u64 alpha = __double2ull_rz(nu);  // < LP * 2^60
@@ -377,7 +383,7 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 2)
         for (int l = 0; l < L; l++) {
             const ModDev& mq = tab->mods[l];
             const u64 q = mq.q;
-            const u64 xq = shoup_canon(smem[l * P + sl(j)], mq.ninv, mq.ninv_s, q);
+            const u64 xq = shoup_canon(smem[l * P + sl(j)], mq.ninvR, mq.ninvR_s, q);
             u64 acc = shoup_lazy(xq, tab->tQS[l][LP], tab->tQS_s[l][LP], q);
 #pragma unroll
             for (int i = 0; i < LP; i++) acc += shoup_lazy(xp[i], tab->tQS[l][i], tab->tQS_s[l][i], q);
@@ -419,16 +425,16 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 2)
 }
 
 // ---- (5) rows: forward, key-switch inner product, add (c0, c1), mask ------------------------------
-// grid (R/8, L, B), 2 + L groups (c0, c1, digit 0..L-1 of limb blockIdx.y)
-__global__ void __launch_bounds__((2 + PSI_MAX_LIMBS) * kGroup) k_rows_relin(const DevTables* __restrict__ tab,
-                                                                            uint32_t logN, const u64* __restrict__ rh,
-                                                                            const u64* __restrict__ dh,
-                                                                            const u64* __restrict__ evk_b,
-                                                                            const u64* __restrict__ evk_a,
-                                                                            const u64* __restrict__ mask,
-                                                                            u64* __restrict__ out) {
+// grid (R/8, L, B), 2 + L groups (c0, c1, digit 0..L-1 of limb blockIdx.y).  evk_bR / evk_aR / maskR are
+// in Montgomery form (times R = 2^64), so each modular product is one 128-bit multiply-accumulate plus a
+// Montgomery reduction that leaves no stray factor:  REDC(sum_i d_i * evkR_i) = sum_i d_i * evk_i.
+template <int L>
+__global__ void __launch_bounds__((2 + L) * kGroup, 2)
+    k_rows_relin(const DevTables* __restrict__ tab, uint32_t logN, const u64* __restrict__ rh, const u64* __restrict__ dh,
+                 const u64* __restrict__ evk_bR, const u64* __restrict__ evk_aR, const u64* __restrict__ maskR,
+                 u64* __restrict__ out) {
     extern __shared__ __align__(16) u64 smem[];
-    const uint32_t N = 1u << logN, L = tab->L;
+    const uint32_t N = 1u << logN;
     const uint32_t m = kLogCols + kRowTileLog, M = 1u << m, P = padded(M);
     const uint32_t g = threadIdx.x / kGroup, tid = threadIdx.x % kGroup;
     const uint32_t kk = blockIdx.y, tile_base = blockIdx.x * M;
@@ -440,26 +446,47 @@ __global__ void __launch_bounds__((2 + PSI_MAX_LIMBS) * kGroup) k_rows_relin(con
     transform<false>(tab, smem, P, 2 + L, [kk](uint32_t) { return kk; }, g, 2 + L, m, kRowTileLog, m, logN - m, tile_base, tid);
 
     const size_t LN = (size_t)L * N;
+    const u64 q = md.q, q2 = 2 * q, qinv = md.qinv;
     for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) {
         const size_t n = (size_t)kk * N + tile_base + j;
-        u64 h0 = 0, l0 = smem[sl(j)], h1 = 0, l1 = smem[P + sl(j)];
+        u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
 #pragma unroll
-        for (int i = 0; i < PSI_MAX_LIMBS; i++)
-            if (i < (int)L) {
-                const u64 d = smem[(2 + i) * P + sl(j)];
-                mac128(h0, l0, d, evk_b[(size_t)i * LN + n]);
-                mac128(h1, l1, d, evk_a[(size_t)i * LN + n]);
-            }
-        u64 r0 = barrett128(h0, l0, md.q, md.mu_hi, md.mu_lo);
-        u64 r1 = barrett128(h1, l1, md.q, md.mu_hi, md.mu_lo);
-        if (mask) {
-            const u64 mv = mask[bin * LN + n];
-            r0 = mulmod(r0, mv, md);
-            r1 = mulmod(r1, mv, md);
+        for (int i = 0; i < L; i++) {
+            const u64 d = lazy_sub_hi(smem[(2 + i) * P + sl(j)], q2);  // < 2q + 2^32: L <= 4 terms stay < q * 2^64
+            mac128(h0, l0, d, evk_bR[(size_t)i * LN + n]);
+            mac128(h1, l1, d, evk_aR[(size_t)i * LN + n]);
+        }
+        // + (c0, c1): forward-transform outputs < 4q + 2^32, reduction outputs < 2q
+        u64 r0 = mont_redc_lazy(h0, l0, q, qinv) + smem[sl(j)];
+        u64 r1 = mont_redc_lazy(h1, l1, q, qinv) + smem[P + sl(j)];
+        if (maskR) {
+            const u64 mv = maskR[bin * LN + n];
+            r0 = mont_redc_lazy(mulhi64(r0, mv), r0 * mv, q, qinv);
+            r1 = mont_redc_lazy(mulhi64(r1, mv), r1 * mv, q, qinv);
+            r0 = r0 >= q ? r0 - q : r0;
+            r1 = r1 >= q ? r1 - q : r1;
+        } else {
+            r0 = reduce_pow2q<3>(r0, q);
+            r1 = reduce_pow2q<3>(r1, q);
         }
         out[(bin * 2) * LN + n] = r0;
         out[(bin * 2 + 1) * LN + n] = r1;
     }
+}
+
+// constants into Montgomery form: dst = src * 2^64 mod q_l, polys laid out [groups][L][N]
+__global__ void __launch_bounds__(256) k_to_montgomery(const DevTables* __restrict__ tab, uint32_t N, size_t total,
+                                                       const u64* __restrict__ src, u64* __restrict__ dst) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const ModDev& md = tab->mods[(i / N) % tab->L];
+    dst[i] = shoup_canon(src[i], md.Rmodq, md.Rmodq_s, md.q);
+}
+cudaError_t launch_to_montgomery(const KCtx& k, uint32_t groups, const u64* src, u64* dst) {
+    const size_t total = (size_t)groups * k.L * k.N;
+    if (total == 0) return cudaSuccess;
+    k_to_montgomery<<<(unsigned)((total + 255) / 256), 256, 0, k.s>>>(k.tab, k.N, total, src, dst);
+    return cudaGetLastError();
 }
 
 // ---- launcher --------------------------------------------------------------------------------------
@@ -506,19 +533,25 @@ cudaError_t launch_fused_mul(const KCtx& k, uint32_t B, const u64* a, const u64*
     const uint32_t logR = k.logN - kLogCols;
     const uint32_t row_tiles = (1u << logR) >> kRowTileLog;
     const size_t row_arr = padded(1u << (kLogCols + kRowTileLog)) * sizeof(u64);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e;
-        if ((e = cudaFuncSetAttribute(k_rows_relin, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
-        attr_set = true;
-    }
     cudaError_t e;
     k_rows_inv<<<dim3(row_tiles, L, B), 4 * kGroup, 4 * row_arr, k.s>>>(k.tab, k.logN, a, b, ha, hb);
     if ((e = dispatch_cols(k, B, ha, hb, e1p, e2h, nullptr, nullptr, nullptr, 0)) != cudaSuccess) return e;
     k_rows_tensor<<<dim3(row_tiles, LT, B), 4 * kGroup, 4 * row_arr, k.s>>>(k.tab, k.logN, a, e1p, e2h, th);
     if ((e = dispatch_cols(k, B, nullptr, nullptr, nullptr, nullptr, th, rh, dh, 1)) != cudaSuccess) return e;
-    k_rows_relin<<<dim3(row_tiles, L, B), (2 + L) * kGroup, (2 + L) * row_arr, k.s>>>(k.tab, k.logN, rh, dh, evk_b,
-                                                                                       evk_a, mask, out);
+    const dim3 rg(row_tiles, L, B);
+    const size_t rs = (2 + L) * row_arr;
+    static bool relin_attr = false;
+    if (!relin_attr) {
+        if ((e = cudaFuncSetAttribute(k_rows_relin<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_rows_relin<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
+        relin_attr = true;
+    }
+    switch (L) {
+        case 1: k_rows_relin<1><<<rg, 3 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
+        case 2: k_rows_relin<2><<<rg, 4 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
+        case 3: k_rows_relin<3><<<rg, 5 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
+        default: k_rows_relin<4><<<rg, 6 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
+    }
     return cudaGetLastError();
 }
 

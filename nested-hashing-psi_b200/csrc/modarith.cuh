@@ -17,6 +17,9 @@ struct ModDev {
     const u64* ws;     // floor(w * 2^64 / q)
     const u64* iw;     // psi^-bitrev(i)           (inverse, Gentleman-Sande)
     const u64* iws;
+    u64 qinv;          // q^-1 mod 2^64 (Montgomery reduction, radix R = 2^64)
+    u64 ninvR, ninvR_s;  // N^-1 * R mod q: undoes the R^-1 left by a Montgomery-reduced tensor product
+    u64 Rmodq, Rmodq_s;  // R mod q
     const ulonglong2* ftw;  // {w, ws} interleaved: one 16-byte load per twiddle (fused kernels)
     const ulonglong2* itw;  // {iw, iws}
 };
@@ -159,6 +162,14 @@ __device__ __forceinline__ void ct_butterfly_asm(u64& x, u64& y, u64 w, u64 ws, 
         "}"
         : "+l"(x), "+l"(y)
         : "l"(w), "l"(ws), "l"(q2), "l"(nq));
+}
+
+// Montgomery reduction (radix 2^64, subtractive form): for T = (hi:lo) < q * 2^64 returns a value in
+// [0, 2q) congruent to T * 2^-64 mod q.  m = lo * q^-1 makes T - m*q divisible by 2^64 exactly, so the
+// quotient is hi - floor(m*q / 2^64) in (-q, q); adding q makes it non-negative.
+__device__ __forceinline__ u64 mont_redc_lazy(u64 hi, u64 lo, u64 q, u64 qinv) {
+    const u64 m = lo * qinv;
+    return hi - mulhi64_4(m, q) + q;
 }
 
 // 128-bit multiply-accumulate: (hi:lo) += a * b

@@ -92,6 +92,8 @@ struct psi_ctx {
     DevBuf<u64> twiddles2;      // [(L+Lp+1)][2][N][2]: {w, ws} and {iw, iws} interleaved
     DevBuf<uint32_t> to_crt;    // packed-encoding permutation
     DevBuf<u64> evk_b, evk_a;   // [L][L][N]
+    DevBuf<u64> evk_bR, evk_aR; // the same times R = 2^64 mod q_k (Montgomery form for the fused relinearisation)
+    DevBuf<u64> maskR;          // masks times R
     bool have_evk = false;
     // database
     uint32_t K = 0, b = 0, E = 0;
@@ -159,6 +161,15 @@ static int build_tables(psi_ctx* c) {
         md.mu_lo = (u64)mu;
         md.ninv = h_powmod(N, q - 2, q);
         md.ninv_s = h_shoup(md.ninv, q);
+        {
+            u64 inv = q;  // Newton iteration for q^-1 mod 2^64 (q odd): 5 steps from 3 correct bits
+            for (int it = 0; it < 6; it++) inv *= 2 - q * inv;
+            md.qinv = inv;
+            md.Rmodq = (u64)((((u128h)1) << 64) % q);
+            md.Rmodq_s = h_shoup(md.Rmodq, q);
+            md.ninvR = h_mulmod(md.ninv, md.Rmodq, q);
+            md.ninvR_s = h_shoup(md.ninvR, q);
+        }
         md.w = c->twiddles.p + ((size_t)m * 4 + 0) * N;
         md.ws = c->twiddles.p + ((size_t)m * 4 + 1) * N;
         md.iw = c->twiddles.p + ((size_t)m * 4 + 2) * N;
@@ -257,8 +268,10 @@ static int mul_ctct_batch(psi_ctx* c, cudaStream_t s, uint32_t B, const u64* a, 
     const size_t N = c->N;
     uint32_t nl = 0;
     if (fused_mul_supported(k)) {
+        // the fused relinearisation takes the key and the masks in Montgomery form
+        const u64* maskR = mask ? c->maskR.p + (mask - c->mask.p) : nullptr;
         CK(launch_fused_mul(k, B, a, bb, c->coef.p, c->coef.p + (size_t)B * 2 * L * N, c->e1.p, c->e2.p, c->ten.p,
-                            c->res.p, c->dig.p, c->evk_b.p, c->evk_a.p, mask, out));
+                            c->res.p, c->dig.p, c->evk_bR.p, c->evk_aR.p, maskR, out));
         if (launches) *launches += 5;
         return PSI_OK;
     }
@@ -340,7 +353,7 @@ int psi_ctx_destroy(psi_ctx* c) {
     if (!c) return PSI_OK;
     cudaSetDevice(c->device);
     if (c->d_tab) cudaFree(c->d_tab);
-    DevBuf<u64>* bufs[] = {&c->twiddles, &c->twiddles2, &c->evk_b, &c->evk_a, &c->pt, &c->mask, &c->idx, &c->minus, &c->acc,
+    DevBuf<u64>* bufs[] = {&c->twiddles, &c->twiddles2, &c->evk_bR, &c->evk_aR, &c->maskR, &c->evk_b, &c->evk_a, &c->pt, &c->mask, &c->idx, &c->minus, &c->acc,
                            &c->coef,     &c->e1,    &c->e2,    &c->ten, &c->res, &c->dig, &c->prod,  &c->out};
     for (auto* b : bufs) b->release();
     c->to_crt.release();
@@ -357,6 +370,14 @@ int psi_set_relin_key(psi_ctx* c, const uint64_t* evk_b, const uint64_t* evk_a) 
     CK(c->evk_a.alloc(n));
     CK(cudaMemcpy(c->evk_b.p, evk_b, n * sizeof(u64), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->evk_a.p, evk_a, n * sizeof(u64), cudaMemcpyHostToDevice));
+    CK(c->evk_bR.alloc(n));
+    CK(c->evk_aR.alloc(n));
+    {
+        const KCtx k = c->k(0);
+        CK(launch_to_montgomery(k, c->L, c->evk_b.p, c->evk_bR.p));
+        CK(launch_to_montgomery(k, c->L, c->evk_a.p, c->evk_aR.p));
+        CK(cudaStreamSynchronize(0));
+    }
     c->have_evk = true;
     return PSI_OK;
 }
@@ -372,6 +393,7 @@ static int db_dims(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E) {
     const size_t LN = (size_t)c->L * c->N;
     CK(c->pt.alloc((size_t)K * b * E * LN));
     CK(c->mask.alloc((size_t)b * LN));
+    CK(c->maskR.alloc((size_t)b * LN));
     CK(c->idx.alloc((size_t)K * E * 2 * LN));
     CK(c->minus.alloc(2 * LN));
     return alloc_work(c);
@@ -387,6 +409,7 @@ int psi_db_load_limbs(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E, const uint
     CK(cudaMemcpy(c->pt.p, pt_limbs, (size_t)K * b * E * LN * sizeof(u64), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->mask.p, mask_limbs, (size_t)b * LN * sizeof(u64), cudaMemcpyHostToDevice));
     CK(launch_split30(0, c->pt.p, (size_t)K * b * E * LN, true));
+    CK(launch_to_montgomery(c->k(0), b, c->mask.p, c->maskR.p));
     CK(cudaStreamSynchronize(0));
     c->have_db = true;
     return PSI_OK;
@@ -445,6 +468,7 @@ int psi_db_encode_slots(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E, uint32_t
     if ((rc = encode_into(c, (size_t)K * b * E, nslots, slots, c->pt.p))) return rc;
     if ((rc = encode_into(c, b, nslots, mask_slots, c->mask.p))) return rc;
     CK(launch_split30(0, c->pt.p, (size_t)K * b * E * (size_t)c->L * c->N, true));  // DB storage format
+    CK(launch_to_montgomery(c->k(0), b, c->mask.p, c->maskR.p));
     CK(cudaStreamSynchronize(0));
     c->have_db = true;
     return PSI_OK;
