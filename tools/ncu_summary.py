@@ -1,0 +1,53 @@
+"""Summarise an ncu report (read on the CPU box: ncu -i ... --page raw --csv) into a small markdown table.
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/rNN_xxx.md"""
+import csv
+import subprocess
+import sys
+
+METRICS = [
+    ("gpu__time_duration.sum", "duration"),
+    ("launch__grid_size", "grid"), ("launch__block_size", "block"), ("launch__registers_per_thread", "regs/thread"),
+    ("launch__occupancy_limit_registers", "CTAs/SM (regs)"), ("launch__occupancy_limit_shared_mem", "CTAs/SM (smem)"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
+    ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM write"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM % of peak"),
+    ("lts__t_sector_hit_rate.pct", "L2 hit %"), ("l1tex__t_sector_hit_rate.pct", "L1 hit %"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
+    ("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "fmaheavy (IMAD) pipe busy %"),
+    ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu pipe inst %"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe %"),
+    ("smsp__inst_executed.sum", "warp instructions"),
+    ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts"),
+    ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall long_scoreboard"),
+    ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall math_pipe_throttle"),
+    ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall wait"),
+    ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall barrier"),
+    ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall not_selected"),
+]
+
+
+def main(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    ki = hdr.index("Kernel Name")
+    names = [r[ki].split("(")[0].replace("void ", "").replace("psi::", "") for r in data]
+    print("| metric | unit | " + " | ".join(names) + " |")
+    print("|---|---|" + "---|" * len(names))
+    for m, label in METRICS:
+        if m not in hdr:
+            continue
+        i = hdr.index(m)
+        vals = []
+        for r in data:
+            try:
+                v = float(r[i].replace(",", ""))
+                vals.append("%.4g" % v)
+            except ValueError:
+                vals.append(r[i])
+        print("| %s | %s | %s |" % (label, units[i], " | ".join(vals)))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
