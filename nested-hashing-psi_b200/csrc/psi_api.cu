@@ -61,6 +61,8 @@ static uint32_t h_bitrev(uint32_t x, int bits) {
     return r;
 }
 
+constexpr size_t kDbChunk = 256;  // plaintexts staged per re-tiling / encode step
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -100,7 +102,8 @@ struct psi_ctx {
     DevBuf<u64> pt, mask;
     bool have_db = false;
     // query
-    DevBuf<u64> idx, minus;
+    DevBuf<u64> idx, idx_in, minus;  // idx: tiled split-30; idx_in: H2D landing buffer [K][E][2][L][N]
+    DevBuf<u64> stage;               // chunk staging for the DB re-tiling
     bool have_query = false;
     // work
     DevBuf<u64> acc, coef, e1, e2, ten, res, dig, prod, out;
@@ -353,7 +356,7 @@ int psi_ctx_destroy(psi_ctx* c) {
     if (!c) return PSI_OK;
     cudaSetDevice(c->device);
     if (c->d_tab) cudaFree(c->d_tab);
-    DevBuf<u64>* bufs[] = {&c->twiddles, &c->twiddles2, &c->evk_bR, &c->evk_aR, &c->maskR, &c->evk_b, &c->evk_a, &c->pt, &c->mask, &c->idx, &c->minus, &c->acc,
+    DevBuf<u64>* bufs[] = {&c->twiddles, &c->twiddles2, &c->evk_bR, &c->evk_aR, &c->maskR, &c->evk_b, &c->evk_a, &c->pt, &c->mask, &c->idx, &c->idx_in, &c->stage, &c->minus, &c->acc,
                            &c->coef,     &c->e1,    &c->e2,    &c->ten, &c->res, &c->dig, &c->prod,  &c->out};
     for (auto* b : bufs) b->release();
     c->to_crt.release();
@@ -394,7 +397,9 @@ static int db_dims(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E) {
     CK(c->pt.alloc((size_t)K * b * E * LN));
     CK(c->mask.alloc((size_t)b * LN));
     CK(c->maskR.alloc((size_t)b * LN));
+    if (LN % 128) return set_error(PSI_ERR_INVALID, "L * N must be a multiple of 128");
     CK(c->idx.alloc((size_t)K * E * 2 * LN));
+    CK(c->idx_in.alloc((size_t)K * E * 2 * LN));
     CK(c->minus.alloc(2 * LN));
     return alloc_work(c);
 }
@@ -406,9 +411,17 @@ int psi_db_load_limbs(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E, const uint
     if (rc) return rc;
     if ((rc = db_dims(c, K, b, E))) return rc;
     const size_t LN = (size_t)c->L * c->N;
-    CK(cudaMemcpy(c->pt.p, pt_limbs, (size_t)K * b * E * LN * sizeof(u64), cudaMemcpyHostToDevice));
+    {
+        const size_t n_pt = (size_t)K * b * E, chunk = n_pt < kDbChunk ? n_pt : kDbChunk;
+        CK(c->stage.alloc(chunk * LN));
+        for (size_t p0 = 0; p0 < n_pt; p0 += chunk) {
+            const size_t n = (n_pt - p0) < chunk ? (n_pt - p0) : chunk;
+            CK(cudaMemcpy(c->stage.p, pt_limbs + p0 * LN, n * LN * sizeof(u64), cudaMemcpyHostToDevice));
+            CK(launch_retile_pt(0, c->stage.p, c->pt.p, LN, E, p0, n, true));
+            CK(cudaStreamSynchronize(0));
+        }
+    }
     CK(cudaMemcpy(c->mask.p, mask_limbs, (size_t)b * LN * sizeof(u64), cudaMemcpyHostToDevice));
-    CK(launch_split30(0, c->pt.p, (size_t)K * b * E * LN, true));
     CK(launch_to_montgomery(c->k(0), b, c->mask.p, c->maskR.p));
     CK(cudaStreamSynchronize(0));
     c->have_db = true;
@@ -417,9 +430,11 @@ int psi_db_load_limbs(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E, const uint
 
 // MakePackedPlaintext + SetFormat(EVALUATION) for n_pt plaintexts, chunked so that the staging
 // buffers stay small next to the DB itself.
-static int encode_into(psi_ctx* c, size_t n_pt, uint32_t nslots, const int64_t* slots, u64* dst) {
+// tiled_E != 0: dst is the tiled plaintext DB (positions per bin = tiled_E); else dst is flat [n_pt][L][N].
+static int encode_into(psi_ctx* c, size_t n_pt, uint32_t nslots, const int64_t* slots, u64* dst, uint32_t tiled_E) {
     const size_t N = c->N, L = c->L;
-    const size_t chunk = n_pt < 256 ? n_pt : 256;
+    const size_t chunk = n_pt < kDbChunk ? n_pt : kDbChunk;
+    if (tiled_E) CK(c->stage.alloc(chunk * L * N));
     DevBuf<long long> d_slots;
     DevBuf<u64> d_crt;
     CK(d_slots.alloc(chunk * nslots));
@@ -436,9 +451,10 @@ static int encode_into(psi_ctx* c, size_t n_pt, uint32_t nslots, const int64_t* 
         }
         if (e == cudaSuccess) {
             // residues in [0,t) are below every q_l: each limb is the same vector, then NTT mod q_l
-            NttBatch nb{d_crt.p, dst + p0 * L * N, n * (uint32_t)L, (uint32_t)L, N, 0, L * N, 0, (uint32_t)L};
+            NttBatch nb{d_crt.p, tiled_E ? c->stage.p : dst + p0 * L * N, n * (uint32_t)L, (uint32_t)L, N, 0, L * N, 0, (uint32_t)L};
             e = launch_ntt(k, nb, false);
         }
+        if (e == cudaSuccess && tiled_E) e = launch_retile_pt(0, c->stage.p, dst, L * N, tiled_E, p0, n, true);
         if (e == cudaSuccess) e = cudaStreamSynchronize(0);
         if (e != cudaSuccess) rc = cuda_fail(e, "psi_db_encode_slots");
     }
@@ -465,9 +481,8 @@ int psi_db_encode_slots(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E, uint32_t
     int rc = ensure_device(c);
     if (rc) return rc;
     if ((rc = db_dims(c, K, b, E))) return rc;
-    if ((rc = encode_into(c, (size_t)K * b * E, nslots, slots, c->pt.p))) return rc;
-    if ((rc = encode_into(c, b, nslots, mask_slots, c->mask.p))) return rc;
-    CK(launch_split30(0, c->pt.p, (size_t)K * b * E * (size_t)c->L * c->N, true));  // DB storage format
+    if ((rc = encode_into(c, (size_t)K * b * E, nslots, slots, c->pt.p, E))) return rc;
+    if ((rc = encode_into(c, b, nslots, mask_slots, c->mask.p, 0))) return rc;
     CK(launch_to_montgomery(c->k(0), b, c->mask.p, c->maskR.p));
     CK(cudaStreamSynchronize(0));
     c->have_db = true;
@@ -481,10 +496,13 @@ int psi_db_get_limbs(psi_ctx* c, uint64_t* pt_limbs, uint64_t* mask_limbs) {
     if (rc) return rc;
     const size_t LN = (size_t)c->L * c->N;
     if (pt_limbs) {
-        const size_t n = (size_t)c->K * c->b * c->E * LN;
-        CK(cudaMemcpy(pt_limbs, c->pt.p, n * sizeof(u64), cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < n; i++)  // split-30 storage -> canonical residues
-            pt_limbs[i] = ((pt_limbs[i] >> 32) << 30) | (pt_limbs[i] & 0x3fffffffull);
+        const size_t n_pt = (size_t)c->K * c->b * c->E, chunk = n_pt < kDbChunk ? n_pt : kDbChunk;
+        CK(c->stage.alloc(chunk * LN));
+        for (size_t p0 = 0; p0 < n_pt; p0 += chunk) {  // tiled split-30 storage -> flat canonical residues
+            const size_t n = (n_pt - p0) < chunk ? (n_pt - p0) : chunk;
+            CK(launch_retile_pt(0, c->stage.p, c->pt.p, LN, c->E, p0, n, false));
+            CK(cudaMemcpy(pt_limbs + p0 * LN, c->stage.p, n * LN * sizeof(u64), cudaMemcpyDeviceToHost));
+        }
     }
     if (mask_limbs) CK(cudaMemcpy(mask_limbs, c->mask.p, (size_t)c->b * LN * sizeof(u64), cudaMemcpyDeviceToHost));
     return PSI_OK;
@@ -497,9 +515,9 @@ int psi_query_set(psi_ctx* c, const uint64_t* idx, const uint64_t* minus, void* 
     if (rc) return rc;
     const size_t LN = (size_t)c->L * c->N;
     cudaStream_t s = (cudaStream_t)stream;
-    CK(cudaMemcpyAsync(c->idx.p, idx, (size_t)c->K * c->E * 2 * LN * sizeof(u64), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->idx_in.p, idx, (size_t)c->K * c->E * 2 * LN * sizeof(u64), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(c->minus.p, minus, 2 * LN * sizeof(u64), cudaMemcpyHostToDevice, s));
-    CK(launch_split30(s, c->idx.p, (size_t)c->K * c->E * 2 * LN, true));  // index cts -> split-30
+    CK(launch_retile_idx(s, c->idx_in.p, c->idx.p, LN, c->K, c->E));  // index cts -> tiled split-30
     c->have_query = true;
     return PSI_OK;
 }

@@ -72,13 +72,19 @@ __global__ void __launch_bounds__(kMacCoeffs* LANES)
 #pragma unroll
         for (int k = 0; k < 2; k++) ll[j][k] = mid[j][k] = hh[j][k] = tlo[j][k] = thi[j][k] = 0;
 
-    const u64* ip = idx + (size_t)hf * E * 2 * LN + c;
+    // tiled storage (see launch_retile_*): for one (hf, bin, 128-coefficient tile) the E positions are
+    // contiguous, 1 KiB apart; for one (hf, tile) the E x 2 index words are contiguous, 2 KiB apart.
+    // A CTA therefore streams whole DRAM pages and every load offset below is an immediate.
+    const size_t T = LN / kMacCoeffs;
+    const uint32_t w = threadIdx.x & (kMacCoeffs - 1);
+    const u64* ip = idx + ((size_t)hf * T + blockIdx.x) * E * 2 * kMacCoeffs + w;
     const size_t bin_stride = (size_t)E * LN;
     // bins past the end of a ragged last block alias bin0 (loaded, accumulated, never stored):
     // keeps the inner loop free of branches so that the loads of a whole sub-block are in flight together
     const u64* pp[BT];
 #pragma unroll
-    for (int j = 0; j < BT; j++) pp[j] = pt + ((size_t)hf * b + bin0 + (j < nb ? j : 0)) * bin_stride + c;
+    for (int j = 0; j < BT; j++)
+        pp[j] = pt + ((size_t)hf * b + bin0 + (j < nb ? j : 0)) * bin_stride + (size_t)blockIdx.x * E * kMacCoeffs + w;
 
     constexpr int U = 4;  // positions per software-pipelined sub-block
     auto sub_block = [&](auto n_tag) {
@@ -86,10 +92,10 @@ __global__ void __launch_bounds__(kMacCoeffs* LANES)
         uint2 i0[n], i1[n], y[n][BT];
 #pragma unroll
         for (int p = 0; p < n; p++) {
-            i0[p] = __ldg(reinterpret_cast<const uint2*>(ip + (size_t)p * 2 * LN));
-            i1[p] = __ldg(reinterpret_cast<const uint2*>(ip + (size_t)p * 2 * LN + LN));
+            i0[p] = __ldg(reinterpret_cast<const uint2*>(ip + p * 2 * kMacCoeffs));
+            i1[p] = __ldg(reinterpret_cast<const uint2*>(ip + p * 2 * kMacCoeffs + kMacCoeffs));
 #pragma unroll
-            for (int j = 0; j < BT; j++) y[p][j] = ld_stream_v2(pp[j] + (size_t)p * LN);
+            for (int j = 0; j < BT; j++) y[p][j] = ld_stream_v2(pp[j] + p * kMacCoeffs);
         }
 #pragma unroll
         for (int p = 0; p < n; p++)
@@ -104,9 +110,9 @@ __global__ void __launch_bounds__(kMacCoeffs* LANES)
                 mid[j][1] = madw(i1[p].y, y[p][j].x, mid[j][1]);
                 hh[j][1] = madw(i1[p].y, y[p][j].y, hh[j][1]);
             }
-        ip += (size_t)n * 2 * LN;
+        ip += n * 2 * kMacCoeffs;
 #pragma unroll
-        for (int j = 0; j < BT; j++) pp[j] += (size_t)n * LN;
+        for (int j = 0; j < BT; j++) pp[j] += n * kMacCoeffs;
     };
     auto fold_all = [&]() {
 #pragma unroll
@@ -155,25 +161,212 @@ __global__ void __launch_bounds__(kMacCoeffs* LANES)
     }
 }
 
+// ---- TMA-fed variant -------------------------------------------------------------------------------
+// Same arithmetic, but the operands are streamed by the copy engine: one producer thread issues
+// cp.async.bulk (SASS UBLKCP) copies of whole position-chunks — 8 positions x 1 KiB per bin, 8 x 2 KiB of
+// index words — into a two-stage shared-memory ring guarded by mbarriers, and 512 consumer threads
+// (128 coefficients x 4 bin-lanes x 2 bins) do nothing but LDS + IMAD.WIDE.  The amount of data in flight
+// per SM (up to 160 KiB) is set by the ring, not by how many loads the compiler keeps in registers.
+constexpr int kMacPosChunk = 8;   // positions per stage == positions between folds
+constexpr int kMacStages = 2;
+constexpr int kMacBT = 2, kMacLanes = 4, kMacBins = kMacBT * kMacLanes;
+constexpr int kMacConsumers = kMacCoeffs * kMacLanes;
+constexpr size_t kMacStageWords = (size_t)kMacPosChunk * kMacCoeffs * (2 + kMacBins);  // idx + pt words per stage
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(kMacConsumers + 32)
+    k_mac_tma(const DevTables* __restrict__ tab, uint32_t N, uint32_t L, uint32_t b, uint32_t E, const u64* __restrict__ pt,
+              const u64* __restrict__ idx, const u64* __restrict__ minus, u64* __restrict__ acc) {
+    extern __shared__ __align__(128) u64 ring[];  // [stage][ idx: 8 x 2 x 128 | pt: 8 bins x 8 x 128 ]
+    __shared__ __align__(8) uint64_t full_bar[kMacStages], empty_bar[kMacStages];
+    const size_t LN = (size_t)L * N, T = LN / kMacCoeffs;
+    const uint32_t nbb = (b + kMacBins - 1) / kMacBins;
+    const uint32_t hf = blockIdx.y / nbb, bin_blk0 = (blockIdx.y % nbb) * kMacBins;
+    const uint32_t nbins = min((uint32_t)kMacBins, b - bin_blk0);
+    const uint32_t nchunks = (E + kMacPosChunk - 1) / kMacPosChunk;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kMacStages; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kMacConsumers);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (threadIdx.x >= kMacConsumers) {
+        // ---- producer: one elected thread keeps the ring full
+        if (threadIdx.x == kMacConsumers) {
+            const u64* isrc = idx + ((size_t)hf * T + blockIdx.x) * E * 2 * kMacCoeffs;
+            const u64* psrc = pt + ((size_t)hf * b + bin_blk0) * (size_t)E * LN + (size_t)blockIdx.x * E * kMacCoeffs;
+            for (uint32_t ch = 0; ch < nchunks; ch++) {
+                const uint32_t s = ch % kMacStages, round = ch / kMacStages;
+                if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+                const uint32_t p0 = ch * kMacPosChunk, np = min((uint32_t)kMacPosChunk, E - p0);
+                u64* st = ring + (size_t)s * kMacStageWords;
+                const uint32_t ibytes = np * 2 * kMacCoeffs * 8, pbytes = np * kMacCoeffs * 8;
+                mbar_expect_tx(&full_bar[s], ibytes + nbins * pbytes);
+                bulk_g2s(st, isrc + (size_t)p0 * 2 * kMacCoeffs, ibytes, &full_bar[s]);
+                for (uint32_t j = 0; j < nbins; j++)
+                    bulk_g2s(st + (size_t)kMacPosChunk * kMacCoeffs * (2 + j), psrc + (size_t)j * E * LN + (size_t)p0 * kMacCoeffs,
+                             pbytes, &full_bar[s]);
+            }
+        }
+        return;
+    }
+
+    // ---- consumers
+    const uint32_t w = threadIdx.x & (kMacCoeffs - 1), lane = threadIdx.x / kMacCoeffs;
+    const size_t c = (size_t)blockIdx.x * kMacCoeffs + w;
+    u64 ll[kMacBT][2], mid[kMacBT][2], hh[kMacBT][2], tlo[kMacBT][2], thi[kMacBT][2];
+#pragma unroll
+    for (int j = 0; j < kMacBT; j++)
+#pragma unroll
+        for (int k = 0; k < 2; k++) ll[j][k] = mid[j][k] = hh[j][k] = tlo[j][k] = thi[j][k] = 0;
+
+    uint32_t folds = 0;
+    for (uint32_t ch = 0; ch < nchunks; ch++) {
+        const uint32_t s = ch % kMacStages, round = ch / kMacStages;
+        const uint32_t np = min((uint32_t)kMacPosChunk, E - ch * kMacPosChunk);
+        mbar_wait(&full_bar[s], round & 1);
+        const uint2* si = reinterpret_cast<const uint2*>(ring + (size_t)s * kMacStageWords) + w;
+        const uint2* sp = si + (size_t)kMacPosChunk * kMacCoeffs * (2 + lane * kMacBT);
+        auto body = [&](int p) {
+            const uint2 i0 = si[p * 2 * kMacCoeffs], i1 = si[p * 2 * kMacCoeffs + kMacCoeffs];
+#pragma unroll
+            for (int j = 0; j < kMacBT; j++) {
+                const uint2 y = sp[(j * kMacPosChunk + p) * kMacCoeffs];
+                ll[j][0] = madw(i0.x, y.x, ll[j][0]);
+                mid[j][0] = madw(i0.x, y.y, mid[j][0]);
+                mid[j][0] = madw(i0.y, y.x, mid[j][0]);
+                hh[j][0] = madw(i0.y, y.y, hh[j][0]);
+                ll[j][1] = madw(i1.x, y.x, ll[j][1]);
+                mid[j][1] = madw(i1.x, y.y, mid[j][1]);
+                mid[j][1] = madw(i1.y, y.x, mid[j][1]);
+                hh[j][1] = madw(i1.y, y.y, hh[j][1]);
+            }
+        };
+        if (np == kMacPosChunk) {
+#pragma unroll
+            for (int p = 0; p < kMacPosChunk; p++) body(p);
+        } else {
+            for (uint32_t p = 0; p < np; p++) body((int)p);
+        }
+        mbar_arrive(&empty_bar[s]);  // this thread is done reading stage s
+#pragma unroll
+        for (int j = 0; j < kMacBT; j++)
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                fold30(thi[j][k], tlo[j][k], ll[j][k], mid[j][k], hh[j][k]);
+                ll[j][k] = mid[j][k] = hh[j][k] = 0;
+            }
+        if (++folds == 16) {  // 128 positions: keep the running total below 2^128 for any E
+            folds = 0;
+            const ModDev& mdr = tab->mods[c / N];
+#pragma unroll
+            for (int j = 0; j < kMacBT; j++)
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    tlo[j][k] = barrett128(thi[j][k], tlo[j][k], mdr.q, mdr.mu_hi, mdr.mu_lo);
+                    thi[j][k] = 0;
+                }
+        }
+    }
+    const ModDev& md = tab->mods[c / N];
+    const u64 q = md.q, mu_hi = md.mu_hi, mu_lo = md.mu_lo;
+    const u64 m0 = minus[c], m1 = minus[LN + c];
+#pragma unroll
+    for (int j = 0; j < kMacBT; j++) {
+        const uint32_t bin = bin_blk0 + lane * kMacBT + j;
+        if (bin < b) {
+            u64* o = acc + (((size_t)hf * b + bin) * 2) * LN + c;
+            o[0] = addmod(barrett128(thi[j][0], tlo[j][0], q, mu_hi, mu_lo), m0, q);
+            o[LN] = addmod(barrett128(thi[j][1], tlo[j][1], q, mu_hi, mu_lo), m1, q);
+        }
+    }
+}
+
 cudaError_t launch_mac(const KCtx& k, uint32_t K, uint32_t b, uint32_t E, const u64* pt, const u64* idx,
                        const u64* minus, u64* acc) {
     const size_t LN = (size_t)k.L * k.N;
-    constexpr int BT = 2, LANES = 4;
-    dim3 grid(cdiv(LN, kMacCoeffs), K * ((b + BT * LANES - 1) / (BT * LANES)));
-    k_mac<BT, LANES><<<grid, kMacCoeffs * LANES, 0, k.s>>>(k.tab, k.N, k.L, b, E, pt, idx, minus, acc);
+    dim3 grid(cdiv(LN, kMacCoeffs), K * ((b + kMacBins - 1) / kMacBins));
+    const size_t smem = kMacStages * kMacStageWords * sizeof(u64);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_mac_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    k_mac_tma<<<grid, kMacConsumers + 32, smem, k.s>>>(k.tab, k.N, k.L, b, E, pt, idx, minus, acc);
     return cudaGetLastError();
 }
 
-// canonical residue < 2^60  <->  split-30 word (hi30 in the upper 32 bits, lo30 in the lower)
-__global__ void __launch_bounds__(256) k_split30(u64* __restrict__ data, size_t n, int to_split) {
+// Storage formats of the two operands of phase 1.  Words: canonical residue < 2^60 <-> split-30 word
+// (hi30 in the upper 32 bits, lo30 in the lower).  Order: with T = L*N/128 tiles of 128 coefficients,
+//   plaintext DB   pt_t [hf*b + bin][tile][pos][128]      from  [p = (hf*b+bin)*E + pos][L*N]
+//   index cts      idx_t[hf][tile][pos][comp][128]        from  [hf][pos][comp][L*N]
+__device__ __forceinline__ u64 to_split30(u64 v) { return ((v >> 30) << 32) | (v & 0x3fffffffull); }
+__device__ __forceinline__ u64 from_split30(u64 v) { return ((v >> 32) << 30) | (v & 0x3fffffffull); }
+
+// chunk of n plaintexts starting at plaintext index p0: flat [n][LN] canonical <-> tiled DB
+__global__ void __launch_bounds__(256) k_retile_pt(u64* __restrict__ flat, u64* __restrict__ tiled, size_t LN, uint32_t E,
+                                                   size_t p0, size_t total, int to_tiled) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const u64 v = data[i];
-    data[i] = to_split ? (((v >> 30) << 32) | (v & 0x3fffffffull)) : (((v >> 32) << 30) | (v & 0x3fffffffull));
+    if (i >= total) return;
+    const size_t p = p0 + i / LN, cidx = i % LN;
+    const size_t g = p / E, pos = p % E, tile = cidx / kMacCoeffs, w = cidx % kMacCoeffs;
+    const size_t T = LN / kMacCoeffs;
+    const size_t d = ((g * T + tile) * E + pos) * kMacCoeffs + w;
+    if (to_tiled)
+        tiled[d] = to_split30(flat[i]);
+    else
+        flat[i] = from_split30(tiled[d]);
 }
-cudaError_t launch_split30(cudaStream_t s, u64* data, size_t n, bool to_split) {
-    if (n == 0) return cudaSuccess;
-    k_split30<<<cdiv(n, 256), 256, 0, s>>>(data, n, to_split ? 1 : 0);
+cudaError_t launch_retile_pt(cudaStream_t s, u64* flat, u64* tiled, size_t LN, uint32_t E, size_t p0, size_t n,
+                             bool to_tiled) {
+    const size_t total = n * LN;
+    if (total == 0) return cudaSuccess;
+    k_retile_pt<<<cdiv(total, 256), 256, 0, s>>>(flat, tiled, LN, E, p0, total, to_tiled ? 1 : 0);
+    return cudaGetLastError();
+}
+__global__ void __launch_bounds__(256) k_retile_idx(const u64* __restrict__ flat, u64* __restrict__ tiled, size_t LN,
+                                                    uint32_t E, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t cidx = i % LN, r = i / LN;  // r = (hf*E + pos)*2 + comp
+    const size_t comp = r & 1, pos = (r >> 1) % E, hf = (r >> 1) / E;
+    const size_t T = LN / kMacCoeffs, tile = cidx / kMacCoeffs, w = cidx % kMacCoeffs;
+    tiled[(((hf * T + tile) * E + pos) * 2 + comp) * kMacCoeffs + w] = to_split30(flat[i]);
+}
+cudaError_t launch_retile_idx(cudaStream_t s, const u64* flat, u64* tiled, size_t LN, uint32_t K, uint32_t E) {
+    const size_t total = (size_t)K * E * 2 * LN;
+    if (total == 0) return cudaSuccess;
+    k_retile_idx<<<cdiv(total, 256), 256, 0, s>>>(flat, tiled, LN, E, total);
     return cudaGetLastError();
 }
 
