@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(kMacCoeffs* LANES)
 // per SM (up to 160 KiB) is set by the ring, not by how many loads the compiler keeps in registers.
 constexpr int kMacPosChunk = 8;   // positions per stage == positions between folds
 constexpr int kMacStages = 2;
-constexpr int kMacBT = 2, kMacLanes = 4, kMacBins = kMacBT * kMacLanes;
+constexpr int kMacBT = 2, kMacLanes = 2, kMacBins = kMacBT * kMacLanes;
 constexpr int kMacConsumers = kMacCoeffs * kMacLanes;
 constexpr size_t kMacStageWords = (size_t)kMacPosChunk * kMacCoeffs * (2 + kMacBins);  // idx + pt words per stage
 
@@ -200,14 +200,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-__global__ void __launch_bounds__(kMacConsumers + 32)
+__global__ void __launch_bounds__(kMacConsumers + 32, 2)
     k_mac_tma(const DevTables* __restrict__ tab, uint32_t N, uint32_t L, uint32_t b, uint32_t E, const u64* __restrict__ pt,
               const u64* __restrict__ idx, const u64* __restrict__ minus, u64* __restrict__ acc) {
     extern __shared__ __align__(128) u64 ring[];  // [stage][ idx: 8 x 2 x 128 | pt: 8 bins x 8 x 128 ]
     __shared__ __align__(8) uint64_t full_bar[kMacStages], empty_bar[kMacStages];
     const size_t LN = (size_t)L * N, T = LN / kMacCoeffs;
+    // CTAs that share an index slice (same hf and tile, different bin blocks) are adjacent in launch
+    // order, so the slice comes from DRAM once and from L2 for the other bin blocks
     const uint32_t nbb = (b + kMacBins - 1) / kMacBins;
-    const uint32_t hf = blockIdx.y / nbb, bin_blk0 = (blockIdx.y % nbb) * kMacBins;
+    const uint32_t hf = blockIdx.y, tile = blockIdx.x / nbb, bin_blk0 = (blockIdx.x % nbb) * kMacBins;
     const uint32_t nbins = min((uint32_t)kMacBins, b - bin_blk0);
     const uint32_t nchunks = (E + kMacPosChunk - 1) / kMacPosChunk;
     if (threadIdx.x == 0) {
@@ -222,8 +224,8 @@ __global__ void __launch_bounds__(kMacConsumers + 32)
     if (threadIdx.x >= kMacConsumers) {
         // ---- producer: one elected thread keeps the ring full
         if (threadIdx.x == kMacConsumers) {
-            const u64* isrc = idx + ((size_t)hf * T + blockIdx.x) * E * 2 * kMacCoeffs;
-            const u64* psrc = pt + ((size_t)hf * b + bin_blk0) * (size_t)E * LN + (size_t)blockIdx.x * E * kMacCoeffs;
+            const u64* isrc = idx + ((size_t)hf * T + tile) * E * 2 * kMacCoeffs;
+            const u64* psrc = pt + ((size_t)hf * b + bin_blk0) * (size_t)E * LN + (size_t)tile * E * kMacCoeffs;
             for (uint32_t ch = 0; ch < nchunks; ch++) {
                 const uint32_t s = ch % kMacStages, round = ch / kMacStages;
                 if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(kMacConsumers + 32)
 
     // ---- consumers
     const uint32_t w = threadIdx.x & (kMacCoeffs - 1), lane = threadIdx.x / kMacCoeffs;
-    const size_t c = (size_t)blockIdx.x * kMacCoeffs + w;
+    const size_t c = (size_t)tile * kMacCoeffs + w;
     u64 ll[kMacBT][2], mid[kMacBT][2], hh[kMacBT][2], tlo[kMacBT][2], thi[kMacBT][2];
 #pragma unroll
     for (int j = 0; j < kMacBT; j++)
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(kMacConsumers + 32)
 cudaError_t launch_mac(const KCtx& k, uint32_t K, uint32_t b, uint32_t E, const u64* pt, const u64* idx,
                        const u64* minus, u64* acc) {
     const size_t LN = (size_t)k.L * k.N;
-    dim3 grid(cdiv(LN, kMacCoeffs), K * ((b + kMacBins - 1) / kMacBins));
+    dim3 grid(cdiv(LN, kMacCoeffs) * ((b + kMacBins - 1) / kMacBins), K);
     const size_t smem = kMacStages * kMacStageWords * sizeof(u64);
     static bool attr_set = false;
     if (!attr_set) {
