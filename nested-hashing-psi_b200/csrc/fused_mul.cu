@@ -140,6 +140,79 @@ __device__ __forceinline__ void transform(const DevTables* __restrict__ tab, u64
     }
 }
 
+// ---- compile-time variant: array size, stage range and radix are template constants, so every
+// shared-memory offset is an immediate, the pass plan has no run-time dispatch, and twiddle addresses that
+// do not depend on the thread (column passes) are computed once on the uniform datapath.
+__host__ __device__ constexpr int ct_pass_width(int rem) { return (rem >= 7 || rem == 4) ? 4 : (rem >= 3 ? 3 : rem); }
+
+template <int M, int SIG0, int R, bool INV>
+__device__ __forceinline__ void radix_pass_ct(u64* __restrict__ sm, const ulonglong2* __restrict__ tw, uint32_t delta,
+                                              uint32_t tile_base, u64 q, uint32_t tid) {
+    constexpr int LT = M - SIG0 - R;
+    constexpr uint32_t NBLK = (1u << M) >> R;
+    const u64 q2 = 2 * q, nq = 0 - q;
+#pragma unroll
+    for (uint32_t it = 0; it < (NBLK + kGroup - 1) / kGroup; it++) {
+        const uint32_t blk = tid + it * kGroup;
+        if ((NBLK % kGroup) != 0 && blk >= NBLK) break;
+        const uint32_t off = blk & ((1u << LT) - 1), grp = blk >> LT;
+        // sl(base + k * 2^LT) == sl(base) + k * 2^LT + ((k * 2^LT) >> 4): the pad of the k-th coefficient
+        // never carries into the next 16-block
+        u64* p0 = sm + sl((grp << (M - SIG0)) + off);
+        u64 v[1 << R];
+#pragma unroll
+        for (int k = 0; k < (1 << R); k++) v[k] = p0[(k << LT) + ((k << LT) >> 4)];
+        RegStages<R, 0, INV>::run(v, tw, M, SIG0, delta, tile_base, grp, q2, nq);
+#pragma unroll
+        for (int k = 0; k < (1 << R); k++) p0[(k << LT) + ((k << LT) >> 4)] = v[k];
+    }
+}
+
+template <bool INV, int M, int LO, int HI>
+struct TransformCT {
+    template <typename ModOf>
+    static __device__ __forceinline__ void run(const DevTables* __restrict__ tab, u64* smem, uint32_t stride, uint32_t n_arr,
+                                               ModOf mod_of, uint32_t g, uint32_t ng, uint32_t delta, uint32_t tile_base,
+                                               uint32_t tid) {
+        constexpr int W = ct_pass_width(HI - LO);
+        constexpr int S0 = INV ? HI - W : LO;
+        for (uint32_t a = g; a < n_arr; a += ng) {
+            const ModDev& md = tab->mods[mod_of(a)];
+            radix_pass_ct<M, S0, W, INV>(smem + a * stride, INV ? md.itw : md.ftw, delta, tile_base, md.q, tid);
+        }
+        __syncthreads();
+        TransformCT<INV, M, INV ? LO : LO + W, INV ? HI - W : HI>::run(tab, smem, stride, n_arr, mod_of, g, ng, delta,
+                                                                      tile_base, tid);
+    }
+};
+template <bool INV, int M, int LO>
+struct TransformCT<INV, M, LO, LO> {
+    template <typename ModOf>
+    static __device__ __forceinline__ void run(const DevTables* __restrict__, u64*, uint32_t, uint32_t, ModOf, uint32_t, uint32_t,
+                                               uint32_t, uint32_t, uint32_t) {}
+};
+
+// row tiles are always 2^10 coefficients, stages [3, 10): one compiled plan serves every ring dimension
+template <bool INV, typename ModOf>
+__device__ __forceinline__ void transform_rows(const DevTables* __restrict__ tab, u64* smem, uint32_t stride, uint32_t n_arr,
+                                               ModOf mod_of, uint32_t g, uint32_t ng, uint32_t logN, uint32_t tile_base,
+                                               uint32_t tid) {
+    constexpr int M = kLogCols + kRowTileLog;
+    TransformCT<INV, M, kRowTileLog, M>::run(tab, smem, stride, n_arr, mod_of, g, ng, logN - M, tile_base, tid);
+}
+// column tiles: LOGN_CT != 0 selects the compiled plan for that ring dimension, 0 the run-time plan
+template <bool INV, int LOGN_CT, typename ModOf>
+__device__ __forceinline__ void transform_cols(const DevTables* __restrict__ tab, u64* smem, uint32_t stride, uint32_t n_arr,
+                                               ModOf mod_of, uint32_t g, uint32_t ng, uint32_t logN, uint32_t tid) {
+    if constexpr (LOGN_CT != 0) {
+        constexpr int LOGR = LOGN_CT - (int)kLogCols, M = LOGR + (int)kColTileLog;
+        TransformCT<INV, M, 0, LOGR>::run(tab, smem, stride, n_arr, mod_of, g, ng, 0, 0, tid);
+    } else {
+        const uint32_t logR = logN - kLogCols;
+        transform<INV>(tab, smem, stride, n_arr, mod_of, g, ng, logR + kColTileLog, 0, logR, 0, 0, tid);
+    }
+}
+
 // ---- small modular helpers ----------------------------------------------------------------------
 // canonical residue of a < 2^K * q by K exact compare-subtract steps
 template <int K>
@@ -211,7 +284,7 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_inv(const DevTables* __r
     const size_t off = ((bin * 2 + (g & 1)) * L + l) * N + tile_base;
     load_rows(smem + g * P, (g < 2 ? a : b) + off, tid);
     __syncthreads();
-    transform<true>(tab, smem, P, 4, [l](uint32_t) { return l; }, g, 4, m, kRowTileLog, m, logN - m, tile_base, tid);
+    transform_rows<true>(tab, smem, P, 4, [l](uint32_t) { return l; }, g, 4, logN, tile_base, tid);
     store_rows(smem + g * P, (g < 2 ? ha : hb) + off, tid);
 }
 
@@ -221,7 +294,7 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_inv(const DevTables* __r
 //   operand 1 (innerProductResult): DCRTPoly::FastExpandCRTBasisPloverQ -> e2h [B][2][LT][N]
 // All modular sums are formed as sums of lazy Shoup products (< 2q each, at most 8 terms < 2^64) and
 // reduced once: the canonical residue, identical to the 128-bit Barrett form of the reference.
-template <int L, int LP>
+template <int L, int LP, int LOGN_CT>
 __global__ void __launch_bounds__(kColGroups* kGroup, 2)
     k_cols_extend(const DevTables* __restrict__ tab, uint32_t logN, const u64* __restrict__ ha, const u64* __restrict__ hb,
                   u64* __restrict__ e1p, u64* __restrict__ e2h) {
@@ -238,7 +311,7 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 2)
     const u64* src = (operand ? hb : ha) + ((bin * 2 + comp) * L) * (size_t)N;
     for (uint32_t a = g; a < L; a += kColGroups) load_cols(smem + a * P, src + (size_t)a * N, logR, c0, tid);
     __syncthreads();
-    transform<true>(tab, smem, P, L, [](uint32_t a) { return a; }, g, kColGroups, m, 0, logR, 0, 0, tid);
+    transform_cols<true, LOGN_CT>(tab, smem, P, L, [](uint32_t a) { return a; }, g, kColGroups, logN, tid);
 
     // coefficient-wise extension; N^-1 of the inverse transform is folded into the first constant
     for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) {
@@ -296,7 +369,7 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 2)
     // column-forward of the produced limbs
     const uint32_t n_out = operand ? LT : LP;
     const uint32_t mod0 = operand ? 0 : L;
-    transform<false>(tab, smem, P, n_out, [mod0](uint32_t a) { return mod0 + a; }, g, kColGroups, m, 0, logR, 0, 0, tid);
+    transform_cols<false, LOGN_CT>(tab, smem, P, n_out, [mod0](uint32_t a) { return mod0 + a; }, g, kColGroups, logN, tid);
     for (uint32_t a = g; a < n_out; a += kColGroups) {
         u64* dst = operand ? e2h + ((bin * 2 + comp) * LT + a) * (size_t)N : e1p + ((bin * 2 + comp) * LP + a) * (size_t)N;
         store_cols(smem + a * P, dst, logR, c0, tid);
@@ -326,8 +399,8 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_tensor(const DevTables* 
     __syncthreads();
     // the Q limbs of the first operand are already in EVALUATION form: arrays 0, 1 are skipped for l < L
     const uint32_t first = l < L ? 2 : 0;
-    transform<false>(tab, smem + first * P, P, 4 - first, [l](uint32_t) { return l; }, g >= first ? g - first : 4, 4 - first,
-                     m, kRowTileLog, m, logN - m, tile_base, tid);
+    transform_rows<false>(tab, smem + first * P, P, 4 - first, [l](uint32_t) { return l; }, g >= first ? g - first : 4,
+                          4 - first, logN, tile_base, tid);
 
     // Tensor product with ONE Montgomery reduction per output: the factor R^-1 it leaves is undone for
     // free by k_cols_scale, whose N^-1 constant is N^-1 * R.  Operands are brought below 2q + 2^32 first
@@ -345,14 +418,14 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_tensor(const DevTables* 
         smem[2 * P + sl(j)] = mont_redc_lazy(mulhi64(a1, b1), a1 * b1, q, qinv);
     }
     __syncthreads();
-    transform<true>(tab, smem, P, 3, [l](uint32_t) { return l; }, g, 4, m, kRowTileLog, m, logN - m, tile_base, tid);
+    transform_rows<true>(tab, smem, P, 3, [l](uint32_t) { return l; }, g, 4, logN, tile_base, tid);
     if (g < 3) store_rows(smem + g * P, th + ((bin * 3 + g) * LT + l) * (size_t)N + tile_base, tid);
 }
 
 // ---- (4) columns: inverse, scale-and-round, digit lift, forward -----------------------------------
 // grid (128/8, 3, B), kColGroups groups.  th: [B][3][LT][N]; rh: [B][2][L][N] (column-forward halves of
 // c0, c1); dh: [B][L][L][N] (column-forward halves of the BV digits of c2)
-template <int L, int LP>
+template <int L, int LP, int LOGN_CT>
 __global__ void __launch_bounds__(kColGroups* kGroup, 2)
     k_cols_scale(const DevTables* __restrict__ tab, uint32_t logN, const u64* __restrict__ th, u64* __restrict__ rh,
                  u64* __restrict__ dh) {
@@ -366,7 +439,7 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 2)
     for (uint32_t a = g; a < LT; a += kColGroups)
         load_cols(smem + a * P, th + ((bin * 3 + comp) * LT + a) * (size_t)N, logR, c0, tid);
     __syncthreads();
-    transform<true>(tab, smem, P, LT, [](uint32_t a) { return a; }, g, kColGroups, m, 0, logR, 0, 0, tid);
+    transform_cols<true, LOGN_CT>(tab, smem, P, LT, [](uint32_t a) { return a; }, g, kColGroups, logN, tid);
 
     // DCRTPoly::ScaleAndRound (t/P, output basis Q) on canonical coefficients
     for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) {
@@ -394,7 +467,7 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 2)
     __syncthreads();
 
     if (comp < 2) {
-        transform<false>(tab, smem, P, L, [](uint32_t a) { return a; }, g, kColGroups, m, 0, logR, 0, 0, tid);
+        transform_cols<false, LOGN_CT>(tab, smem, P, L, [](uint32_t a) { return a; }, g, kColGroups, logN, tid);
         for (uint32_t a = g; a < L; a += kColGroups)
             store_cols(smem + a * P, rh + ((bin * 2 + comp) * L + a) * (size_t)N, logR, c0, tid);
         return;
@@ -417,7 +490,7 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 2)
             }
         }
         __syncthreads();
-        transform<false>(tab, smem + L * P, P, L, [](uint32_t a) { return a; }, g, kColGroups, m, 0, logR, 0, 0, tid);
+        transform_cols<false, LOGN_CT>(tab, smem + L * P, P, L, [](uint32_t a) { return a; }, g, kColGroups, logN, tid);
         for (uint32_t kk = g; kk < L; kk += kColGroups)
             store_cols(smem + (L + kk) * P, dh + ((bin * L + i) * L + kk) * (size_t)N, logR, c0, tid);
         __syncthreads();
@@ -443,7 +516,7 @@ __global__ void __launch_bounds__((2 + L) * kGroup, 2)
     const u64* src = g < 2 ? rh + ((bin * 2 + g) * L + kk) * (size_t)N : dh + ((bin * L + (g - 2)) * L + kk) * (size_t)N;
     load_rows(smem + g * P, src + tile_base, tid);
     __syncthreads();
-    transform<false>(tab, smem, P, 2 + L, [kk](uint32_t) { return kk; }, g, 2 + L, m, kRowTileLog, m, logN - m, tile_base, tid);
+    transform_rows<false>(tab, smem, P, 2 + L, [kk](uint32_t) { return kk; }, g, 2 + L, logN, tile_base, tid);
 
     const size_t LN = (size_t)L * N;
     const u64 q = md.q, q2 = 2 * q, qinv = md.qinv;
@@ -496,7 +569,7 @@ bool fused_mul_supported(const KCtx& k) {
     return k.logN >= kLogCols + kRowTileLog && k.L >= 1 && k.L <= 4 && (k.Lp == k.L || k.Lp == k.L + 1) && k.L + k.Lp <= 8;
 }
 
-template <int L, int LP>
+template <int L, int LP, int LOGN_CT>
 static cudaError_t launch_cols(const KCtx& k, uint32_t B, const u64* ha, const u64* hb, u64* e1p, u64* e2h, const u64* th,
                                u64* rh, u64* dh, int which) {
     const uint32_t logR = k.logN - kLogCols, col_tiles = (1u << kLogCols) >> kColTileLog;
@@ -504,21 +577,26 @@ static cudaError_t launch_cols(const KCtx& k, uint32_t B, const u64* ha, const u
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e;
-        if ((e = cudaFuncSetAttribute(k_cols_extend<L, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(k_cols_scale<L, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_cols_extend<L, LP, LOGN_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_cols_scale<L, LP, LOGN_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
         attr_set = true;
     }
     if (which == 0)
-        k_cols_extend<L, LP><<<dim3(col_tiles, 4, B), kColGroups * kGroup, smem, k.s>>>(k.tab, k.logN, ha, hb, e1p, e2h);
+        k_cols_extend<L, LP, LOGN_CT><<<dim3(col_tiles, 4, B), kColGroups * kGroup, smem, k.s>>>(k.tab, k.logN, ha, hb, e1p, e2h);
     else
-        k_cols_scale<L, LP><<<dim3(col_tiles, 3, B), kColGroups * kGroup, smem, k.s>>>(k.tab, k.logN, th, rh, dh);
+        k_cols_scale<L, LP, LOGN_CT><<<dim3(col_tiles, 3, B), kColGroups * kGroup, smem, k.s>>>(k.tab, k.logN, th, rh, dh);
     return cudaGetLastError();
 }
 
 static cudaError_t dispatch_cols(const KCtx& k, uint32_t B, const u64* ha, const u64* hb, u64* e1p, u64* e2h, const u64* th,
                                  u64* rh, u64* dh, int which) {
-#define PSI_COLS_CASE(l, lp) \
-    if (k.L == l && k.Lp == lp) return launch_cols<l, lp>(k, B, ha, hb, e1p, e2h, th, rh, dh, which);
+    // compiled stage plans for the ring dimensions the reference uses (16384: client :73; 8192: the unit test)
+#define PSI_COLS_CASE(l, lp)                                                                               \
+    if (k.L == l && k.Lp == lp) {                                                                          \
+        if (k.logN == 14) return launch_cols<l, lp, 14>(k, B, ha, hb, e1p, e2h, th, rh, dh, which);       \
+        if (k.logN == 13) return launch_cols<l, lp, 13>(k, B, ha, hb, e1p, e2h, th, rh, dh, which);       \
+        return launch_cols<l, lp, 0>(k, B, ha, hb, e1p, e2h, th, rh, dh, which);                           \
+    }
     PSI_COLS_CASE(1, 1) PSI_COLS_CASE(1, 2) PSI_COLS_CASE(2, 2) PSI_COLS_CASE(2, 3)
     PSI_COLS_CASE(3, 3) PSI_COLS_CASE(3, 4) PSI_COLS_CASE(4, 4)
 #undef PSI_COLS_CASE
