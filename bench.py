@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--cpu-sample-bins", type=int, default=8)
+    ap.add_argument("--cpu-sample-bins", type=int, default=0, help="bins per CPU-baseline repetition (0 = all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--synthetic-db", action="store_true",
                     help="random slot values instead of hashing a real server set (same shapes, same timing)")
@@ -147,10 +147,8 @@ def run_reference(args, w, rank):
         return
     import psi_b200 as P
     params = P.params_generate(w["N"], T32, P.depth_for_E(w["E"]))
-    n_bins = min(w["b"], max(args.cpu_sample_bins, 8))
-    for _ in range(max(args.warmup - 1, 0)):
-        pass  # the oracle call below warms itself once; further warm-up adds nothing on the CPU
-    rate, dt, threads, n_bins = cpu_oracle_rate(w, params, n_bins, max(args.steps, 1))
+    n_bins = w["b"]  # the whole query per step: OpenMP over bins keeps every host thread busy
+    rate, dt, threads, n_bins = cpu_oracle_rate(w, params, n_bins, max(args.steps, 1))  # (warms itself once)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "items/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * w["b"] / n_bins,
@@ -330,16 +328,32 @@ def main():
         peak_hbm, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     bytes1 = phase1_bytes(L, N, K, b_local, E)
     ach = bytes1 / (ms_p1 * 1e-3) / 1e9
-    roofline = {"kernel": "k_mac (inner product, phase 1)", "bound": "hbm", "achieved": ach, "peak": peak_hbm,
+    roofline = {"kernel": "k_mac_tma (inner product, phase 1)", "bound": "hbm", "achieved": ach, "peak": peak_hbm,
                 "unit": "GB/s", "frac": ach / peak_hbm, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes1, "launch_ms": ms_p1}
+    # phase 2 against the integer pipe: butterflies of the 88-NTT HPSPOVERQ + BV pipeline per second vs the
+    # measured register-resident butterfly rate of this GPU (psi_bench_pipe_peak, same process, same clocks)
+    import ctypes
+    Lp = params.Lp
+    ntt_per_mul = 4 * L + 2 * Lp + 2 * (L + Lp) + 3 * (L + Lp) + 2 * L + L * L
+    logN = N.bit_length() - 1
+    butterflies = b_local * (K - 1) * ntt_per_mul * (N // 2) * logN
+    bf_peak, imad_peak = ctypes.c_double(), ctypes.c_double()
+    P.capi.check(P.lib().psi_bench_pipe_peak(local_rank, 1, ctypes.byref(bf_peak)))
+    P.capi.check(P.lib().psi_bench_pipe_peak(local_rank, 0, ctypes.byref(imad_peak)))
+    roofline_int = {"kernels": "k_rows_inv + k_cols_extend + k_rows_tensor + k_cols_scale + k_rows_relin (phase 2)",
+                    "bound": "integer pipe", "achieved": butterflies / (ms_p2 * 1e-3), "peak": bf_peak.value,
+                    "unit": "butterflies/s", "frac": butterflies / (ms_p2 * 1e-3) / bf_peak.value,
+                    "butterflies_per_launch_set": butterflies, "ntt_per_ct_mult": ntt_per_mul,
+                    "imad_wide_peak_per_s": imad_peak.value,
+                    "peak_source": "measured in this run: 64-bit Harvey/Shoup butterflies, operands in registers"}
     phases = {"inner_product_ms": ms_p1, "multiply_relin_mask_ms": ms_p2, "run_ms": ms_step,
               "launches_per_run": launches_per_run}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         t0 = time.perf_counter()
-        rate, dt, threads, nb = cpu_oracle_rate(w, params, args.cpu_sample_bins, 3)
+        rate, dt, threads, nb = cpu_oracle_rate(w, params, args.cpu_sample_bins or w["b"], 3)
         cpu = {"value": rate, "unit": "items/s", "cores": threads, "kind": "port",
                "sample": "%d of %d bins x 3 repetitions (%.1f s of CPU work), warm plaintexts, OpenMP over bins; "
                          "port = oracle/psi_oracle.c, the real reference (OpenFHE) cannot be built in this image"
@@ -352,7 +366,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": workload_config(args, w, params, world),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "roofline_int": roofline_int, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "items/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
                     "path": "pinned host query -> psi_query_set -> psi_run -> psi_result_get -> pinned host"
