@@ -288,29 +288,79 @@ def main():
     ms_p2 = timed(lambda: cc.run(sp, phases=2), args.steps) / args.steps
 
     # ---- e2e: host query in, host results out, every step ---------------------------------------------
-    res_dev = None
+    # (a) serial: one query at a time (latency);  (b) pipelined: what a server with a stream of queries
+    # does — the upload of query i+1 (psi_query_upload, copy engine) and the download of result i-1 overlap
+    # the evaluation of query i on three streams; results are double-buffered on the device.  Every step
+    # still moves its own query H2D and its own results D2H inside the timed region.
+    r_host2 = torch.empty(b_local * ct_words, dtype=torch.int64, pin_memory=True)
     if world > 1:
-        res_dev = P.ShardedPIE.device_result_tensor(cc).view(b_local, ct_words)
-        gather_bufs = [torch.empty_like(res_dev) for _ in range(world)] if rank == 0 else None
+        gather_bufs = [torch.empty((b_local, ct_words), dtype=torch.int64, device="cuda") for _ in range(world)] if rank == 0 else None
         R_host = torch.empty(world * b_local * ct_words, dtype=torch.int64, pin_memory=True) if rank == 0 else None
 
-    def e2e_step():
+    def fetch_result(st, host_buf):
+        """D2H of the current result buffer on torch stream `st` (N > 1: NCCL gather to rank 0 first)."""
+        if world == 1:
+            cc.result_get_ptr(host_buf.data_ptr(), st.cuda_stream)
+            return
+        res_dev = P.ShardedPIE.device_result_tensor(cc).view(b_local, ct_words)
+        with torch.cuda.stream(st):
+            dist.gather(res_dev, gather_bufs, dst=0)   # the response gather: the only cross-GPU traffic
+            if rank == 0:
+                for r in range(world):
+                    R_host[r * b_local * ct_words:(r + 1) * b_local * ct_words].copy_(gather_bufs[r].view(-1), non_blocking=True)
+
+    def e2e_serial_step():
         cc.query_set_ptr(idx_ptr, minus_ptr, sp)
         cc.run(sp)
-        if world == 1:
-            cc.result_get_ptr(r_host.data_ptr(), sp)
-        else:
-            # the response gather: the only cross-GPU traffic (NCCL over NVLink), then one D2H on rank 0
-            with torch.cuda.stream(stream):
-                dist.gather(res_dev, gather_bufs, dst=0)
-                if rank == 0:
-                    for r in range(world):
-                        R_host[r * b_local * ct_words:(r + 1) * b_local * ct_words].copy_(gather_bufs[r].view(-1), non_blocking=True)
+        fetch_result(stream, r_host)
 
     for _ in range(3):
-        e2e_step()
+        e2e_serial_step()
     cc.sync(sp)
-    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    ms_e2e_serial = timed(e2e_serial_step, args.steps) / args.steps
+
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def e2e_pipelined(steps):
+        """Returns elapsed ms for `steps` queries through the 3-stream pipeline."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev_commit = None
+        ev_d2h = [None, None]
+        e0.record(s_in)
+        stream.wait_event(e0)
+        s_out.wait_event(e0)
+        for i in range(steps):
+            if ev_commit is not None:
+                s_in.wait_event(ev_commit)            # landing buffers are free once the previous commit ran
+            cc.query_upload_ptr(idx_ptr, minus_ptr, s_in.cuda_stream)
+            ev_up = torch.cuda.Event()
+            ev_up.record(s_in)
+            stream.wait_event(ev_up)
+            cc.query_commit(sp)
+            ev_commit = torch.cuda.Event()
+            ev_commit.record(stream)
+            if ev_d2h[i & 1] is not None:
+                stream.wait_event(ev_d2h[i & 1])       # run i reuses the result buffer of run i-2
+            cc.run(sp)
+            ev_run = torch.cuda.Event()
+            ev_run.record(stream)
+            s_out.wait_event(ev_run)
+            fetch_result(s_out, r_host if (i & 1) == 0 else r_host2)
+            ev_d2h[i & 1] = torch.cuda.Event()
+            ev_d2h[i & 1].record(s_out)
+        e1.record(s_out)
+        e1.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        return ms
+
+    e2e_pipelined(3)
+    ms_e2e = e2e_pipelined(args.steps) / args.steps
     sampler.active = False
     sampler.stop_flag = True
 
@@ -368,9 +418,12 @@ def main():
             "config": workload_config(args, w, params, world),
             "roofline": roofline, "roofline_int": roofline_int, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "items/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h,
-                    "path": "pinned host query -> psi_query_set -> psi_run -> psi_result_get -> pinned host"
-                            + (" (+ NCCL gather to rank 0)" if world > 1 else "")},
+                    "d2h_bytes_per_step": d2h, "serial_ms_per_step": ms_e2e_serial,
+                    "serial_value": total_items / (ms_e2e_serial * 1e-3),
+                    "path": "pinned host query -> psi_query_upload | psi_query_commit -> psi_run -> psi_result_get -> "
+                            "pinned host, three streams: upload of query i+1 and download of result i-1 overlap "
+                            "run i (serial_* = one query at a time)"
+                            + (" (+ NCCL gather to rank 0 before the D2H)" if world > 1 else "")},
             "gpu_launches": launches_per_run * args.steps,
             "phases": phases, "clocks": sampler.summary(), "offline_build_s": offline_s,
         }

@@ -132,6 +132,13 @@ int psi_db_get_limbs(psi_ctx* ctx, uint64_t* pt_limbs, uint64_t* mask_limbs);
  * H2D on `stream` (a cudaStream_t, NULL = legacy default stream). */
 int psi_query_set(psi_ctx* ctx, const uint64_t* idx, const uint64_t* minus, void* stream);
 
+/* The same in two steps, so that a server with a stream of queries can overlap the PCIe upload of the
+ * next query with the evaluation of the current one: psi_query_upload only copies host -> device landing
+ * buffers (no kernel reads them), psi_query_commit makes the uploaded query the active one (re-tiling
+ * kernel, must be ordered after the previous psi_run by the caller's streams/events). */
+int psi_query_upload(psi_ctx* ctx, const uint64_t* idx, const uint64_t* minus, void* stream);
+int psi_query_commit(psi_ctx* ctx, void* stream);
+
 /* BatchedFHEHIPPIE::run (BatchedFHEHIPPIE.cpp:88-129): enqueues all kernels on
  * `stream`; does not synchronise. */
 int psi_run(psi_ctx* ctx, void* stream);
@@ -146,7 +153,9 @@ enum { PSI_PHASE_INNER_PRODUCT = 1, PSI_PHASE_MULTIPLY_MASK = 2, PSI_PHASE_ALL =
 int psi_run_phases(psi_ctx* ctx, uint32_t phases, void* stream);
 
 /* getResultList (BatchedFHEHIPPIE.hpp:35-38): asynchronous D2H of [b][2][L][N]
- * on `stream`; the caller synchronises the stream before reading `out`. */
+ * on `stream`; the caller synchronises the stream before reading `out`.  Results are double-buffered on
+ * the device: the call reads the buffer of the most recently ENQUEUED psi_run, and the next psi_run writes
+ * the other one, so this copy may overlap the next evaluation. */
 int psi_result_get(psi_ctx* ctx, uint64_t* out, void* stream);
 
 int psi_stream_sync(void* stream);

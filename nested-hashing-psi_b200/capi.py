@@ -67,6 +67,8 @@ SYMBOLS = {
     "psi_db_encode_slots": (_int, [_vp, _u32, _u32, _u32, _u32, _i64p, _i64p]),
     "psi_db_get_limbs": (_int, [_vp, _u64p, _u64p]),
     "psi_query_set": (_int, [_vp, _u64p, _u64p, _vp]),
+    "psi_query_upload": (_int, [_vp, _u64p, _u64p, _vp]),
+    "psi_query_commit": (_int, [_vp, _vp]),
     "psi_run": (_int, [_vp, _vp]),
     "psi_run_phases": (_int, [_vp, _u32, _vp]),
     "psi_result_get": (_int, [_vp, _u64p, _vp]),

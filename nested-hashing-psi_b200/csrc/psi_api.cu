@@ -106,7 +106,12 @@ struct psi_ctx {
     DevBuf<u64> stage;               // chunk staging for the DB re-tiling
     bool have_query = false;
     // work
-    DevBuf<u64> acc, coef, e1, e2, ten, res, dig, prod, out;
+    DevBuf<u64> acc, coef, e1, e2, ten, res, dig, prod, out, out2;
+    DevBuf<u64> minus_in;  // H2D landing buffer of minusCompareElement
+    // results are double-buffered: run() i writes out[i & 1], so the D2H of query i can overlap run() i+1
+    uint32_t out_cur = 0;
+    bool uploaded = false;
+    u64* out_buf(uint32_t which) { return which ? out2.p : out.p; }
     bool ran = false;
     uint32_t launches_per_run = 0;
 
@@ -249,6 +254,7 @@ static int alloc_work(psi_ctx* c) {
     const size_t N = c->N, L = c->L, LT = c->L + c->Lp, b = c->b, K = c->K;
     CK(c->acc.alloc(K * b * 2 * L * N));
     CK(c->out.alloc(b * 2 * L * N));
+    CK(c->out2.alloc(b * 2 * L * N));
     if (K > 1) {
         CK(c->coef.alloc(b * 4 * L * N));
         CK(c->e1.alloc(b * 2 * LT * N));
@@ -357,7 +363,7 @@ int psi_ctx_destroy(psi_ctx* c) {
     cudaSetDevice(c->device);
     if (c->d_tab) cudaFree(c->d_tab);
     DevBuf<u64>* bufs[] = {&c->twiddles, &c->twiddles2, &c->evk_bR, &c->evk_aR, &c->maskR, &c->evk_b, &c->evk_a, &c->pt, &c->mask, &c->idx, &c->idx_in, &c->stage, &c->minus, &c->acc,
-                           &c->coef,     &c->e1,    &c->e2,    &c->ten, &c->res, &c->dig, &c->prod,  &c->out};
+                           &c->coef,     &c->e1,    &c->e2,    &c->ten, &c->res, &c->dig, &c->prod,  &c->out, &c->out2, &c->minus_in};
     for (auto* b : bufs) b->release();
     c->to_crt.release();
     delete c;
@@ -401,6 +407,7 @@ static int db_dims(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E) {
     CK(c->idx.alloc((size_t)K * E * 2 * LN));
     CK(c->idx_in.alloc((size_t)K * E * 2 * LN));
     CK(c->minus.alloc(2 * LN));
+    CK(c->minus_in.alloc(2 * LN));
     return alloc_work(c);
 }
 
@@ -509,6 +516,12 @@ int psi_db_get_limbs(psi_ctx* c, uint64_t* pt_limbs, uint64_t* mask_limbs) {
 }
 
 int psi_query_set(psi_ctx* c, const uint64_t* idx, const uint64_t* minus, void* stream) {
+    int rc = psi_query_upload(c, idx, minus, stream);
+    if (rc) return rc;
+    return psi_query_commit(c, stream);
+}
+
+int psi_query_upload(psi_ctx* c, const uint64_t* idx, const uint64_t* minus, void* stream) {
     if (!c || !idx || !minus) return set_error(PSI_ERR_INVALID, "null argument");
     if (!c->have_db) return set_error(PSI_ERR_STATE, "load the database before the query (it fixes K and E)");
     int rc = ensure_device(c);
@@ -516,8 +529,20 @@ int psi_query_set(psi_ctx* c, const uint64_t* idx, const uint64_t* minus, void* 
     const size_t LN = (size_t)c->L * c->N;
     cudaStream_t s = (cudaStream_t)stream;
     CK(cudaMemcpyAsync(c->idx_in.p, idx, (size_t)c->K * c->E * 2 * LN * sizeof(u64), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(c->minus.p, minus, 2 * LN * sizeof(u64), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->minus_in.p, minus, 2 * LN * sizeof(u64), cudaMemcpyHostToDevice, s));
+    c->uploaded = true;
+    return PSI_OK;
+}
+
+int psi_query_commit(psi_ctx* c, void* stream) {
+    if (!c) return set_error(PSI_ERR_INVALID, "null argument");
+    if (!c->uploaded) return set_error(PSI_ERR_STATE, "psi_query_commit before psi_query_upload");
+    int rc = ensure_device(c);
+    if (rc) return rc;
+    const size_t LN = (size_t)c->L * c->N;
+    cudaStream_t s = (cudaStream_t)stream;
     CK(launch_retile_idx(s, c->idx_in.p, c->idx.p, LN, c->K, c->E));  // index cts -> tiled split-30
+    CK(cudaMemcpyAsync(c->minus.p, c->minus_in.p, 2 * LN * sizeof(u64), cudaMemcpyDeviceToDevice, s));
     c->have_query = true;
     return PSI_OK;
 }
@@ -542,13 +567,15 @@ int psi_run_phases(psi_ctx* c, uint32_t phases, void* stream) {
         c->launches_per_run = nl;
         return PSI_OK;
     }
+    c->out_cur ^= 1u;  // this run's result buffer
+    u64* const result = c->out_buf(c->out_cur);
     if (c->K == 1) {
-        CK(launch_mul_ctpt(k, c->b, c->acc.p, c->mask.p, c->out.p)); nl++;
+        CK(launch_mul_ctpt(k, c->b, c->acc.p, c->mask.p, result)); nl++;
     } else {
         const u64* prod = c->acc.p;  // hf = 0
         for (uint32_t hf = 1; hf < c->K; hf++) {
             const bool last = hf + 1 == c->K;
-            u64* dst = last ? c->out.p : c->prod.p;
+            u64* dst = last ? result : c->prod.p;
             if ((rc = mul_ctct_batch(c, s, c->b, prod, c->acc.p + (size_t)hf * c->b * ct, last ? c->mask.p : nullptr,
                                      dst, &nl)))
                 return rc;
@@ -565,7 +592,7 @@ int psi_result_get(psi_ctx* c, uint64_t* out, void* stream) {
     if (!c->ran) return set_error(PSI_ERR_STATE, "getResultList() before run()");
     int rc = ensure_device(c);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(out, c->out.p, (size_t)c->b * 2 * c->L * c->N * sizeof(u64), cudaMemcpyDeviceToHost,
+    CK(cudaMemcpyAsync(out, c->out_buf(c->out_cur), (size_t)c->b * 2 * c->L * c->N * sizeof(u64), cudaMemcpyDeviceToHost,
                        (cudaStream_t)stream));
     return PSI_OK;
 }
@@ -585,7 +612,7 @@ int psi_run_launch_count(psi_ctx* c, uint32_t* out) {
 int psi_result_device_ptr(psi_ctx* c, void** out, size_t* bytes) {
     if (!c || !out || !bytes) return set_error(PSI_ERR_INVALID, "null argument");
     if (!c->have_db) return set_error(PSI_ERR_STATE, "no database loaded");
-    *out = c->out.p;
+    *out = c->out_buf(c->out_cur);
     *bytes = (size_t)c->b * 2 * c->L * c->N * sizeof(u64);
     return PSI_OK;
 }

@@ -113,6 +113,14 @@ class CryptoContext:
         check(lib().psi_query_set(self._h, ctypes.cast(idx_ptr, ctypes.POINTER(ctypes.c_uint64)),
                                   ctypes.cast(minus_ptr, ctypes.POINTER(ctypes.c_uint64)), stream))
 
+    def query_upload_ptr(self, idx_ptr, minus_ptr, stream=None):
+        """H2D of the next query into landing buffers only (overlaps a running evaluation)."""
+        check(lib().psi_query_upload(self._h, ctypes.cast(idx_ptr, ctypes.POINTER(ctypes.c_uint64)),
+                                     ctypes.cast(minus_ptr, ctypes.POINTER(ctypes.c_uint64)), stream))
+
+    def query_commit(self, stream=None):
+        check(lib().psi_query_commit(self._h, stream))
+
     def run(self, stream=None, phases=3):
         """psi_run / psi_run_phases: 1 = inner products only, 2 = ct x ct + mask only, 3 = all."""
         check(lib().psi_run_phases(self._h, phases, stream))

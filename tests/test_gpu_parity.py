@@ -230,3 +230,29 @@ def test_error_behaviour():
         P.BatchedFHEHIPPIE(cc, P.PublicKey(), hct)
     with pytest.raises(ValueError, match="combined"):
         P.HierarchicalCuckooHashTable(h, 4, 3, 0, 2, 2, False, True, 2)
+
+
+def test_pipelined_queries_double_buffered_results():
+    """psi_query_upload / psi_query_commit / double-buffered results: two different queries in flight give
+    each its own result (the bench's pipelined e2e path), and re-running the first after the second too."""
+    cc, o, params = ctx_and_oracle(1024, 2)
+    rng = np.random.default_rng(77)
+    sk, evk_b, evk_a = o.keygen(6)
+    cc.InsertEvalMultKey(evk_b, evk_a)
+    K, b, E = 2, 3, 4
+    pt = sc.random_pt(rng, params, (K, b, E))
+    mask = sc.random_pt(rng, params, (b,))
+    cc.db_load_limbs(pt, mask)
+    queries = [(sc.random_ct(rng, params, (K, E)), sc.random_ct(rng, params)) for _ in range(3)]
+    want = [o.run(pt, mask, q[0], q[1], evk_b, evk_a) for q in queries]
+    outs = [np.empty((b, 2, params.L, params.N), dtype=np.uint64) for _ in queries]
+    for i, (idx, minus) in enumerate(queries):
+        idx = np.ascontiguousarray(idx)
+        minus = np.ascontiguousarray(minus)
+        cc.query_upload_ptr(idx.ctypes.data, minus.ctypes.data)   # default stream: ordered, pageable host memory
+        cc.query_commit()
+        cc.run()
+        cc.result_get(outs[i], sync=False)                          # read back only after everything is queued
+    cc.sync()
+    for i in range(3):
+        assert np.array_equal(outs[i], want[i]), "query %d" % i
