@@ -59,6 +59,10 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-sample-bins", type=int, default=0, help="bins per CPU-baseline repetition (0 = all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="host", choices=["host", "nccl"],
+                    help="N > 1 response gather inside e2e: 'host' = every rank copies its own result ciphertexts to "
+                         "pinned host memory over its own PCIe link (what a one-process server does with one pinned "
+                         "buffer); 'nccl' = NCCL gather to rank 0 over NVLink, then one D2H on rank 0")
     ap.add_argument("--synthetic-db", action="store_true",
                     help="random slot values instead of hashing a real server set (same shapes, same timing)")
     return ap.parse_args()
@@ -299,7 +303,7 @@ def main():
 
     def fetch_result(st, host_buf):
         """D2H of the current result buffer on torch stream `st` (N > 1: NCCL gather to rank 0 first)."""
-        if world == 1:
+        if world == 1 or args.gather == "host":
             cc.result_get_ptr(host_buf.data_ptr(), st.cuda_stream)
             return
         res_dev = P.ShardedPIE.device_result_tensor(cc).view(b_local, ct_words)
@@ -369,7 +373,7 @@ def main():
     value = total_items / (ms_step * 1e-3)
     e2e_value = total_items / (ms_e2e * 1e-3)
     h2d = (K * E + 1) * ct_words * 8
-    d2h = b_local * ct_words * 8 * (world if (world > 1) else 1)
+    d2h = b_local * ct_words * 8 * world  # whole job: every rank's result ciphertexts reach host memory
 
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -423,7 +427,9 @@ def main():
                     "path": "pinned host query -> psi_query_upload | psi_query_commit -> psi_run -> psi_result_get -> "
                             "pinned host, three streams: upload of query i+1 and download of result i-1 overlap "
                             "run i (serial_* = one query at a time)"
-                            + (" (+ NCCL gather to rank 0 before the D2H)" if world > 1 else "")},
+                            + ((" (N > 1: NCCL gather to rank 0 over NVLink, then one D2H)" if args.gather == "nccl" else
+                                " (N > 1: every rank downloads its own bins over its own PCIe link)") if world > 1 else ""),
+                    "gather": args.gather if world > 1 else None},
             "gpu_launches": launches_per_run * args.steps,
             "phases": phases, "clocks": sampler.summary(), "offline_build_s": offline_s,
         }
