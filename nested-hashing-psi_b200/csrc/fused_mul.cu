@@ -23,6 +23,7 @@
 // (Harvey); every value that feeds a double-precision rounding decision or leaves the pipeline is the
 // canonical residue, so results are bit-identical to the unfused reference sequence (oracle/psi_oracle.c).
 #include "psi_kernels.cuh"
+#include "async_copy.cuh"
 
 namespace psi {
 
@@ -56,12 +57,12 @@ __device__ __forceinline__ void gs_bf(u64& x, u64& y, const ulonglong2 tw, u64 q
 
 // One stage (local stage sig0 + r) of a radix-2^R register pass.  All loop bounds are template constants
 // so that every index into v[] is a compile-time constant (the array must stay in registers).
-template <int R, int r, bool INV>
+template <int R, int r, bool INV, bool TWS = false>
 __device__ __forceinline__ void reg_stage(u64 (&v)[1 << R], const ulonglong2* __restrict__ tw, uint32_t w0, u64 q2, u64 nq) {
     constexpr int half = 1 << (R - 1 - r);
 #pragma unroll
     for (int j = 0; j < (1 << r); j++) {
-        const ulonglong2 t = __ldg(tw + w0 + j);
+        const ulonglong2 t = TWS ? tw[w0 + j] : __ldg(tw + w0 + j);
 #pragma unroll
         for (int i = 0; i < half; i++) {
             if (INV)
@@ -71,18 +72,21 @@ __device__ __forceinline__ void reg_stage(u64 (&v)[1 << R], const ulonglong2* __
         }
     }
 }
-template <int R, int rr, bool INV>
+// TWS: `tw` is the row tile's twiddle table staged in shared memory (stage_row_twiddles): the 8 * 2^u
+// twiddles of row stage u start at entry 8 * (2^u - 1)
+template <int R, int rr, bool INV, bool TWS = false>
 struct RegStages {
     static __device__ __forceinline__ void run(u64 (&v)[1 << R], const ulonglong2* __restrict__ tw, uint32_t m, uint32_t sig0,
                                                uint32_t delta, uint32_t tile_base, uint32_t grp, u64 q2, u64 nq) {
         constexpr int r = INV ? R - 1 - rr : rr;
-        const uint32_t w0 = (1u << (sig0 + r + delta)) + (tile_base >> (m - sig0 - r)) + (grp << r);
-        reg_stage<R, r, INV>(v, tw, w0, q2, nq);
-        RegStages<R, rr + 1, INV>::run(v, tw, m, sig0, delta, tile_base, grp, q2, nq);
+        const uint32_t w0 = TWS ? ((8u << (sig0 + r - kRowTileLog)) - 8u) + (grp << r)
+                                : (1u << (sig0 + r + delta)) + (tile_base >> (m - sig0 - r)) + (grp << r);
+        reg_stage<R, r, INV, TWS>(v, tw, w0, q2, nq);
+        RegStages<R, rr + 1, INV, TWS>::run(v, tw, m, sig0, delta, tile_base, grp, q2, nq);
     }
 };
-template <int R, bool INV>
-struct RegStages<R, R, INV> {
+template <int R, bool INV, bool TWS>
+struct RegStages<R, R, INV, TWS> {
     static __device__ __forceinline__ void run(u64 (&)[1 << R], const ulonglong2* __restrict__, uint32_t, uint32_t, uint32_t,
                                                uint32_t, uint32_t, u64, u64) {}
 };
@@ -145,7 +149,7 @@ __device__ __forceinline__ void transform(const DevTables* __restrict__ tab, u64
 // do not depend on the thread (column passes) are computed once on the uniform datapath.
 __host__ __device__ constexpr int ct_pass_width(int rem) { return (rem >= 7 || rem == 4) ? 4 : (rem >= 3 ? 3 : rem); }
 
-template <int M, int SIG0, int R, bool INV>
+template <int M, int SIG0, int R, bool INV, bool TWS = false>
 __device__ __forceinline__ void radix_pass_ct(u64* __restrict__ sm, const ulonglong2* __restrict__ tw, uint32_t delta,
                                               uint32_t tile_base, u64 q, uint32_t tid) {
     constexpr int LT = M - SIG0 - R;
@@ -162,43 +166,56 @@ __device__ __forceinline__ void radix_pass_ct(u64* __restrict__ sm, const ulongl
         u64 v[1 << R];
 #pragma unroll
         for (int k = 0; k < (1 << R); k++) v[k] = p0[(k << LT) + ((k << LT) >> 4)];
-        RegStages<R, 0, INV>::run(v, tw, M, SIG0, delta, tile_base, grp, q2, nq);
+        RegStages<R, 0, INV, TWS>::run(v, tw, M, SIG0, delta, tile_base, grp, q2, nq);
 #pragma unroll
         for (int k = 0; k < (1 << R); k++) p0[(k << LT) + ((k << LT) >> 4)] = v[k];
     }
 }
 
-template <bool INV, int M, int LO, int HI>
+template <bool INV, int M, int LO, int HI, bool TWS = false>
 struct TransformCT {
     template <typename ModOf>
     static __device__ __forceinline__ void run(const DevTables* __restrict__ tab, u64* smem, uint32_t stride, uint32_t n_arr,
                                                ModOf mod_of, uint32_t g, uint32_t ng, uint32_t delta, uint32_t tile_base,
-                                               uint32_t tid) {
+                                               uint32_t tid, const ulonglong2* tws = nullptr) {
         constexpr int W = ct_pass_width(HI - LO);
         constexpr int S0 = INV ? HI - W : LO;
         for (uint32_t a = g; a < n_arr; a += ng) {
             const ModDev& md = tab->mods[mod_of(a)];
-            radix_pass_ct<M, S0, W, INV>(smem + a * stride, INV ? md.itw : md.ftw, delta, tile_base, md.q, tid);
+            radix_pass_ct<M, S0, W, INV, TWS>(smem + a * stride, TWS ? tws : (INV ? md.itw : md.ftw), delta, tile_base, md.q,
+                                              tid);
         }
         __syncthreads();
-        TransformCT<INV, M, INV ? LO : LO + W, INV ? HI - W : HI>::run(tab, smem, stride, n_arr, mod_of, g, ng, delta,
-                                                                      tile_base, tid);
+        TransformCT<INV, M, INV ? LO : LO + W, INV ? HI - W : HI, TWS>::run(tab, smem, stride, n_arr, mod_of, g, ng, delta,
+                                                                           tile_base, tid, tws);
     }
 };
-template <bool INV, int M, int LO>
-struct TransformCT<INV, M, LO, LO> {
+template <bool INV, int M, int LO, bool TWS>
+struct TransformCT<INV, M, LO, LO, TWS> {
     template <typename ModOf>
     static __device__ __forceinline__ void run(const DevTables* __restrict__, u64*, uint32_t, uint32_t, ModOf, uint32_t, uint32_t,
-                                               uint32_t, uint32_t, uint32_t) {}
+                                               uint32_t, uint32_t, uint32_t, const ulonglong2* = nullptr) {}
 };
+
+// Row-tile twiddles through the copy engine: for the 8 rows starting at row r0 the twiddles of row stage u
+// (global stage logN - 7 + u) are the contiguous run [2^s + r0 * 2^u, + 8 * 2^u) of the table, so seven bulk
+// copies (128 B ... 8 KiB) bring all 1016 {w, w'} pairs of one direction; one thread issues them.
+constexpr uint32_t kRowTwEntries = 8u * 127u;
+constexpr uint32_t kRowTwWords = 2u * kRowTwEntries;  // u64 words per staged table
+__device__ __forceinline__ void stage_row_twiddles(ulonglong2* dst, const ulonglong2* __restrict__ gtw, uint32_t logN,
+                                                   uint32_t r0, uint64_t* bar) {
+#pragma unroll
+    for (uint32_t u = 0; u < kLogCols; u++)
+        bulk_g2s(dst + ((8u << u) - 8u), gtw + (1u << (logN - kLogCols + u)) + (r0 << u), (8u << u) * 16u, bar);
+}
 
 // row tiles are always 2^10 coefficients, stages [3, 10): one compiled plan serves every ring dimension
 template <bool INV, typename ModOf>
 __device__ __forceinline__ void transform_rows(const DevTables* __restrict__ tab, u64* smem, uint32_t stride, uint32_t n_arr,
                                                ModOf mod_of, uint32_t g, uint32_t ng, uint32_t logN, uint32_t tile_base,
-                                               uint32_t tid) {
+                                               uint32_t tid, const ulonglong2* tws) {
     constexpr int M = kLogCols + kRowTileLog;
-    TransformCT<INV, M, kRowTileLog, M>::run(tab, smem, stride, n_arr, mod_of, g, ng, logN - M, tile_base, tid);
+    TransformCT<INV, M, kRowTileLog, M, true>::run(tab, smem, stride, n_arr, mod_of, g, ng, logN - M, tile_base, tid, tws);
 }
 // column tiles: LOGN_CT != 0 selects the compiled plan for that ring dimension, 0 the run-time plan
 template <bool INV, int LOGN_CT, typename ModOf>
@@ -282,10 +299,20 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_inv(const DevTables* __r
     const uint32_t l = blockIdx.y, tile_base = blockIdx.x * M;
     const size_t bin = blockIdx.z;
     const size_t off = ((bin * 2 + (g & 1)) * L + l) * N + tile_base;
-    load_rows(smem + g * P, (g < 2 ? a : b) + off, tid);
+    __shared__ __align__(8) uint64_t tw_bar;
+    ulonglong2* tws = reinterpret_cast<ulonglong2*>(smem);  // [1016] inverse twiddles of this row tile
+    u64* arr = smem + kRowTwWords;
+    if (threadIdx.x == 0) {
+        mbar_init(&tw_bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&tw_bar, kRowTwEntries * 16u);
+        stage_row_twiddles(tws, tab->mods[l].itw, logN, tile_base >> kLogCols, &tw_bar);
+    }
+    load_rows(arr + g * P, (g < 2 ? a : b) + off, tid);
     __syncthreads();
-    transform_rows<true>(tab, smem, P, 4, [l](uint32_t) { return l; }, g, 4, logN, tile_base, tid);
-    store_rows(smem + g * P, (g < 2 ? ha : hb) + off, tid);
+    mbar_wait(&tw_bar, 0);
+    transform_rows<true>(tab, arr, P, 4, [l](uint32_t) { return l; }, g, 4, logN, tile_base, tid, tws);
+    store_rows(arr + g * P, (g < 2 ? ha : hb) + off, tid);
 }
 
 // ---- (2) columns: inverse, basis extension, forward -----------------------------------------------
@@ -395,12 +422,24 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_tensor(const DevTables* 
         src = l < L ? a + ((bin * 2 + comp) * L + l) * (size_t)N : e1p + ((bin * 2 + comp) * Lp + (l - L)) * (size_t)N;
     else
         src = e2h + ((bin * 2 + comp) * LT + l) * (size_t)N;
-    load_rows(smem + g * P, src + tile_base, tid);
+    __shared__ __align__(8) uint64_t tw_bar;
+    ulonglong2* tws_f = reinterpret_cast<ulonglong2*>(smem);                  // forward twiddles of this row tile
+    ulonglong2* tws_i = reinterpret_cast<ulonglong2*>(smem + kRowTwWords);    // inverse twiddles
+    u64* arr = smem + 2 * kRowTwWords;
+    if (threadIdx.x == 0) {
+        mbar_init(&tw_bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&tw_bar, 2 * kRowTwEntries * 16u);
+        stage_row_twiddles(tws_f, md.ftw, logN, tile_base >> kLogCols, &tw_bar);
+        stage_row_twiddles(tws_i, md.itw, logN, tile_base >> kLogCols, &tw_bar);
+    }
+    load_rows(arr + g * P, src + tile_base, tid);
     __syncthreads();
+    mbar_wait(&tw_bar, 0);
     // the Q limbs of the first operand are already in EVALUATION form: arrays 0, 1 are skipped for l < L
     const uint32_t first = l < L ? 2 : 0;
-    transform_rows<false>(tab, smem + first * P, P, 4 - first, [l](uint32_t) { return l; }, g >= first ? g - first : 4,
-                          4 - first, logN, tile_base, tid);
+    transform_rows<false>(tab, arr + first * P, P, 4 - first, [l](uint32_t) { return l; }, g >= first ? g - first : 4,
+                          4 - first, logN, tile_base, tid, tws_f);
 
     // Tensor product with ONE Montgomery reduction per output: the factor R^-1 it leaves is undone for
     // free by k_cols_scale, whose N^-1 constant is N^-1 * R.  Operands are brought below 2q + 2^32 first
@@ -408,18 +447,18 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_tensor(const DevTables* 
     // accepts as is.
     const u64 q = md.q, q2 = 2 * q, qinv = md.qinv;
     for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) {
-        const u64 a0 = lazy_sub_hi(smem[sl(j)], q2), a1 = lazy_sub_hi(smem[P + sl(j)], q2);
-        const u64 b0 = lazy_sub_hi(smem[2 * P + sl(j)], q2), b1 = lazy_sub_hi(smem[3 * P + sl(j)], q2);
-        smem[sl(j)] = mont_redc_lazy(mulhi64(a0, b0), a0 * b0, q, qinv);
+        const u64 a0 = lazy_sub_hi(arr[sl(j)], q2), a1 = lazy_sub_hi(arr[P + sl(j)], q2);
+        const u64 b0 = lazy_sub_hi(arr[2 * P + sl(j)], q2), b1 = lazy_sub_hi(arr[3 * P + sl(j)], q2);
+        arr[sl(j)] = mont_redc_lazy(mulhi64(a0, b0), a0 * b0, q, qinv);
         u64 hi = 0, lo = 0;
         mac128(hi, lo, a0, b1);
         mac128(hi, lo, a1, b0);
-        smem[P + sl(j)] = mont_redc_lazy(hi, lo, q, qinv);
-        smem[2 * P + sl(j)] = mont_redc_lazy(mulhi64(a1, b1), a1 * b1, q, qinv);
+        arr[P + sl(j)] = mont_redc_lazy(hi, lo, q, qinv);
+        arr[2 * P + sl(j)] = mont_redc_lazy(mulhi64(a1, b1), a1 * b1, q, qinv);
     }
     __syncthreads();
-    transform_rows<true>(tab, smem, P, 3, [l](uint32_t) { return l; }, g, 4, logN, tile_base, tid);
-    if (g < 3) store_rows(smem + g * P, th + ((bin * 3 + g) * LT + l) * (size_t)N + tile_base, tid);
+    transform_rows<true>(tab, arr, P, 3, [l](uint32_t) { return l; }, g, 4, logN, tile_base, tid, tws_i);
+    if (g < 3) store_rows(arr + g * P, th + ((bin * 3 + g) * LT + l) * (size_t)N + tile_base, tid);
 }
 
 // ---- (4) columns: inverse, scale-and-round, digit lift, forward -----------------------------------
@@ -514,9 +553,19 @@ __global__ void __launch_bounds__((2 + L) * kGroup, 2)
     const size_t bin = blockIdx.z;
     const ModDev& md = tab->mods[kk];
     const u64* src = g < 2 ? rh + ((bin * 2 + g) * L + kk) * (size_t)N : dh + ((bin * L + (g - 2)) * L + kk) * (size_t)N;
-    load_rows(smem + g * P, src + tile_base, tid);
+    __shared__ __align__(8) uint64_t tw_bar;
+    ulonglong2* tws = reinterpret_cast<ulonglong2*>(smem);  // forward twiddles of this row tile
+    u64* arr = smem + kRowTwWords;
+    if (threadIdx.x == 0) {
+        mbar_init(&tw_bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&tw_bar, kRowTwEntries * 16u);
+        stage_row_twiddles(tws, md.ftw, logN, tile_base >> kLogCols, &tw_bar);
+    }
+    load_rows(arr + g * P, src + tile_base, tid);
     __syncthreads();
-    transform_rows<false>(tab, smem, P, 2 + L, [kk](uint32_t) { return kk; }, g, 2 + L, logN, tile_base, tid);
+    mbar_wait(&tw_bar, 0);
+    transform_rows<false>(tab, arr, P, 2 + L, [kk](uint32_t) { return kk; }, g, 2 + L, logN, tile_base, tid, tws);
 
     const size_t LN = (size_t)L * N;
     const u64 q = md.q, q2 = 2 * q, qinv = md.qinv;
@@ -525,13 +574,13 @@ __global__ void __launch_bounds__((2 + L) * kGroup, 2)
         u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
 #pragma unroll
         for (int i = 0; i < L; i++) {
-            const u64 d = lazy_sub_hi(smem[(2 + i) * P + sl(j)], q2);  // < 2q + 2^32: L <= 4 terms stay < q * 2^64
+            const u64 d = lazy_sub_hi(arr[(2 + i) * P + sl(j)], q2);  // < 2q + 2^32: L <= 4 terms stay < q * 2^64
             mac128(h0, l0, d, evk_bR[(size_t)i * LN + n]);
             mac128(h1, l1, d, evk_aR[(size_t)i * LN + n]);
         }
         // + (c0, c1): forward-transform outputs < 4q + 2^32, reduction outputs < 2q
-        u64 r0 = mont_redc_lazy(h0, l0, q, qinv) + smem[sl(j)];
-        u64 r1 = mont_redc_lazy(h1, l1, q, qinv) + smem[P + sl(j)];
+        u64 r0 = mont_redc_lazy(h0, l0, q, qinv) + arr[sl(j)];
+        u64 r1 = mont_redc_lazy(h1, l1, q, qinv) + arr[P + sl(j)];
         if (maskR) {
             const u64 mv = maskR[bin * LN + n];
             r0 = mont_redc_lazy(mulhi64(r0, mv), r0 * mv, q, qinv);
@@ -611,19 +660,25 @@ cudaError_t launch_fused_mul(const KCtx& k, uint32_t B, const u64* a, const u64*
     const uint32_t logR = k.logN - kLogCols;
     const uint32_t row_tiles = (1u << logR) >> kRowTileLog;
     const size_t row_arr = padded(1u << (kLogCols + kRowTileLog)) * sizeof(u64);
+    const size_t tw_bytes = kRowTwWords * sizeof(u64);
     cudaError_t e;
-    k_rows_inv<<<dim3(row_tiles, L, B), 4 * kGroup, 4 * row_arr, k.s>>>(k.tab, k.logN, a, b, ha, hb);
-    if ((e = dispatch_cols(k, B, ha, hb, e1p, e2h, nullptr, nullptr, nullptr, 0)) != cudaSuccess) return e;
-    k_rows_tensor<<<dim3(row_tiles, LT, B), 4 * kGroup, 4 * row_arr, k.s>>>(k.tab, k.logN, a, e1p, e2h, th);
-    if ((e = dispatch_cols(k, B, nullptr, nullptr, nullptr, nullptr, th, rh, dh, 1)) != cudaSuccess) return e;
-    const dim3 rg(row_tiles, L, B);
-    const size_t rs = (2 + L) * row_arr;
     static bool relin_attr = false;
     if (!relin_attr) {
-        if ((e = cudaFuncSetAttribute(k_rows_relin<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(k_rows_relin<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_rows_tensor, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_rows_relin<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_rows_relin<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_rows_relin<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_rows_relin<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
         relin_attr = true;
     }
+
+    k_rows_inv<<<dim3(row_tiles, L, B), 4 * kGroup, 4 * row_arr + tw_bytes, k.s>>>(k.tab, k.logN, a, b, ha, hb);
+    if ((e = dispatch_cols(k, B, ha, hb, e1p, e2h, nullptr, nullptr, nullptr, 0)) != cudaSuccess) return e;
+    k_rows_tensor<<<dim3(row_tiles, LT, B), 4 * kGroup, 4 * row_arr + 2 * tw_bytes, k.s>>>(k.tab, k.logN, a, e1p, e2h, th);
+    if ((e = dispatch_cols(k, B, nullptr, nullptr, nullptr, nullptr, th, rh, dh, 1)) != cudaSuccess) return e;
+    const dim3 rg(row_tiles, L, B);
+    const size_t rs = (2 + L) * row_arr + tw_bytes;
     switch (L) {
         case 1: k_rows_relin<1><<<rg, 3 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
         case 2: k_rows_relin<2><<<rg, 4 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;

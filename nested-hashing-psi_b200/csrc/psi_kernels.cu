@@ -2,6 +2,7 @@
 // lives in ntt.cu).  Each kernel names the OpenFHE operation at the reference call site it
 // replaces; the CPU restatement it is checked against is oracle/psi_oracle.c.
 #include "psi_kernels.cuh"
+#include "async_copy.cuh"
 
 #include <type_traits>
 
@@ -173,33 +174,6 @@ constexpr int kMacBT = 2, kMacLanes = 2, kMacBins = kMacBT * kMacLanes;
 constexpr int kMacConsumers = kMacCoeffs * kMacLanes;
 constexpr size_t kMacStageWords = (size_t)kMacPosChunk * kMacCoeffs * (2 + kMacBins);  // idx + pt words per stage
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 __global__ void __launch_bounds__(kMacConsumers + 32, 2)
     k_mac_tma(const DevTables* __restrict__ tab, uint32_t N, uint32_t L, uint32_t b, uint32_t E, const u64* __restrict__ pt,
               const u64* __restrict__ idx, const u64* __restrict__ minus, u64* __restrict__ acc) {
@@ -217,7 +191,7 @@ __global__ void __launch_bounds__(kMacConsumers + 32, 2)
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], kMacConsumers);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     __syncthreads();
 
