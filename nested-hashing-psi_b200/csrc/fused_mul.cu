@@ -42,7 +42,7 @@ __host__ __device__ constexpr uint32_t padded(uint32_t n) { return n + (n >> 4) 
 // forward (Cooley-Tukey): inputs < 4q + 2^32, outputs < 4q + 2^32
 __device__ __forceinline__ void ct_bf(u64& x, u64& y, const ulonglong2 tw, u64 q2, u64 nq) {
     const u64 u = lazy_sub_hi(x, q2);
-    const u64 v = mul_shoup_lazy_nq(y, tw.x, tw.y, nq);
+    const u64 v = mul_shoup_lazy(y, tw.x, tw.y, 0 - nq);
     x = u + v;
     y = u - v + q2;
 }
@@ -52,7 +52,7 @@ __device__ __forceinline__ void gs_bf(u64& x, u64& y, const ulonglong2 tw, u64 q
     const u64 s = lazy_sub_hi(x + y, q2);
     const u64 d = x - y + 2 * q2;
     x = s;
-    y = mul_shoup_lazy_nq(d, tw.x, tw.y, nq);
+    y = mul_shoup_lazy(d, tw.x, tw.y, 0 - nq);
 }
 
 // One stage (local stage sig0 + r) of a radix-2^R register pass.  All loop bounds are template constants
@@ -241,7 +241,7 @@ __device__ __forceinline__ u64 reduce_pow2q(u64 a, u64 q) {
     }
     return a;
 }
-__device__ __forceinline__ u64 shoup_lazy(u64 x, u64 c, u64 cs, u64 q) { return mul_shoup_lazy_nq(x, c, cs, 0 - q); }
+__device__ __forceinline__ u64 shoup_lazy(u64 x, u64 c, u64 cs, u64 q) { return mul_shoup_lazy(x, c, cs, q); }
 __device__ __forceinline__ u64 shoup_canon(u64 x, u64 c, u64 cs, u64 q) {
     const u64 r = shoup_lazy(x, c, cs, q);
     return r >= q ? r - q : r;

@@ -169,7 +169,7 @@ __device__ __forceinline__ void ct_butterfly_asm(u64& x, u64& y, u64 w, u64 ws, 
 // quotient is hi - floor(m*q / 2^64) in (-q, q); adding q makes it non-negative.
 __device__ __forceinline__ u64 mont_redc_lazy(u64 hi, u64 lo, u64 q, u64 qinv) {
     const u64 m = lo * qinv;
-    return hi - mulhi64_4(m, q) + q;
+    return hi - mulhi64(m, q) + q;
 }
 
 // 128-bit multiply-accumulate: (hi:lo) += a * b
