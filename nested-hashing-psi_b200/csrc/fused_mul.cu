@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_inv(const DevTables* __r
 // All modular sums are formed as sums of lazy Shoup products (< 2q each, at most 8 terms < 2^64) and
 // reduced once: the canonical residue, identical to the 128-bit Barrett form of the reference.
 template <int L, int LP, int LOGN_CT>
-__global__ void __launch_bounds__(kColGroups* kGroup, 2)
+__global__ void __launch_bounds__(kColGroups* kGroup, 3)
     k_cols_extend(const DevTables* __restrict__ tab, uint32_t logN, const u64* __restrict__ ha, const u64* __restrict__ hb,
                   u64* __restrict__ e1p, u64* __restrict__ e2h) {
     extern __shared__ __align__(16) u64 smem[];
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_tensor(const DevTables* 
 // grid (128/8, 3, B), kColGroups groups.  th: [B][3][LT][N]; rh: [B][2][L][N] (column-forward halves of
 // c0, c1); dh: [B][L][L][N] (column-forward halves of the BV digits of c2)
 template <int L, int LP, int LOGN_CT>
-__global__ void __launch_bounds__(kColGroups* kGroup, 2)
+__global__ void __launch_bounds__(kColGroups* kGroup, 3)
     k_cols_scale(const DevTables* __restrict__ tab, uint32_t logN, const u64* __restrict__ th, u64* __restrict__ rh,
                  u64* __restrict__ dh) {
     extern __shared__ __align__(16) u64 smem[];
