@@ -10,13 +10,6 @@ namespace psi {
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
-__device__ __forceinline__ u64 ld_stream(const u64* p) {
-    // read-once data (plaintext DB): keep it out of L1
-    u64 v;
-    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
-    return v;
-}
-
 // ------------------------------------------------------------------------------------------
 // Phase 1 — the encrypted one-hot inner product.
 // Replaces the EvalMult(ct,pt) / EvalAdd loop and the EvalAdd of minusCompareElement
@@ -30,14 +23,9 @@ __device__ __forceinline__ u64 ld_stream(const u64* p) {
 // 8 positions fit before a fold).  Every 8 positions the partial sums are folded into a 128-bit
 // running total, which is reduced once at the end: the canonical residue of the same sum OpenFHE
 // forms term by term (ModMul / ModAdd), hence bit-identical.
-// A CTA covers 128 coefficients x (LANES bin-lanes x BT bins); the LANES threads of a coefficient
-// read the same index words, so those come from L1 after the first lane.
+// A CTA covers 128 coefficients (one row of one limb) x 4 bins; CTAs of the same row are adjacent in
+// launch order, so the index words of that row come from DRAM once and from L2 afterwards.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint2 ld_stream_v2(const u64* p) {
-    uint2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-    return v;
-}
 __device__ __forceinline__ u64 madw(uint32_t a, uint32_t b, u64 c) {
     u64 d;
     asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
@@ -51,123 +39,13 @@ __device__ __forceinline__ void fold30(u64& hi, u64& lo, u64 ll, u64 mid, u64 hh
     hi = (u64)(t >> 64);
 }
 
-constexpr int kMacCoeffs = 128;  // coefficients per CTA
+constexpr int kMacCoeffs = 128;  // coefficients per CTA tile (= one row of one limb)
 
-template <int BT, int LANES>
-__global__ void __launch_bounds__(kMacCoeffs* LANES)
-    k_mac(const DevTables* __restrict__ tab, uint32_t N, uint32_t L, uint32_t b, uint32_t E,
-          const u64* __restrict__ pt, const u64* __restrict__ idx, const u64* __restrict__ minus,
-          u64* __restrict__ acc) {
-    const size_t LN = (size_t)L * N;
-    const size_t c = (size_t)blockIdx.x * kMacCoeffs + (threadIdx.x & (kMacCoeffs - 1));
-    const uint32_t lane = threadIdx.x / kMacCoeffs;
-    const uint32_t nbb = (b + BT * LANES - 1) / (BT * LANES);
-    const uint32_t hf = blockIdx.y / nbb;
-    const uint32_t bin0 = (blockIdx.y % nbb) * (BT * LANES) + lane * BT;
-    if (c >= LN || bin0 >= b) return;
-    const int nb = (int)min((uint32_t)BT, b - bin0);
-
-    u64 ll[BT][2], mid[BT][2], hh[BT][2], tlo[BT][2], thi[BT][2];
-#pragma unroll
-    for (int j = 0; j < BT; j++)
-#pragma unroll
-        for (int k = 0; k < 2; k++) ll[j][k] = mid[j][k] = hh[j][k] = tlo[j][k] = thi[j][k] = 0;
-
-    // tiled storage (see launch_retile_*): for one (hf, bin, 128-coefficient tile) the E positions are
-    // contiguous, 1 KiB apart; for one (hf, tile) the E x 2 index words are contiguous, 2 KiB apart.
-    // A CTA therefore streams whole DRAM pages and every load offset below is an immediate.
-    const size_t T = LN / kMacCoeffs;
-    const uint32_t w = threadIdx.x & (kMacCoeffs - 1);
-    const u64* ip = idx + ((size_t)hf * T + blockIdx.x) * E * 2 * kMacCoeffs + w;
-    const size_t bin_stride = (size_t)E * LN;
-    // bins past the end of a ragged last block alias bin0 (loaded, accumulated, never stored):
-    // keeps the inner loop free of branches so that the loads of a whole sub-block are in flight together
-    const u64* pp[BT];
-#pragma unroll
-    for (int j = 0; j < BT; j++)
-        pp[j] = pt + ((size_t)hf * b + bin0 + (j < nb ? j : 0)) * bin_stride + (size_t)blockIdx.x * E * kMacCoeffs + w;
-
-    constexpr int U = 4;  // positions per software-pipelined sub-block
-    auto sub_block = [&](auto n_tag) {
-        constexpr int n = decltype(n_tag)::value;
-        uint2 i0[n], i1[n], y[n][BT];
-#pragma unroll
-        for (int p = 0; p < n; p++) {
-            i0[p] = __ldg(reinterpret_cast<const uint2*>(ip + p * 2 * kMacCoeffs));
-            i1[p] = __ldg(reinterpret_cast<const uint2*>(ip + p * 2 * kMacCoeffs + kMacCoeffs));
-#pragma unroll
-            for (int j = 0; j < BT; j++) y[p][j] = ld_stream_v2(pp[j] + p * kMacCoeffs);
-        }
-#pragma unroll
-        for (int p = 0; p < n; p++)
-#pragma unroll
-            for (int j = 0; j < BT; j++) {
-                ll[j][0] = madw(i0[p].x, y[p][j].x, ll[j][0]);
-                mid[j][0] = madw(i0[p].x, y[p][j].y, mid[j][0]);
-                mid[j][0] = madw(i0[p].y, y[p][j].x, mid[j][0]);
-                hh[j][0] = madw(i0[p].y, y[p][j].y, hh[j][0]);
-                ll[j][1] = madw(i1[p].x, y[p][j].x, ll[j][1]);
-                mid[j][1] = madw(i1[p].x, y[p][j].y, mid[j][1]);
-                mid[j][1] = madw(i1[p].y, y[p][j].x, mid[j][1]);
-                hh[j][1] = madw(i1[p].y, y[p][j].y, hh[j][1]);
-            }
-        ip += n * 2 * kMacCoeffs;
-#pragma unroll
-        for (int j = 0; j < BT; j++) pp[j] += n * kMacCoeffs;
-    };
-    auto fold_all = [&]() {
-#pragma unroll
-        for (int j = 0; j < BT; j++)
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                fold30(thi[j][k], tlo[j][k], ll[j][k], mid[j][k], hh[j][k]);
-                ll[j][k] = mid[j][k] = hh[j][k] = 0;
-            }
-    };
-
-    uint32_t folds = 0;
-    uint32_t pos = 0;
-    for (; pos + 2 * U <= E; pos += 2 * U) {  // 8 positions between folds: every partial sum stays < 2^64
-        sub_block(std::integral_constant<int, U>());
-        sub_block(std::integral_constant<int, U>());
-        fold_all();
-        if (++folds == 16) {  // 128 positions: keep the running total below 2^128 for any E
-            folds = 0;
-            const ModDev& mdr = tab->mods[c / N];
-#pragma unroll
-            for (int j = 0; j < BT; j++)
-#pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    tlo[j][k] = barrett128(thi[j][k], tlo[j][k], mdr.q, mdr.mu_hi, mdr.mu_lo);
-                    thi[j][k] = 0;
-                }
-        }
-    }
-    if (pos + U <= E) {
-        sub_block(std::integral_constant<int, U>());
-        pos += U;
-    }
-    for (; pos < E; pos++) sub_block(std::integral_constant<int, 1>());
-    fold_all();
-    const ModDev& md = tab->mods[c / N];
-    const u64 q = md.q, mu_hi = md.mu_hi, mu_lo = md.mu_lo;
-    const u64 m0 = minus[c], m1 = minus[LN + c];
-#pragma unroll
-    for (int j = 0; j < BT; j++) {
-        if (j < nb) {
-            u64* o = acc + (((size_t)hf * b + bin0 + j) * 2) * LN + c;
-            o[0] = addmod(barrett128(thi[j][0], tlo[j][0], q, mu_hi, mu_lo), m0, q);
-            o[LN] = addmod(barrett128(thi[j][1], tlo[j][1], q, mu_hi, mu_lo), m1, q);
-        }
-    }
-}
-
-// ---- TMA-fed variant -------------------------------------------------------------------------------
-// Same arithmetic, but the operands are streamed by the copy engine: one producer thread issues
-// cp.async.bulk (SASS UBLKCP) copies of whole position-chunks — 8 positions x 1 KiB per bin, 8 x 2 KiB of
-// index words — into a two-stage shared-memory ring guarded by mbarriers, and 512 consumer threads
-// (128 coefficients x 4 bin-lanes x 2 bins) do nothing but LDS + IMAD.WIDE.  The amount of data in flight
-// per SM (up to 160 KiB) is set by the ring, not by how many loads the compiler keeps in registers.
+// The operands are streamed by the copy engine: one producer thread issues cp.async.bulk (SASS UBLKCP)
+// copies of whole position-chunks — 8 positions x 1 KiB per bin, 8 x 2 KiB of index words — into a
+// two-stage shared-memory ring guarded by mbarriers, and 256 consumer threads (128 coefficients x 2
+// bin-lanes x 2 bins) do nothing but LDS + IMAD.WIDE.  Two CTAs per SM; the data in flight per SM (up to
+// 192 KiB) is set by the rings, not by how many loads the compiler keeps in registers.
 constexpr int kMacPosChunk = 8;   // positions per stage == positions between folds
 constexpr int kMacStages = 2;
 constexpr int kMacBT = 2, kMacLanes = 2, kMacBins = kMacBT * kMacLanes;
