@@ -79,8 +79,19 @@ struct RegStages {
     static __device__ __forceinline__ void run(u64 (&v)[1 << R], const ulonglong2* __restrict__ tw, uint32_t m, uint32_t sig0,
                                                uint32_t delta, uint32_t tile_base, uint32_t grp, u64 q2, u64 nq) {
         constexpr int r = INV ? R - 1 - rr : rr;
-        const uint32_t w0 = TWS ? ((8u << (sig0 + r - kRowTileLog)) - 8u) + (grp << r)
-                                : (1u << (sig0 + r + delta)) + (tile_base >> (m - sig0 - r)) + (grp << r);
+        // TWS: packed row-tile table (layout: psi_api.cu build_tables).  The radix pass whose blocks are
+        // single threads' contiguous coefficients (lt == 0) reads its own 2^R - 1 twiddles back to back; the
+        // other pass reads the stage-major part shared by the threads of a row.
+        uint32_t w0;
+        if (TWS) {
+            const bool own = (m - sig0 - R) == 0;
+            if (!INV)
+                w0 = own ? 120u + ((1u << R) - 1u) * grp + ((1u << r) - 1u) : ((8u << (sig0 + r - kRowTileLog)) - 8u) + (grp << r);
+            else
+                w0 = own ? ((1u << R) - 1u) * grp + ((1u << r) - 1u) : 960u + ((8u << (sig0 + r - kRowTileLog)) - 8u) + (grp << r);
+        } else {
+            w0 = (1u << (sig0 + r + delta)) + (tile_base >> (m - sig0 - r)) + (grp << r);
+        }
         reg_stage<R, r, INV, TWS>(v, tw, w0, q2, nq);
         RegStages<R, rr + 1, INV, TWS>::run(v, tw, m, sig0, delta, tile_base, grp, q2, nq);
     }
@@ -197,16 +208,13 @@ struct TransformCT<INV, M, LO, LO, TWS> {
                                                uint32_t, uint32_t, uint32_t, const ulonglong2* = nullptr) {}
 };
 
-// Row-tile twiddles through the copy engine: for the 8 rows starting at row r0 the twiddles of row stage u
-// (global stage logN - 7 + u) are the contiguous run [2^s + r0 * 2^u, + 8 * 2^u) of the table, so seven bulk
-// copies (128 B ... 8 KiB) bring all 1016 {w, w'} pairs of one direction; one thread issues them.
+// Row-tile twiddles through the copy engine: the 1016 {w, w'} pairs the 7 row stages of one tile need are
+// pre-packed per tile in read order (ModDev::ftw_rows / itw_rows), so one 16 KiB bulk copy brings them.
 constexpr uint32_t kRowTwEntries = 8u * 127u;
 constexpr uint32_t kRowTwWords = 2u * kRowTwEntries;  // u64 words per staged table
-__device__ __forceinline__ void stage_row_twiddles(ulonglong2* dst, const ulonglong2* __restrict__ gtw, uint32_t logN,
-                                                   uint32_t r0, uint64_t* bar) {
-#pragma unroll
-    for (uint32_t u = 0; u < kLogCols; u++)
-        bulk_g2s(dst + ((8u << u) - 8u), gtw + (1u << (logN - kLogCols + u)) + (r0 << u), (8u << u) * 16u, bar);
+__device__ __forceinline__ void stage_row_twiddles(ulonglong2* dst, const ulonglong2* __restrict__ packed, uint32_t tile,
+                                                   uint64_t* bar) {
+    bulk_g2s(dst, packed + (size_t)tile * kRowTwEntries, kRowTwEntries * 16u, bar);
 }
 
 // row tiles are always 2^10 coefficients, stages [3, 10): one compiled plan serves every ring dimension
@@ -306,7 +314,7 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_inv(const DevTables* __r
         mbar_init(&tw_bar, 1);
         mbar_fence_init();
         mbar_expect_tx(&tw_bar, kRowTwEntries * 16u);
-        stage_row_twiddles(tws, tab->mods[l].itw, logN, tile_base >> kLogCols, &tw_bar);
+        stage_row_twiddles(tws, tab->mods[l].itw_rows, blockIdx.x, &tw_bar);
     }
     load_rows(arr + g * P, (g < 2 ? a : b) + off, tid);
     __syncthreads();
@@ -430,8 +438,8 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_tensor(const DevTables* 
         mbar_init(&tw_bar, 1);
         mbar_fence_init();
         mbar_expect_tx(&tw_bar, 2 * kRowTwEntries * 16u);
-        stage_row_twiddles(tws_f, md.ftw, logN, tile_base >> kLogCols, &tw_bar);
-        stage_row_twiddles(tws_i, md.itw, logN, tile_base >> kLogCols, &tw_bar);
+        stage_row_twiddles(tws_f, md.ftw_rows, blockIdx.x, &tw_bar);
+        stage_row_twiddles(tws_i, md.itw_rows, blockIdx.x, &tw_bar);
     }
     load_rows(arr + g * P, src + tile_base, tid);
     __syncthreads();
@@ -560,7 +568,7 @@ __global__ void __launch_bounds__((2 + L) * kGroup, 2)
         mbar_init(&tw_bar, 1);
         mbar_fence_init();
         mbar_expect_tx(&tw_bar, kRowTwEntries * 16u);
-        stage_row_twiddles(tws, md.ftw, logN, tile_base >> kLogCols, &tw_bar);
+        stage_row_twiddles(tws, md.ftw_rows, blockIdx.x, &tw_bar);
     }
     load_rows(arr + g * P, src + tile_base, tid);
     __syncthreads();

@@ -22,6 +22,10 @@ struct ModDev {
     u64 Rmodq, Rmodq_s;  // R mod q
     const ulonglong2* ftw;  // {w, ws} interleaved: one 16-byte load per twiddle (fused kernels)
     const ulonglong2* itw;  // {iw, iws}
+    // per row tile (8 rows of 128 coefficients): the 1016 twiddles of the 7 row stages packed in the order
+    // the fused row kernels read them (one 16 KiB bulk copy per tile, bank-conflict-free reads), or null
+    const ulonglong2* ftw_rows;
+    const ulonglong2* itw_rows;
 };
 
 __device__ __forceinline__ u64 mulhi64(u64 a, u64 b) { return __umul64hi(a, b); }

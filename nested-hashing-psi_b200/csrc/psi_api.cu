@@ -92,6 +92,7 @@ struct psi_ctx {
     DevTables* d_tab = nullptr;
     DevBuf<u64> twiddles;       // [(L+Lp+1)][4][N]
     DevBuf<u64> twiddles2;      // [(L+Lp+1)][2][N][2]: {w, ws} and {iw, iws} interleaved
+    DevBuf<u64> twiddles_rows;  // [(L+Lp)][2][N/1024][1016][2]: row-stage twiddles packed per row tile
     DevBuf<uint32_t> to_crt;    // packed-encoding permutation
     DevBuf<u64> evk_b, evk_a;   // [L][L][N]
     DevBuf<u64> evk_bR, evk_aR; // the same times R = 2^64 mod q_k (Montgomery form for the fused relinearisation)
@@ -194,6 +195,45 @@ static int build_tables(psi_ctx* c) {
         md.itw = reinterpret_cast<const ulonglong2*>(c->twiddles2.p + ((size_t)m * 2 + 1) * 2 * N);
     }
     CK(cudaMemcpy(c->twiddles2.p, tw2.data(), tw2.size() * sizeof(u64), cudaMemcpyHostToDevice));
+    if (c->logN >= 10) {
+        // Row-stage twiddles per row tile, in the read order of fused_mul.cu (row tile = 2^10 coefficients,
+        // forward plan: radix-16 over row stages u = 0..3 then radix-8 over u = 4..6; inverse: radix-16 over
+        // u = 6..3 then radix-8 over u = 2..0):
+        //   forward: [0,120)   stage-major, shared by the 8 threads of a row: 8*(2^u - 1) + i
+        //            [120,1016) per radix-8 block g (128 of them): 120 + 7 g + (2^r - 1) + j,  u = 4 + r
+        //   inverse: [0,960)   per radix-16 block g (64 of them): 15 g + (2^r - 1) + j,        u = 3 + r
+        //            [960,1016) stage-major, u = 0..2: 960 + 8*(2^u - 1) + i
+        const uint32_t tiles = N >> 10, per_tile = 1016, nmq = L + Lp;
+        std::vector<u64> tr((size_t)nmq * 2 * tiles * per_tile * 2);
+        CK(c->twiddles_rows.alloc(tr.size()));
+        for (uint32_t m = 0; m < nmq; m++) {
+            const u64* f2 = &tw2[((size_t)m * 2 + 0) * 2 * N];
+            const u64* i2 = &tw2[((size_t)m * 2 + 1) * 2 * N];
+            for (uint32_t t = 0; t < tiles; t++) {
+                u64* fo = &tr[(((size_t)m * 2 + 0) * tiles + t) * per_tile * 2];
+                u64* io = &tr[(((size_t)m * 2 + 1) * tiles + t) * per_tile * 2];
+                const uint32_t r0 = t * 8;
+                auto gidx = [&](uint32_t u, uint32_t i) { return (1u << (c->logN - 7 + u)) + (r0 << u) + i; };
+                auto put = [](u64* dst, uint32_t e, const u64* src, uint32_t g) {
+                    dst[2 * e] = src[2 * g];
+                    dst[2 * e + 1] = src[2 * g + 1];
+                };
+                for (uint32_t u = 0; u < 4; u++)
+                    for (uint32_t i = 0; i < (8u << u); i++) put(fo, ((8u << u) - 8u) + i, f2, gidx(u, i));
+                for (uint32_t g = 0; g < 128; g++)
+                    for (uint32_t r = 0; r < 3; r++)
+                        for (uint32_t j = 0; j < (1u << r); j++) put(fo, 120 + 7 * g + ((1u << r) - 1) + j, f2, gidx(4 + r, (g << r) + j));
+                for (uint32_t g = 0; g < 64; g++)
+                    for (uint32_t r = 0; r < 4; r++)
+                        for (uint32_t j = 0; j < (1u << r); j++) put(io, 15 * g + ((1u << r) - 1) + j, i2, gidx(3 + r, (g << r) + j));
+                for (uint32_t u = 0; u < 3; u++)
+                    for (uint32_t i = 0; i < (8u << u); i++) put(io, 960 + ((8u << u) - 8u) + i, i2, gidx(u, i));
+            }
+            T.mods[m].ftw_rows = reinterpret_cast<const ulonglong2*>(c->twiddles_rows.p + (((size_t)m * 2 + 0) * tiles) * per_tile * 2);
+            T.mods[m].itw_rows = reinterpret_cast<const ulonglong2*>(c->twiddles_rows.p + (((size_t)m * 2 + 1) * tiles) * per_tile * 2);
+        }
+        CK(cudaMemcpy(c->twiddles_rows.p, tr.data(), tr.size() * sizeof(u64), cudaMemcpyHostToDevice));
+    }
     CK(cudaMemcpy(c->twiddles.p, tw.data(), tw.size() * sizeof(u64), cudaMemcpyHostToDevice));
     for (uint32_t i = 0; i < L; i++) {
         T.QHatInvModq[i] = P.QHatInvModq[i];
@@ -362,7 +402,7 @@ int psi_ctx_destroy(psi_ctx* c) {
     if (!c) return PSI_OK;
     cudaSetDevice(c->device);
     if (c->d_tab) cudaFree(c->d_tab);
-    DevBuf<u64>* bufs[] = {&c->twiddles, &c->twiddles2, &c->evk_bR, &c->evk_aR, &c->maskR, &c->evk_b, &c->evk_a, &c->pt, &c->mask, &c->idx, &c->idx_in, &c->stage, &c->minus, &c->acc,
+    DevBuf<u64>* bufs[] = {&c->twiddles, &c->twiddles2, &c->twiddles_rows, &c->evk_bR, &c->evk_aR, &c->maskR, &c->evk_b, &c->evk_a, &c->pt, &c->mask, &c->idx, &c->idx_in, &c->stage, &c->minus, &c->acc,
                            &c->coef,     &c->e1,    &c->e2,    &c->ten, &c->res, &c->dig, &c->prod,  &c->out, &c->out2, &c->minus_in};
     for (auto* b : bufs) b->release();
     c->to_crt.release();
