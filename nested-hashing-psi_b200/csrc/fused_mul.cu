@@ -255,6 +255,25 @@ __device__ __forceinline__ u64 shoup_canon(u64 x, u64 c, u64 cs, u64 q) {
     return r >= q ? r - q : r;
 }
 
+// RNS inner products sum_i x_i * c_i mod q with at most 8 terms: the constants are stored in Montgomery form
+// (times 2^64 mod q) and split-30, the residues x_i < 2^60 are split once, every product is four IMAD.WIDE.U32
+// into three carry-free partial sums, and ONE Montgomery reduction returns the canonical residue of the sum.
+struct Acc3 {
+    u64 ll = 0, mid = 0, hh = 0;
+};
+__device__ __forceinline__ void acc3_mad(Acc3& a, uint32_t x0, uint32_t x1, u64 c_split) {
+    const uint32_t c0 = (uint32_t)c_split, c1 = (uint32_t)(c_split >> 32);
+    a.ll = madw32(x0, c0, a.ll);
+    a.mid = madw32(x0, c1, a.mid);
+    a.mid = madw32(x1, c0, a.mid);
+    a.hh = madw32(x1, c1, a.hh);
+}
+__device__ __forceinline__ u64 acc3_reduce(const Acc3& a, u64 q, u64 qinv) {
+    const u128 t = (u128)a.ll + ((u128)a.mid << 30) + ((u128)a.hh << 60);
+    const u64 r = mont_redc_lazy((u64)(t >> 64), (u64)t, q, qinv);
+    return r >= q ? r - q : r;
+}
+
 // ---- tile movers (16-byte global accesses) ------------------------------------------------------
 // row tile: 2^(7+kRowTileLog) contiguous coefficients
 __device__ __forceinline__ void load_rows(u64* sm, const u64* __restrict__ poly_tile, uint32_t tid) {
@@ -359,14 +378,20 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 3)
                 nu = __dadd_rn(nu, __dmul_rn(__ull2double_rn(y[i]), tab->qInv[i]));
             }
             const unsigned alpha = (unsigned)nu;
+            uint32_t y0[L], y1[L];
+#pragma unroll
+            for (int i = 0; i < L; i++) {
+                y0[i] = (uint32_t)y[i] & 0x3fffffffu;
+                y1[i] = (uint32_t)(y[i] >> 30);
+            }
 #pragma unroll
             for (int jj = 0; jj < LP; jj++) {
-                const u64 p = tab->mods[L + jj].q;
-                u64 acc = 0;
+                const ModDev& mp = tab->mods[L + jj];
+                Acc3 acc;
 #pragma unroll
-                for (int i = 0; i < L; i++) acc += shoup_lazy(y[i], tab->QHatModp[jj][i], tab->QHatModp_s[jj][i], p);
-                const u64 v = reduce_pow2q<4>(acc, p);
-                smem[jj * P + sl(j)] = submod(v, tab->alphaQModp[alpha][jj], p);
+                for (int i = 0; i < L; i++) acc3_mad(acc, y0[i], y1[i], tab->QHatModp_m[jj][i]);
+                const u64 v = acc3_reduce(acc, mp.q, mp.qinv);
+                smem[jj * P + sl(j)] = submod(v, tab->alphaQModp[alpha][jj], mp.q);
             }
         } else {
             u64 pp[LP], z[LP];
@@ -374,26 +399,34 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 3)
             for (int i = 0; i < L; i++)
                 y[i] = shoup_canon(smem[i * P + sl(j)], tab->negPQHatInvNinv[i], tab->negPQHatInvNinv_s[i], tab->mods[i].q);
             double nu = 0.5;
+            uint32_t y0[L], y1[L], z0[LP], z1[LP];
+#pragma unroll
+            for (int i = 0; i < L; i++) {
+                y0[i] = (uint32_t)y[i] & 0x3fffffffu;
+                y1[i] = (uint32_t)(y[i] >> 30);
+            }
 #pragma unroll
             for (int jj = 0; jj < LP; jj++) {
-                const u64 p = tab->mods[L + jj].q;
-                u64 acc = 0;
+                const ModDev& mp = tab->mods[L + jj];
+                Acc3 acc;
 #pragma unroll
-                for (int i = 0; i < L; i++) acc += shoup_lazy(y[i], tab->qInvModp[i][jj], tab->qInvModp_s[i][jj], p);
-                pp[jj] = reduce_pow2q<4>(acc, p);
+                for (int i = 0; i < L; i++) acc3_mad(acc, y0[i], y1[i], tab->qInvModp_m[i][jj]);
+                pp[jj] = acc3_reduce(acc, mp.q, mp.qinv);
                 // exact P -> Q (DCRTPoly::SwitchCRTBasis)
-                z[jj] = shoup_canon(pp[jj], tab->PHatInvModp[jj], tab->PHatInvModp_s[jj], p);
+                z[jj] = shoup_canon(pp[jj], tab->PHatInvModp[jj], tab->PHatInvModp_s[jj], mp.q);
                 nu = __dadd_rn(nu, __dmul_rn(__ull2double_rn(z[jj]), tab->pInv[jj]));
+                z0[jj] = (uint32_t)z[jj] & 0x3fffffffu;
+                z1[jj] = (uint32_t)(z[jj] >> 30);
             }
             const unsigned alpha = (unsigned)nu;
 #pragma unroll
             for (int i = 0; i < L; i++) {
-                const u64 q = tab->mods[i].q;
-                u64 acc = 0;
+                const ModDev& mq = tab->mods[i];
+                Acc3 acc;
 #pragma unroll
-                for (int jj = 0; jj < LP; jj++) acc += shoup_lazy(z[jj], tab->PHatModq[i][jj], tab->PHatModq_s[i][jj], q);
-                const u64 v = reduce_pow2q<4>(acc, q);
-                smem[i * P + sl(j)] = submod(v, tab->alphaPModq[alpha][i], q);
+                for (int jj = 0; jj < LP; jj++) acc3_mad(acc, z0[jj], z1[jj], tab->PHatModq_m[i][jj]);
+                const u64 v = acc3_reduce(acc, mq.q, mq.qinv);
+                smem[i * P + sl(j)] = submod(v, tab->alphaPModq[alpha][i], mq.q);
             }
 #pragma unroll
             for (int jj = 0; jj < LP; jj++) smem[(L + jj) * P + sl(j)] = pp[jj];
@@ -499,16 +532,23 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 3)
             nu = __dadd_rn(nu, __dmul_rn(tab->tQSfrac[i], __ull2double_rn(xp[i])));
         }
         const u64 alpha = __double2ull_rz(nu);  // < LP * 2^60
+        uint32_t xp0[LP], xp1[LP];
+#pragma unroll
+        for (int i = 0; i < LP; i++) {
+            xp0[i] = (uint32_t)xp[i] & 0x3fffffffu;
+            xp1[i] = (uint32_t)(xp[i] >> 30);
+        }
 #pragma unroll
         for (int l = 0; l < L; l++) {
             const ModDev& mq = tab->mods[l];
             const u64 q = mq.q;
             const u64 xq = shoup_canon(smem[l * P + sl(j)], mq.ninvR, mq.ninvR_s, q);
-            u64 acc = shoup_lazy(xq, tab->tQS[l][LP], tab->tQS_s[l][LP], q);
+            Acc3 acc;
+            acc3_mad(acc, (uint32_t)xq & 0x3fffffffu, (uint32_t)(xq >> 30), tab->tQS_m[l][LP]);
 #pragma unroll
-            for (int i = 0; i < LP; i++) acc += shoup_lazy(xp[i], tab->tQS[l][i], tab->tQS_s[l][i], q);
-            // acc < 2 (LP + 1) q, alpha < 16 q: reduce both, add
-            smem[l * P + sl(j)] = addmod(reduce_pow2q<4>(acc, q), alpha < (q << 4) ? reduce_pow2q<4>(alpha, q) : alpha % q, q);
+            for (int i = 0; i < LP; i++) acc3_mad(acc, xp0[i], xp1[i], tab->tQS_m[l][i]);
+            // alpha < 16 q for 60-bit moduli; smaller moduli take the division
+            smem[l * P + sl(j)] = addmod(acc3_reduce(acc, q, mq.qinv), alpha < (q << 4) ? reduce_pow2q<4>(alpha, q) : alpha % q, q);
         }
     }
     __syncthreads();

@@ -55,6 +55,11 @@ static u64 h_powmod(u64 a, u64 e, u64 q) {
     return r;
 }
 static u64 h_shoup(u64 w, u64 q) { return (u64)(((u128h)w << 64) / q); }
+// c * 2^64 mod q, in split-30 storage (hi30 : lo30)
+static u64 h_mont_split(u64 c, u64 q) {
+    const u64 m = (u64)(((u128h)c << 64) % q);
+    return ((m >> 30) << 32) | (m & 0x3fffffffull);
+}
 static uint32_t h_bitrev(uint32_t x, int bits) {
     uint32_t r = 0;
     for (int i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
@@ -244,12 +249,15 @@ static int build_tables(psi_ctx* c) {
         for (uint32_t j = 0; j < Lp; j++) {
             T.qInvModp[i][j] = P.qInvModp[i][j];
             T.qInvModp_s[i][j] = h_shoup(P.qInvModp[i][j], P.p[j]);
+            T.qInvModp_m[i][j] = h_mont_split(P.qInvModp[i][j], P.p[j]);
+            T.PHatModq_m[i][j] = h_mont_split(P.PHatModq[i][j], P.q[i]);
             T.PHatModq[i][j] = P.PHatModq[i][j];
             T.PHatModq_s[i][j] = h_shoup(P.PHatModq[i][j], P.q[i]);
         }
         for (uint32_t j = 0; j <= Lp; j++) {
             T.tQS[i][j] = P.tQSHatInvModsDivsModq[i][j];
             T.tQS_s[i][j] = h_shoup(P.tQSHatInvModsDivsModq[i][j], P.q[i]);
+            T.tQS_m[i][j] = h_mont_split(P.tQSHatInvModsDivsModq[i][j], P.q[i]);
         }
         for (uint32_t k = 0; k < L; k++) T.qModq[i][k] = P.q[i] % P.q[k];
         T.QHatInvNinv[i] = h_mulmod(P.QHatInvModq[i], T.mods[i].ninv, P.q[i]);
@@ -265,6 +273,7 @@ static int build_tables(psi_ctx* c) {
         for (uint32_t i = 0; i < L; i++) {
             T.QHatModp[j][i] = P.QHatModp[j][i];
             T.QHatModp_s[j][i] = h_shoup(P.QHatModp[j][i], P.p[j]);
+            T.QHatModp_m[j][i] = h_mont_split(P.QHatModp[j][i], P.p[j]);
         }
     }
     for (uint32_t a = 0; a <= L; a++)

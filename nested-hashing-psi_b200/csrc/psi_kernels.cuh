@@ -36,6 +36,12 @@ struct DevTables {
     u64 qInvModp_s[PSI_MAX_LIMBS][PSI_MAX_LIMBS];
     u64 PHatModq_s[PSI_MAX_LIMBS][PSI_MAX_LIMBS];
     u64 tQS_s[PSI_MAX_LIMBS][PSI_MAX_LIMBS + 1];
+    // the same matrices in Montgomery form (times 2^64 mod the row's modulus), stored split-30: the fused
+    // kernels form each RNS sum as carry-free IMAD.WIDE partial sums + ONE Montgomery reduction
+    u64 QHatModp_m[PSI_MAX_LIMBS][PSI_MAX_LIMBS];
+    u64 qInvModp_m[PSI_MAX_LIMBS][PSI_MAX_LIMBS];
+    u64 PHatModq_m[PSI_MAX_LIMBS][PSI_MAX_LIMBS];
+    u64 tQS_m[PSI_MAX_LIMBS][PSI_MAX_LIMBS + 1];
     ModDev mods[kMaxMods];                    // 0..L-1: q, L..L+Lp-1: p, L+Lp: t
 };
 
