@@ -671,12 +671,10 @@ static cudaError_t launch_cols(const KCtx& k, uint32_t B, const u64* ha, const u
                                u64* rh, u64* dh, int which) {
     const uint32_t logR = k.logN - kLogCols, col_tiles = (1u << kLogCols) >> kColTileLog;
     const size_t smem = (size_t)(L + LP) * padded(1u << (logR + kColTileLog)) * sizeof(u64);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (which < 0) {  // per-device set-up (psi_ctx_create): opt in to > 48 KiB of dynamic shared memory
         cudaError_t e;
         if ((e = cudaFuncSetAttribute(k_cols_extend<L, LP, LOGN_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(k_cols_scale<L, LP, LOGN_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
-        attr_set = true;
+        return cudaFuncSetAttribute(k_cols_scale<L, LP, LOGN_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     }
     if (which == 0)
         k_cols_extend<L, LP, LOGN_CT><<<dim3(col_tiles, 4, B), kColGroups * kGroup, smem, k.s>>>(k.tab, k.logN, ha, hb, e1p, e2h);
@@ -700,26 +698,32 @@ static cudaError_t dispatch_cols(const KCtx& k, uint32_t B, const u64* ha, const
     return cudaErrorInvalidValue;
 }
 
+// Function attributes are per device: psi_ctx_create calls this once for the context's device.
+cudaError_t fused_mul_init_device(const KCtx& k) {
+    if (!fused_mul_supported(k)) return cudaSuccess;
+    return launch_fused_mul(k, 0xffffffffu, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                            nullptr, nullptr, nullptr, nullptr);
+}
+
 cudaError_t launch_fused_mul(const KCtx& k, uint32_t B, const u64* a, const u64* b, u64* ha, u64* hb, u64* e1p,
                              u64* e2h, u64* th, u64* rh, u64* dh, const u64* evk_b, const u64* evk_a, const u64* mask,
                              u64* out) {
-    if (B == 0) return cudaSuccess;
     const uint32_t L = k.L, LT = k.L + k.Lp;
     const uint32_t logR = k.logN - kLogCols;
     const uint32_t row_tiles = (1u << logR) >> kRowTileLog;
     const size_t row_arr = padded(1u << (kLogCols + kRowTileLog)) * sizeof(u64);
     const size_t tw_bytes = kRowTwWords * sizeof(u64);
     cudaError_t e;
-    static bool relin_attr = false;
-    if (!relin_attr) {
+    if (B == 0xffffffffu) {  // per-device set-up (fused_mul_init_device)
+        if ((e = dispatch_cols(k, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, -1)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(k_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(k_rows_tensor, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(k_rows_relin<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(k_rows_relin<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(k_rows_relin<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(k_rows_relin<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
-        relin_attr = true;
+        return cudaFuncSetAttribute(k_rows_relin<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
     }
+    if (B == 0) return cudaSuccess;
 
     k_rows_inv<<<dim3(row_tiles, L, B), 4 * kGroup, 4 * row_arr + tw_bytes, k.s>>>(k.tab, k.logN, a, b, ha, hb);
     if ((e = dispatch_cols(k, B, ha, hb, e1p, e2h, nullptr, nullptr, nullptr, 0)) != cudaSuccess) return e;

@@ -161,17 +161,15 @@ __global__ void __launch_bounds__(kNttThreads) k_ntt(const DevTables* __restrict
     }
 }
 
+cudaError_t ntt_init_device() {
+    cudaError_t e = cudaFuncSetAttribute(k_ntt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_ntt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
 cudaError_t launch_ntt(const KCtx& k, const NttBatch& b, bool inverse) {
     if (b.n_polys == 0) return cudaSuccess;
     const size_t smem = ((size_t)k.N + (k.N >> 5) + 1) * sizeof(u64);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_ntt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_ntt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
     const int threads = k.N >= 4096 ? kNttThreads : (k.N >= 1024 ? 128 : 32);
     if (inverse)
         k_ntt<true><<<b.n_polys, threads, smem, k.s>>>(k.tab, k.logN, b);

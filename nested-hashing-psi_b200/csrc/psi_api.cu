@@ -399,6 +399,12 @@ int psi_ctx_create(const psi_params* p, int device, psi_ctx** out) {
     while ((1u << c->logN) < N) c->logN++;
     int rc = ensure_device(c);
     if (rc == PSI_OK) rc = build_tables(c);
+    if (rc == PSI_OK) {
+        cudaError_t e2 = ntt_init_device();
+        if (e2 == cudaSuccess) e2 = mac_init_device();
+        if (e2 == cudaSuccess) e2 = fused_mul_init_device(c->k(0));
+        if (e2 != cudaSuccess) rc = cuda_fail(e2, "kernel attribute set-up");
+    }
     if (rc != PSI_OK) {
         psi_ctx_destroy(c);
         return rc;

@@ -165,17 +165,16 @@ __global__ void __launch_bounds__(kMacConsumers + 32, 2)
     }
 }
 
+cudaError_t mac_init_device() {
+    return cudaFuncSetAttribute(k_mac_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(kMacStages * kMacStageWords * sizeof(u64)));
+}
+
 cudaError_t launch_mac(const KCtx& k, uint32_t K, uint32_t b, uint32_t E, const u64* pt, const u64* idx,
                        const u64* minus, u64* acc) {
     const size_t LN = (size_t)k.L * k.N;
     dim3 grid(cdiv(LN, kMacCoeffs) * ((b + kMacBins - 1) / kMacBins), K);
     const size_t smem = kMacStages * kMacStageWords * sizeof(u64);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_mac_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
     k_mac_tma<<<grid, kMacConsumers + 32, smem, k.s>>>(k.tab, k.N, k.L, b, E, pt, idx, minus, acc);
     return cudaGetLastError();
 }

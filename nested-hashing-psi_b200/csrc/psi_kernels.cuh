@@ -84,6 +84,10 @@ cudaError_t launch_relin_accum(const KCtx& k, uint32_t B, const u64* res_eval, c
 // Fused EvalMult(ct,ct) + relinearise (+ mask), fused_mul.cu.  a, b: [B][2][L][N] EVALUATION; scratch:
 // ha, hb [B][2][L][N], e1p [B][2][Lp][N], e2h [B][2][LT][N], th [B][3][LT][N], rh [B][2][L][N], dh [B][L][L][N].
 bool fused_mul_supported(const KCtx& k);
+// per-device function attributes (dynamic shared memory above 48 KiB); called by psi_ctx_create
+cudaError_t fused_mul_init_device(const KCtx& k);
+cudaError_t ntt_init_device();
+cudaError_t mac_init_device();
 // dst[g][l][n] = src[g][l][n] * 2^64 mod q_l  (groups of L limb-polys): Montgomery form of constants
 cudaError_t launch_to_montgomery(const KCtx& k, uint32_t groups, const u64* src, u64* dst);
 cudaError_t launch_fused_mul(const KCtx& k, uint32_t B, const u64* a, const u64* b, u64* ha, u64* hb, u64* e1p,
