@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 3)
 // in Montgomery form (times R = 2^64), so each modular product is one 128-bit multiply-accumulate plus a
 // Montgomery reduction that leaves no stray factor:  REDC(sum_i d_i * evkR_i) = sum_i d_i * evk_i.
 template <int L>
-__global__ void __launch_bounds__((2 + L) * kGroup, 2)
+__global__ void __launch_bounds__((2 + L) * kGroup, L <= 4 ? 2 : 1)
     k_rows_relin(const DevTables* __restrict__ tab, uint32_t logN, const u64* __restrict__ rh, const u64* __restrict__ dh,
                  const u64* __restrict__ evk_bR, const u64* __restrict__ evk_aR, const u64* __restrict__ maskR,
                  u64* __restrict__ out) {
@@ -660,10 +660,12 @@ cudaError_t launch_to_montgomery(const KCtx& k, uint32_t groups, const u64* src,
 }
 
 // ---- launcher --------------------------------------------------------------------------------------
-// The column kernels are instantiated for the limb counts BFVrns produces for this path (sizeQ 1..4,
-// sizeP = sizeQ or sizeQ + 1); anything else takes the unfused kernels.
+// The column kernels are instantiated for the limb counts BFVrns produces for this path: sizeQ 1..7 (depth 3
+// gives 4, depth 5 — E >= 500, BatchedFHEPSIClient.cpp:50-53 — gives 6 at N = 16384), sizeP = sizeQ or
+// sizeQ + 1; anything else takes the unfused kernels.  Bounds that hold up to 7 limbs: 8-term split-30 sums
+// (16 products < 2^60 per partial sum), L * (2q + 2^32) < 2^64 for the key-switch Montgomery reduction.
 bool fused_mul_supported(const KCtx& k) {
-    return k.logN >= kLogCols + kRowTileLog && k.L >= 1 && k.L <= 4 && (k.Lp == k.L || k.Lp == k.L + 1) && k.L + k.Lp <= 8;
+    return k.logN >= kLogCols + kRowTileLog && k.L >= 1 && k.L <= 7 && (k.Lp == k.L || (k.Lp == k.L + 1 && k.L <= 6));
 }
 
 template <int L, int LP, int LOGN_CT>
@@ -673,8 +675,8 @@ static cudaError_t launch_cols(const KCtx& k, uint32_t B, const u64* ha, const u
     const size_t smem = (size_t)(L + LP) * padded(1u << (logR + kColTileLog)) * sizeof(u64);
     if (which < 0) {  // per-device set-up (psi_ctx_create): opt in to > 48 KiB of dynamic shared memory
         cudaError_t e;
-        if ((e = cudaFuncSetAttribute(k_cols_extend<L, LP, LOGN_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
-        return cudaFuncSetAttribute(k_cols_scale<L, LP, LOGN_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if ((e = cudaFuncSetAttribute(k_cols_extend<L, LP, LOGN_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
+        return cudaFuncSetAttribute(k_cols_scale<L, LP, LOGN_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     }
     if (which == 0)
         k_cols_extend<L, LP, LOGN_CT><<<dim3(col_tiles, 4, B), kColGroups * kGroup, smem, k.s>>>(k.tab, k.logN, ha, hb, e1p, e2h);
@@ -695,6 +697,15 @@ static cudaError_t dispatch_cols(const KCtx& k, uint32_t B, const u64* ha, const
     PSI_COLS_CASE(1, 1) PSI_COLS_CASE(1, 2) PSI_COLS_CASE(2, 2) PSI_COLS_CASE(2, 3)
     PSI_COLS_CASE(3, 3) PSI_COLS_CASE(3, 4) PSI_COLS_CASE(4, 4)
 #undef PSI_COLS_CASE
+    // deeper contexts: compiled plan for N = 16384 only
+#define PSI_COLS_CASE_BIG(l, lp)                                                                           \
+    if (k.L == l && k.Lp == lp) {                                                                          \
+        if (k.logN == 14) return launch_cols<l, lp, 14>(k, B, ha, hb, e1p, e2h, th, rh, dh, which);       \
+        return launch_cols<l, lp, 0>(k, B, ha, hb, e1p, e2h, th, rh, dh, which);                           \
+    }
+    PSI_COLS_CASE_BIG(4, 5) PSI_COLS_CASE_BIG(5, 5) PSI_COLS_CASE_BIG(5, 6) PSI_COLS_CASE_BIG(6, 6)
+    PSI_COLS_CASE_BIG(6, 7) PSI_COLS_CASE_BIG(7, 7)
+#undef PSI_COLS_CASE_BIG
     return cudaErrorInvalidValue;
 }
 
@@ -721,7 +732,10 @@ cudaError_t launch_fused_mul(const KCtx& k, uint32_t B, const u64* a, const u64*
         if ((e = cudaFuncSetAttribute(k_rows_relin<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(k_rows_relin<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(k_rows_relin<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
-        return cudaFuncSetAttribute(k_rows_relin<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+        if ((e = cudaFuncSetAttribute(k_rows_relin<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_rows_relin<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_rows_relin<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
+        return cudaFuncSetAttribute(k_rows_relin<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     }
     if (B == 0) return cudaSuccess;
 
@@ -735,7 +749,10 @@ cudaError_t launch_fused_mul(const KCtx& k, uint32_t B, const u64* a, const u64*
         case 1: k_rows_relin<1><<<rg, 3 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
         case 2: k_rows_relin<2><<<rg, 4 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
         case 3: k_rows_relin<3><<<rg, 5 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
-        default: k_rows_relin<4><<<rg, 6 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
+        case 4: k_rows_relin<4><<<rg, 6 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
+        case 5: k_rows_relin<5><<<rg, 7 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
+        case 6: k_rows_relin<6><<<rg, 8 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
+        default: k_rows_relin<7><<<rg, 9 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
     }
     return cudaGetLastError();
 }

@@ -48,7 +48,7 @@ def test_ntt_every_modulus(N, L):
     assert np.array_equal(cc.debug_ntt(fwd, mods, inverse=True), polys)
 
 
-@pytest.mark.parametrize("N,L", [(16384, 4), (8192, 3), (1024, 2), (256, 1)])
+@pytest.mark.parametrize("N,L", [(16384, 4), (8192, 3), (1024, 2), (256, 1), (16384, 6), (2048, 5), (1024, 7), (4096, 8)])
 def test_mul_ctct_relin(N, L):
     """EvalMult(ct,ct) + relinearisation, random (worst-case: uniformly distributed) operands."""
     cc, o, params = ctx_and_oracle(N, L)
@@ -96,6 +96,8 @@ CASES = [
     (2048, 3, 2, 9, 2),
     (512, 2, 2, 2, 300),    # E > 128: the lazy 128-bit accumulator is folded mid-way
     (8192, 3, 2, 4, 5),
+    (16384, 6, 2, 2, 3),    # depth-5 context (E >= 500 in the client's rule): sizeQ = sizeP = 6
+    (2048, 5, 3, 2, 2),
 ]
 
 
