@@ -258,3 +258,15 @@ def test_pipelined_queries_double_buffered_results():
     cc.sync()
     for i in range(3):
         assert np.array_equal(outs[i], want[i]), "query %d" % i
+
+
+def test_cpp_known_answer_program():
+    """tests/cpp/TestBatchedFHEPIE.cpp: the reference's own test program re-targeted at the C++ drop-in class;
+    success criterion of the reference: the string "Matches" printed exactly twice (TestBatchedFHEPIE.cpp:73)."""
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp")
+    subprocess.check_call(["make", "-C", here, "-s"])
+    out = subprocess.run([os.path.join(here, "TestBatchedFHEPIE")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("Matches\n") == 2
+    assert "Test should output matches twice" in out.stdout
