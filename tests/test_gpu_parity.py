@@ -270,3 +270,29 @@ def test_cpp_known_answer_program():
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("Matches\n") == 2
     assert "Test should output matches twice" in out.stdout
+
+
+def test_run_randomised_shapes():
+    """Seeded sweep over ragged shapes and limb counts: every draw is a full run() compared limb for limb."""
+    rng = np.random.default_rng(20261018)
+    for trial in range(10):
+        N = int(rng.choice([256, 512, 1024, 2048, 4096]))
+        L = int(rng.integers(1, 6))
+        K = int(rng.choice([1, 2, 2, 2, 3]))
+        b = int(rng.integers(1, 12))
+        E = int(rng.integers(1, 20))
+        cc, o, params = ctx_and_oracle(N, L)
+        sk, evk_b, evk_a = o.keygen(100 + trial)
+        cc.InsertEvalMultKey(evk_b, evk_a)
+        pt = sc.random_pt(rng, params, (K, b, E))
+        mask = sc.random_pt(rng, params, (b,))
+        idx = sc.random_ct(rng, params, (K, E))
+        minus = sc.random_ct(rng, params)
+        cc.db_load_limbs(pt, mask)
+        got_pt, got_mask = cc.db_get_limbs()               # tile-major split-30 storage round trip
+        assert np.array_equal(got_pt, pt) and np.array_equal(got_mask, mask)
+        cc.query_set(idx, minus)
+        cc.run()
+        want = o.run(pt, mask, idx, minus, evk_b, evk_a, nthreads=8)
+        assert np.array_equal(cc.result_get(), want), (trial, N, L, K, b, E)
+        cc.close()
