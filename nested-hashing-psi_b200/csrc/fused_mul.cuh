@@ -275,14 +275,20 @@ __device__ __forceinline__ u64 acc3_reduce(const Acc3& a, u64 q, u64 qinv) {
     return r >= q ? r - q : r;
 }
 
+// streamed-once tile data must not evict the twiddles from L1
+__device__ __forceinline__ ulonglong2 ld_tile16(const u64* p) {
+    ulonglong2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+    return v;
+}
+
 // ---- tile movers (16-byte global accesses) ------------------------------------------------------
 // row tile: 2^(7+kRowTileLog) contiguous coefficients
 __device__ __forceinline__ void load_rows(u64* sm, const u64* __restrict__ poly_tile, uint32_t tid) {
     const uint32_t M2 = 1u << (kLogCols + kRowTileLog - 1);
-    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(poly_tile);
 #pragma unroll 4
     for (uint32_t j = tid; j < M2; j += kGroup) {
-        const ulonglong2 v = src[j];
+        const ulonglong2 v = ld_tile16(poly_tile + 2 * j);
         sm[sl(2 * j)] = v.x;
         sm[sl(2 * j) + 1] = v.y;
     }
@@ -299,8 +305,7 @@ __device__ __forceinline__ void load_cols(u64* sm, const u64* __restrict__ poly,
 #pragma unroll 4
     for (uint32_t j = tid; j < M2; j += kGroup) {
         const uint32_t e = 2 * j;
-        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(
-            poly + ((e >> kColTileLog) << kLogCols) + c0 + (e & ((1u << kColTileLog) - 1)));
+        const ulonglong2 v = ld_tile16(poly + ((e >> kColTileLog) << kLogCols) + c0 + (e & ((1u << kColTileLog) - 1)));
         sm[sl(e)] = v.x;
         sm[sl(e) + 1] = v.y;
     }
