@@ -63,6 +63,8 @@ def parse():
                     help="N > 1 response gather inside e2e: 'host' = every rank copies its own result ciphertexts to "
                          "pinned host memory over its own PCIe link (what a one-process server does with one pinned "
                          "buffer); 'nccl' = NCCL gather to rank 0 over NVLink, then one D2H on rank 0")
+    ap.add_argument("--host-build", action="store_true",
+                    help="build the nested cuckoo table on the host (OpenMP) instead of on the GPU")
     ap.add_argument("--synthetic-db", action="store_true",
                     help="random slot values instead of hashing a real server set (same shapes, same timing)")
     return ap.parse_args()
@@ -223,9 +225,16 @@ def main():
         seed = 123456789 + (rank if args.scaling == "weak" else 0)      # itemSeed (CLI.cpp:67)
         data = P.RandomDataInput(w["S"], w["C"], w["I"], seed, w["bits"])
         hashf = P.TabulationHashing(987654321, w["k"] + K)               # hashSeed (CLI.cpp:68)
-        hct = P.HierarchicalCuckooHashTable(hashf, w["e"], E, 0, w["k"], K, True, True, w["b"])
-        hct.insertAll(data.serverSet)
-        if args.scaling == "weak" or world == 1:
+        if not args.host_build and (args.scaling == "weak" or world == 1):
+            # offline phase on the device: table build, shuffle, transposition, encode
+            P.BatchedFHEHIPPIE.fromServerSet(cc, P.PublicKey(), hashf, w["e"], E, w["k"], K, w["b"], data.serverSet)
+            hct = None
+        else:
+            hct = P.HierarchicalCuckooHashTable(hashf, w["e"], E, 0, w["k"], K, True, True, w["b"])
+            hct.insertAll(data.serverSet)
+        if hct is None:
+            pass
+        elif args.scaling == "weak" or world == 1:
             pie = P.BatchedFHEHIPPIE(cc, P.PublicKey(), hct)             # shuffles, transposes, encodes on the GPU
             del pie
         else:

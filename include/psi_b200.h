@@ -208,6 +208,18 @@ int psi_hct_insert_all(psi_hct* h, const uint64_t* items, size_t n);
 int psi_hct_get_cells(psi_hct* h, uint64_t* cells);
 int psi_hct_destroy(psi_hct* h);
 
+/* The same table built ON THE DEVICE of ctx (one warp per inner cuckoo table; SURVEY 8f "next" #3):
+ * bit-identical cells to psi_hct_create + psi_hct_insert_all with the same seeds (multi-tables, no stash). */
+int psi_hct_build_device(psi_ctx* ctx, uint64_t hash_seed, uint32_t k, uint64_t e, uint32_t K, uint64_t E, uint64_t b,
+                         uint64_t eviction_seed, const uint64_t* items, size_t n, uint64_t* cells);
+/* Whole constructor data path on the device: table build, bin shuffle, transposition, MakePackedPlaintext +
+ * SetFormat(EVALUATION) (BatchedFHEHIPPIE.cpp:25-82, HierarchicalCuckooHashTable.cpp:55-73); the table never
+ * visits the host.  Leaves ctx with the same database psi_pie_create produces from a host-built table with
+ * the same seeds. */
+int psi_db_build_from_items(psi_ctx* ctx, uint64_t hash_seed, uint32_t k, uint64_t e, uint32_t K, uint64_t E, uint64_t b,
+                            uint64_t eviction_seed, const uint64_t* items, size_t n, uint64_t shuffle_seed,
+                            uint64_t mask_seed);
+
 /* calculateHashIndex (HashUtils.cpp:34-37) for n items with TabulationHashing(hash_seed, n_hash_functions). */
 int psi_hash_index(uint64_t hash_seed, uint32_t n_hash_functions, const uint64_t* items, size_t n, uint32_t hf,
                    uint32_t table_size, uint64_t* out);

@@ -83,6 +83,8 @@ SYMBOLS = {
     "psi_hct_insert_all": (_int, [_vp, _u64p, _sz]),
     "psi_hct_get_cells": (_int, [_vp, _u64p]),
     "psi_hct_destroy": (_int, [_vp]),
+    "psi_hct_build_device": (_int, [_vp, _u64, _u32, _u64, _u32, _u64, _u64, _u64, _u64p, _sz, _u64p]),
+    "psi_db_build_from_items": (_int, [_vp, _u64, _u32, _u64, _u32, _u64, _u64, _u64, _u64p, _sz, _u64, _u64]),
     "psi_hash_index": (_int, [_u64, _u32, _u64p, _sz, _u32, _u32, _u64p]),
     "psi_client_table": (_int, [_u64, _u32, _u64, _u32, _u64p, _sz, _u64, _u64p]),
     "psi_random_data_input": (_int, [_sz, _sz, _sz, _u64, _u64, _u64p, _u64p, _u64p]),

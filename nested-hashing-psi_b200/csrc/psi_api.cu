@@ -17,6 +17,7 @@
 
 #include "psi_b200.h"
 #include "psi_kernels.cuh"
+#include "../host/hashing.hpp"
 #include "../host/psi_host_internal.hpp"
 
 namespace psi {
@@ -546,6 +547,104 @@ int psi_db_encode_slots(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E, uint32_t
     if ((rc = encode_into(c, (size_t)K * b * E, nslots, slots, c->pt.p, E))) return rc;
     if ((rc = encode_into(c, b, nslots, mask_slots, c->mask.p, 0))) return rc;
     CK(launch_to_montgomery(c->k(0), b, c->mask.p, c->maskR.p));
+    CK(cudaStreamSynchronize(0));
+    c->have_db = true;
+    return PSI_OK;
+}
+
+// Device-resident constructor path: hash the server set, build the nested cuckoo tables, apply the bin
+// shuffle, transpose and encode without the table ever visiting the host.
+static int hct_on_device(psi_ctx* c, uint64_t hash_seed, uint32_t k, uint32_t e, uint32_t K, uint32_t E, uint32_t b,
+                         uint64_t eviction_seed, const uint64_t* items, size_t n, DevBuf<u64>& d_cells) {
+    if (k < 1 || e < 1 || K < 2 || E < 1 || b < 1) return set_error(PSI_ERR_INVALID, "table sizes must be positive, K >= 2");
+    if (n > 0x7fffffffull) return set_error(PSI_ERR_INVALID, "server set too large for one device build");
+    TabulationHashing hashf(hash_seed, k + K);
+    DevBuf<u64> d_T, d_items;
+    const std::vector<uint64_t>& T = hashf.tables();
+    CK(d_T.alloc(T.size()));
+    CK(d_items.alloc(n ? n : 1));
+    CK(d_cells.alloc((size_t)k * e * K * b * E));
+    CK(cudaMemcpy(d_T.p, T.data(), T.size() * sizeof(u64), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_items.p, items, n * sizeof(u64), cudaMemcpyHostToDevice));
+    int failed = 0;
+    cudaError_t err = hct_build_device(0, d_T.p, k, e, K, b, E, eviction_seed, d_items.p, n, d_cells.p, &failed);
+    d_T.release();
+    d_items.release();
+    if (err != cudaSuccess) return cuda_fail(err, "device table build");
+    if (failed) return set_error(PSI_ERR_STATE, "(Blocked) Cuckoo hashing error");  // CuckooHashTable.cpp:113
+    return PSI_OK;
+}
+
+int psi_hct_build_device(psi_ctx* c, uint64_t hash_seed, uint32_t k, uint64_t e, uint32_t K, uint64_t E, uint64_t b,
+                         uint64_t eviction_seed, const uint64_t* items, size_t n, uint64_t* cells) {
+    if (!c || (!items && n) || !cells) return set_error(PSI_ERR_INVALID, "null argument");
+    int rc = ensure_device(c);
+    if (rc) return rc;
+    DevBuf<u64> d_cells;
+    rc = hct_on_device(c, hash_seed, k, (uint32_t)e, K, (uint32_t)E, (uint32_t)b, eviction_seed, items, n, d_cells);
+    if (rc == PSI_OK) {
+        cudaError_t err = cudaMemcpy(cells, d_cells.p, (size_t)k * e * K * b * E * sizeof(u64), cudaMemcpyDeviceToHost);
+        if (err != cudaSuccess) rc = cuda_fail(err, "psi_hct_build_device");
+    }
+    d_cells.release();
+    return rc;
+}
+
+int psi_db_build_from_items(psi_ctx* c, uint64_t hash_seed, uint32_t k, uint64_t e, uint32_t K, uint64_t E, uint64_t b,
+                            uint64_t eviction_seed, const uint64_t* items, size_t n, uint64_t shuffle_seed,
+                            uint64_t mask_seed) {
+    if (!c || (!items && n)) return set_error(PSI_ERR_INVALID, "null argument");
+    const size_t nslots = (size_t)k * e;
+    if (nslots > c->N) return set_error(PSI_ERR_INVALID, "batch size exceeds the ring dimension");
+    if (b > 65535) return set_error(PSI_ERR_INVALID, "bin size too large");
+    const uint64_t t = c->P.t;
+    for (size_t i = 0; i < n; i++)
+        if (items[i] >= t) return set_error(PSI_ERR_INVALID, "slot value out of range of the plaintext modulus");
+    int rc = ensure_device(c);
+    if (rc) return rc;
+    DevBuf<u64> d_cells;
+    if ((rc = hct_on_device(c, hash_seed, k, (uint32_t)e, K, (uint32_t)E, (uint32_t)b, eviction_seed, items, n, d_cells))) {
+        d_cells.release();
+        return rc;
+    }
+    // bin shuffle (BatchedFHEHIPPIE.cpp:25-35) as permutations, masks (:73-82): same generators as the host ctor
+    std::mt19937 mt((uint32_t)shuffle_seed);
+    const std::vector<uint16_t> perm = makeBinShuffle(k, e, K, b, mt);
+    std::vector<int64_t> mask_slots((size_t)b * nslots);
+    std::mt19937_64 mm(mask_seed);
+    for (auto& v : mask_slots) v = (int64_t)(mm() % (t - 1) + 1);
+    DevBuf<uint16_t> d_perm;
+    DevBuf<u64> d_crt;
+    cudaError_t err = d_perm.alloc(perm.size());
+    if (err == cudaSuccess) err = cudaMemcpy(d_perm.p, perm.data(), perm.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
+    if (err == cudaSuccess && (rc = db_dims(c, K, (uint32_t)b, (uint32_t)E)) == PSI_OK) {
+        const size_t N = c->N, L = c->L, n_pt = (size_t)K * b * E, chunk = n_pt < kDbChunk ? n_pt : kDbChunk;
+        const KCtx kc = c->k(0);
+        err = d_crt.alloc(chunk * N);
+        if (err == cudaSuccess) err = c->stage.alloc(chunk * L * N);
+        for (size_t p0 = 0; p0 < n_pt && err == cudaSuccess; p0 += chunk) {
+            const uint32_t np = (uint32_t)((n_pt - p0) < chunk ? (n_pt - p0) : chunk);
+            err = launch_cells_to_crt(kc, np, (uint32_t)p0, (uint32_t)nslots, K, (uint32_t)b, (uint32_t)E, d_cells.p, d_perm.p,
+                                      c->to_crt.p, d_crt.p);
+            if (err == cudaSuccess) {
+                NttBatch nb{d_crt.p, d_crt.p, np, 1, N, 0, N, c->L + c->Lp, 1};
+                err = launch_ntt(kc, nb, true);
+            }
+            if (err == cudaSuccess) {
+                NttBatch nb{d_crt.p, c->stage.p, np * (uint32_t)L, (uint32_t)L, N, 0, L * N, 0, (uint32_t)L};
+                err = launch_ntt(kc, nb, false);
+            }
+            if (err == cudaSuccess) err = launch_retile_pt(0, c->stage.p, c->pt.p, L * N, (uint32_t)E, p0, np, true);
+            if (err == cudaSuccess) err = cudaStreamSynchronize(0);
+        }
+    }
+    d_cells.release();
+    d_perm.release();
+    d_crt.release();
+    if (rc) return rc;
+    if (err != cudaSuccess) return cuda_fail(err, "psi_db_build_from_items");
+    if ((rc = encode_into(c, b, (uint32_t)nslots, mask_slots.data(), c->mask.p, 0))) return rc;
+    CK(launch_to_montgomery(c->k(0), (uint32_t)b, c->mask.p, c->maskR.p));
     CK(cudaStreamSynchronize(0));
     c->have_db = true;
     return PSI_OK;

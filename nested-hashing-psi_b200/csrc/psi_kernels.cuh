@@ -99,6 +99,12 @@ cudaError_t launch_mul_ctpt(const KCtx& k, uint32_t B, const u64* ct, const u64*
 cudaError_t launch_slots_to_crt(const KCtx& k, uint32_t n_pt, uint32_t nslots, const long long* slots,
                                 const uint32_t* to_crt, u64* out);
 
+// Device-side nested cuckoo table build and constructor transposition (hashing_dev.cu)
+cudaError_t hct_build_device(cudaStream_t s, const u64* T, uint32_t k, uint32_t e, uint32_t K, uint32_t b, uint32_t E,
+                             u64 eviction_seed, const u64* items, size_t n, u64* cells, int* failed);
+cudaError_t launch_cells_to_crt(const KCtx& k, uint32_t n_pt, uint32_t p0, uint32_t nslots, uint32_t K, uint32_t b, uint32_t E,
+                                const u64* cells, const uint16_t* perm, const uint32_t* to_crt, u64* out);
+
 cudaError_t pipe_peak(int device, int kind, double* per_second);
 
 }  // namespace psi

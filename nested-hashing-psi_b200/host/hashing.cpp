@@ -104,6 +104,20 @@ void CuckooHashTable::shuffleBins(std::mt19937& rng) {
     }
 }
 
+std::vector<uint16_t> makeBinShuffle(size_t nSimpleTables, uint64_t simpleSize, unsigned nCuckooHf, uint64_t binSize,
+                                     std::mt19937& rng) {
+    std::vector<uint16_t> out;
+    out.reserve(nSimpleTables * simpleSize * nCuckooHf * binSize);
+    std::vector<uint32_t> perm(binSize);
+    for (size_t t = 0; t < nSimpleTables * simpleSize; t++)
+        for (unsigned hf = 0; hf < nCuckooHf; hf++) {
+            std::iota(perm.begin(), perm.end(), 0u);
+            std::shuffle(perm.begin(), perm.end(), rng);  // same call, same order as CuckooHashTable::shuffleBins
+            for (uint32_t v : perm) out.push_back((uint16_t)v);
+        }
+    return out;
+}
+
 HierarchicalCuckooHashTable::HierarchicalCuckooHashTable(const TabulationHashing& hashfunction,
                                                          uint64_t eachSimpleTableSize, uint64_t eachCuckooTableSize,
                                                          uint64_t serverStashSize, unsigned numberOfSimpleHashFunctions,

@@ -38,6 +38,7 @@ class TabulationHashing {
     explicit TabulationHashing(uint64_t seed = 342797434736ull, size_t numberOfHashfunctions = 3);
     uint64_t hashWithIndicator(item_t input, unsigned hfInd) const;
     size_t numberOfHashFunctions() const { return nHashfunctions; }
+    const std::vector<uint64_t>& tables() const { return tTable; }  // [hf][chunk][256], for the device build
 
    private:
     size_t nHashfunctions;
@@ -117,6 +118,12 @@ class HierarchicalCuckooHashTable {
     bool simpleMulti, cuckooMulti;
     uint64_t binSize;
 };
+
+// The bin shuffle of the PIE constructor (BatchedFHEHIPPIE.cpp:28-35) as explicit permutations, in the order
+// shuffleBins() consumes the generator: [outerHf][outerPos][innerHf][bin] -> source bin.  The device-side
+// constructor path applies them while transposing.
+std::vector<uint16_t> makeBinShuffle(size_t nSimpleTables, uint64_t simpleSize, unsigned nCuckooHf, uint64_t binSize,
+                                     std::mt19937& mt);
 
 // Synthetic sets with a planted intersection (RandomDataInput): the first I draws of the server
 // stream are the intersection; the client puts them in its last I positions.

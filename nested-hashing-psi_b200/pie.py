@@ -101,6 +101,32 @@ class CryptoContext:
                                      mask.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
         return pt, mask
 
+    def hct_build_device(self, hashfunction, k, e, K, E, b, items, evictionSeed=0x5EED):
+        """Nested cuckoo table built on this context's GPU; cells [k][e][K][b][E], identical to the host build."""
+        (items, pi) = _u64(items)
+        cells = np.empty((k, e, K, b, E), dtype=np.uint64)
+        try:
+            check(lib().psi_hct_build_device(self._h, hashfunction.seed, k, e, K, E, b, evictionSeed, pi, items.shape[0],
+                                             cells.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
+        except PsiError as err:
+            if err.status == capi.PSI_ERR_STATE:
+                raise RuntimeError(err.message) from None
+            _raise_like_reference(err)
+        return cells
+
+    def db_build_from_items(self, hashfunction, k, e, K, E, b, items, evictionSeed=0x5EED, shuffleSeed=0x5EED0001,
+                            maskSeed=0x5EED0002):
+        """The PIE constructor's whole data path on the device (table build, shuffle, transposition, encode)."""
+        (items, pi) = _u64(items)
+        try:
+            check(lib().psi_db_build_from_items(self._h, hashfunction.seed, k, e, K, E, b, evictionSeed, pi, items.shape[0],
+                                                shuffleSeed, maskSeed))
+        except PsiError as err:
+            if err.status == capi.PSI_ERR_STATE:
+                raise RuntimeError(err.message) from None
+            _raise_like_reference(err)
+        self._dims = (K, b, E)
+
     def query_set(self, idx, minus, stream=None):
         (idx, pi), (minus, pm) = _u64(idx), _u64(minus)
         K, b, E = self._dims
@@ -315,6 +341,23 @@ class BatchedFHEHIPPIE:
         self._uploaded = False
         self._resultList = None
 
+    @classmethod
+    def fromServerSet(cls, cryptoContext, pK, hashfunction, eachSimpleTableSize, eachCuckooTableSize,
+                      numberOfSimpleHashFunctions, numberOfCuckooHashFunctions, maxItemsPerPosition, serverSet,
+                      evictionSeed=0x5EED, shuffleSeed=0x5EED0001, maskSeed=0x5EED0002):
+        """Offline phase entirely on the device: HierarchicalCuckooHashTable::insertAll + the PIE constructor
+        (table build, bin shuffle, transposition, MakePackedPlaintext, SetFormat) without the table ever visiting
+        the host.  Same database as BatchedFHEHIPPIE(ctx, pk, host-built table) with the same seeds."""
+        self = cls.__new__(cls)
+        self.cryptoContext, self.pK, self._h = cryptoContext, pK, None
+        k, e, K, E, b = (numberOfSimpleHashFunctions, eachSimpleTableSize, numberOfCuckooHashFunctions,
+                         eachCuckooTableSize, maxItemsPerPosition)
+        cryptoContext.db_build_from_items(hashfunction, k, e, K, E, b, serverSet, evictionSeed, shuffleSeed, maskSeed)
+        self.K, self.b, self.E, self.batchSize = K, b, E, k * e
+        self.indexMatrix = self.minusCompareElement = self._resultList = None
+        self._uploaded = False
+        return self
+
     def setIndex(self, indexMatrix):
         """indexMatrix: K x E ciphertexts (nested lists of [2][L][N] arrays, or one [K][E][2][L][N] array)."""
         self.indexMatrix = indexMatrix
@@ -337,21 +380,31 @@ class BatchedFHEHIPPIE:
         if minus.shape != (2, cc.L, cc.N):
             raise ValueError("minusCompareElement must be one ciphertext of [2][L][N] limbs")
         try:
-            check(lib().psi_pie_set_query(self._h, pi, pm))
+            if self._h is None:       # device-built database: the raw C-ABI calls
+                cc.query_set(idx, minus)
+                cc.sync()
+            else:
+                check(lib().psi_pie_set_query(self._h, pi, pm))
         except PsiError as e:
             _raise_like_reference(e)
         self._uploaded = True
 
     def run(self):
         self._upload()
-        check(lib().psi_pie_run(self._h))
+        if self._h is None:
+            self.cryptoContext.run()
+        else:
+            check(lib().psi_pie_run(self._h))
         self._resultList = None
 
     def getResultList(self):
         if self._resultList is None:
             cc = self.cryptoContext
             out = np.empty((self.b, 2, cc.L, cc.N), dtype=np.uint64)
-            check(lib().psi_pie_get_result_list(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
+            if self._h is None:
+                cc.result_get(out)
+            else:
+                check(lib().psi_pie_get_result_list(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
             self._resultList = out
         return self._resultList
 
