@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_tensor(const DevTables* 
     const uint32_t first = l < L ? 2 : 0;
     transform_rows<false>(tab, arr + first * P, P, 4 - first, [l](uint32_t) { return l; }, g >= first ? g - first : 4,
                           4 - first, logN, tile_base, tid, tws_f);
+    __syncthreads();  // the tensor product reads all four arrays
 
     // Tensor product with ONE Montgomery reduction per output: the factor R^-1 it leaves is undone for
     // free by k_cols_scale, whose N^-1 constant is N^-1 * R.  Operands are brought below 2q + 2^32 first
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__((2 + L) * kGroup, L <= 4 ? 2 : 1)
     __syncthreads();
     mbar_wait(&tw_bar, 0);
     transform_rows<false>(tab, arr, P, 2 + L, [kk](uint32_t) { return kk; }, g, 2 + L, logN, tile_base, tid, tws);
+    __syncthreads();  // the key-switch inner product reads all 2 + L arrays
 
     const size_t LN = (size_t)L * N;
     const u64 q = md.q, q2 = 2 * q, qinv = md.qinv;

@@ -39,6 +39,14 @@ constexpr uint32_t kColGroups = 4;   // groups per CTA in the column kernels (ar
 __device__ __forceinline__ uint32_t sl(uint32_t i) { return i + (i >> 4); }
 __host__ __device__ constexpr uint32_t padded(uint32_t n) { return n + (n >> 4) + 1; }
 
+// The arrays of a transform are dealt to 64-thread groups and a group only ever touches its own arrays, so
+// the barrier between two register passes is a NAMED barrier over the group's two warps (ids 1..15; id 0 is
+// __syncthreads), not a CTA-wide one: groups drift freely and idle groups do not wait at all.  Callers
+// place a CTA-wide barrier where the next phase reads across arrays.
+__device__ __forceinline__ void group_sync() {
+    asm volatile("bar.sync %0, %1;" ::"r"(1u + threadIdx.x / kGroup), "r"(kGroup) : "memory");
+}
+
 // ---- lazy butterflies ------------------------------------------------------------------------
 // forward (Cooley-Tukey): inputs < 4q + 2^32, outputs < 4q + 2^32
 __device__ __forceinline__ void ct_bf(u64& x, u64& y, const ulonglong2 tw, u64 q2, u64 nq) {
@@ -152,7 +160,7 @@ __device__ __forceinline__ void transform(const DevTables* __restrict__ tab, u64
         }
         s = INV ? s - w : s + w;
         rem -= w;
-        __syncthreads();
+        if (g < n_arr) group_sync();
     }
 }
 
@@ -197,7 +205,7 @@ struct TransformCT {
             radix_pass_ct<M, S0, W, INV, TWS>(smem + a * stride, TWS ? tws : (INV ? md.itw : md.ftw), delta, tile_base, md.q,
                                               tid);
         }
-        __syncthreads();
+        if (g < n_arr) group_sync();
         TransformCT<INV, M, INV ? LO : LO + W, INV ? HI - W : HI, TWS>::run(tab, smem, stride, n_arr, mod_of, g, ng, delta,
                                                                            tile_base, tid, tws);
     }
@@ -344,6 +352,7 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 3)
     for (uint32_t a = g; a < L; a += kColGroups) load_cols(smem + a * P, src + (size_t)a * N, logR, c0, tid);
     __syncthreads();
     transform_cols<true, LOGN_CT>(tab, smem, P, L, [](uint32_t a) { return a; }, g, kColGroups, logN, tid);
+    __syncthreads();  // the extension reads every limb of a coefficient
 
     // coefficient-wise extension; N^-1 of the inverse transform is folded into the first constant
     for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) {
@@ -440,6 +449,7 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 3)
         load_cols(smem + a * P, th + ((bin * 3 + comp) * LT + a) * (size_t)N, logR, c0, tid);
     __syncthreads();
     transform_cols<true, LOGN_CT>(tab, smem, P, LT, [](uint32_t a) { return a; }, g, kColGroups, logN, tid);
+    __syncthreads();  // scale-and-round reads every limb of a coefficient
 
     // DCRTPoly::ScaleAndRound (t/P, output basis Q) on canonical coefficients
     for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) {
@@ -496,11 +506,12 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 3)
                 dst[sl(j)] = r;
             }
         }
-        __syncthreads();
+        // the lift, the transform and the store of digit limb kk all belong to group kk % kColGroups
+        group_sync();
         transform_cols<false, LOGN_CT>(tab, smem + L * P, P, L, [](uint32_t a) { return a; }, g, kColGroups, logN, tid);
         for (uint32_t kk = g; kk < L; kk += kColGroups)
             store_cols(smem + (L + kk) * P, dh + ((bin * L + i) * L + kk) * (size_t)N, logR, c0, tid);
-        __syncthreads();
+        group_sync();
     }
 }
 
