@@ -389,10 +389,18 @@ def main():
         peak_hbm, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         peak_hbm, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    # ncu-measured DRAM traffic of the dominant kernel for exactly this workload (one launch), if profiled
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json"))).get(args.workload)
+        if tr and b_local == w["b"]:
+            traffic = tr["dram_bytes_per_launch"].get("k_mac_tma")
+    except Exception:
+        traffic = None
     bytes1 = phase1_bytes(L, N, K, b_local, E)
     ach = bytes1 / (ms_p1 * 1e-3) / 1e9
     roofline = {"kernel": "k_mac_tma (inner product, phase 1)", "bound": "hbm", "achieved": ach, "peak": peak_hbm,
-                "unit": "GB/s", "frac": ach / peak_hbm, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": ach / peak_hbm, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes1, "launch_ms": ms_p1}
     # phase 2 against the integer pipe: butterflies of the 88-NTT HPSPOVERQ + BV pipeline per second vs the
     # measured register-resident butterfly rate of this GPU (psi_bench_pipe_peak, same process, same clocks)
