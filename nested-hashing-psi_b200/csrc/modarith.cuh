@@ -72,11 +72,7 @@ __device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q) { return a >= b ? a -
 // ---- hand-scheduled variants for the NTT inner loop -------------------------------------------
 // The integer pipe (IMAD on the fma pipe, 64 lanes/clk/SM measured) is the NTT's roofline, so the
 // butterfly is written to spend exactly 10 multiply issues and as few ALU issues as possible.
-__device__ __forceinline__ u64 madw32(uint32_t a, uint32_t b, u64 c) {
-    u64 d;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
-    return d;
-}
+__device__ __forceinline__ u64 madw32(uint32_t a, uint32_t b, u64 c) { return c + (u64)a * b; }  // IMAD.WIDE.U32
 __device__ __forceinline__ uint32_t lo32(u64 x) { return (uint32_t)x; }
 __device__ __forceinline__ uint32_t hi32(u64 x) { return (uint32_t)(x >> 32); }
 

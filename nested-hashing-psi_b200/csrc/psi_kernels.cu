@@ -26,11 +26,10 @@ static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) 
 // A CTA covers 128 coefficients (one row of one limb) x 4 bins; CTAs of the same row are adjacent in
 // launch order, so the index words of that row come from DRAM once and from L2 afterwards.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ u64 madw(uint32_t a, uint32_t b, u64 c) {
-    u64 d;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
-    return d;
-}
+// 32 x 32 + 64 -> 64 multiply-add.  Written in C, not inline PTX: with the inline-asm form ptxas splits every
+// pair of accumulating mad.wide into two multiplies plus a 3-input add (twice the issue slots); the
+// compiler's own code keeps IMAD.WIDE with its 64-bit addend.
+__device__ __forceinline__ u64 madw(uint32_t a, uint32_t b, u64 c) { return c + (u64)a * b; }
 __device__ __forceinline__ void fold30(u64& hi, u64& lo, u64 ll, u64 mid, u64 hh) {
     // (hi:lo) += ll + mid * 2^30 + hh * 2^60
     u128 t = (u128)ll + ((u128)mid << 30) + ((u128)hh << 60);
