@@ -79,12 +79,14 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_tensor(const DevTables* 
     for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) {
         const u64 a0 = lazy_sub_hi(arr[sl(j)], q2), a1 = lazy_sub_hi(arr[P + sl(j)], q2);
         const u64 b0 = lazy_sub_hi(arr[2 * P + sl(j)], q2), b1 = lazy_sub_hi(arr[3 * P + sl(j)], q2);
-        arr[sl(j)] = mont_redc_lazy(mulhi64(a0, b0), a0 * b0, q, qinv);
-        u64 hi = 0, lo = 0;
-        mac128(hi, lo, a0, b1);
+        u64 hi, lo;
+        mul128(hi, lo, a0, b0);
+        arr[sl(j)] = mont_redc_lazy(hi, lo, q, qinv);
+        mul128(hi, lo, a0, b1);
         mac128(hi, lo, a1, b0);
         arr[P + sl(j)] = mont_redc_lazy(hi, lo, q, qinv);
-        arr[2 * P + sl(j)] = mont_redc_lazy(mulhi64(a1, b1), a1 * b1, q, qinv);
+        mul128(hi, lo, a1, b1);
+        arr[2 * P + sl(j)] = mont_redc_lazy(hi, lo, q, qinv);
     }
     __syncthreads();
     transform_rows<true>(tab, arr, P, 3, [l](uint32_t) { return l; }, g, 4, logN, tile_base, tid, tws_i);
@@ -139,8 +141,11 @@ __global__ void __launch_bounds__((2 + L) * kGroup, L <= 4 ? 2 : 1)
         u64 r1 = mont_redc_lazy(h1, l1, q, qinv) + arr[P + sl(j)];
         if (maskR) {
             const u64 mv = maskR[bin * LN + n];
-            r0 = mont_redc_lazy(mulhi64(r0, mv), r0 * mv, q, qinv);
-            r1 = mont_redc_lazy(mulhi64(r1, mv), r1 * mv, q, qinv);
+            u64 ph, pl;
+            mul128(ph, pl, r0, mv);
+            r0 = mont_redc_lazy(ph, pl, q, qinv);
+            mul128(ph, pl, r1, mv);
+            r1 = mont_redc_lazy(ph, pl, q, qinv);
             r0 = r0 >= q ? r0 - q : r0;
             r1 = r1 >= q ? r1 - q : r1;
         } else {

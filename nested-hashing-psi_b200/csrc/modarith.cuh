@@ -174,9 +174,18 @@ __device__ __forceinline__ u64 mont_redc_lazy(u64 hi, u64 lo, u64 q, u64 qinv) {
 
 // 128-bit multiply-accumulate: (hi:lo) += a * b
 __device__ __forceinline__ void mac128(u64& hi, u64& lo, u64 a, u64 b) {
-    u64 pl = a * b, ph = mulhi64(a, b);
-    lo += pl;
-    hi += ph + (lo < pl);
+    // written on unsigned __int128: the compiler emits four IMAD.WIDE with the carries chained through
+    // their addends (about 8 issue slots) instead of separate mul.lo / mul.hi / compare / add (about 13)
+    u128 t = ((u128)hi << 64) | lo;
+    t += (u128)a * b;
+    lo = (u64)t;
+    hi = (u64)(t >> 64);
+}
+// full 64 x 64 -> 128 product
+__device__ __forceinline__ void mul128(u64& hi, u64& lo, u64 a, u64 b) {
+    const u128 t = (u128)a * b;
+    lo = (u64)t;
+    hi = (u64)(t >> 64);
 }
 
 }  // namespace psi
