@@ -17,8 +17,8 @@ T32 = 4296540161
 T16 = 65537
 
 
-def ctx_and_oracle(N, L, t=T32):
-    params = RefParams(N, t, L=L).to_struct()
+def ctx_and_oracle(N, L, t=T32, Lp=None):
+    params = RefParams(N, t, L=L, Lp=Lp).to_struct()
     return P.CryptoContext(params), Oracle(params), params
 
 
@@ -68,6 +68,30 @@ def test_mul_ctct_relin(N, L):
         assert np.array_equal(got, want)
     # operand order matters (the two operands are extended differently)
     assert not np.array_equal(cc.debug_mul_ctct(ct2, ct1), want) or np.array_equal(ct1, ct2)
+
+
+@pytest.mark.parametrize("N,L,Lp", [(2048, 1, 2), (1024, 2, 3), (16384, 3, 4), (2048, 4, 5), (1024, 5, 6), (2048, 6, 7)])
+def test_mul_ctct_auxiliary_basis_one_limb_larger(N, L, Lp):
+    """sizeP = sizeQ + 1 (the shape of the plain HPS auxiliary basis): every (L, Lp) instantiation of the
+    fused column kernels, real ciphertexts, limbs and decrypted product."""
+    cc, o, params = ctx_and_oracle(N, L, Lp=Lp)
+    assert (params.L, params.Lp) == (L, Lp)
+    rng = np.random.default_rng(N + 10 * L)
+    sk, evk_b, evk_a = o.keygen(3)
+    cc.InsertEvalMultKey(evk_b, evk_a)
+    t = int(params.t)
+    m1 = rng.integers(-(t // 2), t // 2, params.N, dtype=np.int64)
+    m2 = rng.integers(-(t // 2), t // 2, params.N, dtype=np.int64)
+    ct1, ct2 = o.encrypt(sk, m1, 1), o.encrypt(sk, m2, 2)
+    got = cc.debug_mul_ctct(ct1, ct2)
+    assert np.array_equal(got, o.mul_ctct(ct1, ct2, evk_b, evk_a))
+    if L >= 2:   # one 60-bit limb leaves no room for a 33-bit plaintext product
+        dec, amb, _ = o.decrypt(sk, got)
+        want = np.array([(int(x) * int(y)) % t for x, y in zip(m1, m2)], dtype=np.int64)
+        want = np.where(want > t // 2, want - t, want)
+        assert amb == 0 and np.array_equal(dec, want)
+    r1, r2 = sc.random_ct(rng, params), sc.random_ct(rng, params)
+    assert np.array_equal(cc.debug_mul_ctct(r1, r2), o.mul_ctct(r1, r2, evk_b, evk_a))
 
 
 def test_mul_ctct_real_ciphertexts_decrypt():
