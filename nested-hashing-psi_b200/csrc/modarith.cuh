@@ -70,7 +70,7 @@ __device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q) {
 __device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
 
 // ---- hand-scheduled variants for the NTT inner loop -------------------------------------------
-// The integer pipe (IMAD on the fma pipe, 64 lanes/clk/SM measured) is the NTT's roofline, so the
+// The multiplier pipe (IMAD on fmaheavy; IMAD.WIDE at a quarter of the FP32 rate, measured) is the NTT's roofline, so the
 // butterfly is written to spend exactly 10 multiply issues and as few ALU issues as possible.
 __device__ __forceinline__ u64 madw32(uint32_t a, uint32_t b, u64 c) { return c + (u64)a * b; }  // IMAD.WIDE.U32
 __device__ __forceinline__ uint32_t lo32(u64 x) { return (uint32_t)x; }

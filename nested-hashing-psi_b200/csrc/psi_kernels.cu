@@ -45,16 +45,29 @@ constexpr int kMacCoeffs = 128;  // coefficients per CTA tile (= one row of one 
 // two-stage shared-memory ring guarded by mbarriers, and 256 consumer threads (128 coefficients x 2
 // bin-lanes x 2 bins) do nothing but LDS + IMAD.WIDE.  Two CTAs per SM; the data in flight per SM (up to
 // 192 KiB) is set by the rings, not by how many loads the compiler keeps in registers.
+//
+// Multiplier work is what limits the consumers (IMAD.WIDE issues at a quarter of the FP32 rate), so one
+// 60 x 60-bit product is formed with THREE 32 x 32 products (Karatsuba on the 30-bit halves):
+//   ll += x0*y0,  hh += x1*y1,  kk += (x0+x1)*(y0+y1),  middle = kk - ll - hh.
+// ll and hh stay below 2^63 over 8 positions; kk may wrap, but the middle sum is < 2^64, so the wrapped
+// 64-bit difference is exact.  Hence the fold into the 128-bit running total after every 8 positions.
 constexpr int kMacPosChunk = 8;   // positions per stage == positions between folds
 constexpr int kMacStages = 2;
 constexpr int kMacBT = 2, kMacLanes = 2, kMacBins = kMacBT * kMacLanes;
 constexpr int kMacConsumers = kMacCoeffs * kMacLanes;
 constexpr size_t kMacStageWords = (size_t)kMacPosChunk * kMacCoeffs * (2 + kMacBins);  // idx + pt words per stage
 
+// canonical residue of hi * 2^64 + lo: hi through the Shoup pair of 2^64 mod q, lo through floor(2^64 / q)
+__device__ __forceinline__ u64 reduce128(u64 hi, u64 lo, const u64 q, const u64 R, const u64 Rs, const u64 qrecip) {
+    u64 r = mul_shoup_lazy(hi, R, Rs, q) + (lo - mulhi64(lo, qrecip) * q);  // [0, 2q) + [0, 2q)
+    if (r >= 2 * q) r -= 2 * q;
+    return r >= q ? r - q : r;
+}
+
 __global__ void __launch_bounds__(kMacConsumers + 32, 2)
     k_mac_tma(const DevTables* __restrict__ tab, uint32_t N, uint32_t L, uint32_t b, uint32_t E, const u64* __restrict__ pt,
               const u64* __restrict__ idx, const u64* __restrict__ minus, u64* __restrict__ acc) {
-    extern __shared__ __align__(128) u64 ring[];  // [stage][ idx: 8 x 2 x 128 | pt: 8 bins x 8 x 128 ]
+    extern __shared__ __align__(128) u64 ring[];  // [stage][ idx: 8 x 2 x 128 | pt: 4 bins x 8 x 128 ]
     __shared__ __align__(8) uint64_t full_bar[kMacStages], empty_bar[kMacStages];
     const size_t LN = (size_t)L * N, T = LN / kMacCoeffs;
     // CTAs that share an index slice (same hf and tile, different bin blocks) are adjacent in launch
@@ -96,11 +109,11 @@ __global__ void __launch_bounds__(kMacConsumers + 32, 2)
     // ---- consumers
     const uint32_t w = threadIdx.x & (kMacCoeffs - 1), lane = threadIdx.x / kMacCoeffs;
     const size_t c = (size_t)tile * kMacCoeffs + w;
-    u64 ll[kMacBT][2], mid[kMacBT][2], hh[kMacBT][2], tlo[kMacBT][2], thi[kMacBT][2];
+    u64 ll[kMacBT][2], kk[kMacBT][2], hh[kMacBT][2], tlo[kMacBT][2], thi[kMacBT][2];
 #pragma unroll
     for (int j = 0; j < kMacBT; j++)
 #pragma unroll
-        for (int k = 0; k < 2; k++) ll[j][k] = mid[j][k] = hh[j][k] = tlo[j][k] = thi[j][k] = 0;
+        for (int k = 0; k < 2; k++) ll[j][k] = kk[j][k] = hh[j][k] = tlo[j][k] = thi[j][k] = 0;
 
     uint32_t folds = 0;
     for (uint32_t ch = 0; ch < nchunks; ch++) {
@@ -111,17 +124,17 @@ __global__ void __launch_bounds__(kMacConsumers + 32, 2)
         const uint2* sp = si + (size_t)kMacPosChunk * kMacCoeffs * (2 + lane * kMacBT);
         auto body = [&](int p) {
             const uint2 i0 = si[p * 2 * kMacCoeffs], i1 = si[p * 2 * kMacCoeffs + kMacCoeffs];
+            const uint32_t s0 = i0.x + i0.y, s1 = i1.x + i1.y;
 #pragma unroll
             for (int j = 0; j < kMacBT; j++) {
                 const uint2 y = sp[(j * kMacPosChunk + p) * kMacCoeffs];
+                const uint32_t sy = y.x + y.y;
                 ll[j][0] = madw(i0.x, y.x, ll[j][0]);
-                mid[j][0] = madw(i0.x, y.y, mid[j][0]);
-                mid[j][0] = madw(i0.y, y.x, mid[j][0]);
                 hh[j][0] = madw(i0.y, y.y, hh[j][0]);
+                kk[j][0] = madw(s0, sy, kk[j][0]);
                 ll[j][1] = madw(i1.x, y.x, ll[j][1]);
-                mid[j][1] = madw(i1.x, y.y, mid[j][1]);
-                mid[j][1] = madw(i1.y, y.x, mid[j][1]);
                 hh[j][1] = madw(i1.y, y.y, hh[j][1]);
+                kk[j][1] = madw(s1, sy, kk[j][1]);
             }
         };
         if (np == kMacPosChunk) {
@@ -135,8 +148,8 @@ __global__ void __launch_bounds__(kMacConsumers + 32, 2)
         for (int j = 0; j < kMacBT; j++)
 #pragma unroll
             for (int k = 0; k < 2; k++) {
-                fold30(thi[j][k], tlo[j][k], ll[j][k], mid[j][k], hh[j][k]);
-                ll[j][k] = mid[j][k] = hh[j][k] = 0;
+                fold30(thi[j][k], tlo[j][k], ll[j][k], kk[j][k] - ll[j][k] - hh[j][k], hh[j][k]);
+                ll[j][k] = kk[j][k] = hh[j][k] = 0;
             }
         if (++folds == 16) {  // 128 positions: keep the running total below 2^128 for any E
             folds = 0;
@@ -145,21 +158,21 @@ __global__ void __launch_bounds__(kMacConsumers + 32, 2)
             for (int j = 0; j < kMacBT; j++)
 #pragma unroll
                 for (int k = 0; k < 2; k++) {
-                    tlo[j][k] = barrett128(thi[j][k], tlo[j][k], mdr.q, mdr.mu_hi, mdr.mu_lo);
+                    tlo[j][k] = reduce128(thi[j][k], tlo[j][k], mdr.q, mdr.Rmodq, mdr.Rmodq_s, mdr.mu_hi);
                     thi[j][k] = 0;
                 }
         }
     }
     const ModDev& md = tab->mods[c / N];
-    const u64 q = md.q, mu_hi = md.mu_hi, mu_lo = md.mu_lo;
+    const u64 q = md.q, qrecip = md.mu_hi, R = md.Rmodq, Rs = md.Rmodq_s;  // floor(2^128/q) >> 64 = floor(2^64/q)
     const u64 m0 = minus[c], m1 = minus[LN + c];
 #pragma unroll
     for (int j = 0; j < kMacBT; j++) {
         const uint32_t bin = bin_blk0 + lane * kMacBT + j;
         if (bin < b) {
             u64* o = acc + (((size_t)hf * b + bin) * 2) * LN + c;
-            o[0] = addmod(barrett128(thi[j][0], tlo[j][0], q, mu_hi, mu_lo), m0, q);
-            o[LN] = addmod(barrett128(thi[j][1], tlo[j][1], q, mu_hi, mu_lo), m1, q);
+            o[0] = addmod(reduce128(thi[j][0], tlo[j][0], q, R, Rs, qrecip), m0, q);
+            o[LN] = addmod(reduce128(thi[j][1], tlo[j][1], q, R, Rs, qrecip), m1, q);
         }
     }
 }
@@ -498,22 +511,19 @@ cudaError_t launch_slots_to_crt(const KCtx& k, uint32_t n_pt, uint32_t nslots, c
 // Independent dependency chains per thread, no memory traffic.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_imad_peak(u64* out, uint32_t iters, uint32_t seed) {
-    uint32_t a = threadIdx.x * 2654435761u + seed, b = blockIdx.x * 40503u + 12345u;
-    u64 c0 = a, c1 = b, c2 = a ^ b, c3 = a + b, c4 = 1, c5 = 2, c6 = 3, c7 = 4;
+    // eight accumulate chains; every multiplier is the high word of its own accumulator, so nothing is loop
+    // invariant (with constant operands ptxas hoists the product and the loop degenerates into 64-bit adds)
+    const uint32_t b = (blockIdx.x * 256u + threadIdx.x) * 40503u + 12345u + seed;
+    u64 c[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) c[u] = out[(blockIdx.x * 256u + threadIdx.x + u) % 1024u] + seed;
     for (uint32_t i = 0; i < iters; i++) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c0) : "r"(a), "r"(b));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c1) : "r"(a), "r"(b));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c2) : "r"(a), "r"(b));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c3) : "r"(a), "r"(b));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c4) : "r"(a), "r"(b));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c5) : "r"(a), "r"(b));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c6) : "r"(a), "r"(b));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c7) : "r"(a), "r"(b));
-        }
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int u = 0; u < 8; u++) c[u] = madw((uint32_t)(c[u] >> 32), b, c[u]);
     }
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = c[0] ^ c[1] ^ c[2] ^ c[3] ^ c[4] ^ c[5] ^ c[6] ^ c[7];
 }
 
 __global__ void __launch_bounds__(256) k_butterfly_peak(u64* out, uint32_t iters, u64 q, u64 w, u64 ws) {
