@@ -265,20 +265,21 @@ __device__ __forceinline__ u64 shoup_canon(u64 x, u64 c, u64 cs, u64 q) {
 }
 
 // RNS inner products sum_i x_i * c_i mod q with at most 8 terms: the constants are stored in Montgomery form
-// (times 2^64 mod q) and split-30, the residues x_i < 2^60 are split once, every product is four IMAD.WIDE.U32
-// into three carry-free partial sums, and ONE Montgomery reduction returns the canonical residue of the sum.
+// (times 2^64 mod q) and split-30, the residues x_i < 2^60 are split once, every product is THREE IMAD.WIDE.U32
+// (Karatsuba on the 30-bit halves: ll += x0 c0, hh += x1 c1, kk += (x0 + x1)(c0 + c1)) into carry-free partial
+// sums, and ONE Montgomery reduction returns the canonical residue of the sum.  ll, hh < 8 * 2^60; kk may wrap,
+// but the middle sum kk - ll - hh is < 8 * 2^61 = 2^64, so the wrapped 64-bit difference is exact.
 struct Acc3 {
-    u64 ll = 0, mid = 0, hh = 0;
+    u64 ll = 0, kk = 0, hh = 0;
 };
 __device__ __forceinline__ void acc3_mad(Acc3& a, uint32_t x0, uint32_t x1, u64 c_split) {
     const uint32_t c0 = (uint32_t)c_split, c1 = (uint32_t)(c_split >> 32);
     a.ll = madw32(x0, c0, a.ll);
-    a.mid = madw32(x0, c1, a.mid);
-    a.mid = madw32(x1, c0, a.mid);
     a.hh = madw32(x1, c1, a.hh);
+    a.kk = madw32(x0 + x1, c0 + c1, a.kk);
 }
 __device__ __forceinline__ u64 acc3_reduce(const Acc3& a, u64 q, u64 qinv) {
-    const u128 t = (u128)a.ll + ((u128)a.mid << 30) + ((u128)a.hh << 60);
+    const u128 t = (u128)a.ll + ((u128)(a.kk - a.ll - a.hh) << 30) + ((u128)a.hh << 60);
     const u64 r = mont_redc_lazy((u64)(t >> 64), (u64)t, q, qinv);
     return r >= q ? r - q : r;
 }
