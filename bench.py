@@ -37,6 +37,14 @@ WORKLOADS = {
     "2^24_vs_2^10": dict(S=1 << 24, C=1 << 10, I=513, k=2, e=4949, K=2, b=47, E=47, N=16384, bits=32),
     # "1024 1048576 513 2 4949 14 14"   (Parameters1.txt:11)  BASELINE configs[1]
     "2^20_vs_2^10": dict(S=1 << 20, C=1 << 10, I=513, k=2, e=4949, K=2, b=14, E=14, N=16384, bits=32),
+    # "4096 16777216 2049 3 1791 75 75" (Parameters1.txt:67)  BASELINE configs[4] (the k = 2 rows for 4096 clients,
+    # e = 13004, need 26008 slots and do not fit N = 16384)
+    "2^24_vs_2^12": dict(S=1 << 24, C=1 << 12, I=2049, k=3, e=1791, K=2, b=75, E=75, N=16384, bits=32),
+    # BASELINE configs[3]: 2^22 is not in Parameters1.txt; b = E found by tools/param_sweep.py (smallest bin size whose
+    # insertion succeeds with stash 0), see profiles/r01_param_sweep_2p22.md
+    "2^22_vs_2^10": dict(S=1 << 22, C=1 << 10, I=513, k=2, e=4949, K=2, b=26, E=26, N=16384, bits=32),
+    # "1024 268435456 513 2 4949 176 176" (Parameters1.txt:23): the largest server set of the file, 32 GB of plaintexts
+    "2^28_vs_2^10": dict(S=1 << 28, C=1 << 10, I=513, k=2, e=4949, K=2, b=176, E=176, N=16384, bits=32),
     # reduced case for quick functional runs (not a BASELINE config)
     "2^16_vs_2^8": dict(S=1 << 16, C=1 << 8, I=129, k=2, e=1900, K=2, b=8, E=8, N=16384, bits=32),
 }
@@ -129,7 +137,9 @@ def cpu_oracle_rate(w, params, n_bins, steps, threads=None):
     threads = threads or max_threads()
     rng = np.random.default_rng(99)
     K, E = w["K"], w["E"]
-    n_bins = min(n_bins, w["b"])
+    # bounded sample: at most ~3 GB of host plaintexts (whole query for the BASELINE configs up to 2^24 vs 2^10)
+    cap = max(threads, int(3.2e9 // (K * E * params.L * params.N * 8)))
+    n_bins = min(n_bins, w["b"], cap)
     pt = random_limbs(rng, params, (K, n_bins, E))
     mask = random_limbs(rng, params, (n_bins,))
     idx = random_limbs(rng, params, (K, E, 2))

@@ -1,4 +1,4 @@
-"""Full-size checks on the B200 (BASELINE.json configs 2^20 and 2^24 server items vs 2^10 client items):
+"""Full-size checks on the B200 (BASELINE.json configs 2^20 and 2^24 server items vs 2^10 / 2^12 client items):
 the real pipeline RandomDataInput -> nested cuckoo table -> BatchedFHEHIPPIE ctor (GPU encode) -> encrypted
 query -> run() -> results, verified by
   * bit-exact limbs against the oracle on randomly sampled bins (the oracle needs ~0.1 s per bin),
@@ -19,10 +19,12 @@ CONFIGS = {
     # Parameters1.txt:11 and :17
     "2^20": dict(S=1 << 20, C=1 << 10, I=513, k=2, e=4949, K=2, b=14, E=14),
     "2^24": dict(S=1 << 24, C=1 << 10, I=513, k=2, e=4949, K=2, b=47, E=47),
+    # Parameters1.txt:67 (BASELINE configs[4]: 2^24 server items vs 2^12 client items, three simple hash functions)
+    "2^24_vs_2^12": dict(S=1 << 24, C=1 << 12, I=2049, k=3, e=1791, K=2, b=75, E=75),
 }
 
 
-@pytest.mark.parametrize("name", ["2^20", "2^24"])
+@pytest.mark.parametrize("name", ["2^20", "2^24", "2^24_vs_2^12"])
 def test_full_protocol(name):
     w = CONFIGS[name]
     k, e, K, b, E = w["k"], w["e"], w["K"], w["b"], w["E"]
