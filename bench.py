@@ -71,6 +71,10 @@ def parse():
                     help="N > 1 response gather inside e2e: 'host' = every rank copies its own result ciphertexts to "
                          "pinned host memory over its own PCIe link (what a one-process server does with one pinned "
                          "buffer); 'nccl' = NCCL gather to rank 0 over NVLink, then one D2H on rank 0")
+    ap.add_argument("--query-dist", default="auto", choices=["auto", "host", "allgather"],
+                    help="N > 1, how the query reaches every GPU inside e2e: 'host' = every rank uploads the whole query "
+                         "over its own PCIe link; 'allgather' = every rank uploads 1/N of the index ciphertexts and the "
+                         "slices are exchanged with one NCCL all-gather over NVLink (auto: allgather when N > 1)")
     ap.add_argument("--host-build", action="store_true",
                     help="build the nested cuckoo table on the host (OpenMP) instead of on the GPU")
     ap.add_argument("--synthetic-db", action="store_true",
@@ -179,6 +183,32 @@ def run_reference(args, w, rank):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(index):
+    """Multi-GPU hosts: run this rank on the CPUs of its GPU's NUMA node BEFORE any pinned buffer is allocated, so
+    that the staging memory of the H2D/D2H copies is local to the GPU's PCIe root (first-touch placement); eight
+    ranks staging through one socket's memory share that socket's bandwidth.  Returns the node or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.lower().split(":", 1)
+        node = int(open("/sys/bus/pci/devices/%s:%s/numa_node" % (dom[-4:], rest)).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def workload_config(args, w, params, world):
     return {"workload": "Server/Client BFV PIE %s: S=%d server items vs C=%d client items, nested cuckoo k=%d e=%d "
                         "K=%d b=%d E=%d (Parameters1.txt), N=%d, sizeQ=%d x 60-bit, sizeP=%d, t=%d, HPSPOVERQ + BV"
@@ -207,6 +237,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU port)")
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -332,8 +363,26 @@ def main():
                 for r in range(world):
                     R_host[r * b_local * ct_words:(r + 1) * b_local * ct_words].copy_(gather_bufs[r].view(-1), non_blocking=True)
 
+    query_dist = args.query_dist
+    if query_dist == "auto":
+        query_dist = "allgather" if world > 1 and (K * E * ct_words) % world == 0 else "host"
+    qd = None
+    if query_dist == "allgather":
+        landing_idx, landing_minus = P.QueryDistributor.landing_tensors(cc)
+        qd = P.QueryDistributor(landing_idx, landing_minus, rank, world)
+        q_idx_host, q_minus_host = q_host[:K * E * ct_words], q_host[K * E * ct_words:]
+
+    def upload_query(st):
+        """This step's query from pinned host memory into the landing buffers, on torch stream `st`."""
+        if qd is None:
+            cc.query_upload_ptr(idx_ptr, minus_ptr, st.cuda_stream)
+        else:
+            with torch.cuda.stream(st):
+                qd.distribute(q_idx_host, q_minus_host)   # 1/N over PCIe + NCCL all-gather over NVLink
+
     def e2e_serial_step():
-        cc.query_set_ptr(idx_ptr, minus_ptr, sp)
+        upload_query(stream)
+        cc.query_commit(sp)
         cc.run(sp)
         fetch_result(stream, r_host)
 
@@ -356,7 +405,7 @@ def main():
         for i in range(steps):
             if ev_commit is not None:
                 s_in.wait_event(ev_commit)            # landing buffers are free once the previous commit ran
-            cc.query_upload_ptr(idx_ptr, minus_ptr, s_in.cuda_stream)
+            upload_query(s_in)
             ev_up = torch.cuda.Event()
             ev_up.record(s_in)
             stream.wait_event(ev_up)
@@ -391,7 +440,9 @@ def main():
     total_items = items_per_gpu * world
     value = total_items / (ms_step * 1e-3)
     e2e_value = total_items / (ms_e2e * 1e-3)
-    h2d = (K * E + 1) * ct_words * 8
+    # whole-job H2D per step: the query crosses PCIe once per GPU ('host') or once in total plus the small minus
+    # ciphertext per GPU ('allgather')
+    h2d = (K * E + 1) * ct_words * 8 * world if qd is None else (K * E + world) * ct_words * 8
     d2h = b_local * ct_words * 8 * world  # whole job: every rank's result ciphertexts reach host memory
 
     try:
@@ -456,7 +507,9 @@ def main():
                             "run i (serial_* = one query at a time)"
                             + ((" (N > 1: NCCL gather to rank 0 over NVLink, then one D2H)" if args.gather == "nccl" else
                                 " (N > 1: every rank downloads its own bins over its own PCIe link)") if world > 1 else ""),
-                    "gather": args.gather if world > 1 else None},
+                    "gather": args.gather if world > 1 else None, "rank0_numa_node": numa_node,
+                    "query_dist": ("1/N of the index ciphertexts per GPU over PCIe + NCCL all-gather over NVLink"
+                                   if qd is not None else "whole query over every GPU's own PCIe link") if world > 1 else None},
             "gpu_launches": launches_per_run * args.steps,
             "phases": phases, "clocks": sampler.summary(), "offline_build_s": offline_s,
         }

@@ -139,6 +139,14 @@ int psi_query_set(psi_ctx* ctx, const uint64_t* idx, const uint64_t* minus, void
 int psi_query_upload(psi_ctx* ctx, const uint64_t* idx, const uint64_t* minus, void* stream);
 int psi_query_commit(psi_ctx* ctx, void* stream);
 
+/* Device addresses of the landing buffers psi_query_upload fills (idx [K][E][2][L][N], minus [2][L][N], u64),
+ * for hosts that distribute one query over several GPUs themselves: every GPU receives 1/G of the index
+ * ciphertexts over its own PCIe link and the slices are exchanged with an all-gather over NVLink (SURVEY 8e,
+ * "query replication = ... sliced H2D + NVLink all-gather") instead of G full uploads.  The caller fills both
+ * buffers on its stream and then calls psi_query_commit on a stream ordered after that; the call marks the
+ * landing buffers as holding an uploaded query. */
+int psi_query_landing_ptr(psi_ctx* ctx, void** idx, size_t* idx_bytes, void** minus, size_t* minus_bytes);
+
 /* BatchedFHEHIPPIE::run (BatchedFHEHIPPIE.cpp:88-129): enqueues all kernels on
  * `stream`; does not synchronise. */
 int psi_run(psi_ctx* ctx, void* stream);

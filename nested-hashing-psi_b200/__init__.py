@@ -12,11 +12,11 @@ from .capi import (PsiError, PsiParams, lib, lib_path, build_library, params_gen
                    depth_for_E, MAX_LIMBS)
 from .pie import (CryptoContext, PublicKey, TabulationHashing, HierarchicalCuckooHashTable, BatchedFHEHIPPIE,
                   RandomDataInput, client_table, hash_index)
-from .sharding import bin_shard, ShardedPIE
+from .sharding import bin_shard, ShardedPIE, QueryDistributor, query_slice
 from .client_query import build_query_slots, extract_intersection
 
 __all__ = [
     "PsiError", "PsiParams", "lib", "lib_path", "build_library", "params_generate", "PLAINTEXT_MODULUS",
     "depth_for_E", "MAX_LIMBS", "CryptoContext", "PublicKey", "TabulationHashing", "HierarchicalCuckooHashTable",
-    "BatchedFHEHIPPIE", "RandomDataInput", "client_table", "hash_index", "bin_shard", "ShardedPIE", "build_query_slots", "extract_intersection",
+    "BatchedFHEHIPPIE", "RandomDataInput", "client_table", "hash_index", "bin_shard", "ShardedPIE", "QueryDistributor", "query_slice", "build_query_slots", "extract_intersection",
 ]

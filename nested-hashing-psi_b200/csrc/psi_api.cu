@@ -688,6 +688,20 @@ int psi_query_upload(psi_ctx* c, const uint64_t* idx, const uint64_t* minus, voi
     return PSI_OK;
 }
 
+int psi_query_landing_ptr(psi_ctx* c, void** idx, size_t* idx_bytes, void** minus, size_t* minus_bytes) {
+    if (!c || !idx || !idx_bytes || !minus || !minus_bytes) return set_error(PSI_ERR_INVALID, "null argument");
+    if (!c->have_db) return set_error(PSI_ERR_STATE, "load the database before the query (it fixes K and E)");
+    int rc = ensure_device(c);
+    if (rc) return rc;
+    const size_t LN = (size_t)c->L * c->N;
+    *idx = c->idx_in.p;
+    *idx_bytes = (size_t)c->K * c->E * 2 * LN * sizeof(u64);
+    *minus = c->minus_in.p;
+    *minus_bytes = 2 * LN * sizeof(u64);
+    c->uploaded = true;
+    return PSI_OK;
+}
+
 int psi_query_commit(psi_ctx* c, void* stream) {
     if (!c) return set_error(PSI_ERR_INVALID, "null argument");
     if (!c->uploaded) return set_error(PSI_ERR_STATE, "psi_query_commit before psi_query_upload");

@@ -147,6 +147,13 @@ class CryptoContext:
     def query_commit(self, stream=None):
         check(lib().psi_query_commit(self._h, stream))
 
+    def query_landing_ptrs(self):
+        """(idx_ptr, idx_bytes, minus_ptr, minus_bytes) of the device landing buffers; the caller fills them
+        (e.g. sliced H2D + all-gather, sharding.QueryDistributor) and then calls query_commit."""
+        pi, pm, ni, nm = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_size_t()
+        check(lib().psi_query_landing_ptr(self._h, ctypes.byref(pi), ctypes.byref(ni), ctypes.byref(pm), ctypes.byref(nm)))
+        return pi.value, ni.value, pm.value, nm.value
+
     def run(self, stream=None, phases=3):
         """psi_run / psi_run_phases: 1 = inner products only, 2 = ct x ct + mask only, 3 = all."""
         check(lib().psi_run_phases(self._h, phases, stream))

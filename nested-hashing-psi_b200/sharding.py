@@ -6,6 +6,11 @@ split into contiguous, balanced blocks, one per rank.  No collective is needed w
 the only cross-GPU traffic is the final gather of the b result ciphertexts to the rank that
 serialises the response (BatchedFHEPSIServer.cpp:143-152).  torch.distributed is the plumbing:
 NCCL over NVLink on the GPUs, gloo in the CPU tests.
+
+The query (K*E + 1 ciphertexts, the same for every bin) has to reach every GPU.  QueryDistributor moves
+it over PCIe ONCE: rank r copies the r-th 1/G of the index ciphertexts from pinned host memory and the
+slices are exchanged with one all-gather over NVLink; G full uploads would each be PCIe-bound at the
+single-GPU time.
 """
 import numpy as np
 
@@ -73,3 +78,49 @@ class ShardedPIE:
 
         ptr, nbytes = ctx.result_device_ptr()
         return torch.as_tensor(_CudaView(ptr, nbytes // 8), device="cuda:%d" % ctx.device)
+
+
+def query_slice(n_words, rank, world):
+    """[begin, end) of the index-ciphertext words rank uploads itself; n_words must divide evenly."""
+    if n_words % world:
+        raise ValueError("index ciphertext words (%d) do not split evenly over %d ranks" % (n_words, world))
+    step = n_words // world
+    return rank * step, (rank + 1) * step
+
+
+class QueryDistributor:
+    """Sliced H2D + all-gather of one query into every rank's landing buffers.
+
+    landing_idx / landing_minus: torch int64 tensors (flat) that receive the full query on this rank: the
+    library's device landing buffers on the GPU box (CryptoContext.query_landing_ptrs through landing_tensors),
+    plain CPU tensors under gloo in the tests."""
+
+    def __init__(self, landing_idx, landing_minus, rank, world, group=None):
+        import torch
+
+        self.idx, self.minus, self.rank, self.world, self.group = landing_idx, landing_minus, rank, world, group
+        self.begin, self.end = query_slice(landing_idx.numel(), rank, world)
+        # NCCL writes straight into the landing buffer; the own slice is staged separately so that the
+        # collective's input never aliases its output
+        self.slice = torch.empty(self.end - self.begin, dtype=landing_idx.dtype, device=landing_idx.device)
+
+    @staticmethod
+    def landing_tensors(ctx):
+        """torch views (int64, flat) of the context's device landing buffers."""
+        import torch
+
+        pi, ni, pm, nm = ctx.query_landing_ptrs()
+        dev = "cuda:%d" % ctx.device
+        return (torch.as_tensor(_CudaView(pi, ni // 8), device=dev), torch.as_tensor(_CudaView(pm, nm // 8), device=dev))
+
+    def distribute(self, host_idx, host_minus):
+        """host_idx / host_minus: flat int64 tensors holding the whole query in (pinned) host memory; every rank
+        passes the same query.  Enqueued on the current torch stream; returns nothing to wait on."""
+        import torch.distributed as dist
+
+        self.slice.copy_(host_idx[self.begin:self.end], non_blocking=True)
+        self.minus.copy_(host_minus, non_blocking=True)
+        if self.world == 1:
+            self.idx.copy_(self.slice, non_blocking=True)
+        else:
+            dist.all_gather_into_tensor(self.idx, self.slice, group=self.group)

@@ -26,6 +26,16 @@ def test_bin_shard_partition():
         P.bin_shard(4, 4, 4)
 
 
+def test_query_slice_partition():
+    for world in (1, 2, 4, 8):
+        n = 2 * 47 * 2 * 4 * 16384
+        cuts = [P.query_slice(n, r, world) for r in range(world)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+    with pytest.raises(ValueError):
+        P.query_slice(10, 0, 3)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -53,6 +63,20 @@ def _worker(rank, world, port, tmpdir):
     mask = sc.random_pt(rng, params, (b,))
     idx = sc.random_ct(rng, params, (K, E))
     minus = sc.random_ct(rng, params)
+    # query distribution: every rank moves only its own 1/world of the index ciphertexts "over PCIe", the rest
+    # arrives by all-gather; the other slices of this rank's host copy are poisoned to prove they are never read
+    idx_flat = torch.from_numpy(idx.view(np.int64).reshape(-1))
+    minus_flat = torch.from_numpy(minus.view(np.int64).reshape(-1))
+    landing_idx, landing_minus = torch.zeros_like(idx_flat), torch.zeros_like(minus_flat)
+    qd = P.QueryDistributor(landing_idx, landing_minus, rank, world)
+    host = idx_flat.clone()
+    host[:qd.begin] = -1
+    host[qd.end:] = -1
+    qd.distribute(host, minus_flat)
+    assert torch.equal(landing_idx, idx_flat) and torch.equal(landing_minus, minus_flat)
+    idx = landing_idx.numpy().view(np.uint64).reshape(idx.shape)
+    minus = landing_minus.numpy().view(np.uint64).reshape(minus.shape)
+
     shard = P.ShardedPIE(b, rank, world)
     pt_l, mask_l = shard.local_db(pt, mask)            # this rank keeps only its bins resident
     local = o.run(pt_l, mask_l, idx, minus, evk_b, evk_a)
