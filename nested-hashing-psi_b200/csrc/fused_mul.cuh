@@ -330,7 +330,7 @@ __device__ __forceinline__ void store_cols(const u64* sm, u64* __restrict__ poly
 }
 
 // ---- (2) columns: inverse, basis extension, forward -----------------------------------------------
-// grid (128/8, 4 = operand*2 + component, B); kColGroups groups.
+// grid (128/8, B, 4 = (operand, component) in launch order (1,0) (1,1) (0,0) (0,1)); kColGroups groups.
 //   operand 0 (multipliedResult):  DCRTPoly::ExpandCRTBasis            -> e1p [B][2][Lp][N]
 //   operand 1 (innerProductResult): DCRTPoly::FastExpandCRTBasisPloverQ -> e2h [B][2][LT][N]
 // All modular sums are formed as sums of lazy Shoup products (< 2q each, at most 8 terms < 2^64) and
@@ -345,8 +345,10 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 3)
     const uint32_t logR = logN - kLogCols, m = logR + kColTileLog, M = 1u << m, P = padded(M);
     const uint32_t g = threadIdx.x / kGroup, tid = threadIdx.x % kGroup;
     const uint32_t c0 = blockIdx.x << kColTileLog;
-    const uint32_t operand = blockIdx.y >> 1, comp = blockIdx.y & 1;
-    const size_t bin = blockIdx.z;
+    // longest work first: the CTAs of operand 1 (L + Lp output limbs) are launched before those of operand 0 (Lp),
+    // so that the tail of the grid is made of the short ones
+    const uint32_t operand = 1u - (blockIdx.z >> 1), comp = blockIdx.z & 1;
+    const size_t bin = blockIdx.y;
 
     // column-inverse of the L input limbs
     const u64* src = (operand ? hb : ha) + ((bin * 2 + comp) * L) * (size_t)N;
@@ -433,7 +435,7 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 3)
 }
 
 // ---- (4) columns: inverse, scale-and-round, digit lift, forward -----------------------------------
-// grid (128/8, 3, B), kColGroups groups.  th: [B][3][LT][N]; rh: [B][2][L][N] (column-forward halves of
+// grid (128/8, B, 3 = component in launch order 2, 0, 1), kColGroups groups.  th: [B][3][LT][N]; rh: [B][2][L][N] (column-forward halves of
 // c0, c1); dh: [B][L][L][N] (column-forward halves of the BV digits of c2)
 template <int L, int LP, int LOGN_CT>
 __global__ void __launch_bounds__(kColGroups* kGroup, 3)
@@ -444,8 +446,9 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 3)
     const uint32_t N = 1u << logN;
     const uint32_t logR = logN - kLogCols, m = logR + kColTileLog, M = 1u << m, P = padded(M);
     const uint32_t g = threadIdx.x / kGroup, tid = threadIdx.x % kGroup;
-    const uint32_t c0 = blockIdx.x << kColTileLog, comp = blockIdx.y;
-    const size_t bin = blockIdx.z;
+    // longest work first: component 2 (L digits = L * L forward limb transforms) is launched before components 0, 1
+    const uint32_t c0 = blockIdx.x << kColTileLog, comp = (blockIdx.z + 2u) % 3u;
+    const size_t bin = blockIdx.y;
     for (uint32_t a = g; a < LT; a += kColGroups)
         load_cols(smem + a * P, th + ((bin * 3 + comp) * LT + a) * (size_t)N, logR, c0, tid);
     __syncthreads();
@@ -527,9 +530,9 @@ cudaError_t launch_cols(const KCtx& k, uint32_t B, const u64* ha, const u64* hb,
         return cudaFuncSetAttribute(k_cols_scale<L, LP, LOGN_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     }
     if (which == 0)
-        k_cols_extend<L, LP, LOGN_CT><<<dim3(col_tiles, 4, B), kColGroups * kGroup, smem, k.s>>>(k.tab, k.logN, ha, hb, e1p, e2h);
+        k_cols_extend<L, LP, LOGN_CT><<<dim3(col_tiles, B, 4), kColGroups * kGroup, smem, k.s>>>(k.tab, k.logN, ha, hb, e1p, e2h);
     else
-        k_cols_scale<L, LP, LOGN_CT><<<dim3(col_tiles, 3, B), kColGroups * kGroup, smem, k.s>>>(k.tab, k.logN, th, rh, dh);
+        k_cols_scale<L, LP, LOGN_CT><<<dim3(col_tiles, B, 3), kColGroups * kGroup, smem, k.s>>>(k.tab, k.logN, th, rh, dh);
     return cudaGetLastError();
 }
 
