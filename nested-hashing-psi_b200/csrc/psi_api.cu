@@ -709,7 +709,7 @@ int psi_query_commit(psi_ctx* c, void* stream) {
     if (rc) return rc;
     const size_t LN = (size_t)c->L * c->N;
     cudaStream_t s = (cudaStream_t)stream;
-    CK(launch_retile_idx(s, c->idx_in.p, c->idx.p, LN, c->K, c->E));  // index cts -> tiled split-30
+    CK(launch_retile_idx(c->k(s), c->idx_in.p, c->idx.p, LN, c->K, c->E));  // index cts -> tiled split-30, Montgomery form
     CK(cudaMemcpyAsync(c->minus.p, c->minus_in.p, 2 * LN * sizeof(u64), cudaMemcpyDeviceToDevice, s));
     c->have_query = true;
     return PSI_OK;

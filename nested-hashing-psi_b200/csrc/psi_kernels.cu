@@ -63,6 +63,15 @@ __device__ __forceinline__ u64 reduce128(u64 hi, u64 lo, const u64 q, const u64 
     if (r >= 2 * q) r -= 2 * q;
     return r >= q ? r - q : r;
 }
+// canonical residue of (hi * 2^64 + lo) * 2^-64 for a sum of at most kMacMaxTerms products of canonical residues
+// (+ one residue): T < (n + 1) q^2 and q < 2^60 give REDC(T) < T / 2^64 + q < (n / 16 + 2) q <= 8 q
+constexpr uint32_t kMacMaxTerms = 96;
+__device__ __forceinline__ u64 redc_canonical(u64 hi, u64 lo, const u64 q, const u64 qinv) {
+    u64 r = mont_redc_lazy(hi, lo, q, qinv);
+    if (r >= 4 * q) r -= 4 * q;
+    if (r >= 2 * q) r -= 2 * q;
+    return r >= q ? r - q : r;
+}
 
 __global__ void __launch_bounds__(kMacConsumers + 32, 2)
     k_mac_tma(const DevTables* __restrict__ tab, uint32_t N, uint32_t L, uint32_t b, uint32_t E, const u64* __restrict__ pt,
@@ -151,7 +160,7 @@ __global__ void __launch_bounds__(kMacConsumers + 32, 2)
                 fold30(thi[j][k], tlo[j][k], ll[j][k], kk[j][k] - ll[j][k] - hh[j][k], hh[j][k]);
                 ll[j][k] = kk[j][k] = hh[j][k] = 0;
             }
-        if (++folds == 16) {  // 128 positions: keep the running total below 2^128 for any E
+        if (++folds == kMacMaxTerms / kMacPosChunk && ch + 1 < nchunks) {  // keep the total within redc_canonical's bound for any E
             folds = 0;
             const ModDev& mdr = tab->mods[c / N];
 #pragma unroll
@@ -164,15 +173,15 @@ __global__ void __launch_bounds__(kMacConsumers + 32, 2)
         }
     }
     const ModDev& md = tab->mods[c / N];
-    const u64 q = md.q, qrecip = md.mu_hi, R = md.Rmodq, Rs = md.Rmodq_s;  // floor(2^128/q) >> 64 = floor(2^64/q)
+    const u64 q = md.q, qinv = md.qinv;
     const u64 m0 = minus[c], m1 = minus[LN + c];
 #pragma unroll
     for (int j = 0; j < kMacBT; j++) {
         const uint32_t bin = bin_blk0 + lane * kMacBT + j;
         if (bin < b) {
             u64* o = acc + (((size_t)hf * b + bin) * 2) * LN + c;
-            o[0] = addmod(reduce128(thi[j][0], tlo[j][0], q, R, Rs, qrecip), m0, q);
-            o[LN] = addmod(reduce128(thi[j][1], tlo[j][1], q, R, Rs, qrecip), m1, q);
+            o[0] = addmod(redc_canonical(thi[j][0], tlo[j][0], q, qinv), m0, q);
+            o[LN] = addmod(redc_canonical(thi[j][1], tlo[j][1], q, qinv), m1, q);
         }
     }
 }
@@ -219,19 +228,23 @@ cudaError_t launch_retile_pt(cudaStream_t s, u64* flat, u64* tiled, size_t LN, u
     k_retile_pt<<<cdiv(total, 256), 256, 0, s>>>(flat, tiled, LN, E, p0, total, to_tiled ? 1 : 0);
     return cudaGetLastError();
 }
-__global__ void __launch_bounds__(256) k_retile_idx(const u64* __restrict__ flat, u64* __restrict__ tiled, size_t LN,
-                                                    uint32_t E, size_t total) {
+// The index words are stored in Montgomery form (times R = 2^64 mod q_l): the inner product of k_mac_tma then ends
+// with ONE Montgomery reduction per output, REDC(sum idx*R*pt) = sum idx*pt, instead of a 128-bit Barrett; the
+// multiplication by R rides on this bandwidth-bound re-tiling pass.
+__global__ void __launch_bounds__(256) k_retile_idx(const DevTables* __restrict__ tab, uint32_t N, const u64* __restrict__ flat,
+                                                    u64* __restrict__ tiled, size_t LN, uint32_t E, size_t total) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const size_t cidx = i % LN, r = i / LN;  // r = (hf*E + pos)*2 + comp
     const size_t comp = r & 1, pos = (r >> 1) % E, hf = (r >> 1) / E;
     const size_t T = LN / kMacCoeffs, tile = cidx / kMacCoeffs, w = cidx % kMacCoeffs;
-    tiled[(((hf * T + tile) * E + pos) * 2 + comp) * kMacCoeffs + w] = to_split30(flat[i]);
+    const ModDev& md = tab->mods[cidx / N];
+    tiled[(((hf * T + tile) * E + pos) * 2 + comp) * kMacCoeffs + w] = to_split30(mul_shoup(flat[i], md.Rmodq, md.Rmodq_s, md.q));
 }
-cudaError_t launch_retile_idx(cudaStream_t s, const u64* flat, u64* tiled, size_t LN, uint32_t K, uint32_t E) {
+cudaError_t launch_retile_idx(const KCtx& k, const u64* flat, u64* tiled, size_t LN, uint32_t K, uint32_t E) {
     const size_t total = (size_t)K * E * 2 * LN;
     if (total == 0) return cudaSuccess;
-    k_retile_idx<<<cdiv(total, 256), 256, 0, s>>>(flat, tiled, LN, E, total);
+    k_retile_idx<<<cdiv(total, 256), 256, 0, k.s>>>(k.tab, k.N, flat, tiled, LN, E, total);
     return cudaGetLastError();
 }
 
