@@ -368,8 +368,7 @@ def main():
         query_dist = "allgather" if world > 1 and (K * E * ct_words) % world == 0 else "host"
     qd = None
     if query_dist == "allgather":
-        landing_idx, landing_minus = P.QueryDistributor.landing_tensors(cc)
-        qd = P.QueryDistributor(landing_idx, landing_minus, rank, world)
+        qd = P.QueryDistributor.for_context(cc, rank, world)
         q_idx_host, q_minus_host = q_host[:K * E * ct_words], q_host[K * E * ct_words:]
 
     def upload_query(st):
@@ -397,21 +396,21 @@ def main():
         """Returns elapsed ms for `steps` queries through the 3-stream pipeline."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev_commit = None
+        ev_commit = [None, None]               # commit events of the two landing buffers
         ev_d2h = [None, None]
         e0.record(s_in)
         stream.wait_event(e0)
         s_out.wait_event(e0)
         for i in range(steps):
-            if ev_commit is not None:
-                s_in.wait_event(ev_commit)            # landing buffers are free once the previous commit ran
+            if ev_commit[i & 1] is not None:
+                s_in.wait_event(ev_commit[i & 1])     # landing buffer i & 1 is free once the commit of query i-2 ran
             upload_query(s_in)
             ev_up = torch.cuda.Event()
             ev_up.record(s_in)
             stream.wait_event(ev_up)
             cc.query_commit(sp)
-            ev_commit = torch.cuda.Event()
-            ev_commit.record(stream)
+            ev_commit[i & 1] = torch.cuda.Event()
+            ev_commit[i & 1].record(stream)
             if ev_d2h[i & 1] is not None:
                 stream.wait_event(ev_d2h[i & 1])       # run i reuses the result buffer of run i-2
             cc.run(sp)

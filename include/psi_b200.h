@@ -134,18 +134,23 @@ int psi_query_set(psi_ctx* ctx, const uint64_t* idx, const uint64_t* minus, void
 
 /* The same in two steps, so that a server with a stream of queries can overlap the PCIe upload of the
  * next query with the evaluation of the current one: psi_query_upload only copies host -> device landing
- * buffers (no kernel reads them), psi_query_commit makes the uploaded query the active one (re-tiling
- * kernel, must be ordered after the previous psi_run by the caller's streams/events). */
+ * buffers (no kernel reads them), psi_query_commit makes the oldest uploaded query the active one (re-tiling
+ * kernel, must be ordered after the previous psi_run by the caller's streams/events).  There are TWO landing
+ * buffers, used in turn: query i+1 may be uploaded before query i is committed (the copy engine never waits for
+ * the compute stream); a third upload before a commit is PSI_ERR_STATE.  The caller orders upload i+2 after
+ * commit i on the device (stream/event), since they touch the same buffer. */
 int psi_query_upload(psi_ctx* ctx, const uint64_t* idx, const uint64_t* minus, void* stream);
 int psi_query_commit(psi_ctx* ctx, void* stream);
 
-/* Device addresses of the landing buffers psi_query_upload fills (idx [K][E][2][L][N], minus [2][L][N], u64),
- * for hosts that distribute one query over several GPUs themselves: every GPU receives 1/G of the index
- * ciphertexts over its own PCIe link and the slices are exchanged with an all-gather over NVLink (SURVEY 8e,
- * "query replication = ... sliced H2D + NVLink all-gather") instead of G full uploads.  The caller fills both
- * buffers on its stream and then calls psi_query_commit on a stream ordered after that; the call marks the
- * landing buffers as holding an uploaded query. */
-int psi_query_landing_ptr(psi_ctx* ctx, void** idx, size_t* idx_bytes, void** minus, size_t* minus_bytes);
+/* Device addresses of landing buffer `which` (0 or 1; idx [K][E][2][L][N], minus [2][L][N], u64), for hosts
+ * that distribute one query over several GPUs themselves: every GPU receives 1/G of the index ciphertexts
+ * over its own PCIe link and the slices are exchanged with an all-gather over NVLink ("query
+ * replication = ... sliced H2D + NVLink all-gather") instead of G full uploads.  psi_query_next_landing tells
+ * which buffer the next query goes to; the caller fills it on its stream, declares it with psi_query_uploaded
+ * and calls psi_query_commit on a stream ordered after the fill. */
+int psi_query_landing_ptr(psi_ctx* ctx, uint32_t which, void** idx, size_t* idx_bytes, void** minus, size_t* minus_bytes);
+int psi_query_next_landing(psi_ctx* ctx, uint32_t* which);
+int psi_query_uploaded(psi_ctx* ctx, uint32_t which);
 
 /* BatchedFHEHIPPIE::run (BatchedFHEHIPPIE.cpp:88-129): enqueues all kernels on
  * `stream`; does not synchronise. */

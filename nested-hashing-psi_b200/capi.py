@@ -69,7 +69,9 @@ SYMBOLS = {
     "psi_query_set": (_int, [_vp, _u64p, _u64p, _vp]),
     "psi_query_upload": (_int, [_vp, _u64p, _u64p, _vp]),
     "psi_query_commit": (_int, [_vp, _vp]),
-    "psi_query_landing_ptr": (_int, [_vp, _vpp, ctypes.POINTER(_sz), _vpp, ctypes.POINTER(_sz)]),
+    "psi_query_landing_ptr": (_int, [_vp, _u32, _vpp, ctypes.POINTER(_sz), _vpp, ctypes.POINTER(_sz)]),
+    "psi_query_next_landing": (_int, [_vp, _u32p]),
+    "psi_query_uploaded": (_int, [_vp, _u32]),
     "psi_run": (_int, [_vp, _vp]),
     "psi_run_phases": (_int, [_vp, _u32, _vp]),
     "psi_result_get": (_int, [_vp, _u64p, _vp]),

@@ -109,15 +109,18 @@ struct psi_ctx {
     DevBuf<u64> pt, mask;
     bool have_db = false;
     // query
-    DevBuf<u64> idx, idx_in, minus;  // idx: tiled split-30; idx_in: H2D landing buffer [K][E][2][L][N]
+    DevBuf<u64> idx, idx_in, minus;  // idx: tiled split-30; idx_in: two H2D landing buffers [2][K][E][2][L][N]
     DevBuf<u64> stage;               // chunk staging for the DB re-tiling
     bool have_query = false;
     // work
     DevBuf<u64> acc, coef, e1, e2, ten, res, dig, prod, out, out2;
-    DevBuf<u64> minus_in;  // H2D landing buffer of minusCompareElement
+    DevBuf<u64> minus_in;  // two H2D landing buffers of minusCompareElement [2][2][L][N]
     // results are double-buffered: run() i writes out[i & 1], so the D2H of query i can overlap run() i+1
     uint32_t out_cur = 0;
-    bool uploaded = false;
+    // landing buffer n & 1 receives the n-th uploaded query; commits consume them in the same order, so the upload
+    // of query i+1 never has to wait for the commit of query i
+    uint32_t n_uploaded = 0, n_committed = 0;
+    size_t idx_words() const { return (size_t)K * E * 2 * L * N; }
     u64* out_buf(uint32_t which) { return which ? out2.p : out.p; }
     bool ran = false;
     uint32_t launches_per_run = 0;
@@ -461,9 +464,10 @@ static int db_dims(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E) {
     CK(c->maskR.alloc((size_t)b * LN));
     if (LN % 128) return set_error(PSI_ERR_INVALID, "L * N must be a multiple of 128");
     CK(c->idx.alloc((size_t)K * E * 2 * LN));
-    CK(c->idx_in.alloc((size_t)K * E * 2 * LN));
+    CK(c->idx_in.alloc((size_t)2 * K * E * 2 * LN));
     CK(c->minus.alloc(2 * LN));
-    CK(c->minus_in.alloc(2 * LN));
+    CK(c->minus_in.alloc(2 * 2 * LN));
+    c->n_uploaded = c->n_committed = 0;
     return alloc_work(c);
 }
 
@@ -675,42 +679,68 @@ int psi_query_set(psi_ctx* c, const uint64_t* idx, const uint64_t* minus, void* 
     return psi_query_commit(c, stream);
 }
 
-int psi_query_upload(psi_ctx* c, const uint64_t* idx, const uint64_t* minus, void* stream) {
-    if (!c || !idx || !minus) return set_error(PSI_ERR_INVALID, "null argument");
+static int landing_slot(psi_ctx* c, uint32_t* which) {
     if (!c->have_db) return set_error(PSI_ERR_STATE, "load the database before the query (it fixes K and E)");
-    int rc = ensure_device(c);
-    if (rc) return rc;
-    const size_t LN = (size_t)c->L * c->N;
-    cudaStream_t s = (cudaStream_t)stream;
-    CK(cudaMemcpyAsync(c->idx_in.p, idx, (size_t)c->K * c->E * 2 * LN * sizeof(u64), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(c->minus_in.p, minus, 2 * LN * sizeof(u64), cudaMemcpyHostToDevice, s));
-    c->uploaded = true;
+    if (c->n_uploaded - c->n_committed >= 2)
+        return set_error(PSI_ERR_STATE, "two uploaded queries are already waiting for psi_query_commit");
+    *which = c->n_uploaded & 1u;
     return PSI_OK;
 }
 
-int psi_query_landing_ptr(psi_ctx* c, void** idx, size_t* idx_bytes, void** minus, size_t* minus_bytes) {
-    if (!c || !idx || !idx_bytes || !minus || !minus_bytes) return set_error(PSI_ERR_INVALID, "null argument");
+int psi_query_upload(psi_ctx* c, const uint64_t* idx, const uint64_t* minus, void* stream) {
+    if (!c || !idx || !minus) return set_error(PSI_ERR_INVALID, "null argument");
+    uint32_t w = 0;
+    int rc = landing_slot(c, &w);
+    if (rc) return rc;
+    if ((rc = ensure_device(c))) return rc;
+    const size_t LN = (size_t)c->L * c->N;
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(c->idx_in.p + w * c->idx_words(), idx, c->idx_words() * sizeof(u64), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->minus_in.p + w * 2 * LN, minus, 2 * LN * sizeof(u64), cudaMemcpyHostToDevice, s));
+    c->n_uploaded++;
+    return PSI_OK;
+}
+
+int psi_query_landing_ptr(psi_ctx* c, uint32_t which, void** idx, size_t* idx_bytes, void** minus, size_t* minus_bytes) {
+    if (!c || !idx || !idx_bytes || !minus || !minus_bytes || which > 1) return set_error(PSI_ERR_INVALID, "bad argument");
     if (!c->have_db) return set_error(PSI_ERR_STATE, "load the database before the query (it fixes K and E)");
     int rc = ensure_device(c);
     if (rc) return rc;
     const size_t LN = (size_t)c->L * c->N;
-    *idx = c->idx_in.p;
-    *idx_bytes = (size_t)c->K * c->E * 2 * LN * sizeof(u64);
-    *minus = c->minus_in.p;
+    *idx = c->idx_in.p + which * c->idx_words();
+    *idx_bytes = c->idx_words() * sizeof(u64);
+    *minus = c->minus_in.p + which * 2 * LN;
     *minus_bytes = 2 * LN * sizeof(u64);
-    c->uploaded = true;
+    return PSI_OK;
+}
+
+int psi_query_next_landing(psi_ctx* c, uint32_t* which) {
+    if (!c || !which) return set_error(PSI_ERR_INVALID, "null argument");
+    return landing_slot(c, which);
+}
+
+int psi_query_uploaded(psi_ctx* c, uint32_t which) {
+    if (!c) return set_error(PSI_ERR_INVALID, "null argument");
+    uint32_t w = 0;
+    int rc = landing_slot(c, &w);
+    if (rc) return rc;
+    if (which != w) return set_error(PSI_ERR_STATE, "landing buffers are filled in turn: see psi_query_next_landing");
+    c->n_uploaded++;
     return PSI_OK;
 }
 
 int psi_query_commit(psi_ctx* c, void* stream) {
     if (!c) return set_error(PSI_ERR_INVALID, "null argument");
-    if (!c->uploaded) return set_error(PSI_ERR_STATE, "psi_query_commit before psi_query_upload");
+    if (c->n_committed == c->n_uploaded) return set_error(PSI_ERR_STATE, "psi_query_commit before psi_query_upload");
     int rc = ensure_device(c);
     if (rc) return rc;
     const size_t LN = (size_t)c->L * c->N;
+    const uint32_t w = c->n_committed & 1u;
     cudaStream_t s = (cudaStream_t)stream;
-    CK(launch_retile_idx(c->k(s), c->idx_in.p, c->idx.p, LN, c->K, c->E));  // index cts -> tiled split-30, Montgomery form
-    CK(cudaMemcpyAsync(c->minus.p, c->minus_in.p, 2 * LN * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+    // index cts -> tiled split-30, Montgomery form
+    CK(launch_retile_idx(c->k(s), c->idx_in.p + w * c->idx_words(), c->idx.p, LN, c->K, c->E));
+    CK(cudaMemcpyAsync(c->minus.p, c->minus_in.p + w * 2 * LN, 2 * LN * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+    c->n_committed++;
     c->have_query = true;
     return PSI_OK;
 }

@@ -147,12 +147,22 @@ class CryptoContext:
     def query_commit(self, stream=None):
         check(lib().psi_query_commit(self._h, stream))
 
-    def query_landing_ptrs(self):
-        """(idx_ptr, idx_bytes, minus_ptr, minus_bytes) of the device landing buffers; the caller fills them
-        (e.g. sliced H2D + all-gather, sharding.QueryDistributor) and then calls query_commit."""
+    def query_landing_ptrs(self, which):
+        """(idx_ptr, idx_bytes, minus_ptr, minus_bytes) of device landing buffer `which` (0 or 1)."""
         pi, pm, ni, nm = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_size_t()
-        check(lib().psi_query_landing_ptr(self._h, ctypes.byref(pi), ctypes.byref(ni), ctypes.byref(pm), ctypes.byref(nm)))
+        check(lib().psi_query_landing_ptr(self._h, which, ctypes.byref(pi), ctypes.byref(ni), ctypes.byref(pm),
+                                          ctypes.byref(nm)))
         return pi.value, ni.value, pm.value, nm.value
+
+    def query_next_landing(self):
+        """Landing buffer the next query goes to (they are used in turn)."""
+        w = ctypes.c_uint32()
+        check(lib().psi_query_next_landing(self._h, ctypes.byref(w)))
+        return w.value
+
+    def query_uploaded(self, which):
+        """Declares landing buffer `which` filled by the caller (sharding.QueryDistributor); query_commit follows."""
+        check(lib().psi_query_uploaded(self._h, which))
 
     def run(self, stream=None, phases=3):
         """psi_run / psi_run_phases: 1 = inner products only, 2 = ct x ct + mask only, 3 = all."""

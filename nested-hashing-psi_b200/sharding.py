@@ -91,36 +91,48 @@ def query_slice(n_words, rank, world):
 class QueryDistributor:
     """Sliced H2D + all-gather of one query into every rank's landing buffers.
 
-    landing_idx / landing_minus: torch int64 tensors (flat) that receive the full query on this rank: the
-    library's device landing buffers on the GPU box (CryptoContext.query_landing_ptrs through landing_tensors),
-    plain CPU tensors under gloo in the tests."""
+    landings: list of (idx, minus) torch int64 tensor pairs (flat) that receive the full query on this rank, used
+    in turn: the library's two device landing buffers on the GPU box (for_context), plain CPU tensors under gloo
+    in the tests.  on_filled(i) is called after the copies of pair i are enqueued."""
 
-    def __init__(self, landing_idx, landing_minus, rank, world, group=None):
+    def __init__(self, landings, rank, world, group=None, next_landing=None, on_filled=None):
         import torch
 
-        self.idx, self.minus, self.rank, self.world, self.group = landing_idx, landing_minus, rank, world, group
-        self.begin, self.end = query_slice(landing_idx.numel(), rank, world)
-        # NCCL writes straight into the landing buffer; the own slice is staged separately so that the
-        # collective's input never aliases its output
-        self.slice = torch.empty(self.end - self.begin, dtype=landing_idx.dtype, device=landing_idx.device)
+        self.landings, self.rank, self.world, self.group = list(landings), rank, world, group
+        self.next_landing, self.on_filled, self.turn = next_landing, on_filled, 0
+        idx0 = self.landings[0][0]
+        self.begin, self.end = query_slice(idx0.numel(), rank, world)
+        # NCCL writes straight into the landing buffer; the own slice is staged separately (one staging slice per
+        # landing buffer) so that the collective's input never aliases its output
+        self.slices = [torch.empty(self.end - self.begin, dtype=idx0.dtype, device=idx0.device) for _ in self.landings]
 
-    @staticmethod
-    def landing_tensors(ctx):
-        """torch views (int64, flat) of the context's device landing buffers."""
+    @classmethod
+    def for_context(cls, ctx, rank, world, group=None):
+        """Distributor over the two device landing buffers of a CryptoContext."""
         import torch
 
-        pi, ni, pm, nm = ctx.query_landing_ptrs()
         dev = "cuda:%d" % ctx.device
-        return (torch.as_tensor(_CudaView(pi, ni // 8), device=dev), torch.as_tensor(_CudaView(pm, nm // 8), device=dev))
+        pairs = []
+        for w in (0, 1):
+            pi, ni, pm, nm = ctx.query_landing_ptrs(w)
+            pairs.append((torch.as_tensor(_CudaView(pi, ni // 8), device=dev), torch.as_tensor(_CudaView(pm, nm // 8), device=dev)))
+        return cls(pairs, rank, world, group, next_landing=ctx.query_next_landing, on_filled=ctx.query_uploaded)
 
     def distribute(self, host_idx, host_minus):
         """host_idx / host_minus: flat int64 tensors holding the whole query in (pinned) host memory; every rank
-        passes the same query.  Enqueued on the current torch stream; returns nothing to wait on."""
+        passes the same query.  Enqueued on the current torch stream; returns the landing pair that was filled."""
         import torch.distributed as dist
 
-        self.slice.copy_(host_idx[self.begin:self.end], non_blocking=True)
-        self.minus.copy_(host_minus, non_blocking=True)
+        i = self.next_landing() if self.next_landing else self.turn % len(self.landings)
+        self.turn += 1
+        idx, minus = self.landings[i]
+        piece = self.slices[i]
+        piece.copy_(host_idx[self.begin:self.end], non_blocking=True)
+        minus.copy_(host_minus, non_blocking=True)
         if self.world == 1:
-            self.idx.copy_(self.slice, non_blocking=True)
+            idx.copy_(piece, non_blocking=True)
         else:
-            dist.all_gather_into_tensor(self.idx, self.slice, group=self.group)
+            dist.all_gather_into_tensor(idx, piece, group=self.group)
+        if self.on_filled:
+            self.on_filled(i)
+        return idx, minus

@@ -42,8 +42,7 @@ def main():
     # query: pinned host copy whose foreign slices are poisoned, so only the all-gather can complete it
     host_idx = torch.from_numpy(idx.view(np.int64).reshape(-1).copy()).pin_memory()
     host_minus = torch.from_numpy(minus.view(np.int64).reshape(-1).copy()).pin_memory()
-    landing_idx, landing_minus = P.QueryDistributor.landing_tensors(cc)
-    qd = P.QueryDistributor(landing_idx, landing_minus, rank, world)
+    qd = P.QueryDistributor.for_context(cc, rank, world)
     host_idx[:qd.begin] = -1
     host_idx[qd.end:] = -1
     qd.distribute(host_idx, host_minus)

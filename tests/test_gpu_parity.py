@@ -284,6 +284,42 @@ def test_pipelined_queries_double_buffered_results():
         assert np.array_equal(outs[i], want[i]), "query %d" % i
 
 
+def test_two_landing_buffers_queue_uploads():
+    """Two landing buffers: query i+1 may be uploaded before query i is committed; commits consume the uploads in
+    order; a third pending upload and a commit without an upload are PSI_ERR_STATE."""
+    cc, o, params = ctx_and_oracle(1024, 2)
+    rng = np.random.default_rng(78)
+    sk, evk_b, evk_a = o.keygen(6)
+    cc.InsertEvalMultKey(evk_b, evk_a)
+    K, b, E = 2, 2, 3
+    pt = sc.random_pt(rng, params, (K, b, E))
+    mask = sc.random_pt(rng, params, (b,))
+    cc.db_load_limbs(pt, mask)
+    queries = [(np.ascontiguousarray(sc.random_ct(rng, params, (K, E))), np.ascontiguousarray(sc.random_ct(rng, params)))
+               for _ in range(3)]
+    want = [o.run(pt, mask, q[0], q[1], evk_b, evk_a) for q in queries]
+    with pytest.raises(P.PsiError) as err:
+        cc.query_commit()
+    assert err.value.status == P.capi.PSI_ERR_STATE
+    assert cc.query_next_landing() == 0
+    cc.query_upload_ptr(queries[0][0].ctypes.data, queries[0][1].ctypes.data)
+    assert cc.query_next_landing() == 1
+    cc.query_upload_ptr(queries[1][0].ctypes.data, queries[1][1].ctypes.data)
+    with pytest.raises(P.PsiError) as err:
+        cc.query_upload_ptr(queries[2][0].ctypes.data, queries[2][1].ctypes.data)
+    assert err.value.status == P.capi.PSI_ERR_STATE
+    outs = []
+    for i in range(3):
+        cc.query_commit()
+        if i == 0:   # buffer 0 is free again: the third query goes there while the second is still pending
+            assert cc.query_next_landing() == 0
+            cc.query_upload_ptr(queries[2][0].ctypes.data, queries[2][1].ctypes.data)
+        cc.run()
+        outs.append(cc.result_get())
+    for i in range(3):
+        assert np.array_equal(outs[i], want[i]), "query %d" % i
+
+
 def test_cpp_known_answer_program():
     """tests/cpp/TestBatchedFHEPIE.cpp: the reference's own test program re-targeted at the C++ drop-in class;
     success criterion of the reference: the string "Matches" printed exactly twice (TestBatchedFHEPIE.cpp:73)."""

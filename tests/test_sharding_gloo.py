@@ -68,7 +68,7 @@ def _worker(rank, world, port, tmpdir):
     idx_flat = torch.from_numpy(idx.view(np.int64).reshape(-1))
     minus_flat = torch.from_numpy(minus.view(np.int64).reshape(-1))
     landing_idx, landing_minus = torch.zeros_like(idx_flat), torch.zeros_like(minus_flat)
-    qd = P.QueryDistributor(landing_idx, landing_minus, rank, world)
+    qd = P.QueryDistributor([(landing_idx, landing_minus)], rank, world)
     host = idx_flat.clone()
     host[:qd.begin] = -1
     host[qd.end:] = -1
