@@ -356,3 +356,34 @@ def test_run_randomised_shapes():
         want = o.run(pt, mask, idx, minus, evk_b, evk_a, nthreads=8)
         assert np.array_equal(cc.result_get(), want), (trial, N, L, K, b, E)
         cc.close()
+
+
+def test_run_is_repeatable_under_load():
+    """Race hunting without a sanitizer (compute-sanitizer is closed on the GPU pool): the full-size ring dimension,
+    enough bins to fill the machine several times over, the same query evaluated 150 times back to back - every
+    result must be bit-identical to the first, and the first to the oracle on a sampled bin.  A missing barrier
+    between register passes, a ring slot released too early or a stale twiddle tile shows up as a flaky limb."""
+    import zlib
+    cc, o, params = ctx_and_oracle(16384, 4)
+    rng = np.random.default_rng(4242)
+    _, evk_b, evk_a = o.keygen(12)
+    cc.InsertEvalMultKey(evk_b, evk_a)
+    K, b, E = 2, 40, 11
+    pt = sc.random_pt(rng, params, (K, b, E))
+    mask = sc.random_pt(rng, params, (b,))
+    idx = sc.random_ct(rng, params, (K, E))
+    minus = sc.random_ct(rng, params)
+    cc.db_load_limbs(pt, mask)
+    cc.query_set(idx, minus)
+    cc.run()
+    first = cc.result_get()
+    bin_ = 23
+    want = o.run(np.ascontiguousarray(pt[:, bin_:bin_ + 1]), np.ascontiguousarray(mask[bin_:bin_ + 1]), idx, minus, evk_b,
+                 evk_a, nthreads=4)
+    assert np.array_equal(first[bin_], want[0])
+    ref = zlib.crc32(first.tobytes())
+    out = np.empty_like(first)
+    for it in range(150):
+        cc.run()
+        cc.result_get(out)
+        assert zlib.crc32(out.tobytes()) == ref, "run %d differs from the first" % it
