@@ -387,3 +387,55 @@ def test_run_is_repeatable_under_load():
         cc.run()
         cc.result_get(out)
         assert zlib.crc32(out.tobytes()) == ref, "run %d differs from the first" % it
+
+
+def test_three_stream_pipeline_returns_every_query_its_own_result():
+    """The choreography bench.py times as e2e (upload stream / compute stream / download stream, two landing
+    buffers, two result buffers, events between them) with DIFFERENT queries in flight: every query must get the
+    oracle's result for its own ciphertexts."""
+    import torch
+    cc, o, params = ctx_and_oracle(2048, 3)
+    rng = np.random.default_rng(99)
+    _, evk_b, evk_a = o.keygen(5)
+    cc.InsertEvalMultKey(evk_b, evk_a)
+    K, b, E, nq = 2, 6, 5, 7
+    pt = sc.random_pt(rng, params, (K, b, E))
+    mask = sc.random_pt(rng, params, (b,))
+    cc.db_load_limbs(pt, mask)
+    ct_words = 2 * params.L * params.N
+    queries, hosts, outs = [], [], []
+    for _ in range(nq):
+        idx, minus = sc.random_ct(rng, params, (K, E)), sc.random_ct(rng, params)
+        queries.append((idx, minus))
+        h = torch.empty((K * E + 1) * ct_words, dtype=torch.int64).pin_memory()
+        h[:K * E * ct_words] = torch.from_numpy(np.ascontiguousarray(idx).view(np.int64).reshape(-1))
+        h[K * E * ct_words:] = torch.from_numpy(np.ascontiguousarray(minus).view(np.int64).reshape(-1))
+        hosts.append(h)
+        outs.append(torch.empty(b * ct_words, dtype=torch.int64).pin_memory())
+    s_in, s_run, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    ev_commit, ev_d2h = [None, None], [None, None]
+    for i in range(nq):
+        if ev_commit[i & 1] is not None:
+            s_in.wait_event(ev_commit[i & 1])          # landing buffer i & 1 is free once query i-2 was committed
+        base = hosts[i].data_ptr()
+        cc.query_upload_ptr(base, base + K * E * ct_words * 8, s_in.cuda_stream)
+        ev_up = torch.cuda.Event()
+        ev_up.record(s_in)
+        s_run.wait_event(ev_up)
+        cc.query_commit(s_run.cuda_stream)
+        ev_commit[i & 1] = torch.cuda.Event()
+        ev_commit[i & 1].record(s_run)
+        if ev_d2h[i & 1] is not None:
+            s_run.wait_event(ev_d2h[i & 1])            # result buffer i & 1 was read back
+        cc.run(s_run.cuda_stream)
+        ev_run = torch.cuda.Event()
+        ev_run.record(s_run)
+        s_out.wait_event(ev_run)
+        cc.result_get_ptr(outs[i].data_ptr(), s_out.cuda_stream)
+        ev_d2h[i & 1] = torch.cuda.Event()
+        ev_d2h[i & 1].record(s_out)
+    torch.cuda.synchronize()
+    for i, (idx, minus) in enumerate(queries):
+        want = o.run(pt, mask, idx, minus, evk_b, evk_a)
+        got = outs[i].numpy().view(np.uint64).reshape(want.shape)
+        assert np.array_equal(got, want), "query %d" % i
