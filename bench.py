@@ -392,18 +392,21 @@ def main():
 
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
 
-    def e2e_pipelined(steps):
-        """Returns elapsed ms for `steps` queries through the 3-stream pipeline."""
+    def e2e_pipelined(steps, warm):
+        """Elapsed ms of `steps` queries through the 3-stream pipeline.  The `warm` untimed queries before them run
+        through the SAME pipeline, so the timed region is the pipeline in steady state: it opens right before the
+        upload of the first timed query and closes when the result of the last one is in host memory, i.e. it
+        contains every H2D, kernel and D2H of exactly `steps` queries (plus whatever the warm-up queries still
+        have in flight when it opens)."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev_commit = [None, None]               # commit events of the two landing buffers
         ev_d2h = [None, None]
-        e0.record(s_in)
-        stream.wait_event(e0)
-        s_out.wait_event(e0)
-        for i in range(steps):
+        for i in range(warm + steps):
             if ev_commit[i & 1] is not None:
                 s_in.wait_event(ev_commit[i & 1])     # landing buffer i & 1 is free once the commit of query i-2 ran
+            if i == warm:
+                e0.record(s_in)
             upload_query(s_in)
             ev_up = torch.cuda.Event()
             ev_up.record(s_in)
@@ -430,8 +433,8 @@ def main():
             ms = float(tms.item())
         return ms
 
-    e2e_pipelined(3)
-    ms_e2e = e2e_pipelined(args.steps) / args.steps
+    e2e_pipelined(3, 0)
+    ms_e2e = e2e_pipelined(args.steps, max(args.warmup, 3)) / args.steps
     sampler.active = False
     sampler.stop_flag = True
 
@@ -507,7 +510,8 @@ def main():
                     "serial_value": total_items / (ms_e2e_serial * 1e-3),
                     "path": "pinned host query -> psi_query_upload | psi_query_commit -> psi_run -> psi_result_get -> "
                             "pinned host, three streams: upload of query i+1 and download of result i-1 overlap "
-                            "run i (serial_* = one query at a time)"
+                            "run i; the warm-up queries run through the same pipeline, the timed region holds every copy "
+                            "and kernel of exactly `steps` queries (serial_* = one query at a time)"
                             + ((" (N > 1: NCCL gather to rank 0 over NVLink, then one D2H)" if args.gather == "nccl" else
                                 " (N > 1: every rank downloads its own bins over its own PCIe link)") if world > 1 else ""),
                     "gather": args.gather if world > 1 else None, "rank0_numa_node": numa_node,
