@@ -244,6 +244,12 @@ int psi_client_table(uint64_t hash_seed, uint32_t k, uint64_t e, uint32_t K, con
 int psi_random_data_input(size_t server_size, size_t client_size, size_t intersection_size, uint64_t seed,
                           uint64_t bit_size, uint64_t* server, uint64_t* client, uint64_t* intersection);
 
+/* Seed value that asks for a fresh std::random_device seed.  shuffle_seed / mask_seed drive the bin shuffle and
+ * the random masks of the PIE constructor (BatchedFHEHIPPIE.cpp:25-35,73-82); the masks are security-critical
+ * (a known mask lets the client divide it out of the response), so production callers pass PSI_SEED_RANDOM,
+ * which is what the reference does.  Explicit seeds are for reproducible tests only. */
+#define PSI_SEED_RANDOM 0xFFFFFFFFFFFFFFFFull
+
 /* BatchedFHEHIPPIE ctor: validates (stash, combined tables -> PSI_ERR_INVALID with the reference's
  * messages), shuffles the bin rows of hct IN PLACE, transposes, encodes on the device. */
 int psi_pie_create(psi_ctx* ctx, const psi_params* params, psi_hct* hct, uint64_t shuffle_seed, uint64_t mask_seed,

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__((2 + L) * kGroup, L <= 4 ? 2 : 1)
         u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
 #pragma unroll
         for (int i = 0; i < L; i++) {
-            const u64 d = lazy_sub_hi(arr[(2 + i) * P + sl(j)], q2);  // < 2q + 2^32: L <= 4 terms stay < q * 2^64
+            const u64 d = lazy_sub_hi(arr[(2 + i) * P + sl(j)], q2);  // < 2q + 2^32: L <= 7 terms, 14 q^2 + small < q * 2^64 for q < 2^60
             mac128(h0, l0, d, evk_bR[(size_t)i * LN + n]);
             mac128(h1, l1, d, evk_aR[(size_t)i * LN + n]);
         }

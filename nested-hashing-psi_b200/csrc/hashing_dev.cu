@@ -157,6 +157,10 @@ cudaError_t hct_build_device(cudaStream_t s, const u64* T, uint32_t k, uint32_t 
     cudaError_t err;
     const size_t n_cells = (size_t)k * e * K * b * E;
     if ((err = cudaMemsetAsync(cells, 0, n_cells * sizeof(u64), s)) != cudaSuccess) return err;
+    if (n == 0) {  // an empty server set is an all-empty table (the host build accepts it too)
+        *failed = 0;
+        return cudaStreamSynchronize(s);
+    }
     uint32_t *keys = nullptr, *keys_sorted = nullptr, *start = nullptr;
     u64* bucketed = nullptr;
     Mt19937* rng = nullptr;

@@ -85,6 +85,10 @@ struct DevBuf {
         p = nullptr;
         n = 0;
     }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }  // locals are freed on every exit path (CK returns early)
 };
 
 }  // namespace psi
@@ -481,12 +485,18 @@ int psi_db_load_limbs(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E, const uint
     {
         const size_t n_pt = (size_t)K * b * E, chunk = n_pt < kDbChunk ? n_pt : kDbChunk;
         CK(c->stage.alloc(chunk * LN));
+        DevBuf<int> d_bad;  // raised by the re-tiling kernel when a limb is not a canonical residue
+        CK(d_bad.alloc(1));
+        CK(cudaMemset(d_bad.p, 0, sizeof(int)));
         for (size_t p0 = 0; p0 < n_pt; p0 += chunk) {
             const size_t n = (n_pt - p0) < chunk ? (n_pt - p0) : chunk;
             CK(cudaMemcpy(c->stage.p, pt_limbs + p0 * LN, n * LN * sizeof(u64), cudaMemcpyHostToDevice));
-            CK(launch_retile_pt(0, c->stage.p, c->pt.p, LN, E, p0, n, true));
+            CK(launch_retile_pt(0, c->stage.p, c->pt.p, LN, E, p0, n, true, c->d_tab, d_bad.p));
             CK(cudaStreamSynchronize(0));
         }
+        int bad = 0;
+        CK(cudaMemcpy(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (bad) return set_error(PSI_ERR_INVALID, "plaintext limbs must be canonical residues (value >= q_l found)");
     }
     CK(cudaMemcpy(c->mask.p, mask_limbs, (size_t)b * LN * sizeof(u64), cudaMemcpyHostToDevice));
     CK(launch_to_montgomery(c->k(0), b, c->mask.p, c->maskR.p));
@@ -612,10 +622,10 @@ int psi_db_build_from_items(psi_ctx* c, uint64_t hash_seed, uint32_t k, uint64_t
         return rc;
     }
     // bin shuffle (BatchedFHEHIPPIE.cpp:25-35) as permutations, masks (:73-82): same generators as the host ctor
-    std::mt19937 mt((uint32_t)shuffle_seed);
+    std::mt19937 mt = seeded_mt19937(resolve_seed(shuffle_seed));
     const std::vector<uint16_t> perm = makeBinShuffle(k, e, K, b, mt);
     std::vector<int64_t> mask_slots((size_t)b * nslots);
-    std::mt19937_64 mm(mask_seed);
+    std::mt19937_64 mm(resolve_seed(mask_seed));
     for (auto& v : mask_slots) v = (int64_t)(mm() % (t - 1) + 1);
     DevBuf<uint16_t> d_perm;
     DevBuf<u64> d_crt;
@@ -765,21 +775,31 @@ int psi_run_phases(psi_ctx* c, uint32_t phases, void* stream) {
         c->launches_per_run = nl;
         return PSI_OK;
     }
-    c->out_cur ^= 1u;  // this run's result buffer
-    u64* const result = c->out_buf(c->out_cur);
+    // this run writes the OTHER result buffer; out_cur / ran only change once every launch has been enqueued, so a
+    // failure part-way never exposes a half-written buffer through psi_result_get
+    const uint32_t next_out = c->out_cur ^ 1u;
+    u64* const result = c->out_buf(next_out);
     if (c->K == 1) {
-        CK(launch_mul_ctpt(k, c->b, c->acc.p, c->mask.p, result)); nl++;
+        cudaError_t e1 = launch_mul_ctpt(k, c->b, c->acc.p, c->mask.p, result);
+        if (e1 != cudaSuccess) {
+            c->ran = false;
+            return cuda_fail(e1, "launch_mul_ctpt");
+        }
+        nl++;
     } else {
         const u64* prod = c->acc.p;  // hf = 0
         for (uint32_t hf = 1; hf < c->K; hf++) {
             const bool last = hf + 1 == c->K;
             u64* dst = last ? result : c->prod.p;
             if ((rc = mul_ctct_batch(c, s, c->b, prod, c->acc.p + (size_t)hf * c->b * ct, last ? c->mask.p : nullptr,
-                                     dst, &nl)))
+                                     dst, &nl))) {
+                c->ran = false;
                 return rc;
+            }
             prod = dst;
         }
     }
+    c->out_cur = next_out;
     c->launches_per_run = nl;
     c->ran = true;
     return PSI_OK;
@@ -852,35 +872,34 @@ int psi_debug_mul_ctct(psi_ctx* c, const uint64_t* ct1, const uint64_t* ct2, uin
     if (!c->have_evk) return set_error(PSI_ERR_STATE, "EvalMult(ct,ct) needs the relinearisation key");
     int rc = ensure_device(c);
     if (rc) return rc;
-    // borrow the work buffers with b = 1, K = 2
-    const uint32_t sK = c->K, sb = c->b, sE = c->E;
-    const bool sdb = c->have_db, sq = c->have_query, sr = c->ran;
+    if (c->have_db && c->K < 2)
+        return set_error(PSI_ERR_STATE, "debug ct x ct needs work buffers of a K >= 2 database (or no database)");
+    // borrow the work buffers with b = 1, K = 2; the guard restores the context and frees the staging buffer on
+    // every exit path
+    struct Guard {
+        psi_ctx* c;
+        uint32_t K, b, E;
+        DevBuf<u64> in;
+        ~Guard() {
+            in.release();
+            c->K = K;
+            c->b = b;
+            c->E = E;
+        }
+    } g{c, c->K, c->b, c->E, {}};
     if (!c->have_db) {
         c->K = 2;
         c->b = 1;
         c->E = 1;
         if ((rc = alloc_work(c))) return rc;
-    } else if (c->K < 2) {
-        return set_error(PSI_ERR_STATE, "debug ct x ct needs work buffers of a K >= 2 database (or no database)");
     }
     const size_t ct = (size_t)2 * c->L * c->N;
-    DevBuf<u64> in;
-    CK(in.alloc(3 * ct));
-    CK(cudaMemcpy(in.p, ct1, ct * sizeof(u64), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(in.p + ct, ct2, ct * sizeof(u64), cudaMemcpyHostToDevice));
-    rc = mul_ctct_batch(c, 0, 1, in.p, in.p + ct, nullptr, in.p + 2 * ct, nullptr);
-    if (rc == PSI_OK) {
-        cudaError_t e = cudaMemcpy(out, in.p + 2 * ct, ct * sizeof(u64), cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) rc = cuda_fail(e, "psi_debug_mul_ctct");
-    }
-    in.release();
-    c->K = sK;
-    c->b = sb;
-    c->E = sE;
-    c->have_db = sdb;
-    c->have_query = sq;
-    c->ran = sr;
-    return rc;
+    CK(g.in.alloc(3 * ct));
+    CK(cudaMemcpy(g.in.p, ct1, ct * sizeof(u64), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(g.in.p + ct, ct2, ct * sizeof(u64), cudaMemcpyHostToDevice));
+    if ((rc = mul_ctct_batch(c, 0, 1, g.in.p, g.in.p + ct, nullptr, g.in.p + 2 * ct, nullptr))) return rc;
+    CK(cudaMemcpy(out, g.in.p + 2 * ct, ct * sizeof(u64), cudaMemcpyDeviceToHost));
+    return PSI_OK;
 }
 
 int psi_bench_imad_peak(int device, double* mads_per_second) { return psi_bench_pipe_peak(device, 0, mads_per_second); }

@@ -208,24 +208,30 @@ __device__ __forceinline__ u64 to_split30(u64 v) { return ((v >> 30) << 32) | (v
 __device__ __forceinline__ u64 from_split30(u64 v) { return ((v >> 32) << 30) | (v & 0x3fffffffull); }
 
 // chunk of n plaintexts starting at plaintext index p0: flat [n][LN] canonical <-> tiled DB
+// range_tab / bad: when given (caller-supplied limbs, psi_db_load_limbs), a residue >= q_l raises *bad instead of
+// being silently truncated by to_split30
 __global__ void __launch_bounds__(256) k_retile_pt(u64* __restrict__ flat, u64* __restrict__ tiled, size_t LN, uint32_t E,
-                                                   size_t p0, size_t total, int to_tiled) {
+                                                   size_t p0, size_t total, int to_tiled,
+                                                   const DevTables* __restrict__ range_tab, int* __restrict__ bad) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const size_t p = p0 + i / LN, cidx = i % LN;
     const size_t g = p / E, pos = p % E, tile = cidx / kMacCoeffs, w = cidx % kMacCoeffs;
     const size_t T = LN / kMacCoeffs;
     const size_t d = ((g * T + tile) * E + pos) * kMacCoeffs + w;
-    if (to_tiled)
-        tiled[d] = to_split30(flat[i]);
-    else
+    if (to_tiled) {
+        const u64 v = flat[i];
+        if (range_tab && v >= range_tab->mods[cidx / range_tab->N].q) *bad = 1;
+        tiled[d] = to_split30(v);
+    } else {
         flat[i] = from_split30(tiled[d]);
+    }
 }
 cudaError_t launch_retile_pt(cudaStream_t s, u64* flat, u64* tiled, size_t LN, uint32_t E, size_t p0, size_t n,
-                             bool to_tiled) {
+                             bool to_tiled, const DevTables* range_tab, int* bad) {
     const size_t total = n * LN;
     if (total == 0) return cudaSuccess;
-    k_retile_pt<<<cdiv(total, 256), 256, 0, s>>>(flat, tiled, LN, E, p0, total, to_tiled ? 1 : 0);
+    k_retile_pt<<<cdiv(total, 256), 256, 0, s>>>(flat, tiled, LN, E, p0, total, to_tiled ? 1 : 0, range_tab, bad);
     return cudaGetLastError();
 }
 // The index words are stored in Montgomery form (times R = 2^64 mod q_l): the inner product of k_mac_tma then ends

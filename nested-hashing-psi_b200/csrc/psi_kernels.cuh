@@ -68,7 +68,7 @@ cudaError_t launch_ntt(const KCtx& k, const NttBatch& b, bool inverse);
 // Phase 1: acc[hf][bin] = sum_pos idx[hf][pos] (.) pt[hf][bin][pos] + minus
 // pt and idx are in tiled split-30 storage (launch_retile_*), minus and acc canonical [..][L][N].
 cudaError_t launch_retile_pt(cudaStream_t s, u64* flat, u64* tiled, size_t LN, uint32_t E, size_t p0, size_t n,
-                             bool to_tiled);
+                             bool to_tiled, const DevTables* range_tab = nullptr, int* bad = nullptr);
 cudaError_t launch_retile_idx(const KCtx& k, const u64* flat, u64* tiled, size_t LN, uint32_t K, uint32_t E);
 cudaError_t launch_mac(const KCtx& k, uint32_t K, uint32_t b, uint32_t E, const u64* pt, const u64* idx,
                        const u64* minus, u64* acc);

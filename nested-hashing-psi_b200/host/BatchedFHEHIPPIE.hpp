@@ -43,11 +43,13 @@ class BatchedFHEHIPPIE {
     bool uploaded = false;
 
    public:
-    // The reference seeds the bin shuffle and the masks from std::random_device
-    // (BatchedFHEHIPPIE.cpp:25-26); the two seeds make them reproducible.  keepSlots retains the
-    // slot vectors the constructor built (tests compare them with the oracle's transposition).
+    // The bin shuffle and the masks are SECURITY-CRITICAL randomness: a client who knows the mask r can divide it
+    // out of r * prod(y_hf - x) and learn about non-matching server items.  Like the reference
+    // (BatchedFHEHIPPIE.cpp:25-26) the default draws both seeds from std::random_device (PSI_SEED_RANDOM).
+    // Explicit seeds exist for TESTS ONLY (they make the database reproducible).  keepSlots retains the slot
+    // vectors the constructor built (tests compare them with the oracle's transposition).
     BatchedFHEHIPPIE(CryptoContext& cryptor, PublicKey& pK, HierarchicalCuckooHashTable& hct,
-                     uint64_t shuffleSeed = 0x5eed0001ull, uint64_t maskSeed = 0x5eed0002ull, bool keepSlots = false);
+                     uint64_t shuffleSeed = PSI_SEED_RANDOM, uint64_t maskSeed = PSI_SEED_RANDOM, bool keepSlots = false);
 
     void run();
 

@@ -31,6 +31,19 @@ inline uint64_t boost_uniform_u64(std::mt19937& mt) {
     return lo | (hi << 32);
 }
 
+// Generators of the security-critical randomness of the PIE constructor (bin shuffle, masks).  The reference
+// seeds a 32-bit mt19937 from std::random_device (BatchedFHEHIPPIE.cpp:25-26); here all 64 bits of a seed are
+// used (seed_seq over both halves), and PSI_SEED_RANDOM asks for a fresh std::random_device seed.
+inline uint64_t resolve_seed(uint64_t seed) {
+    if (seed != ~0ull) return seed;  // PSI_SEED_RANDOM
+    std::random_device rd;
+    return ((uint64_t)rd() << 32) | (uint64_t)rd();
+}
+inline std::mt19937 seeded_mt19937(uint64_t seed) {
+    std::seed_seq sq{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    return std::mt19937(sq);
+}
+
 class TabulationHashing {
    public:
     static constexpr size_t kChunks = 16;  // tParam: bytes of input consumed

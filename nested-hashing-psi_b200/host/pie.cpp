@@ -28,7 +28,7 @@ BatchedFHEHIPPIE::BatchedFHEHIPPIE(CryptoContext& cryptor, PublicKey& pK_, Hiera
 
     // Shuffle bins beforehand (BatchedFHEHIPPIE.cpp:25-35): the rows of every hash-function table of
     // every inner cuckoo table are permuted; this mutates the caller's table, as the reference does.
-    std::mt19937 mt((uint32_t)shuffleSeed);
+    std::mt19937 mt = seeded_mt19937(resolve_seed(shuffleSeed));
     for (auto& hctRow : hct.hierarchicalCuckooTable)
         for (auto& ct : hctRow) ct.shuffleBins(mt);
 
@@ -55,7 +55,7 @@ BatchedFHEHIPPIE::BatchedFHEHIPPIE(CryptoContext& cryptor, PublicKey& pK_, Hiera
     // Random non-zero masks r in [1, t-1] (BatchedFHEHIPPIE.cpp:73-82); generator documented in
     // DESIGN.md (the reference draws from a random_device-seeded boost::mt19937, so no sequence is pinned).
     std::vector<int64_t> maskSlots((size_t)b * batchSize);
-    std::mt19937_64 mm(maskSeed);
+    std::mt19937_64 mm(resolve_seed(maskSeed));
     for (auto& v : maskSlots) v = (int64_t)(mm() % (t - 1) + 1);
 
     check(psi_db_encode_slots(cryptoContext.device_ctx, K, b, E, nslots, slots.data(), maskSlots.data()),

@@ -40,6 +40,13 @@ def _raise_like_reference(err):
     raise err
 
 
+SEED_RANDOM = 0xFFFFFFFFFFFFFFFF   # PSI_SEED_RANDOM
+
+
+def _seed(s):
+    return SEED_RANDOM if s is None else int(s)
+
+
 class PublicKey:
     """Stored but never used by run() (BatchedFHEHIPPIE.hpp:22); kept for signature parity."""
 
@@ -114,10 +121,13 @@ class CryptoContext:
             _raise_like_reference(err)
         return cells
 
-    def db_build_from_items(self, hashfunction, k, e, K, E, b, items, evictionSeed=0x5EED, shuffleSeed=0x5EED0001,
-                            maskSeed=0x5EED0002):
-        """The PIE constructor's whole data path on the device (table build, shuffle, transposition, encode)."""
+    def db_build_from_items(self, hashfunction, k, e, K, E, b, items, evictionSeed=0x5EED, shuffleSeed=None,
+                            maskSeed=None):
+        """The PIE constructor's whole data path on the device (table build, shuffle, transposition, encode).
+        shuffleSeed / maskSeed: None = fresh std::random_device seeds (the reference's behaviour; the masks are
+        security-critical), explicit values only for reproducible tests."""
         (items, pi) = _u64(items)
+        shuffleSeed, maskSeed = _seed(shuffleSeed), _seed(maskSeed)
         try:
             check(lib().psi_db_build_from_items(self._h, hashfunction.seed, k, e, K, E, b, evictionSeed, pi, items.shape[0],
                                                 shuffleSeed, maskSeed))
@@ -339,13 +349,15 @@ class BatchedFHEHIPPIE:
     """The reference's operator, same five entry points.  The constructor mutates `hct` (bin shuffle),
     exactly as BatchedFHEHIPPIE.cpp:28-35 does."""
 
-    def __init__(self, cryptoContext, pK, hct, shuffleSeed=0x5EED0001, maskSeed=0x5EED0002, keepSlots=False):
+    def __init__(self, cryptoContext, pK, hct, shuffleSeed=None, maskSeed=None, keepSlots=False):
+        """shuffleSeed / maskSeed: None (default) draws them from std::random_device like the reference
+        (BatchedFHEHIPPIE.cpp:25-26); the masks are security-critical, explicit seeds are for tests only."""
         self.cryptoContext = cryptoContext
         self.pK = pK
         h = ctypes.c_void_p()
         try:
-            check(lib().psi_pie_create(cryptoContext._h, ctypes.byref(cryptoContext.params), hct._h, shuffleSeed,
-                                       maskSeed, int(keepSlots), ctypes.byref(h)))
+            check(lib().psi_pie_create(cryptoContext._h, ctypes.byref(cryptoContext.params), hct._h, _seed(shuffleSeed),
+                                       _seed(maskSeed), int(keepSlots), ctypes.byref(h)))
         except PsiError as e:
             _raise_like_reference(e)
         self._h = h
@@ -361,7 +373,7 @@ class BatchedFHEHIPPIE:
     @classmethod
     def fromServerSet(cls, cryptoContext, pK, hashfunction, eachSimpleTableSize, eachCuckooTableSize,
                       numberOfSimpleHashFunctions, numberOfCuckooHashFunctions, maxItemsPerPosition, serverSet,
-                      evictionSeed=0x5EED, shuffleSeed=0x5EED0001, maskSeed=0x5EED0002):
+                      evictionSeed=0x5EED, shuffleSeed=None, maskSeed=None):
         """Offline phase entirely on the device: HierarchicalCuckooHashTable::insertAll + the PIE constructor
         (table build, bin shuffle, transposition, MakePackedPlaintext, SetFormat) without the table ever visiting
         the host.  Same database as BatchedFHEHIPPIE(ctx, pk, host-built table) with the same seeds."""

@@ -38,6 +38,10 @@ class ShardedPIE:
     """
 
     def __init__(self, b, rank, world):
+        if world > b:
+            # an empty bin block would leave that rank outside the evaluation while the others wait for it in the
+            # NCCL gather; the caller shrinks the process group instead (b bins keep at most b GPUs busy)
+            raise ValueError("more ranks (%d) than bins (%d): run at most one rank per bin" % (world, b))
         self.b, self.rank, self.world = b, rank, world
         self.begin, self.end = bin_shard(b, rank, world)
         self.sizes = [bin_shard(b, r, world)[1] - bin_shard(b, r, world)[0] for r in range(world)]
