@@ -8,13 +8,22 @@ BatchedFHEPSIServer.cpp:99-106).
   value      server items matched / s, query and database already resident in HBM, CUDA-event time of
              K run() calls on the launching stream, max over ranks
   e2e        same metric through the reference-facing call sequence with HOST buffers: pinned-host
-             query -> psi_query_set (H2D) -> psi_run -> psi_result_get (D2H) [+ NCCL gather for N > 1]
+             query -> psi_query_upload/commit (H2D) -> psi_run -> psi_result_get (D2H); serial_* = one query at a
+             time (the reference's one-query-per-session case), limb_vectors = the query held as K*E*2*L separately
+             allocated pageable vectors (what OpenFHE holds) through psi_query_upload_limbs / psi_result_get_limbs
   roofline   the inner-product kernel (HBM-bound): algorithmic bytes / its own event-timed duration
   cpu_baseline  the CPU oracle (restatement of the OpenFHE path; the real reference cannot be built
-             here) on the host cores, on a bounded sample of bins of the same workload
+             here) on the host cores: warm (plaintexts already in EVALUATION form) and cold
+             (plaintext transforms inside run(), what the reference's one-query-per-process run() pays)
+  parity_checked_bins  bins of THIS run's results (>= 1 per rank) re-computed by the oracle on rank 0, outside the
+             timed region; the run aborts if a limb differs
 
-python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload NAME] [--scaling weak|strong]
-Under torchrun one rank per GPU; rank 0 prints ONE JSON line.
+N > 1 (torchrun, one rank per GPU): default --scaling strong = ONE 2^24-item query whose 47 bins are sharded over the
+N GPUs (BASELINE configs[2]; the same query on every rank, bins [47 r/N, 47 (r+1)/N) on rank r); the weak-scaling
+figures (every GPU a full 47-bin block of an N-times larger server set) ride in the same line under "weak".
+
+python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload NAME] [--scaling strong|weak]
+Rank 0 prints ONE JSON line.
 """
 import argparse
 import json
@@ -45,8 +54,10 @@ WORKLOADS = {
     "2^22_vs_2^10": dict(S=1 << 22, C=1 << 10, I=513, k=2, e=4949, K=2, b=26, E=26, N=16384, bits=32),
     # "1024 268435456 513 2 4949 176 176" (Parameters1.txt:23): the largest server set of the file, 32 GB of plaintexts
     "2^28_vs_2^10": dict(S=1 << 28, C=1 << 10, I=513, k=2, e=4949, K=2, b=176, E=176, N=16384, bits=32),
-    # reduced case for quick functional runs (not a BASELINE config)
-    "2^16_vs_2^8": dict(S=1 << 16, C=1 << 8, I=129, k=2, e=1900, K=2, b=8, E=8, N=16384, bits=32),
+    # BASELINE configs[0]: the reference's own CPU-runnable case, TestBatchedFHEPIE's context (t = 2^32 + 2^20 + 2^19 + 1,
+    # depth 2, ring dimension chosen by the library = 8192, TestBatchedFHEPIE.cpp:14-26) at 2^16 server items vs 2^8
+    # client items; no Parameters1.txt row exists for 256 clients: e interpolated, b = E by insertion success
+    "2^16_vs_2^8": dict(S=1 << 16, C=1 << 8, I=129, k=2, e=1900, K=2, b=8, E=8, N=8192, bits=32, depth=2),
 }
 DEFAULT_WORKLOAD = "2^24_vs_2^10"
 METRIC = "server items matched/sec (BatchedFHEPIE run(), ms per client query in ms_per_step)"
@@ -64,9 +75,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
+    ap.add_argument("--no-weak", action="store_true", help="N > 1, strong scaling: skip the extra weak-scaling measurement")
     ap.add_argument("--cpu-sample-bins", type=int, default=0, help="bins per CPU-baseline repetition (0 = all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-limb-leg", action="store_true", help="skip the e2e leg with separately allocated limb vectors")
     ap.add_argument("--gather", default="host", choices=["host", "nccl"],
                     help="N > 1 response gather inside e2e: 'host' = every rank copies its own result ciphertexts to "
                          "pinned host memory over its own PCIe link (what a one-process server does with one pinned "
@@ -80,6 +93,15 @@ def parse():
     ap.add_argument("--synthetic-db", action="store_true",
                     help="random slot values instead of hashing a real server set (same shapes, same timing)")
     return ap.parse_args()
+
+
+def workload_depth(w):
+    """Multiplicative depth of the context: the client's rule (BatchedFHEPSIClient.cpp:46-57) unless the workload
+    pins it (configs[0] uses TestBatchedFHEPIE's depth 2)."""
+    if "depth" in w:
+        return w["depth"]
+    E = w["E"]
+    return 3 if E < 500 else (5 if E < 5000 else 10)
 
 
 def random_limbs(rng, params, lead):
@@ -133,50 +155,82 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_oracle_rate(w, params, n_bins, steps, threads=None):
+def host_threads():
+    """Host cores this process may use.  torch.distributed.run exports OMP_NUM_THREADS=1 for its workers; the CPU arm
+    is not a worker of the GPU job, so the variable is cleared (before libgomp loads) and the count comes from the
+    affinity mask."""
+    os.environ.pop("OMP_NUM_THREADS", None)
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def ref_params(w):
+    """psi_params from the ORACLE's own exact generator (oracle/params_ref.py): the reference arm never maps
+    libpsi_b200.so."""
+    from oracle.params_ref import RefParams
+    return RefParams(w["N"], T32, depth=workload_depth(w)).to_struct()
+
+
+def cpu_oracle_rate(w, params, n_bins, steps, threads, cold=False):
     """Oracle (CPU restatement, oracle/psi_oracle.c) on `n_bins` bins of the workload with random limbs.
-    Returns (items_per_s, seconds_per_step, threads)."""
-    from oracle.oracle import Oracle, max_threads
+    cold: the plaintexts are still packed coefficients and are lifted + transformed inside every run (the reference's
+    first run()).  Returns (items_per_s, seconds_per_step, threads, bins)."""
+    from oracle.oracle import Oracle, run_cold
     o = Oracle(params)
-    threads = threads or max_threads()
     rng = np.random.default_rng(99)
     K, E = w["K"], w["E"]
     # bounded sample: at most ~3 GB of host plaintexts (whole query for the BASELINE configs up to 2^24 vs 2^10)
     cap = max(min(threads, n_bins), int(3.2e9 // (K * E * params.L * params.N * 8)))
     n_bins = min(n_bins, w["b"], cap)
-    pt = random_limbs(rng, params, (K, n_bins, E))
-    mask = random_limbs(rng, params, (n_bins,))
     idx = random_limbs(rng, params, (K, E, 2))
     minus = random_limbs(rng, params, (2,))
     evk_b = random_limbs(rng, params, (params.L,))
     evk_a = random_limbs(rng, params, (params.L,))
-    o.run(pt, mask, idx, minus, evk_b, evk_a, nthreads=threads)  # warm-up (page in, twiddles hot)
+    if cold:
+        ptc = rng.integers(0, int(params.t), size=(K, n_bins, E, params.N), dtype=np.uint64)
+        mc = rng.integers(0, int(params.t), size=(n_bins, params.N), dtype=np.uint64)
+        fn = lambda: run_cold(o, ptc, mc, idx, minus, evk_b, evk_a, nthreads=threads)  # noqa: E731
+    else:
+        pt = random_limbs(rng, params, (K, n_bins, E))
+        mask = random_limbs(rng, params, (n_bins,))
+        fn = lambda: o.run(pt, mask, idx, minus, evk_b, evk_a, nthreads=threads)  # noqa: E731
+    fn()  # warm-up (page in, twiddles hot)
     t0 = time.perf_counter()
     for _ in range(steps):
-        o.run(pt, mask, idx, minus, evk_b, evk_a, nthreads=threads)
+        fn()
     dt = (time.perf_counter() - t0) / steps
     items = w["S"] * n_bins / w["b"]
     return items / dt, dt, threads, n_bins
 
 
-def run_reference(args, w, rank):
+def run_reference(args, w, rank, world):
     """--impl reference: the reference's CPU implementation of the path on the host cores.  The real
     reference (OpenFHE + libscapi + Boost 1.71) cannot be built in this image, so this is the oracle
-    PORT of it, all host threads, each step a bounded sample of bins of the same workload."""
+    PORT of it, all host threads.  Same workload as the GPU arm at every N: with the default strong scaling the job
+    is ONE query against the 2^24-item database whatever N is; with --scaling weak it is N such databases (the port
+    evaluates one and the rate is what N of them would take one after the other, i.e. the same rate)."""
     if rank != 0:
         return
-    import psi_b200 as P
-    params = P.params_generate(w["N"], T32, P.depth_for_E(w["E"]))
-    n_bins = w["b"]  # the whole query per step: OpenMP over bins keeps every host thread busy
-    rate, dt, threads, n_bins = cpu_oracle_rate(w, params, n_bins, max(args.steps, 1))  # (warms itself once)
+    threads = host_threads()
+    params = ref_params(w)
+    steps = max(args.steps, 1)
+    rate, dt, threads, n_bins = cpu_oracle_rate(w, params, w["b"], steps, threads)   # the whole query per step
+    cold_steps = max(1, min(steps, 3))
+    rate_c, dt_c, _, n_bins_c = cpu_oracle_rate(w, params, w["b"], cold_steps, threads, cold=True)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "items/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * w["b"] / n_bins,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": workload_config(args, w, params, 1),
+        "config": workload_config(args, w, params, world),
         "cpu_baseline": {"value": rate, "unit": "items/s", "cores": threads, "kind": "port",
                          "sample": "%d of %d bins per step, warm plaintexts (already in EVALUATION form), "
-                                   "OpenMP over bins" % (n_bins, w["b"])},
+                                   "OpenMP over bins" % (n_bins, w["b"]),
+                         "cold": {"value": rate_c, "unit": "items/s", "ms_per_step": dt_c * 1e3 * w["b"] / n_bins_c,
+                                  "steps": cold_steps,
+                                  "sample": "%d of %d bins per step; K*b*E + b plaintexts lifted and transformed inside "
+                                            "run(), the reference's one-query-per-process case" % (n_bins_c, w["b"])}},
         "e2e": {"value": rate, "unit": "items/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -214,10 +268,10 @@ def workload_config(args, w, params, world):
                         "K=%d b=%d E=%d (Parameters1.txt), N=%d, sizeQ=%d x 60-bit, sizeP=%d, t=%d, HPSPOVERQ + BV"
                         % (args.workload, w["S"], w["C"], w["k"], w["e"], w["K"], w["b"], w["E"], params.N, params.L,
                            params.Lp, params.t),
-            "bins_per_gpu": w["b"] if args.scaling == "weak" else "%d/%d" % (w["b"], world),
+            "bins_per_gpu": w["b"] if (args.scaling == "weak" or world == 1) else "%d/%d" % (w["b"], world),
             "server_items_total": w["S"] * (world if args.scaling == "weak" else 1),
             "sharding": "bins" if world > 1 else "none",
-            "l2_policy": "inputs larger than L2 (plaintext DB %.2f GB per GPU streams from HBM every step)"
+            "l2_policy": "inputs larger than L2 (plaintext DB %.2f GB in total streams from HBM every step)"
                          % (8.0 * params.L * params.N * w["K"] * w["b"] * w["E"] / 1e9)}
 
 
@@ -228,7 +282,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, w, rank)
+        run_reference(args, w, rank, world)
         return
 
     import torch
@@ -237,6 +291,8 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU port)")
+    if world > w["b"]:
+        raise SystemExit("bench.py: %d ranks for %d bins" % (world, w["b"]))
     numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -244,73 +300,76 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
 
-    params = P.params_generate(w["N"], T32, P.depth_for_E(w["E"]))
+    params = P.params_generate(w["N"], T32, workload_depth(w))
     L, N, K, E = params.L, params.N, w["K"], w["E"]
+    ct_words = 2 * L * N
     cc = P.CryptoContext(params, device=local_rank)
-    rng = np.random.default_rng(1234 + rank)
-
-    # ---- offline phase: server set -> nested cuckoo table -> BatchedFHEHIPPIE ctor (GPU encode) ----------
-    t_off = time.perf_counter()
-    shard = P.ShardedPIE(w["b"], rank, world)
-    if args.scaling == "weak":
-        b_local = w["b"]          # every GPU holds a full block of b bins of an N-times larger server set
-    else:
-        b_local = shard.end - shard.begin
     nslots = w["k"] * w["e"]
-    if args.synthetic_db:
-        slots = rng.integers(1, T32, (K, b_local, E, nslots), dtype=np.int64)
-        mask_slots = rng.integers(1, T32, (b_local, nslots), dtype=np.int64)
-        cc.db_encode_slots(slots, mask_slots)
-        del slots
-    else:
-        seed = 123456789 + (rank if args.scaling == "weak" else 0)      # itemSeed (CLI.cpp:67)
+    hashf = P.TabulationHashing(987654321, w["k"] + K)               # hashSeed (CLI.cpp:68)
+
+    def build_db(scaling):
+        """Offline phase: server set -> nested cuckoo table -> BatchedFHEHIPPIE ctor (GPU build + encode).  Returns
+        (b_local, first global bin)."""
+        shard = P.ShardedPIE(w["b"], rank, world)
+        sharded = scaling == "strong" and world > 1
+        b0, b1 = (shard.begin, shard.end) if sharded else (0, w["b"])
+        rng_db = np.random.default_rng(77 + (0 if sharded else rank))
+        if args.synthetic_db:
+            slots = rng_db.integers(1, T32, (K, b1 - b0, E, nslots), dtype=np.int64)
+            mask_slots = rng_db.integers(1, T32, (b1 - b0, nslots), dtype=np.int64)
+            cc.db_encode_slots(slots, mask_slots)
+            return b1 - b0, b0
+        # itemSeed (CLI.cpp:67); weak scaling: every GPU its own server set, strong: ONE set for all
+        seed = 123456789 + (0 if sharded else rank)
         data = P.RandomDataInput(w["S"], w["C"], w["I"], seed, w["bits"])
-        hashf = P.TabulationHashing(987654321, w["k"] + K)               # hashSeed (CLI.cpp:68)
-        if not args.host_build and (args.scaling == "weak" or world == 1):
-            # offline phase on the device: table build, shuffle, transposition, encode
-            P.BatchedFHEHIPPIE.fromServerSet(cc, P.PublicKey(), hashf, w["e"], E, w["k"], K, w["b"], data.serverSet)
-            hct = None
-        else:
+        if args.host_build:
             hct = P.HierarchicalCuckooHashTable(hashf, w["e"], E, 0, w["k"], K, True, True, w["b"])
             hct.insertAll(data.serverSet)
-        if hct is None:
-            pass
-        elif args.scaling == "weak" or world == 1:
-            pie = P.BatchedFHEHIPPIE(cc, P.PublicKey(), hct)             # shuffles, transposes, encodes on the GPU
-            del pie
-        else:
             cells = hct.cells()
             k_, e_ = cells.shape[:2]
-            slots = np.ascontiguousarray(cells.reshape(k_ * e_, K, w["b"], E).transpose(1, 2, 3, 0)[:, shard.begin:shard.end]).astype(np.int64)
-            mask_slots = np.random.default_rng(5).integers(1, T32, (w["b"], nslots), dtype=np.int64)[shard.begin:shard.end]
-            cc.db_encode_slots(slots, np.ascontiguousarray(mask_slots))
-            del cells, slots
-        del hct, data
-    cc._dims = (K, b_local, E)
+            slots = np.ascontiguousarray(cells.reshape(k_ * e_, K, w["b"], E).transpose(1, 2, 3, 0)).astype(np.int64)
+            mask_slots = np.random.default_rng(5).integers(1, T32, (w["b"], nslots), dtype=np.int64)
+            cc.db_encode_slots_shard(slots, mask_slots, b0, b1)
+        else:
+            # table build, shuffle, transposition and encode on the device; a shard keeps its own bins of the one
+            # database (all ranks: same table, same shuffle seed, same mask seed)
+            cc.db_build_from_items_shard(hashf, w["k"], w["e"], K, E, w["b"], data.serverSet, b0, b1, evictionSeed=0x5EED,
+                                         shuffleSeed=0xB0B0 + seed, maskSeed=0xA11CE + seed)
+        return b1 - b0, b0
+
+    t_off = time.perf_counter()
+    b_local, bin0 = build_db(args.scaling)
     offline_s = time.perf_counter() - t_off
 
-    # ---- the query: K*E + 1 ciphertexts.  Uniform residues (what BFV ciphertexts look like); the server's
-    # work does not depend on their content.  Held in PINNED host memory for the e2e leg.
-    ct_words = 2 * L * N
+    # ---- the query: K*E + 1 ciphertexts.  Uniform residues (what BFV ciphertexts look like); the server's work does
+    # not depend on their content.  Strong scaling: the SAME query on every rank (it is one query).  Held in PINNED
+    # host memory for the e2e legs.
+    rng = np.random.default_rng(1234 + (rank if args.scaling == "weak" else 0))
     q_host = torch.empty((K * E + 1) * ct_words, dtype=torch.int64, pin_memory=True)
     q_np = q_host.numpy().view(np.uint64)
     q_np[:K * E * ct_words] = random_limbs(rng, params, (K, E, 2)).reshape(-1)
     q_np[K * E * ct_words:] = random_limbs(rng, params, (2,)).reshape(-1)
     idx_ptr = q_host.data_ptr()
     minus_ptr = idx_ptr + K * E * ct_words * 8
-    r_host = torch.empty(b_local * ct_words, dtype=torch.int64, pin_memory=True)
-    cc.InsertEvalMultKey(random_limbs(rng, params, (L,)), random_limbs(rng, params, (L,)))
+    evk_b, evk_a = random_limbs(rng, params, (L,)), random_limbs(rng, params, (L,))
+    cc.InsertEvalMultKey(evk_b, evk_a)
 
     stream = torch.cuda.Stream()
     sp = stream.cuda_stream
-    cc.query_set_ptr(idx_ptr, minus_ptr, sp)
-    cc.sync(sp)
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        return ms
 
     def timed(fn, steps):
         """CUDA-event time (ms) of `steps` calls of fn on `stream`; barrier + synchronize both sides."""
@@ -322,149 +381,231 @@ def main():
         e1.record(stream)
         e1.synchronize()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-            ms = float(tms.item())
-        return ms
+        return max_over_ranks(e0.elapsed_time(e1))
 
-    # ---- warm-up, then the headline: K x run() with everything resident ------------------------------
-    for _ in range(max(args.warmup, 3)):
-        cc.run(sp)
-    cc.sync(sp)
-    launches_per_run = cc.run_launch_count()
-    sampler.active = True
-    ms_total = timed(lambda: cc.run(sp), args.steps)
-    ms_step = ms_total / args.steps
-    # per-phase (same stream, same residency): the roofline numerator/denominator come from these
-    ms_p1 = timed(lambda: cc.run(sp, phases=1), args.steps) / args.steps
-    ms_p2 = timed(lambda: cc.run(sp, phases=2), args.steps) / args.steps
-
-    # ---- e2e: host query in, host results out, every step ---------------------------------------------
-    # (a) serial: one query at a time (latency);  (b) pipelined: what a server with a stream of queries
-    # does — the upload of query i+1 (psi_query_upload, copy engine) and the download of result i-1 overlap
-    # the evaluation of query i on three streams; results are double-buffered on the device.  Every step
-    # still moves its own query H2D and its own results D2H inside the timed region.
-    r_host2 = torch.empty(b_local * ct_words, dtype=torch.int64, pin_memory=True)
-    if world > 1:
-        gather_bufs = [torch.empty((b_local, ct_words), dtype=torch.int64, device="cuda") for _ in range(world)] if rank == 0 else None
-        R_host = torch.empty(world * b_local * ct_words, dtype=torch.int64, pin_memory=True) if rank == 0 else None
-
-    def fetch_result(st, host_buf):
-        """D2H of the current result buffer on torch stream `st` (N > 1: NCCL gather to rank 0 first)."""
-        if world == 1 or args.gather == "host":
-            cc.result_get_ptr(host_buf.data_ptr(), st.cuda_stream)
-            return
-        res_dev = P.ShardedPIE.device_result_tensor(cc).view(b_local, ct_words)
-        with torch.cuda.stream(st):
-            dist.gather(res_dev, gather_bufs, dst=0)   # the response gather: the only cross-GPU traffic
-            if rank == 0:
-                for r in range(world):
-                    R_host[r * b_local * ct_words:(r + 1) * b_local * ct_words].copy_(gather_bufs[r].view(-1), non_blocking=True)
-
-    query_dist = args.query_dist
-    if query_dist == "auto":
-        query_dist = "allgather" if world > 1 and (K * E * ct_words) % world == 0 else "host"
-    qd = None
-    if query_dist == "allgather":
-        qd = P.QueryDistributor.for_context(cc, rank, world)
-        q_idx_host, q_minus_host = q_host[:K * E * ct_words], q_host[K * E * ct_words:]
-
-    def upload_query(st):
-        """This step's query from pinned host memory into the landing buffers, on torch stream `st`."""
-        if qd is None:
-            cc.query_upload_ptr(idx_ptr, minus_ptr, st.cuda_stream)
-        else:
-            with torch.cuda.stream(st):
-                qd.distribute(q_idx_host, q_minus_host)   # 1/N over PCIe + NCCL all-gather over NVLink
-
-    def e2e_serial_step():
-        upload_query(stream)
-        cc.query_commit(sp)
-        cc.run(sp)
-        fetch_result(stream, r_host)
-
-    for _ in range(3):
-        e2e_serial_step()
-    cc.sync(sp)
-    ms_e2e_serial = timed(e2e_serial_step, args.steps) / args.steps
-
-    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-
-    def e2e_pipelined(steps, warm):
-        """Elapsed ms of `steps` queries through the 3-stream pipeline.  The `warm` untimed queries before them run
-        through the SAME pipeline, so the timed region is the pipeline in steady state: it opens right before the
-        upload of the first timed query and closes when the result of the last one is in host memory, i.e. it
-        contains every H2D, kernel and D2H of exactly `steps` queries (plus whatever the warm-up queries still
-        have in flight when it opens)."""
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev_commit = [None, None]               # commit events of the two landing buffers
-        ev_d2h = [None, None]
-        for i in range(warm + steps):
-            if ev_commit[i & 1] is not None:
-                s_in.wait_event(ev_commit[i & 1])     # landing buffer i & 1 is free once the commit of query i-2 ran
-            if i == warm:
-                e0.record(s_in)
-            upload_query(s_in)
-            ev_up = torch.cuda.Event()
-            ev_up.record(s_in)
-            stream.wait_event(ev_up)
-            cc.query_commit(sp)
-            ev_commit[i & 1] = torch.cuda.Event()
-            ev_commit[i & 1].record(stream)
-            if ev_d2h[i & 1] is not None:
-                stream.wait_event(ev_d2h[i & 1])       # run i reuses the result buffer of run i-2
+    def measure(b_loc, with_phases):
+        """All timed legs for the database currently resident (b_loc bins on this rank)."""
+        m = {}
+        r_host = torch.empty(b_loc * ct_words, dtype=torch.int64, pin_memory=True)
+        r_host2 = torch.empty(b_loc * ct_words, dtype=torch.int64, pin_memory=True)
+        cc._dims = (K, b_loc, E)
+        cc.query_set_ptr(idx_ptr, minus_ptr, sp)
+        cc.sync(sp)
+        # ---- warm-up, then the headline: K x run() with everything resident
+        for _ in range(max(args.warmup, 3)):
             cc.run(sp)
-            ev_run = torch.cuda.Event()
-            ev_run.record(stream)
-            s_out.wait_event(ev_run)
-            fetch_result(s_out, r_host if (i & 1) == 0 else r_host2)
-            ev_d2h[i & 1] = torch.cuda.Event()
-            ev_d2h[i & 1].record(s_out)
-        e1.record(s_out)
-        e1.synchronize()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-            ms = float(tms.item())
-        return ms
+        cc.sync(sp)
+        m["launches_per_run"] = cc.run_launch_count()
+        m["ms_step"] = timed(lambda: cc.run(sp), args.steps) / args.steps
+        if with_phases:
+            # per-phase (same stream, same residency): the roofline numerator/denominator come from these
+            m["ms_p1"] = timed(lambda: cc.run(sp, phases=1), args.steps) / args.steps
+            m["ms_p2"] = timed(lambda: cc.run(sp, phases=2), args.steps) / args.steps
 
-    e2e_pipelined(3, 0)
-    ms_e2e = e2e_pipelined(args.steps, max(args.warmup, 3)) / args.steps
+        # ---- e2e: host query in, host results out, every step
+        if world > 1 and args.gather == "nccl":
+            gather_bufs = [torch.empty((b_loc, ct_words), dtype=torch.int64, device="cuda") for _ in range(world)] if rank == 0 else None
+            R_host = torch.empty(world * b_loc * ct_words, dtype=torch.int64, pin_memory=True) if rank == 0 else None
+
+        def fetch_result(st, host_buf):
+            """D2H of the current result buffer on torch stream `st` (N > 1, --gather nccl: NCCL gather first)."""
+            if world == 1 or args.gather == "host":
+                cc.result_get_ptr(host_buf.data_ptr(), st.cuda_stream)
+                return
+            res_dev = P.ShardedPIE.device_result_tensor(cc).view(b_loc, ct_words)
+            with torch.cuda.stream(st):
+                dist.gather(res_dev, gather_bufs, dst=0)
+                if rank == 0:
+                    for r in range(world):
+                        R_host[r * b_loc * ct_words:(r + 1) * b_loc * ct_words].copy_(gather_bufs[r].view(-1), non_blocking=True)
+
+        query_dist = args.query_dist
+        if query_dist == "auto":
+            query_dist = "allgather" if world > 1 and (K * E * ct_words) % world == 0 else "host"
+        qd = None
+        if query_dist == "allgather":
+            qd = P.QueryDistributor.for_context(cc, rank, world)
+            q_idx_host, q_minus_host = q_host[:K * E * ct_words], q_host[K * E * ct_words:]
+        m["qd"] = qd is not None
+
+        def upload_query(st):
+            """This step's query from pinned host memory into the landing buffers, on torch stream `st`."""
+            if qd is None:
+                cc.query_upload_ptr(idx_ptr, minus_ptr, st.cuda_stream)
+            else:
+                with torch.cuda.stream(st):
+                    qd.distribute(q_idx_host, q_minus_host)   # 1/N over PCIe + NCCL all-gather over NVLink
+
+        def e2e_serial_step():
+            upload_query(stream)
+            cc.query_commit(sp)
+            cc.run(sp)
+            fetch_result(stream, r_host)
+
+        for _ in range(3):
+            e2e_serial_step()
+        cc.sync(sp)
+        m["ms_e2e_serial"] = timed(e2e_serial_step, args.steps) / args.steps
+        m["last_result"] = r_host
+
+        def e2e_pipelined(steps, warm):
+            """Elapsed ms of `steps` queries through the 3-stream pipeline (upload of query i+1 and download of result
+            i-1 overlap run i).  The `warm` untimed queries before them run through the SAME pipeline, so the timed
+            region is the pipeline in steady state: it opens right before the upload of the first timed query and
+            closes when the result of the last one is in host memory, i.e. it contains every H2D, kernel and D2H of
+            exactly `steps` queries."""
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev_commit = [None, None]               # commit events of the two landing buffers
+            ev_d2h = [None, None]
+            for i in range(warm + steps):
+                if ev_commit[i & 1] is not None:
+                    s_in.wait_event(ev_commit[i & 1])     # landing buffer i & 1 is free once the commit of query i-2 ran
+                if i == warm:
+                    e0.record(s_in)
+                upload_query(s_in)
+                ev_up = torch.cuda.Event()
+                ev_up.record(s_in)
+                stream.wait_event(ev_up)
+                cc.query_commit(sp)
+                ev_commit[i & 1] = torch.cuda.Event()
+                ev_commit[i & 1].record(stream)
+                if ev_d2h[i & 1] is not None:
+                    stream.wait_event(ev_d2h[i & 1])       # run i reuses the result buffer of run i-2
+                cc.run(sp)
+                ev_run = torch.cuda.Event()
+                ev_run.record(stream)
+                s_out.wait_event(ev_run)
+                fetch_result(s_out, r_host if (i & 1) == 0 else r_host2)
+                ev_d2h[i & 1] = torch.cuda.Event()
+                ev_d2h[i & 1].record(s_out)
+            e1.record(s_out)
+            e1.synchronize()
+            barrier()
+            return max_over_ranks(e0.elapsed_time(e1))
+
+        e2e_pipelined(3, 0)
+        m["ms_e2e"] = e2e_pipelined(args.steps, max(args.warmup, 3)) / args.steps
+        return m
+
+    sampler.active = True
+    m = measure(b_local, True)
     sampler.active = False
+
+    # ---- e2e with the query held the way OpenFHE holds it: K*E*2*L + 2*L separately allocated PAGEABLE limb vectors
+    # in, b*2*L vectors out (psi_query_upload_limbs / psi_result_get_limbs; N = 1 only — the multi-rank equivalent is
+    # the single-process psi_multi_query_set_limbs, tests/test_gpu_multi.py)
+    limb_leg = None
+    if world == 1 and not args.no_limb_leg:
+        nvec = K * E * 2 * L
+        iv = [q_np[i * N:(i + 1) * N].copy() for i in range(nvec)]
+        mv = [q_np[(nvec + i) * N:(nvec + i + 1) * N].copy() for i in range(2 * L)]
+        ov = [np.empty(N, dtype=np.uint64) for _ in range(b_local * 2 * L)]
+        ai, am, ao = P.MultiContext._ptr_array(iv), P.MultiContext._ptr_array(mv), P.MultiContext._ptr_array(ov)
+        cc.set_host_threads(min(16, max(1, len(os.sched_getaffinity(0)))))
+
+        def limb_step():
+            cc.query_upload_limbs(ai, am, sp)
+            cc.query_commit(sp)
+            cc.run(sp)
+            cc.result_get_limbs(ao, sp)    # synchronous: results are in the vectors on return
+
+        for _ in range(3):
+            limb_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            limb_step()
+        ms_limb = (time.perf_counter() - t0) * 1e3 / args.steps
+        same = np.array_equal(np.concatenate(ov), m["last_result"].numpy().view(np.uint64))
+        limb_leg = {"serial_ms_per_step": ms_limb, "vs_pinned_serial": ms_limb / m["ms_e2e_serial"],
+                    "query_vectors": nvec + 2 * L, "result_vectors": len(ov), "bytes_per_vector": N * 8,
+                    "host_threads": min(16, max(1, len(os.sched_getaffinity(0)))),
+                    "timing": "host wall clock around upload_limbs -> commit -> run -> result_get_limbs (returns when the "
+                              "result vectors are filled)", "matches_pinned_path": bool(same)}
+        if not same:
+            raise SystemExit("bench.py: limb-vector e2e leg returned different results than the pinned path")
+
+    # ---- in-run parity: rank 0 re-computes >= 1 bin of every rank with the oracle (outside the timed regions)
+    from oracle.oracle import Oracle
+    check_local = [0] if world > 1 else sorted({0, b_local - 1})
+    res_np = m["last_result"].numpy().view(np.uint64).reshape(b_local, 2, L, N)
+    packs = []
+    for lb in check_local:
+        pt_bin, mask_bin = cc.db_get_bin_limbs(lb)
+        packs.append((bin0 + lb, pt_bin, mask_bin, res_np[lb].copy()))
+    checked, bad = [], []
+    if world > 1:
+        flat = torch.from_numpy(np.concatenate([np.concatenate([p[1].reshape(-1), p[2].reshape(-1), p[3].reshape(-1)])
+                                                for p in packs]).view(np.int64)).cuda()
+        bins_t = torch.tensor([p[0] for p in packs], device="cuda", dtype=torch.int64)
+        gl = [torch.empty_like(flat) for _ in range(world)] if rank == 0 else None
+        gb = [torch.empty_like(bins_t) for _ in range(world)] if rank == 0 else None
+        dist.gather(flat, gl, dst=0)
+        dist.gather(bins_t, gb, dst=0)
+        if rank == 0:
+            packs = []
+            n_pt, n_m, n_r = K * E * L * N, L * N, 2 * L * N
+            for r in range(world):
+                a = gl[r].cpu().numpy().view(np.uint64)
+                for i, gbin in enumerate(gb[r].cpu().tolist()):
+                    o0 = i * (n_pt + n_m + n_r)
+                    packs.append((gbin, a[o0:o0 + n_pt].reshape(K, E, L, N), a[o0 + n_pt:o0 + n_pt + n_m].reshape(L, N),
+                                  a[o0 + n_pt + n_m:o0 + n_pt + n_m + n_r].reshape(2, L, N)))
+    if rank == 0:
+        o = Oracle(params)
+        idx_np = q_np[:K * E * ct_words].reshape(K, E, 2, L, N)
+        minus_np = q_np[K * E * ct_words:].reshape(2, L, N)
+        for gbin, pt_bin, mask_bin, got in packs:
+            want = o.run(np.ascontiguousarray(pt_bin[:, None]), np.ascontiguousarray(mask_bin[None]), idx_np, minus_np,
+                         evk_b, evk_a, nthreads=min(8, host_threads()))
+            (checked if np.array_equal(want[0], got) else bad).append(int(gbin))
+        if bad:
+            raise SystemExit("bench.py: PARITY FAILURE against the oracle in bins %s" % bad)
+
+    # ---- N > 1, strong: the weak-scaling figures in the same line (every GPU a full block of b bins)
+    weak = None
+    if world > 1 and args.scaling == "strong" and not args.no_weak:
+        b_w, _ = build_db("weak")
+        mw = measure(b_w, False)
+        weak = {"value": w["S"] * world / (mw["ms_step"] * 1e-3), "unit": "items/s", "ms_per_step": mw["ms_step"],
+                "server_items_total": w["S"] * world, "bins_per_gpu": b_w,
+                "e2e_ms_per_step": mw["ms_e2e"], "e2e_serial_ms_per_step": mw["ms_e2e_serial"],
+                "e2e_value": w["S"] * world / (mw["ms_e2e"] * 1e-3),
+                "note": "independent b-bin replicas, no data-path collective: near-linear by construction"}
     sampler.stop_flag = True
 
-    items_per_gpu = w["S"] if args.scaling == "weak" else w["S"] / world
-    total_items = items_per_gpu * world
+    ms_step, ms_p1, ms_p2 = m["ms_step"], m["ms_p1"], m["ms_p2"]
+    total_items = w["S"] * (world if args.scaling == "weak" else 1)
     value = total_items / (ms_step * 1e-3)
-    e2e_value = total_items / (ms_e2e * 1e-3)
+    e2e_value = total_items / (m["ms_e2e"] * 1e-3)
     # whole-job H2D per step: the query crosses PCIe once per GPU ('host') or once in total plus the small minus
     # ciphertext per GPU ('allgather')
-    h2d = (K * E + 1) * ct_words * 8 * world if qd is None else (K * E + world) * ct_words * 8
-    d2h = b_local * ct_words * 8 * world  # whole job: every rank's result ciphertexts reach host memory
+    h2d = (K * E + 1) * ct_words * 8 * world if not m["qd"] else (K * E + world) * ct_words * 8
+    d2h = (w["b"] * (world if args.scaling == "weak" else 1)) * ct_words * 8  # every result ciphertext reaches host memory
 
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         peak_hbm, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         peak_hbm, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    # ncu-measured DRAM traffic of the dominant kernel for exactly this workload (one launch), if profiled
+    # ncu-measured DRAM traffic of the dominant kernel for exactly this workload (one launch), from the committed
+    # capture under profiles/ (static: not re-measured in this run)
     traffic = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json"))).get(args.workload)
-        if tr and b_local == w["b"]:
-            traffic = tr["dram_bytes_per_launch"].get("k_mac_tma")
-    except Exception:
-        traffic = None
+    for name in ("r02_dram_traffic.json", "r01_dram_traffic.json"):
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", name))).get(args.workload)
+            if tr and b_local == w["b"]:
+                traffic = tr["dram_bytes_per_launch"].get("k_mac_tma")
+                break
+        except Exception:
+            pass
     bytes1 = phase1_bytes(L, N, K, b_local, E)
     ach = bytes1 / (ms_p1 * 1e-3) / 1e9
     roofline = {"kernel": "k_mac_tma (inner product, phase 1)", "bound": "hbm", "achieved": ach, "peak": peak_hbm,
-                "unit": "GB/s", "frac": ach / peak_hbm, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": bytes1, "launch_ms": ms_p1}
+                "unit": "GB/s", "frac": ach / peak_hbm, "traffic": traffic,
+                "traffic_source": "static: ncu --set full capture committed under profiles/" if traffic else None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes1, "launch_ms": ms_p1}
     # phase 2 against the integer pipe: butterflies of the 88-NTT HPSPOVERQ + BV pipeline per second vs the
     # measured register-resident butterfly rate of this GPU (psi_bench_pipe_peak, same process, same clocks)
     import ctypes
@@ -482,21 +623,26 @@ def main():
                     "imad_wide_peak_per_s": imad_peak.value,
                     "peak_source": "measured in this run: 64-bit Harvey/Shoup butterflies, operands in registers"}
     phases = {"inner_product_ms": ms_p1, "multiply_relin_mask_ms": ms_p2, "run_ms": ms_step,
-              "launches_per_run": launches_per_run}
+              "launches_per_run": m["launches_per_run"]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = host_threads()
         t0 = time.perf_counter()
-        rate, dt, threads, nb = cpu_oracle_rate(w, params, args.cpu_sample_bins or w["b"], 3)
+        rate, dt, threads, nb = cpu_oracle_rate(w, params, args.cpu_sample_bins or w["b"], 3, threads)
         cpu = {"value": rate, "unit": "items/s", "cores": threads, "kind": "port",
                "sample": "%d of %d bins x 3 repetitions (%.1f s of CPU work), warm plaintexts, OpenMP over bins; "
                          "port = oracle/psi_oracle.c, the real reference (OpenFHE) cannot be built in this image"
                          % (nb, w["b"], time.perf_counter() - t0),
                "ms_per_query_extrapolated": dt * 1e3 * w["b"] / nb}
         # the same port on ONE host thread, two bins (SURVEY 8d asks for 1 thread and all threads)
-        rate1, dt1, _, nb1 = cpu_oracle_rate(w, params, 2, 1, threads=1)
+        rate1, dt1, _, nb1 = cpu_oracle_rate(w, params, 2, 1, 1)
         cpu["single_thread"] = {"value": rate1, "unit": "items/s", "cores": 1, "sample": "%d of %d bins" % (nb1, w["b"]),
                                 "ms_per_query_extrapolated": dt1 * 1e3 * w["b"] / nb1}
+        # cold: plaintext lifts + transforms inside run() (the reference's first run())
+        ratec, dtc, _, nbc = cpu_oracle_rate(w, params, args.cpu_sample_bins or w["b"], 1, threads, cold=True)
+        cpu["cold"] = {"value": ratec, "unit": "items/s", "cores": threads, "sample": "%d of %d bins x 1" % (nbc, w["b"]),
+                       "ms_per_query_extrapolated": dtc * 1e3 * w["b"] / nbc}
 
     if rank == 0:
         line = {
@@ -505,9 +651,10 @@ def main():
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": workload_config(args, w, params, world),
             "roofline": roofline, "roofline_int": roofline_int, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "items/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "serial_ms_per_step": ms_e2e_serial,
-                    "serial_value": total_items / (ms_e2e_serial * 1e-3),
+            "e2e": {"value": e2e_value, "unit": "items/s", "ms_per_step": m["ms_e2e"], "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "serial_ms_per_step": m["ms_e2e_serial"],
+                    "serial_value": total_items / (m["ms_e2e_serial"] * 1e-3),
+                    "limb_vectors": limb_leg,
                     "path": "pinned host query -> psi_query_upload | psi_query_commit -> psi_run -> psi_result_get -> "
                             "pinned host, three streams: upload of query i+1 and download of result i-1 overlap "
                             "run i; the warm-up queries run through the same pipeline, the timed region holds every copy "
@@ -516,8 +663,10 @@ def main():
                                 " (N > 1: every rank downloads its own bins over its own PCIe link)") if world > 1 else ""),
                     "gather": args.gather if world > 1 else None, "rank0_numa_node": numa_node,
                     "query_dist": ("1/N of the index ciphertexts per GPU over PCIe + NCCL all-gather over NVLink"
-                                   if qd is not None else "whole query over every GPU's own PCIe link") if world > 1 else None},
-            "gpu_launches": launches_per_run * args.steps,
+                                   if m["qd"] else "whole query over every GPU's own PCIe link") if world > 1 else None},
+            "gpu_launches": m["launches_per_run"] * args.steps,
+            "parity_checked_bins": len(checked), "parity_checked_bin_ids": checked, "parity_ok": not bad,
+            "weak": weak,
             "phases": phases, "clocks": sampler.summary(), "offline_build_s": offline_s,
         }
         print(json.dumps(line), flush=True)

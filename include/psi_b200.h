@@ -103,6 +103,12 @@ typedef struct psi_ctx psi_ctx; /* opaque, one per device */
 int psi_params_generate(uint32_t N, uint64_t t, uint32_t mult_depth, uint32_t L_override,
                         psi_params* out);
 
+/* The same tables for moduli and roots that come from the host library (the OpenFHE adapter reads them from
+ * ILDCRTParams: q / psi_q = ciphertext basis Q, p / psi_p = auxiliary basis of EvalMult, psi_t = the packed
+ * encoding's 2N-th root mod t); no choice of primes involved. */
+int psi_params_from_moduli(uint32_t N, uint64_t t, uint32_t L, const uint64_t* q, const uint64_t* psi_q, uint32_t Lp,
+                           const uint64_t* p, const uint64_t* psi_p, uint64_t psi_t, psi_params* out);
+
 /* Replaces the server's context deserialisation result as far as run() needs it
  * (BatchedFHEPSIServer.cpp:28). */
 int psi_ctx_create(const psi_params* p, int device, psi_ctx** out);
@@ -125,6 +131,36 @@ int psi_db_load_limbs(psi_ctx* ctx, uint32_t K, uint32_t b, uint32_t E, const ui
 int psi_db_encode_slots(psi_ctx* ctx, uint32_t K, uint32_t b, uint32_t E, uint32_t nslots,
                         const int64_t* slots, const int64_t* mask_slots);
 
+/* How MakePackedPlaintext lifts the packed coefficients from [0, t) to the limbs mod q_l before the first-use
+ * SetFormat(EVALUATION) (BatchedFHEHIPPIE.cpp:68,81 -> OpenFHE PackedEncoding::Encode):
+ *   PSI_ENCODE_LIFT_PLAIN    the coefficient itself in every limb (OpenFHE >= 1.0 as recalled; default)
+ *   PSI_ENCODE_LIFT_CENTRED  c > t/2 -> q_l - (t - c), the signed representative (SURVEY.md Appendix A's reading)
+ * Both decrypt identically; only limb parity with the host library depends on it.  Set before the psi_db_* calls
+ * that encode (risk register). */
+enum { PSI_ENCODE_LIFT_PLAIN = 0, PSI_ENCODE_LIFT_CENTRED = 1 };
+int psi_set_encode_lift(psi_ctx* ctx, uint32_t mode);
+/* Slot order of the packed encoding (PackedEncoding::SetParams_2n): slots N/2.. sit at exponents cofactor * 5^i with
+ *   PSI_PACK_COFACTOR_3     cofactor 3 (OpenFHE 1.0.x as recalled; default)
+ *   PSI_PACK_COFACTOR_CONJ  cofactor 2N - 1 (conjugation; the other reading)
+ * Matters whenever the server encodes the database itself while the client encodes the query with the host
+ * library: both sides must use the same slot order (risk register). */
+enum { PSI_PACK_COFACTOR_3 = 0, PSI_PACK_COFACTOR_CONJ = 1 };
+int psi_set_packing_cofactor(psi_ctx* ctx, uint32_t mode);
+
+/* Sharded variants (single-process multi-device evaluation, psi_multi_* below, and one-process-per-GPU hosts):
+ * the arrays are the FULL database of b_total bins in the layouts of the unsharded calls; bins
+ * [bin_begin, bin_end) become this context's resident database (b_local = bin_end - bin_begin).  A sharded
+ * psi_db_build_from_items needs an explicit shuffle seed shared by all shards (PSI_SEED_RANDOM is rejected). */
+int psi_db_load_limbs_shard(psi_ctx* ctx, uint32_t K, uint32_t b_total, uint32_t bin_begin, uint32_t bin_end, uint32_t E,
+                            const uint64_t* pt_limbs, const uint64_t* mask_limbs);
+int psi_db_encode_slots_shard(psi_ctx* ctx, uint32_t K, uint32_t b_total, uint32_t bin_begin, uint32_t bin_end, uint32_t E,
+                              uint32_t nslots, const int64_t* slots, const int64_t* mask_slots);
+int psi_db_build_from_items_shard(psi_ctx* ctx, uint64_t hash_seed, uint32_t k, uint64_t e, uint32_t K, uint64_t E, uint64_t b,
+                                  uint64_t eviction_seed, const uint64_t* items, size_t n, uint64_t shuffle_seed,
+                                  uint64_t mask_seed, uint32_t bin_begin, uint32_t bin_end);
+/* One resident bin back to the host: pt [K][E][L][N], mask [L][N] (tests, bench.py's in-run parity check). */
+int psi_db_get_bin_limbs(psi_ctx* ctx, uint32_t bin, uint64_t* pt_limbs, uint64_t* mask_limbs);
+
 /* Copies the encoded DB back (tests / caching): pt [K][b][E][L][N], mask [b][L][N]. */
 int psi_db_get_limbs(psi_ctx* ctx, uint64_t* pt_limbs, uint64_t* mask_limbs);
 
@@ -141,6 +177,17 @@ int psi_query_set(psi_ctx* ctx, const uint64_t* idx, const uint64_t* minus, void
  * commit i on the device (stream/event), since they touch the same buffer. */
 int psi_query_upload(psi_ctx* ctx, const uint64_t* idx, const uint64_t* minus, void* stream);
 int psi_query_commit(psi_ctx* ctx, void* stream);
+
+/* The same upload from SEPARATE limb vectors, the layout OpenFHE holds after receiveIndexMatrix /
+ * receiveEncryptedMinusElements (BatchedFHEPSIServer.cpp:114-141): idx_limbs = K*E*2*L pointers in
+ * [hf][pos][comp][limb] order, minus_limbs = 2*L pointers, each to N words (pageable memory is fine).  Host
+ * threads (psi_set_host_threads, default 8) gather the vectors into a pinned pool piece by piece while the pieces
+ * already gathered are uploaded; the vectors may be freed on return.  psi_query_commit follows as usual.
+ * psi_result_get_limbs is the mirror for getResultList / sendResult (:143-152): b*2*L pointers in
+ * [bin][comp][limb] order; synchronous (the vectors are filled when it returns). */
+int psi_query_upload_limbs(psi_ctx* ctx, const uint64_t* const* idx_limbs, const uint64_t* const* minus_limbs, void* stream);
+int psi_result_get_limbs(psi_ctx* ctx, uint64_t* const* out_limbs, void* stream);
+int psi_set_host_threads(psi_ctx* ctx, int n);
 
 /* Device addresses of landing buffer `which` (0 or 1; idx [K][E][2][L][N], minus [2][L][N], u64), for hosts
  * that distribute one query over several GPUs themselves: every GPU receives 1/G of the index ciphertexts
@@ -262,6 +309,58 @@ int psi_pie_set_query(psi_pie* p, const uint64_t* idx, const uint64_t* minus);
 int psi_pie_run(psi_pie* p);
 int psi_pie_get_result_list(psi_pie* p, uint64_t* out);
 int psi_pie_destroy(psi_pie* p);
+
+/* ------------------------------------------------------------------------------------------
+ * Single-process multi-device evaluation.  The reference's server is ONE process whose single PIE object is
+ * called once per session (BatchedFHEPSIServer.cpp:86,101-108); psi_multi keeps that shape on several GPUs:
+ * one host thread, one psi_ctx per device, bins [b*d/n, b*(d+1)/n) resident on device d (the loop over bins at
+ * BatchedFHEHIPPIE.cpp:91 carries nothing from bin to bin).  The query crosses PCIe once (1/n per device) and
+ * the slices are exchanged device-to-device (cudaMemcpyPeerAsync, NVLink when peer access is available); every
+ * device copies its own result ciphertexts straight into the caller's single [b][2][L][N] buffer.  All calls are
+ * asynchronous with respect to the devices; psi_multi_sync waits for everything enqueued.  A device may be
+ * listed more than once (several contexts on one GPU; the tests use this on single-GPU boxes).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct psi_multi psi_multi;
+int psi_multi_create(const psi_params* p, const int* devices, uint32_t n_devices, psi_multi** out);
+int psi_multi_destroy(psi_multi* m);
+int psi_multi_device_count(psi_multi* m, uint32_t* n);
+/* bins of device `index` (after a psi_multi_db_* call) and its context (read-only use: debugging, tests) */
+int psi_multi_bin_range(psi_multi* m, uint32_t index, uint32_t* bin_begin, uint32_t* bin_end);
+int psi_multi_ctx(psi_multi* m, uint32_t index, psi_ctx** ctx);
+int psi_multi_set_encode_lift(psi_multi* m, uint32_t mode);
+int psi_multi_set_host_threads(psi_multi* m, int n); /* threads of the *_limbs staging copies (default 8) */
+/* DeserializeEvalMultKey (BatchedFHEPSIServer.cpp:49): replicated on every device */
+int psi_multi_set_relin_key(psi_multi* m, const uint64_t* evk_b, const uint64_t* evk_a);
+/* the ctor's vectorizedHCT / preCalcRandomMask (BatchedFHEHIPPIE.cpp:37-82); same arrays as the psi_db_* calls,
+ * FULL database, sharded inside */
+int psi_multi_db_load_limbs(psi_multi* m, uint32_t K, uint32_t b, uint32_t E, const uint64_t* pt_limbs,
+                            const uint64_t* mask_limbs);
+int psi_multi_db_encode_slots(psi_multi* m, uint32_t K, uint32_t b, uint32_t E, uint32_t nslots, const int64_t* slots,
+                              const int64_t* mask_slots);
+int psi_multi_db_build_from_items(psi_multi* m, uint64_t hash_seed, uint32_t k, uint64_t e, uint32_t K, uint64_t E,
+                                  uint64_t b, uint64_t eviction_seed, const uint64_t* items, size_t n,
+                                  uint64_t shuffle_seed, uint64_t mask_seed);
+/* setIndex + setMinusCompareElement (BatchedFHEHIPPIE.hpp:40-48): idx [K][E][2][L][N], minus [2][L][N]; the host
+ * buffers must stay valid until the copies have run (psi_multi_sync, or the next psi_multi_result_get + sync) */
+int psi_multi_query_set(psi_multi* m, const uint64_t* idx, const uint64_t* minus);
+/* The same from SEPARATE limb vectors, the layout an OpenFHE ciphertext holds (receiveIndexMatrix,
+ * BatchedFHEPSIServer.cpp:124-141, leaves K*E ciphertexts of 2 DCRTPolys of L NativeVectors): idx_limbs has
+ * K*E*2*L pointers in [hf][pos][comp][limb] order, minus_limbs 2*L, each to N words in pageable memory.  Host
+ * threads copy them into a pinned pool piece by piece while the pieces already staged are being uploaded; the
+ * vectors may be freed when the call returns. */
+int psi_multi_query_set_limbs(psi_multi* m, const uint64_t* const* idx_limbs, const uint64_t* const* minus_limbs);
+/* run() (BatchedFHEHIPPIE.cpp:88-129) on every device */
+int psi_multi_run(psi_multi* m);
+/* getResultList (BatchedFHEHIPPIE.hpp:35-38): out [b][2][L][N]; read it after psi_multi_sync */
+int psi_multi_result_get(psi_multi* m, uint64_t* out);
+/* the same into b*2*L separate limb vectors ([bin][comp][limb] order, N words each; sendResult serialises
+ * ciphertext by ciphertext, BatchedFHEPSIServer.cpp:143-152); synchronous: the vectors are filled on return */
+int psi_multi_result_get_limbs(psi_multi* m, uint64_t* const* out_limbs);
+int psi_multi_sync(psi_multi* m);
+int psi_multi_run_launch_count(psi_multi* m, uint32_t* out);
+/* BatchedFHEHIPPIE over a psi_multi (same constructor semantics as psi_pie_create) */
+int psi_pie_create_multi(psi_multi* m, const psi_params* params, psi_hct* hct, uint64_t shuffle_seed, uint64_t mask_seed,
+                         int keep_slots, psi_pie** out);
 
 const char* psi_last_error(void);
 const char* psi_version(void);

@@ -98,6 +98,35 @@ SYMBOLS = {
     "psi_pie_run": (_int, [_vp]),
     "psi_pie_get_result_list": (_int, [_vp, _u64p]),
     "psi_pie_destroy": (_int, [_vp]),
+    "psi_set_encode_lift": (_int, [_vp, _u32]),
+    "psi_set_packing_cofactor": (_int, [_vp, _u32]),
+    "psi_params_from_moduli": (_int, [_u32, _u64, _u32, _u64p, _u64p, _u32, _u64p, _u64p, _u64, _pp]),
+    "psi_query_upload_limbs": (_int, [_vp, ctypes.POINTER(_u64p), ctypes.POINTER(_u64p), _vp]),
+    "psi_result_get_limbs": (_int, [_vp, ctypes.POINTER(_u64p), _vp]),
+    "psi_set_host_threads": (_int, [_vp, _int]),
+    "psi_db_load_limbs_shard": (_int, [_vp, _u32, _u32, _u32, _u32, _u32, _u64p, _u64p]),
+    "psi_db_encode_slots_shard": (_int, [_vp, _u32, _u32, _u32, _u32, _u32, _u32, _i64p, _i64p]),
+    "psi_db_build_from_items_shard": (_int, [_vp, _u64, _u32, _u64, _u32, _u64, _u64, _u64, _u64p, _sz, _u64, _u64, _u32, _u32]),
+    "psi_db_get_bin_limbs": (_int, [_vp, _u32, _u64p, _u64p]),
+    "psi_multi_create": (_int, [_pp, ctypes.POINTER(_int), _u32, _vpp]),
+    "psi_multi_destroy": (_int, [_vp]),
+    "psi_multi_device_count": (_int, [_vp, _u32p]),
+    "psi_multi_bin_range": (_int, [_vp, _u32, _u32p, _u32p]),
+    "psi_multi_ctx": (_int, [_vp, _u32, _vpp]),
+    "psi_multi_set_encode_lift": (_int, [_vp, _u32]),
+    "psi_multi_set_host_threads": (_int, [_vp, _int]),
+    "psi_multi_set_relin_key": (_int, [_vp, _u64p, _u64p]),
+    "psi_multi_db_load_limbs": (_int, [_vp, _u32, _u32, _u32, _u64p, _u64p]),
+    "psi_multi_db_encode_slots": (_int, [_vp, _u32, _u32, _u32, _u32, _i64p, _i64p]),
+    "psi_multi_db_build_from_items": (_int, [_vp, _u64, _u32, _u64, _u32, _u64, _u64, _u64, _u64p, _sz, _u64, _u64]),
+    "psi_multi_query_set": (_int, [_vp, _u64p, _u64p]),
+    "psi_multi_query_set_limbs": (_int, [_vp, ctypes.POINTER(_u64p), ctypes.POINTER(_u64p)]),
+    "psi_multi_run": (_int, [_vp]),
+    "psi_multi_result_get": (_int, [_vp, _u64p]),
+    "psi_multi_result_get_limbs": (_int, [_vp, ctypes.POINTER(_u64p)]),
+    "psi_multi_sync": (_int, [_vp]),
+    "psi_multi_run_launch_count": (_int, [_vp, _u32p]),
+    "psi_pie_create_multi": (_int, [_vp, _pp, _vp, _u64, _u64, _int, _vpp]),
     "psi_last_error": (ctypes.c_char_p, []),
     "psi_version": (ctypes.c_char_p, []),
 }

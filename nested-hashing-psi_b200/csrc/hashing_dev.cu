@@ -209,13 +209,15 @@ done:
 //   slot s = outerHf*e + outerPos  holds  cells[s][hf][perm[s][hf][bin]][pos]   (perm = the ctor's bin shuffle)
 // out: [n_pt][N] residues mod t in transform order.
 __global__ void __launch_bounds__(256) k_cells_to_crt(uint32_t N, uint32_t n_pt, uint32_t p0, uint32_t nslots, uint32_t K,
-                                                      uint32_t b, uint32_t E, const u64* __restrict__ cells,
+                                                      uint32_t b, uint32_t E, uint32_t bin_begin, uint32_t b_local,
+                                                      const u64* __restrict__ cells,
                                                       const uint16_t* __restrict__ perm, const uint32_t* __restrict__ to_crt,
                                                       u64* __restrict__ out) {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (size_t)n_pt * N) return;
     const uint32_t p = p0 + (uint32_t)(tid / N), i = (uint32_t)(tid % N);
-    const uint32_t pos = p % E, bin = (p / E) % b, hf = p / (E * b);
+    // p counts the plaintexts of the shard: (hf * b_local + local bin) * E + pos
+    const uint32_t pos = p % E, bin = bin_begin + (p / E) % b_local, hf = p / (E * b_local);
     const uint32_t s = to_crt[i];
     u64 r = 0;
     if (s < nslots) {
@@ -225,10 +227,11 @@ __global__ void __launch_bounds__(256) k_cells_to_crt(uint32_t N, uint32_t n_pt,
     out[tid] = r;
 }
 cudaError_t launch_cells_to_crt(const KCtx& k, uint32_t n_pt, uint32_t p0, uint32_t nslots, uint32_t K, uint32_t b, uint32_t E,
-                                const u64* cells, const uint16_t* perm, const uint32_t* to_crt, u64* out) {
+                                uint32_t bin_begin, uint32_t b_local, const u64* cells, const uint16_t* perm,
+                                const uint32_t* to_crt, u64* out) {
     const size_t total = (size_t)n_pt * k.N;
     if (total == 0) return cudaSuccess;
-    k_cells_to_crt<<<(unsigned)((total + 255) / 256), 256, 0, k.s>>>(k.N, n_pt, p0, nslots, K, b, E, cells, perm, to_crt, out);
+    k_cells_to_crt<<<(unsigned)((total + 255) / 256), 256, 0, k.s>>>(k.N, n_pt, p0, nslots, K, b, E, bin_begin, b_local, cells, perm, to_crt, out);
     return cudaGetLastError();
 }
 

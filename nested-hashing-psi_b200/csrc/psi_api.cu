@@ -112,6 +112,7 @@ struct psi_ctx {
     uint32_t K = 0, b = 0, E = 0;
     DevBuf<u64> pt, mask;
     bool have_db = false;
+    uint32_t encode_lift = PSI_ENCODE_LIFT_PLAIN;
     // query
     DevBuf<u64> idx, idx_in, minus;  // idx: tiled split-30; idx_in: two H2D landing buffers [2][K][E][2][L][N]
     DevBuf<u64> stage;               // chunk staging for the DB re-tiling
@@ -128,6 +129,12 @@ struct psi_ctx {
     u64* out_buf(uint32_t which) { return which ? out2.p : out.p; }
     bool ran = false;
     uint32_t launches_per_run = 0;
+    // pinned staging pools of the *_limbs entry points (separate limb vectors <-> one DMA-able buffer)
+    u64* pool_in = nullptr;
+    u64* pool_out = nullptr;
+    size_t pool_in_words = 0, pool_out_words = 0;
+    cudaEvent_t ev_pool_in = nullptr;  // last upload that read pool_in
+    int host_threads = 8;
 
     KCtx k(cudaStream_t s) const { return KCtx{d_tab, N, logN, L, Lp, s}; }
 };
@@ -136,6 +143,26 @@ namespace psi {
 
 static int ensure_device(psi_ctx* c) {
     CK(cudaSetDevice(c->device));
+    return PSI_OK;
+}
+
+// PackedEncoding slot permutation (OpenFHE PackedEncoding::SetParams_2n as restated in oracle/psi_oracle.c):
+// slot i <-> exponent 5^i, slot i + N/2 <-> cofactor * 5^i, bit-reversed transform order.  The co-factor is 3 in
+// the OpenFHE 1.0.x line as recalled and 2N - 1 (the conjugation) in the other reading; the server and the client
+// must agree on it whenever the server encodes the database itself (psi_set_packing_cofactor).
+static int build_pack_perm(psi_ctx* c, uint32_t mode) {
+    const uint32_t N = c->N;
+    std::vector<uint32_t> perm(N);
+    const u64 m2 = 2ull * N, cofactor = mode == PSI_PACK_COFACTOR_CONJ ? m2 - 1 : 3;
+    u64 cur = 1;
+    for (uint32_t i = 0; i < N / 2; i++) {
+        perm[h_bitrev((uint32_t)((cur - 1) / 2), (int)c->logN)] = i;
+        const u64 cof = (cur * cofactor) % m2;
+        perm[h_bitrev((uint32_t)((cof - 1) / 2), (int)c->logN)] = i + N / 2;
+        cur = (cur * 5) % m2;
+    }
+    CK(c->to_crt.alloc(N));
+    CK(cudaMemcpy(c->to_crt.p, perm.data(), N * sizeof(uint32_t), cudaMemcpyHostToDevice));
     return PSI_OK;
 }
 
@@ -291,20 +318,7 @@ static int build_tables(psi_ctx* c) {
     CK(cudaMalloc(&c->d_tab, sizeof(DevTables)));
     CK(cudaMemcpy(c->d_tab, &T, sizeof(T), cudaMemcpyHostToDevice));
 
-    // PackedEncoding slot permutation (OpenFHE PackedEncoding::SetParams_2n as restated in
-    // oracle/psi_oracle.c: slot i <-> exponent 5^i, slot i+N/2 <-> 3*5^i, bit-reversed transform order)
-    std::vector<uint32_t> perm(N);
-    const u64 m2 = 2ull * N;
-    u64 cur = 1;
-    for (uint32_t i = 0; i < N / 2; i++) {
-        perm[h_bitrev((uint32_t)((cur - 1) / 2), (int)c->logN)] = i;
-        const u64 cof = (cur * 3) % m2;
-        perm[h_bitrev((uint32_t)((cof - 1) / 2), (int)c->logN)] = i + N / 2;
-        cur = (cur * 5) % m2;
-    }
-    CK(c->to_crt.alloc(N));
-    CK(cudaMemcpy(c->to_crt.p, perm.data(), N * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    return PSI_OK;
+    return build_pack_perm(c, PSI_PACK_COFACTOR_3);
 }
 
 static int alloc_work(psi_ctx* c) {
@@ -429,7 +443,25 @@ int psi_ctx_destroy(psi_ctx* c) {
                            &c->coef,     &c->e1,    &c->e2,    &c->ten, &c->res, &c->dig, &c->prod,  &c->out, &c->out2, &c->minus_in};
     for (auto* b : bufs) b->release();
     c->to_crt.release();
+    if (c->pool_in) cudaFreeHost(c->pool_in);
+    if (c->pool_out) cudaFreeHost(c->pool_out);
+    if (c->ev_pool_in) cudaEventDestroy(c->ev_pool_in);
     delete c;
+    return PSI_OK;
+}
+
+int psi_set_packing_cofactor(psi_ctx* c, uint32_t mode) {
+    if (!c) return set_error(PSI_ERR_INVALID, "null argument");
+    if (mode != PSI_PACK_COFACTOR_3 && mode != PSI_PACK_COFACTOR_CONJ) return set_error(PSI_ERR_INVALID, "unknown packing co-factor");
+    int rc = ensure_device(c);
+    if (rc) return rc;
+    return build_pack_perm(c, mode);
+}
+
+int psi_set_encode_lift(psi_ctx* c, uint32_t mode) {
+    if (!c) return set_error(PSI_ERR_INVALID, "null argument");
+    if (mode != PSI_ENCODE_LIFT_PLAIN && mode != PSI_ENCODE_LIFT_CENTRED) return set_error(PSI_ERR_INVALID, "unknown encode lift");
+    c->encode_lift = mode;
     return PSI_OK;
 }
 
@@ -475,40 +507,78 @@ static int db_dims(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E) {
     return alloc_work(c);
 }
 
-int psi_db_load_limbs(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E, const uint64_t* pt_limbs,
-                      const uint64_t* mask_limbs) {
+// One database shard: bins [bin_begin, bin_end) of a b_total-bin database become the resident database of this
+// context (b_local = bin_end - bin_begin).  The full-array layouts are those of the unsharded calls; for every
+// hash function the shard's plaintexts / slot vectors are one contiguous block of them.
+static int check_shard(uint32_t b_total, uint32_t bin_begin, uint32_t bin_end) {
+    if (bin_begin >= bin_end || bin_end > b_total) return set_error(PSI_ERR_INVALID, "bin range must be a non-empty part of [0, b)");
+    return PSI_OK;
+}
+
+int psi_db_load_limbs_shard(psi_ctx* c, uint32_t K, uint32_t b_total, uint32_t bin_begin, uint32_t bin_end, uint32_t E,
+                            const uint64_t* pt_limbs, const uint64_t* mask_limbs) {
     if (!c || !pt_limbs || !mask_limbs) return set_error(PSI_ERR_INVALID, "null argument");
-    int rc = ensure_device(c);
+    int rc = check_shard(b_total, bin_begin, bin_end);
     if (rc) return rc;
+    if ((rc = ensure_device(c))) return rc;
+    const uint32_t b = bin_end - bin_begin;
     if ((rc = db_dims(c, K, b, E))) return rc;
     const size_t LN = (size_t)c->L * c->N;
     {
-        const size_t n_pt = (size_t)K * b * E, chunk = n_pt < kDbChunk ? n_pt : kDbChunk;
+        const size_t n_hf = (size_t)b * E, chunk = n_hf < kDbChunk ? n_hf : kDbChunk;
         CK(c->stage.alloc(chunk * LN));
         DevBuf<int> d_bad;  // raised by the re-tiling kernel when a limb is not a canonical residue
         CK(d_bad.alloc(1));
         CK(cudaMemset(d_bad.p, 0, sizeof(int)));
-        for (size_t p0 = 0; p0 < n_pt; p0 += chunk) {
-            const size_t n = (n_pt - p0) < chunk ? (n_pt - p0) : chunk;
-            CK(cudaMemcpy(c->stage.p, pt_limbs + p0 * LN, n * LN * sizeof(u64), cudaMemcpyHostToDevice));
-            CK(launch_retile_pt(0, c->stage.p, c->pt.p, LN, E, p0, n, true, c->d_tab, d_bad.p));
-            CK(cudaStreamSynchronize(0));
+        for (uint32_t hf = 0; hf < K; hf++) {
+            const uint64_t* src = pt_limbs + (((size_t)hf * b_total + bin_begin) * E) * LN;
+            for (size_t p0 = 0; p0 < n_hf; p0 += chunk) {
+                const size_t n = (n_hf - p0) < chunk ? (n_hf - p0) : chunk;
+                CK(cudaMemcpy(c->stage.p, src + p0 * LN, n * LN * sizeof(u64), cudaMemcpyHostToDevice));
+                CK(launch_retile_pt(0, c->stage.p, c->pt.p, LN, E, (size_t)hf * n_hf + p0, n, true, c->d_tab, d_bad.p));
+                CK(cudaStreamSynchronize(0));
+            }
         }
         int bad = 0;
         CK(cudaMemcpy(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost));
         if (bad) return set_error(PSI_ERR_INVALID, "plaintext limbs must be canonical residues (value >= q_l found)");
     }
-    CK(cudaMemcpy(c->mask.p, mask_limbs, (size_t)b * LN * sizeof(u64), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->mask.p, mask_limbs + (size_t)bin_begin * LN, (size_t)b * LN * sizeof(u64), cudaMemcpyHostToDevice));
     CK(launch_to_montgomery(c->k(0), b, c->mask.p, c->maskR.p));
     CK(cudaStreamSynchronize(0));
     c->have_db = true;
     return PSI_OK;
 }
 
+int psi_db_load_limbs(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E, const uint64_t* pt_limbs,
+                      const uint64_t* mask_limbs) {
+    return psi_db_load_limbs_shard(c, K, b, 0, b, E, pt_limbs, mask_limbs);
+}
+
+// Packed coefficients mod t ([n][N], in [0, t)) -> EVALUATION limbs [n][L][N] at ntt_dst.
+//   PLAIN:   every limb is the same vector (residues in [0, t) are below every q_l); OpenFHE >= 1.0 as recalled:
+//            PackedEncoding::Encode copies the coefficients into the first tower and SwitchModulus (centred about
+//            q_0, so values < t stay) spreads them.
+//   CENTRED: c > t/2 becomes q_l - (t - c), the signed representative lifted to q_l (SURVEY.md Appendix A's
+//            reading).  Both decrypt identically; only the limbs differ, hence the switch (risk register).
+static cudaError_t lift_and_ntt(psi_ctx* c, const KCtx& k, uint32_t n, const u64* d_crt, u64* ntt_dst) {
+    const size_t N = c->N, L = c->L;
+    if (c->encode_lift == PSI_ENCODE_LIFT_CENTRED) {
+        cudaError_t e = launch_centre_lift(k, n, d_crt, ntt_dst);
+        if (e != cudaSuccess) return e;
+        NttBatch nb{ntt_dst, ntt_dst, n * (uint32_t)L, (uint32_t)L, L * N, N, L * N, 0, (uint32_t)L};
+        return launch_ntt(k, nb, false);
+    }
+    NttBatch nb{d_crt, ntt_dst, n * (uint32_t)L, (uint32_t)L, N, 0, L * N, 0, (uint32_t)L};
+    return launch_ntt(k, nb, false);
+}
+
 // MakePackedPlaintext + SetFormat(EVALUATION) for n_pt plaintexts, chunked so that the staging
 // buffers stay small next to the DB itself.
-// tiled_E != 0: dst is the tiled plaintext DB (positions per bin = tiled_E); else dst is flat [n_pt][L][N].
-static int encode_into(psi_ctx* c, size_t n_pt, uint32_t nslots, const int64_t* slots, u64* dst, uint32_t tiled_E) {
+// tiled_E != 0: dst is the tiled plaintext DB (positions per bin = tiled_E) and the plaintexts are numbers
+// p_base .. p_base + n_pt - 1 of it; else dst is flat [n_pt][L][N].
+static int encode_into(psi_ctx* c, size_t n_pt, uint32_t nslots, const int64_t* slots, u64* dst, uint32_t tiled_E,
+                       size_t p_base = 0) {
     const size_t N = c->N, L = c->L;
     const size_t chunk = n_pt < kDbChunk ? n_pt : kDbChunk;
     if (tiled_E) CK(c->stage.alloc(chunk * L * N));
@@ -517,53 +587,60 @@ static int encode_into(psi_ctx* c, size_t n_pt, uint32_t nslots, const int64_t* 
     CK(d_slots.alloc(chunk * nslots));
     CK(d_crt.alloc(chunk * N));
     const KCtx k = c->k(0);
-    int rc = PSI_OK;
-    for (size_t p0 = 0; p0 < n_pt && rc == PSI_OK; p0 += chunk) {
+    for (size_t p0 = 0; p0 < n_pt; p0 += chunk) {
         const uint32_t n = (uint32_t)((n_pt - p0) < chunk ? (n_pt - p0) : chunk);
-        cudaError_t e = cudaMemcpy(d_slots.p, slots + p0 * nslots, (size_t)n * nslots * sizeof(int64_t), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = launch_slots_to_crt(k, n, nslots, d_slots.p, c->to_crt.p, d_crt.p);
-        if (e == cudaSuccess) {
+        CK(cudaMemcpy(d_slots.p, slots + p0 * nslots, (size_t)n * nslots * sizeof(int64_t), cudaMemcpyHostToDevice));
+        CK(launch_slots_to_crt(k, n, nslots, d_slots.p, c->to_crt.p, d_crt.p));
+        {
             NttBatch nb{d_crt.p, d_crt.p, n, 1, N, 0, N, c->L + c->Lp, 1};
-            e = launch_ntt(k, nb, true);  // slots -> coefficients mod t
+            CK(launch_ntt(k, nb, true));  // slots -> coefficients mod t
         }
-        if (e == cudaSuccess) {
-            // residues in [0,t) are below every q_l: each limb is the same vector, then NTT mod q_l
-            NttBatch nb{d_crt.p, tiled_E ? c->stage.p : dst + p0 * L * N, n * (uint32_t)L, (uint32_t)L, N, 0, L * N, 0, (uint32_t)L};
-            e = launch_ntt(k, nb, false);
-        }
-        if (e == cudaSuccess && tiled_E) e = launch_retile_pt(0, c->stage.p, dst, L * N, tiled_E, p0, n, true);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-        if (e != cudaSuccess) rc = cuda_fail(e, "psi_db_encode_slots");
+        // lift of the coefficients from [0, t) to every q_l (see psi_set_encode_lift), then NTT mod q_l
+        CK(lift_and_ntt(c, k, n, d_crt.p, tiled_E ? c->stage.p : dst + p0 * L * N));
+        if (tiled_E) CK(launch_retile_pt(0, c->stage.p, dst, L * N, tiled_E, p_base + p0, n, true));
+        CK(cudaStreamSynchronize(0));
     }
-    d_slots.release();
-    d_crt.release();
-    return rc;
+    return PSI_OK;
 }
 
-int psi_db_encode_slots(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E, uint32_t nslots, const int64_t* slots,
-                        const int64_t* mask_slots) {
+int psi_db_encode_slots_shard(psi_ctx* c, uint32_t K, uint32_t b_total, uint32_t bin_begin, uint32_t bin_end, uint32_t E,
+                              uint32_t nslots, const int64_t* slots, const int64_t* mask_slots) {
     if (!c || !slots || !mask_slots) return set_error(PSI_ERR_INVALID, "null argument");
     if (nslots < 1 || nslots > c->N) return set_error(PSI_ERR_INVALID, "batch size must be in [1, N]");
+    int rc = check_shard(b_total, bin_begin, bin_end);
+    if (rc) return rc;
+    const uint32_t b = bin_end - bin_begin;
     // PackedEncoding::Encode rejects |v| >= t
     const uint64_t t = c->P.t;
-    const size_t n_slots_total = (size_t)K * b * E * nslots, n_mask_total = (size_t)b * nslots;
-    for (size_t i = 0; i < n_slots_total; i++) {
-        const int64_t v = slots[i];
-        if ((uint64_t)(v < 0 ? -v : v) >= t) return set_error(PSI_ERR_INVALID, "slot value out of range of the plaintext modulus");
+    const size_t n_hf = (size_t)b * E * nslots, n_mask = (size_t)b * nslots;
+    for (uint32_t hf = 0; hf < K; hf++) {
+        const int64_t* sv = slots + (((size_t)hf * b_total + bin_begin) * E) * nslots;
+        for (size_t i = 0; i < n_hf; i++) {
+            const int64_t v = sv[i];
+            if ((uint64_t)(v < 0 ? -v : v) >= t) return set_error(PSI_ERR_INVALID, "slot value out of range of the plaintext modulus");
+        }
     }
-    for (size_t i = 0; i < n_mask_total; i++) {
-        const int64_t v = mask_slots[i];
+    const int64_t* mv = mask_slots + (size_t)bin_begin * nslots;
+    for (size_t i = 0; i < n_mask; i++) {
+        const int64_t v = mv[i];
         if ((uint64_t)(v < 0 ? -v : v) >= t) return set_error(PSI_ERR_INVALID, "mask value out of range of the plaintext modulus");
     }
-    int rc = ensure_device(c);
-    if (rc) return rc;
+    if ((rc = ensure_device(c))) return rc;
     if ((rc = db_dims(c, K, b, E))) return rc;
-    if ((rc = encode_into(c, (size_t)K * b * E, nslots, slots, c->pt.p, E))) return rc;
-    if ((rc = encode_into(c, b, nslots, mask_slots, c->mask.p, 0))) return rc;
+    for (uint32_t hf = 0; hf < K; hf++)
+        if ((rc = encode_into(c, (size_t)b * E, nslots, slots + (((size_t)hf * b_total + bin_begin) * E) * nslots, c->pt.p, E,
+                              (size_t)hf * b * E)))
+            return rc;
+    if ((rc = encode_into(c, b, nslots, mv, c->mask.p, 0))) return rc;
     CK(launch_to_montgomery(c->k(0), b, c->mask.p, c->maskR.p));
     CK(cudaStreamSynchronize(0));
     c->have_db = true;
     return PSI_OK;
+}
+
+int psi_db_encode_slots(psi_ctx* c, uint32_t K, uint32_t b, uint32_t E, uint32_t nslots, const int64_t* slots,
+                        const int64_t* mask_slots) {
+    return psi_db_encode_slots_shard(c, K, b, 0, b, E, nslots, slots, mask_slots);
 }
 
 // Device-resident constructor path: hash the server set, build the nested cuckoo tables, apply the bin
@@ -573,17 +650,15 @@ static int hct_on_device(psi_ctx* c, uint64_t hash_seed, uint32_t k, uint32_t e,
     if (k < 1 || e < 1 || K < 2 || E < 1 || b < 1) return set_error(PSI_ERR_INVALID, "table sizes must be positive, K >= 2");
     if (n > 0x7fffffffull) return set_error(PSI_ERR_INVALID, "server set too large for one device build");
     TabulationHashing hashf(hash_seed, k + K);
-    DevBuf<u64> d_T, d_items;
+    DevBuf<u64> d_T, d_items;  // freed on every exit path
     const std::vector<uint64_t>& T = hashf.tables();
     CK(d_T.alloc(T.size()));
     CK(d_items.alloc(n ? n : 1));
     CK(d_cells.alloc((size_t)k * e * K * b * E));
     CK(cudaMemcpy(d_T.p, T.data(), T.size() * sizeof(u64), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_items.p, items, n * sizeof(u64), cudaMemcpyHostToDevice));
+    if (n) CK(cudaMemcpy(d_items.p, items, n * sizeof(u64), cudaMemcpyHostToDevice));
     int failed = 0;
     cudaError_t err = hct_build_device(0, d_T.p, k, e, K, b, E, eviction_seed, d_items.p, n, d_cells.p, &failed);
-    d_T.release();
-    d_items.release();
     if (err != cudaSuccess) return cuda_fail(err, "device table build");
     if (failed) return set_error(PSI_ERR_STATE, "(Blocked) Cuckoo hashing error");  // CuckooHashTable.cpp:113
     return PSI_OK;
@@ -595,72 +670,91 @@ int psi_hct_build_device(psi_ctx* c, uint64_t hash_seed, uint32_t k, uint64_t e,
     int rc = ensure_device(c);
     if (rc) return rc;
     DevBuf<u64> d_cells;
-    rc = hct_on_device(c, hash_seed, k, (uint32_t)e, K, (uint32_t)E, (uint32_t)b, eviction_seed, items, n, d_cells);
-    if (rc == PSI_OK) {
-        cudaError_t err = cudaMemcpy(cells, d_cells.p, (size_t)k * e * K * b * E * sizeof(u64), cudaMemcpyDeviceToHost);
-        if (err != cudaSuccess) rc = cuda_fail(err, "psi_hct_build_device");
-    }
-    d_cells.release();
-    return rc;
+    if ((rc = hct_on_device(c, hash_seed, k, (uint32_t)e, K, (uint32_t)E, (uint32_t)b, eviction_seed, items, n, d_cells))) return rc;
+    CK(cudaMemcpy(cells, d_cells.p, (size_t)k * e * K * b * E * sizeof(u64), cudaMemcpyDeviceToHost));
+    return PSI_OK;
 }
 
-int psi_db_build_from_items(psi_ctx* c, uint64_t hash_seed, uint32_t k, uint64_t e, uint32_t K, uint64_t E, uint64_t b,
-                            uint64_t eviction_seed, const uint64_t* items, size_t n, uint64_t shuffle_seed,
-                            uint64_t mask_seed) {
+int psi_db_build_from_items_shard(psi_ctx* c, uint64_t hash_seed, uint32_t k, uint64_t e, uint32_t K, uint64_t E, uint64_t b,
+                                  uint64_t eviction_seed, const uint64_t* items, size_t n, uint64_t shuffle_seed,
+                                  uint64_t mask_seed, uint32_t bin_begin, uint32_t bin_end) {
     if (!c || (!items && n)) return set_error(PSI_ERR_INVALID, "null argument");
     const size_t nslots = (size_t)k * e;
     if (nslots > c->N) return set_error(PSI_ERR_INVALID, "batch size exceeds the ring dimension");
     if (b > 65535) return set_error(PSI_ERR_INVALID, "bin size too large");
+    int rc = check_shard((uint32_t)b, bin_begin, bin_end);
+    if (rc) return rc;
+    if (shuffle_seed == PSI_SEED_RANDOM && !(bin_begin == 0 && bin_end == b))
+        return set_error(PSI_ERR_INVALID, "a sharded build needs an explicit shuffle seed shared by all shards (draw it once)");
     const uint64_t t = c->P.t;
     for (size_t i = 0; i < n; i++)
         if (items[i] >= t) return set_error(PSI_ERR_INVALID, "slot value out of range of the plaintext modulus");
-    int rc = ensure_device(c);
-    if (rc) return rc;
+    if ((rc = ensure_device(c))) return rc;
     DevBuf<u64> d_cells;
-    if ((rc = hct_on_device(c, hash_seed, k, (uint32_t)e, K, (uint32_t)E, (uint32_t)b, eviction_seed, items, n, d_cells))) {
-        d_cells.release();
-        return rc;
-    }
-    // bin shuffle (BatchedFHEHIPPIE.cpp:25-35) as permutations, masks (:73-82): same generators as the host ctor
+    if ((rc = hct_on_device(c, hash_seed, k, (uint32_t)e, K, (uint32_t)E, (uint32_t)b, eviction_seed, items, n, d_cells))) return rc;
+    // bin shuffle (BatchedFHEHIPPIE.cpp:25-35) as permutations, masks (:73-82): same generators as the host ctor,
+    // drawn for ALL b bins so that every shard of one database sees the same shuffle and the same masks
     std::mt19937 mt = seeded_mt19937(resolve_seed(shuffle_seed));
     const std::vector<uint16_t> perm = makeBinShuffle(k, e, K, b, mt);
     std::vector<int64_t> mask_slots((size_t)b * nslots);
     std::mt19937_64 mm(resolve_seed(mask_seed));
     for (auto& v : mask_slots) v = (int64_t)(mm() % (t - 1) + 1);
+    const uint32_t bl = bin_end - bin_begin;
     DevBuf<uint16_t> d_perm;
     DevBuf<u64> d_crt;
-    cudaError_t err = d_perm.alloc(perm.size());
-    if (err == cudaSuccess) err = cudaMemcpy(d_perm.p, perm.data(), perm.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
-    if (err == cudaSuccess && (rc = db_dims(c, K, (uint32_t)b, (uint32_t)E)) == PSI_OK) {
-        const size_t N = c->N, L = c->L, n_pt = (size_t)K * b * E, chunk = n_pt < kDbChunk ? n_pt : kDbChunk;
+    CK(d_perm.alloc(perm.size()));
+    CK(cudaMemcpy(d_perm.p, perm.data(), perm.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    if ((rc = db_dims(c, K, bl, (uint32_t)E))) return rc;
+    {
+        const size_t N = c->N, L = c->L, n_pt = (size_t)K * bl * E, chunk = n_pt < kDbChunk ? n_pt : kDbChunk;
         const KCtx kc = c->k(0);
-        err = d_crt.alloc(chunk * N);
-        if (err == cudaSuccess) err = c->stage.alloc(chunk * L * N);
-        for (size_t p0 = 0; p0 < n_pt && err == cudaSuccess; p0 += chunk) {
+        CK(d_crt.alloc(chunk * N));
+        CK(c->stage.alloc(chunk * L * N));
+        for (size_t p0 = 0; p0 < n_pt; p0 += chunk) {
             const uint32_t np = (uint32_t)((n_pt - p0) < chunk ? (n_pt - p0) : chunk);
-            err = launch_cells_to_crt(kc, np, (uint32_t)p0, (uint32_t)nslots, K, (uint32_t)b, (uint32_t)E, d_cells.p, d_perm.p,
-                                      c->to_crt.p, d_crt.p);
-            if (err == cudaSuccess) {
+            CK(launch_cells_to_crt(kc, np, (uint32_t)p0, (uint32_t)nslots, K, (uint32_t)b, (uint32_t)E, bin_begin, bl, d_cells.p,
+                                   d_perm.p, c->to_crt.p, d_crt.p));
+            {
                 NttBatch nb{d_crt.p, d_crt.p, np, 1, N, 0, N, c->L + c->Lp, 1};
-                err = launch_ntt(kc, nb, true);
+                CK(launch_ntt(kc, nb, true));
             }
-            if (err == cudaSuccess) {
-                NttBatch nb{d_crt.p, c->stage.p, np * (uint32_t)L, (uint32_t)L, N, 0, L * N, 0, (uint32_t)L};
-                err = launch_ntt(kc, nb, false);
-            }
-            if (err == cudaSuccess) err = launch_retile_pt(0, c->stage.p, c->pt.p, L * N, (uint32_t)E, p0, np, true);
-            if (err == cudaSuccess) err = cudaStreamSynchronize(0);
+            CK(lift_and_ntt(c, kc, np, d_crt.p, c->stage.p));
+            CK(launch_retile_pt(0, c->stage.p, c->pt.p, L * N, (uint32_t)E, p0, np, true));
+            CK(cudaStreamSynchronize(0));
         }
     }
-    d_cells.release();
-    d_perm.release();
-    d_crt.release();
-    if (rc) return rc;
-    if (err != cudaSuccess) return cuda_fail(err, "psi_db_build_from_items");
-    if ((rc = encode_into(c, b, (uint32_t)nslots, mask_slots.data(), c->mask.p, 0))) return rc;
-    CK(launch_to_montgomery(c->k(0), (uint32_t)b, c->mask.p, c->maskR.p));
+    if ((rc = encode_into(c, bl, (uint32_t)nslots, mask_slots.data() + (size_t)bin_begin * nslots, c->mask.p, 0))) return rc;
+    CK(launch_to_montgomery(c->k(0), bl, c->mask.p, c->maskR.p));
     CK(cudaStreamSynchronize(0));
     c->have_db = true;
+    return PSI_OK;
+}
+
+int psi_db_build_from_items(psi_ctx* c, uint64_t hash_seed, uint32_t k, uint64_t e, uint32_t K, uint64_t E, uint64_t b,
+                            uint64_t eviction_seed, const uint64_t* items, size_t n, uint64_t shuffle_seed,
+                            uint64_t mask_seed) {
+    return psi_db_build_from_items_shard(c, hash_seed, k, e, K, E, b, eviction_seed, items, n, shuffle_seed, mask_seed, 0,
+                                         (uint32_t)b);
+}
+
+// One bin of the resident database back to the host (tests, in-run parity checks of bench.py):
+// pt [K][E][L][N], mask [L][N], canonical residues.
+int psi_db_get_bin_limbs(psi_ctx* c, uint32_t bin, uint64_t* pt_limbs, uint64_t* mask_limbs) {
+    if (!c || !pt_limbs || !mask_limbs) return set_error(PSI_ERR_INVALID, "null argument");
+    if (!c->have_db) return set_error(PSI_ERR_STATE, "no database loaded");
+    if (bin >= c->b) return set_error(PSI_ERR_INVALID, "bin out of range");
+    int rc = ensure_device(c);
+    if (rc) return rc;
+    const size_t LN = (size_t)c->L * c->N;
+    DevBuf<u64> tmp;
+    CK(tmp.alloc((size_t)c->E * LN));
+    for (uint32_t hf = 0; hf < c->K; hf++) {
+        CK(cudaMemset(tmp.p, 0, (size_t)c->E * LN * sizeof(u64)));
+        // retile works on (plaintext index - p0) inside the flat buffer
+        CK(launch_retile_pt(0, tmp.p, c->pt.p, LN, c->E, ((size_t)hf * c->b + bin) * c->E, c->E, false));
+        CK(cudaMemcpy(pt_limbs + (size_t)hf * c->E * LN, tmp.p, (size_t)c->E * LN * sizeof(u64), cudaMemcpyDeviceToHost));
+    }
+    CK(cudaMemcpy(mask_limbs, c->mask.p + (size_t)bin * LN, LN * sizeof(u64), cudaMemcpyDeviceToHost));
     return PSI_OK;
 }
 
@@ -708,6 +802,93 @@ int psi_query_upload(psi_ctx* c, const uint64_t* idx, const uint64_t* minus, voi
     CK(cudaMemcpyAsync(c->idx_in.p + w * c->idx_words(), idx, c->idx_words() * sizeof(u64), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(c->minus_in.p + w * 2 * LN, minus, 2 * LN * sizeof(u64), cudaMemcpyHostToDevice, s));
     c->n_uploaded++;
+    return PSI_OK;
+}
+
+static int ensure_pool(u64** p, size_t* have, size_t words) {
+    if (*p && *have >= words) return PSI_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    *have = 0;
+    CK(cudaHostAlloc((void**)p, words * sizeof(u64), cudaHostAllocPortable));
+    *have = words;
+    return PSI_OK;
+}
+
+constexpr uint32_t kLimbPieces = 8;  // staging granularity: host copy of piece i+1 overlaps the DMA of piece i
+
+// setIndex + setMinusCompareElement from SEPARATE limb vectors (what a deserialised OpenFHE query holds,
+// BatchedFHEPSIServer.cpp:114-141): K*E*2*L pointers in [hf][pos][comp][limb] order + 2*L for minus, N words each,
+// pageable memory.  A few host threads copy the vectors of a piece into the pinned pool, the copy engine uploads
+// the piece while the next one is being staged.  The vectors may be freed when the call returns.
+int psi_query_upload_limbs(psi_ctx* c, const uint64_t* const* idx_limbs, const uint64_t* const* minus_limbs, void* stream) {
+    if (!c || !idx_limbs || !minus_limbs) return set_error(PSI_ERR_INVALID, "null argument");
+    uint32_t w = 0;
+    int rc = landing_slot(c, &w);
+    if (rc) return rc;
+    if ((rc = ensure_device(c))) return rc;
+    const size_t N = c->N, LN = (size_t)c->L * N, W = c->idx_words(), nvec = W / N;
+    if ((rc = ensure_pool(&c->pool_in, &c->pool_in_words, W + 2 * LN))) return rc;
+    if (!c->ev_pool_in) CK(cudaEventCreateWithFlags(&c->ev_pool_in, cudaEventDisableTiming));
+    CK(cudaEventSynchronize(c->ev_pool_in));  // the previous upload has read the pool
+    cudaStream_t s = (cudaStream_t)stream;
+    u64* pool = c->pool_in;
+    for (size_t v = 0; v < 2 * (size_t)c->L; v++) std::memcpy(pool + W + v * N, minus_limbs[v], N * sizeof(u64));
+    CK(cudaMemcpyAsync(c->minus_in.p + w * 2 * LN, pool + W, 2 * LN * sizeof(u64), cudaMemcpyHostToDevice, s));
+    const int nt = c->host_threads;
+    (void)nt;
+    for (uint32_t piece = 0; piece < kLimbPieces; piece++) {
+        const long v0 = (long)(nvec * piece / kLimbPieces), v1 = (long)(nvec * (piece + 1) / kLimbPieces);
+        if (v1 == v0) continue;
+#pragma omp parallel for schedule(static) num_threads(nt) if (v1 - v0 >= 16)
+        for (long v = v0; v < v1; v++) std::memcpy(pool + (size_t)v * N, idx_limbs[v], N * sizeof(u64));
+        CK(cudaMemcpyAsync(c->idx_in.p + w * W + (size_t)v0 * N, pool + (size_t)v0 * N, (size_t)(v1 - v0) * N * sizeof(u64),
+                           cudaMemcpyHostToDevice, s));
+    }
+    CK(cudaEventRecord(c->ev_pool_in, s));
+    c->n_uploaded++;
+    return PSI_OK;
+}
+
+// getResultList into b*2*L separate limb vectors ([bin][comp][limb] order): the download is split into pieces,
+// each scattered by host threads as soon as it has arrived.  Synchronous: the vectors are filled on return.
+int psi_result_get_limbs(psi_ctx* c, uint64_t* const* out_limbs, void* stream) {
+    if (!c || !out_limbs) return set_error(PSI_ERR_INVALID, "null argument");
+    if (!c->ran) return set_error(PSI_ERR_STATE, "getResultList() before run()");
+    int rc = ensure_device(c);
+    if (rc) return rc;
+    const size_t N = c->N, W = (size_t)c->b * 2 * c->L * N, nvec = W / N;
+    if ((rc = ensure_pool(&c->pool_out, &c->pool_out_words, W))) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaEvent_t ev[kLimbPieces] = {};
+    struct EvGuard {
+        cudaEvent_t* e;
+        ~EvGuard() {
+            for (uint32_t i = 0; i < kLimbPieces; i++)
+                if (e[i]) cudaEventDestroy(e[i]);
+        }
+    } guard{ev};
+    const u64* src = c->out_buf(c->out_cur);
+    for (uint32_t piece = 0; piece < kLimbPieces; piece++) {
+        const size_t v0 = nvec * piece / kLimbPieces, v1 = nvec * (piece + 1) / kLimbPieces;
+        CK(cudaEventCreateWithFlags(&ev[piece], cudaEventDisableTiming));
+        if (v1 > v0) CK(cudaMemcpyAsync(c->pool_out + v0 * N, src + v0 * N, (v1 - v0) * N * sizeof(u64), cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(ev[piece], s));
+    }
+    const int nt = c->host_threads;
+    (void)nt;
+    for (uint32_t piece = 0; piece < kLimbPieces; piece++) {
+        const long v0 = (long)(nvec * piece / kLimbPieces), v1 = (long)(nvec * (piece + 1) / kLimbPieces);
+        CK(cudaEventSynchronize(ev[piece]));
+#pragma omp parallel for schedule(static) num_threads(nt) if (v1 - v0 >= 16)
+        for (long v = v0; v < v1; v++) std::memcpy(out_limbs[v], c->pool_out + (size_t)v * N, N * sizeof(u64));
+    }
+    return PSI_OK;
+}
+
+int psi_set_host_threads(psi_ctx* c, int n) {
+    if (!c || n < 1 || n > 256) return set_error(PSI_ERR_INVALID, "host thread count must be in [1, 256]");
+    c->host_threads = n;
     return PSI_OK;
 }
 

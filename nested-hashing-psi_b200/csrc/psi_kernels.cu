@@ -492,6 +492,18 @@ __global__ void __launch_bounds__(256) k_slots_to_crt(const DevTables* __restric
     out[tid] = r;
 }
 
+// Centred lift of packed-encoding coefficients: crt [n][N] in [0, t) -> out [n][L][N], limb l holds c for
+// c <= t/2 and q_l - (t - c) otherwise (the signed representative of c mod t, reduced mod q_l).
+__global__ void __launch_bounds__(256) k_centre_lift(const DevTables* __restrict__ tab, uint32_t N, uint32_t n,
+                                                     const u64* __restrict__ crt, u64* __restrict__ out) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)n * N) return;
+    const size_t p = tid / N, i = tid % N;
+    const u64 t = tab->t, v = crt[tid];
+    const int L = tab->L;
+    for (int l = 0; l < L; l++) out[(p * L + l) * N + i] = v > (t >> 1) ? v + (tab->mods[l].q - t) : v;
+}
+
 #define LAUNCH_1D(kernel, total, ...)                                 \
     kernel<<<cdiv((total), 256), 256, 0, k.s>>>(k.tab, k.N, __VA_ARGS__); \
     return cudaGetLastError();
@@ -517,6 +529,9 @@ cudaError_t launch_relin_accum(const KCtx& k, uint32_t B, const u64* res_eval, c
 }
 cudaError_t launch_mul_ctpt(const KCtx& k, uint32_t B, const u64* ct, const u64* pt, u64* out) {
     LAUNCH_1D(k_mul_ctpt, (size_t)B * k.L * k.N, B, ct, pt, out)
+}
+cudaError_t launch_centre_lift(const KCtx& k, uint32_t n, const u64* crt, u64* out) {
+    LAUNCH_1D(k_centre_lift, (size_t)n * k.N, n, crt, out)
 }
 cudaError_t launch_slots_to_crt(const KCtx& k, uint32_t n_pt, uint32_t nslots, const long long* slots,
                                 const uint32_t* to_crt, u64* out) {

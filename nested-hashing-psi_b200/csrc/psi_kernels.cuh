@@ -95,6 +95,8 @@ cudaError_t launch_fused_mul(const KCtx& k, uint32_t B, const u64* a, const u64*
                              u64* out);
 cudaError_t launch_mul_ctpt(const KCtx& k, uint32_t B, const u64* ct, const u64* pt, u64* out);
 
+// Packed encoding, centred lift: crt [n][N] in [0, t) -> out [n][L][N]
+cudaError_t launch_centre_lift(const KCtx& k, uint32_t n, const u64* crt, u64* out);
 // Packed encoding front end: slot values -> CRT-ordered residues mod t
 cudaError_t launch_slots_to_crt(const KCtx& k, uint32_t n_pt, uint32_t nslots, const long long* slots,
                                 const uint32_t* to_crt, u64* out);
@@ -102,8 +104,10 @@ cudaError_t launch_slots_to_crt(const KCtx& k, uint32_t n_pt, uint32_t nslots, c
 // Device-side nested cuckoo table build and constructor transposition (hashing_dev.cu)
 cudaError_t hct_build_device(cudaStream_t s, const u64* T, uint32_t k, uint32_t e, uint32_t K, uint32_t b, uint32_t E,
                              u64 eviction_seed, const u64* items, size_t n, u64* cells, int* failed);
+// plaintexts p0 .. p0+n_pt-1 of the shard [bin_begin, bin_begin + b_local) of a b-bin table (p counts inside the shard)
 cudaError_t launch_cells_to_crt(const KCtx& k, uint32_t n_pt, uint32_t p0, uint32_t nslots, uint32_t K, uint32_t b, uint32_t E,
-                                const u64* cells, const uint16_t* perm, const uint32_t* to_crt, u64* out);
+                                uint32_t bin_begin, uint32_t b_local, const u64* cells, const uint16_t* perm,
+                                const uint32_t* to_crt, u64* out);
 
 cudaError_t pipe_peak(int device, int kind, double* per_second);
 

@@ -23,7 +23,9 @@ namespace psi {
 // (GetCryptoParameters()->GetPlaintextModulus(), BatchedFHEHIPPIE.cpp:43) and the evaluator.
 struct CryptoContext {
     psi_params params;
-    psi_ctx* device_ctx;  // owned by the caller (the server object owns the context in the reference too)
+    psi_ctx* device_ctx;           // owned by the caller (the server object owns the context in the reference too)
+    psi_multi* multi = nullptr;    // when set, the evaluator is a single-process multi-device one (a device list);
+                                   // device_ctx is then unused
     uint64_t GetPlaintextModulus() const { return params.t; }
 };
 

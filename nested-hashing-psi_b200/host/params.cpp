@@ -114,32 +114,14 @@ static uint32_t derive_size_q(uint32_t N, uint64_t t, uint32_t depth) {
     return (uint32_t)std::ceil((std::ceil(logq / std::log(2.0)) + 1.0) / dcrt_bits);
 }
 
-int generate_params(uint32_t N, uint64_t t, uint32_t depth, uint32_t L_override, psi_params* out) {
-    if (!out) return PSI_ERR_INVALID;
-    if (N < 8 || (N & (N - 1)) != 0 || N > 65536) return set_error(PSI_ERR_INVALID, "ring dimension must be a power of two");
-    const uint64_t m = 2ull * N;
-    if (t < 2 || (t - 1) % m != 0 || !is_prime_u64(t))
-        return set_error(PSI_ERR_INVALID, "plaintext modulus must be a prime congruent to 1 mod 2N");
-    uint32_t L = L_override ? L_override : derive_size_q(N, t, depth ? depth : 1);
-    if (L < 1 || L > PSI_MAX_LIMBS) return set_error(PSI_ERR_INVALID, "sizeQ out of range (1..PSI_MAX_LIMBS)");
-    std::memset(out, 0, sizeof(*out));
-    const uint32_t Lp = L;
-    out->N = N;
-    out->L = L;
-    out->Lp = Lp;
-    out->mult_technique = PSI_MULT_HPSPOVERQ;
-    out->ks_technique = PSI_KS_BV;
-    out->t = t;
-    uint64_t* q = out->q;
-    uint64_t* p = out->p;
-    q[0] = previous_prime(first_prime(60, m), m);
-    for (uint32_t i = 1; i < L; ++i) q[i] = previous_prime(q[i - 1], m);
-    p[0] = previous_prime(q[L - 1], m);
-    for (uint32_t j = 1; j < Lp; ++j) p[j] = previous_prime(p[j - 1], m);
-    for (uint32_t i = 0; i < L; ++i) out->psi_q[i] = min_primitive_root(m, q[i]);
-    for (uint32_t j = 0; j < Lp; ++j) out->psi_p[j] = min_primitive_root(m, p[j]);
-    out->psi_t = min_primitive_root(m, t);
-
+// Every table of psi_params that is a function of the moduli alone (all of them except the moduli and roots).
+// Requires N, L, Lp, t, q[], p[] set.  The double tables follow OpenFHE's construction as recalled:
+// qInv = 1.0 / (double) q_i, frac = (double) remainder / (double) p_i.
+static void fill_tables(psi_params* out) {
+    const uint32_t L = out->L, Lp = out->Lp;
+    const uint64_t t = out->t;
+    const uint64_t* q = out->q;
+    const uint64_t* p = out->p;
     auto prod_mod = [](const uint64_t* v, uint32_t n, int skip, uint64_t mod) {
         uint64_t r = 1 % mod;
         for (uint32_t i = 0; i < n; ++i)
@@ -186,10 +168,78 @@ int generate_params(uint32_t N, uint64_t t, uint32_t depth, uint32_t L_override,
         uint64_t shat = mulmod(qhat, prod_mod(p, Lp, -1, q[j]), q[j]);      // (S/q_j) mod q_j
         out->tQSHatInvModsDivsModq[j][Lp] = mulmod(mulmod(t % q[j], qhat, q[j]), invmod_prime(shat, q[j]), q[j]);
     }
+}
+
+
+int generate_params(uint32_t N, uint64_t t, uint32_t depth, uint32_t L_override, psi_params* out) {
+    if (!out) return PSI_ERR_INVALID;
+    if (N < 8 || (N & (N - 1)) != 0 || N > 65536) return set_error(PSI_ERR_INVALID, "ring dimension must be a power of two");
+    const uint64_t m = 2ull * N;
+    if (t < 2 || (t - 1) % m != 0 || !is_prime_u64(t))
+        return set_error(PSI_ERR_INVALID, "plaintext modulus must be a prime congruent to 1 mod 2N");
+    uint32_t L = L_override ? L_override : derive_size_q(N, t, depth ? depth : 1);
+    if (L < 1 || L > PSI_MAX_LIMBS) return set_error(PSI_ERR_INVALID, "sizeQ out of range (1..PSI_MAX_LIMBS)");
+    std::memset(out, 0, sizeof(*out));
+    const uint32_t Lp = L;
+    out->N = N;
+    out->L = L;
+    out->Lp = Lp;
+    out->mult_technique = PSI_MULT_HPSPOVERQ;
+    out->ks_technique = PSI_KS_BV;
+    out->t = t;
+    uint64_t* q = out->q;
+    uint64_t* p = out->p;
+    q[0] = previous_prime(first_prime(60, m), m);
+    for (uint32_t i = 1; i < L; ++i) q[i] = previous_prime(q[i - 1], m);
+    p[0] = previous_prime(q[L - 1], m);
+    for (uint32_t j = 1; j < Lp; ++j) p[j] = previous_prime(p[j - 1], m);
+    for (uint32_t i = 0; i < L; ++i) out->psi_q[i] = min_primitive_root(m, q[i]);
+    for (uint32_t j = 0; j < Lp; ++j) out->psi_p[j] = min_primitive_root(m, p[j]);
+    out->psi_t = min_primitive_root(m, t);
+    fill_tables(out);
     return PSI_OK;
 }
 
+
 }  // namespace psi
+
+// psi_params for a context whose moduli and roots come from the host library (the adapter reads them from
+// OpenFHE's ILDCRTParams): same tables as psi_params_generate, no choice of primes involved.
+extern "C" int psi_params_from_moduli(uint32_t N, uint64_t t, uint32_t L, const uint64_t* q, const uint64_t* psi_q, uint32_t Lp,
+                                      const uint64_t* p, const uint64_t* psi_p, uint64_t psi_t, psi_params* out) {
+    using namespace psi;
+    if (!out || !q || !psi_q || !p || !psi_p) return set_error(PSI_ERR_INVALID, "null argument");
+    if (N < 8 || (N & (N - 1)) != 0 || N > 65536) return set_error(PSI_ERR_INVALID, "ring dimension must be a power of two");
+    if (L < 1 || L > PSI_MAX_LIMBS || Lp < 1 || Lp > PSI_MAX_LIMBS) return set_error(PSI_ERR_INVALID, "sizeQ / sizeP out of range");
+    const uint64_t m = 2ull * N;
+    std::memset(out, 0, sizeof(*out));
+    out->N = N;
+    out->L = L;
+    out->Lp = Lp;
+    out->mult_technique = PSI_MULT_HPSPOVERQ;
+    out->ks_technique = PSI_KS_BV;
+    out->t = t;
+    out->psi_t = psi_t;
+    for (uint32_t i = 0; i < L + Lp; i++) {
+        const uint64_t mod = i < L ? q[i] : p[i - L], root = i < L ? psi_q[i] : psi_p[i - L];
+        if (mod >= (1ull << 60) || (mod - 1) % m != 0 || !is_prime_u64(mod))
+            return set_error(PSI_ERR_INVALID, "moduli must be primes below 2^60 congruent to 1 mod 2N");
+        for (uint32_t j = 0; j < i; j++)
+            if ((j < L ? q[j] : p[j - L]) == mod) return set_error(PSI_ERR_INVALID, "moduli must be pairwise distinct");
+        if (powmod(root, N, mod) != mod - 1) return set_error(PSI_ERR_INVALID, "root is not a primitive 2N-th root of unity");
+        if (i < L) {
+            out->q[i] = mod;
+            out->psi_q[i] = root;
+        } else {
+            out->p[i - L] = mod;
+            out->psi_p[i - L] = root;
+        }
+    }
+    if (t < 2 || (t - 1) % m != 0 || powmod(psi_t, N, t) != t - 1)
+        return set_error(PSI_ERR_INVALID, "plaintext modulus / root: t = 1 mod 2N and psi_t a primitive 2N-th root needed");
+    fill_tables(out);
+    return PSI_OK;
+}
 
 extern "C" int psi_params_generate(uint32_t N, uint64_t t, uint32_t mult_depth, uint32_t L_override, psi_params* out) {
     return psi::generate_params(N, t, mult_depth, L_override, out);

@@ -58,8 +58,12 @@ BatchedFHEHIPPIE::BatchedFHEHIPPIE(CryptoContext& cryptor, PublicKey& pK_, Hiera
     std::mt19937_64 mm(resolve_seed(maskSeed));
     for (auto& v : maskSlots) v = (int64_t)(mm() % (t - 1) + 1);
 
-    check(psi_db_encode_slots(cryptoContext.device_ctx, K, b, E, nslots, slots.data(), maskSlots.data()),
-          "MakePackedPlaintext on device");
+    if (cryptoContext.multi)
+        check(psi_multi_db_encode_slots(cryptoContext.multi, K, b, E, nslots, slots.data(), maskSlots.data()),
+              "MakePackedPlaintext on the devices");
+    else
+        check(psi_db_encode_slots(cryptoContext.device_ctx, K, b, E, nslots, slots.data(), maskSlots.data()),
+              "MakePackedPlaintext on device");
     if (keepSlots) {
         keptSlots.swap(slots);
         keptMaskSlots.swap(maskSlots);
@@ -86,23 +90,67 @@ void BatchedFHEHIPPIE::upload() {
 }
 
 void BatchedFHEHIPPIE::setQueryFlat(const uint64_t* idx, const uint64_t* minus) {
-    check(psi_query_set(cryptoContext.device_ctx, idx, minus, nullptr), "setIndex / setMinusCompareElement");
-    check(psi_stream_sync(nullptr), "query upload");
+    if (cryptoContext.multi) {
+        check(psi_multi_query_set(cryptoContext.multi, idx, minus), "setIndex / setMinusCompareElement");
+        check(psi_multi_sync(cryptoContext.multi), "query upload");
+    } else {
+        check(psi_query_set(cryptoContext.device_ctx, idx, minus, nullptr), "setIndex / setMinusCompareElement");
+        check(psi_stream_sync(nullptr), "query upload");
+    }
     uploaded = true;
 }
 
 void BatchedFHEHIPPIE::run() {
+    if (!uploaded && cryptoContext.multi) {
+        // the ciphertexts the reference hands over are separate limb containers: no flat copy on the host, the
+        // staging pool of psi_multi_query_set_limbs gathers them while the first pieces are already uploading
+        const size_t L = cryptoContext.params.L, N = cryptoContext.params.N, ct = 2 * L * N;
+        if (indexMatrix.size() != K) throw std::invalid_argument("indexMatrix must have one row per cuckoo hash function");
+        std::vector<const uint64_t*> limbs((size_t)K * E * 2 * L), mlimbs(2 * L);
+        for (uint32_t hf = 0; hf < K; hf++) {
+            if (indexMatrix[hf].size() != E) throw std::invalid_argument("indexMatrix row length must equal the cuckoo table size");
+            for (uint32_t pos = 0; pos < E; pos++) {
+                const Ciphertext& c = indexMatrix[hf][pos];
+                if (!c || c->size() != ct) throw std::invalid_argument("index ciphertext has the wrong number of limbs");
+                for (size_t v = 0; v < 2 * L; v++) limbs[((size_t)hf * E + pos) * 2 * L + v] = c->data() + v * N;
+            }
+        }
+        if (!minusCompareElement || minusCompareElement->size() != ct)
+            throw std::invalid_argument("minusCompareElement is not set or has the wrong number of limbs");
+        for (size_t v = 0; v < 2 * L; v++) mlimbs[v] = minusCompareElement->data() + v * N;
+        check(psi_multi_query_set_limbs(cryptoContext.multi, limbs.data(), mlimbs.data()), "setIndex / setMinusCompareElement");
+        uploaded = true;
+    }
     upload();
-    check(psi_run(cryptoContext.device_ctx, nullptr), "run");
+    if (cryptoContext.multi)
+        check(psi_multi_run(cryptoContext.multi), "run");
+    else
+        check(psi_run(cryptoContext.device_ctx, nullptr), "run");
     resultsFetched = false;
 }
 
 void BatchedFHEHIPPIE::getResultFlat(uint64_t* out) {
+    if (cryptoContext.multi) {
+        check(psi_multi_result_get(cryptoContext.multi, out), "getResultList");
+        check(psi_multi_sync(cryptoContext.multi), "getResultList");
+        return;
+    }
     check(psi_result_get(cryptoContext.device_ctx, out, nullptr), "getResultList");
     check(psi_stream_sync(nullptr), "getResultList");
 }
 
 std::vector<Ciphertext>& BatchedFHEHIPPIE::getResultList() {
+    if (!resultsFetched && cryptoContext.multi) {
+        // straight into the b result containers (scatter from the pinned pool, no flat intermediate)
+        const size_t L = cryptoContext.params.L, N = cryptoContext.params.N, ct = 2 * L * N;
+        std::vector<uint64_t*> limbs((size_t)b * 2 * L);
+        for (uint32_t bin = 0; bin < b; bin++) {
+            resultList[bin] = std::make_shared<std::vector<uint64_t>>(ct);
+            for (size_t v = 0; v < 2 * L; v++) limbs[(size_t)bin * 2 * L + v] = resultList[bin]->data() + v * N;
+        }
+        check(psi_multi_result_get_limbs(cryptoContext.multi, limbs.data()), "getResultList");
+        resultsFetched = true;
+    }
     if (!resultsFetched) {
         const size_t ct = (size_t)2 * cryptoContext.params.L * cryptoContext.params.N;
         std::vector<uint64_t> flat((size_t)b * ct);
@@ -227,6 +275,26 @@ int psi_pie_create(psi_ctx* ctx, const psi_params* params, psi_hct* hct, uint64_
     if (!p) return psi::set_error(PSI_ERR_INVALID, "out of host memory");
     p->cc.params = *params;
     p->cc.device_ctx = ctx;
+    int rc = guarded([&] {
+        p->pie.reset(new psi::BatchedFHEHIPPIE(p->cc, p->pk, hct->table, shuffle_seed, mask_seed, keep_slots != 0));
+    });
+    if (rc != PSI_OK) {
+        delete p;
+        return rc;
+    }
+    *out = p;
+    return PSI_OK;
+}
+
+int psi_pie_create_multi(psi_multi* m, const psi_params* params, psi_hct* hct, uint64_t shuffle_seed, uint64_t mask_seed,
+                         int keep_slots, psi_pie** out) {
+    if (!m || !params || !hct || !out) return psi::set_error(PSI_ERR_INVALID, "null argument");
+    *out = nullptr;
+    psi_pie* p = new (std::nothrow) psi_pie();
+    if (!p) return psi::set_error(PSI_ERR_INVALID, "out of host memory");
+    p->cc.params = *params;
+    p->cc.device_ctx = nullptr;
+    p->cc.multi = m;
     int rc = guarded([&] {
         p->pie.reset(new psi::BatchedFHEHIPPIE(p->cc, p->pk, hct->table, shuffle_seed, mask_seed, keep_slots != 0));
     });

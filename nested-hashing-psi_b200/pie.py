@@ -100,6 +100,52 @@ class CryptoContext:
             _raise_like_reference(e)
         self._dims = (K, b, E)
 
+    def set_encode_lift(self, mode):
+        """0 = PSI_ENCODE_LIFT_PLAIN, 1 = PSI_ENCODE_LIFT_CENTRED; before the encoding db_* calls."""
+        check(lib().psi_set_encode_lift(self._h, mode))
+
+    def set_packing_cofactor(self, mode):
+        """0 = PSI_PACK_COFACTOR_3, 1 = PSI_PACK_COFACTOR_CONJ; before the encoding db_* calls."""
+        check(lib().psi_set_packing_cofactor(self._h, mode))
+
+    def db_load_limbs_shard(self, pt, mask, bin_begin, bin_end):
+        """Full database arrays; bins [bin_begin, bin_end) become resident."""
+        (pt, pp), (mask, pm) = _u64(pt), _u64(mask)
+        K, b, E = pt.shape[:3]
+        check(lib().psi_db_load_limbs_shard(self._h, K, b, bin_begin, bin_end, E, pp, pm))
+        self._dims = (K, bin_end - bin_begin, E)
+
+    def db_encode_slots_shard(self, slots, mask_slots, bin_begin, bin_end):
+        (slots, ps), (mask_slots, pm) = _i64(slots), _i64(mask_slots)
+        K, b, E, n = slots.shape
+        try:
+            check(lib().psi_db_encode_slots_shard(self._h, K, b, bin_begin, bin_end, E, n, ps, pm))
+        except PsiError as e:
+            _raise_like_reference(e)
+        self._dims = (K, bin_end - bin_begin, E)
+
+    def db_build_from_items_shard(self, hashfunction, k, e, K, E, b, items, bin_begin, bin_end, evictionSeed=0x5EED,
+                                  shuffleSeed=1, maskSeed=2):
+        """One shard of the device-built database; all shards of one database share the three seeds."""
+        (items, pi) = _u64(items)
+        try:
+            check(lib().psi_db_build_from_items_shard(self._h, hashfunction.seed, k, e, K, E, b, evictionSeed, pi,
+                                                      items.shape[0], _seed(shuffleSeed), _seed(maskSeed), bin_begin, bin_end))
+        except PsiError as err:
+            if err.status == capi.PSI_ERR_STATE:
+                raise RuntimeError(err.message) from None
+            _raise_like_reference(err)
+        self._dims = (K, bin_end - bin_begin, E)
+
+    def db_get_bin_limbs(self, bin_):
+        """(pt [K][E][L][N], mask [L][N]) of one resident bin."""
+        K, b, E = self._dims
+        pt = np.empty((K, E, self.L, self.N), dtype=np.uint64)
+        mask = np.empty((self.L, self.N), dtype=np.uint64)
+        p = ctypes.POINTER(ctypes.c_uint64)
+        check(lib().psi_db_get_bin_limbs(self._h, bin_, pt.ctypes.data_as(p), mask.ctypes.data_as(p)))
+        return pt, mask
+
     def db_get_limbs(self):
         K, b, E = self._dims
         pt = np.empty((K, b, E, self.L, self.N), dtype=np.uint64)
@@ -156,6 +202,28 @@ class CryptoContext:
 
     def query_commit(self, stream=None):
         check(lib().psi_query_commit(self._h, stream))
+
+    def query_upload_limbs(self, idx_vectors, minus_vectors, stream=None):
+        """Upload from K*E*2*L + 2*L separately allocated uint64[N] arrays ([hf][pos][comp][limb] order); accepts
+        prepared ctypes pointer arrays too (bench.py builds them once)."""
+        ai = idx_vectors if isinstance(idx_vectors, ctypes.Array) else MultiContext._ptr_array(idx_vectors)
+        am = minus_vectors if isinstance(minus_vectors, ctypes.Array) else MultiContext._ptr_array(minus_vectors)
+        check(lib().psi_query_upload_limbs(self._h, ai, am, stream))
+
+    def result_get_limbs(self, out_vectors=None, stream=None):
+        """Results into b*2*L separate uint64[N] arrays ([bin][comp][limb] order); synchronous."""
+        K, b, E = self._dims
+        vecs = None
+        if out_vectors is None:
+            vecs = [np.empty(self.N, dtype=np.uint64) for _ in range(b * 2 * self.L)]
+            out_vectors = MultiContext._ptr_array(vecs)
+        elif not isinstance(out_vectors, ctypes.Array):
+            vecs, out_vectors = out_vectors, MultiContext._ptr_array(out_vectors)
+        check(lib().psi_result_get_limbs(self._h, out_vectors, stream))
+        return vecs
+
+    def set_host_threads(self, n):
+        check(lib().psi_set_host_threads(self._h, n))
 
     def query_landing_ptrs(self, which):
         """(idx_ptr, idx_bytes, minus_ptr, minus_bytes) of device landing buffer `which` (0 or 1)."""
@@ -221,6 +289,144 @@ class CryptoContext:
     def close(self):
         if getattr(self, "_h", None):
             lib().psi_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiContext:
+    """CryptoContext over a device list: the single-process multi-device evaluator (psi_multi_*).  Same raw calls as
+    CryptoContext; the arrays are always the FULL database / query / result, sharding happens inside the library."""
+
+    def __init__(self, params, devices=(0,)):
+        if not isinstance(params, capi.PsiParams):
+            if ctypes.sizeof(params) != ctypes.sizeof(capi.PsiParams):
+                raise ValueError("params is not a struct psi_params")
+            params = capi.PsiParams.from_buffer_copy(bytes(params))
+        self.params = params
+        self.devices = list(devices)
+        self.N, self.L, self.Lp, self.t = params.N, params.L, params.Lp, params.t
+        h = ctypes.c_void_p()
+        arr = (ctypes.c_int * len(self.devices))(*self.devices)
+        check(lib().psi_multi_create(ctypes.byref(params), arr, len(self.devices), ctypes.byref(h)))
+        self._h = h
+
+    def GetPlaintextModulus(self):
+        return self.t
+
+    def set_encode_lift(self, mode):
+        check(lib().psi_multi_set_encode_lift(self._h, mode))
+
+    def InsertEvalMultKey(self, evk_b, evk_a):
+        (evk_b, pb), (evk_a, pa) = _u64(evk_b), _u64(evk_a)
+        assert evk_b.shape == (self.L, self.L, self.N) and evk_a.shape == evk_b.shape
+        check(lib().psi_multi_set_relin_key(self._h, pb, pa))
+
+    def db_load_limbs(self, pt, mask):
+        (pt, pp), (mask, pm) = _u64(pt), _u64(mask)
+        K, b, E = pt.shape[:3]
+        assert pt.shape == (K, b, E, self.L, self.N) and mask.shape == (b, self.L, self.N)
+        try:
+            check(lib().psi_multi_db_load_limbs(self._h, K, b, E, pp, pm))
+        except PsiError as e:
+            _raise_like_reference(e)
+        self._dims = (K, b, E)
+
+    def db_encode_slots(self, slots, mask_slots):
+        (slots, ps), (mask_slots, pm) = _i64(slots), _i64(mask_slots)
+        K, b, E, n = slots.shape
+        assert mask_slots.shape == (b, n)
+        try:
+            check(lib().psi_multi_db_encode_slots(self._h, K, b, E, n, ps, pm))
+        except PsiError as e:
+            _raise_like_reference(e)
+        self._dims = (K, b, E)
+
+    def db_build_from_items(self, hashfunction, k, e, K, E, b, items, evictionSeed=0x5EED, shuffleSeed=None, maskSeed=None):
+        (items, pi) = _u64(items)
+        try:
+            check(lib().psi_multi_db_build_from_items(self._h, hashfunction.seed, k, e, K, E, b, evictionSeed, pi,
+                                                      items.shape[0], _seed(shuffleSeed), _seed(maskSeed)))
+        except PsiError as err:
+            if err.status == capi.PSI_ERR_STATE:
+                raise RuntimeError(err.message) from None
+            _raise_like_reference(err)
+        self._dims = (K, b, E)
+
+    def bin_ranges(self):
+        out = []
+        for d in range(len(self.devices)):
+            b0, b1 = ctypes.c_uint32(), ctypes.c_uint32()
+            check(lib().psi_multi_bin_range(self._h, d, ctypes.byref(b0), ctypes.byref(b1)))
+            out.append((b0.value, b1.value))
+        return out
+
+    def query_set(self, idx, minus):
+        (idx, pi), (minus, pm) = _u64(idx), _u64(minus)
+        K, b, E = self._dims
+        assert idx.shape == (K, E, 2, self.L, self.N) and minus.shape == (2, self.L, self.N)
+        check(lib().psi_multi_query_set(self._h, pi, pm))
+        self._keep = (idx, minus)
+
+    def query_set_ptr(self, idx_ptr, minus_ptr):
+        check(lib().psi_multi_query_set(self._h, ctypes.cast(idx_ptr, ctypes.POINTER(ctypes.c_uint64)),
+                                        ctypes.cast(minus_ptr, ctypes.POINTER(ctypes.c_uint64))))
+
+    @staticmethod
+    def _ptr_array(vectors):
+        P64 = ctypes.POINTER(ctypes.c_uint64)
+        arr = (P64 * len(vectors))()
+        for i, v in enumerate(vectors):
+            assert v.dtype == np.uint64 and v.flags["C_CONTIGUOUS"]
+            arr[i] = v.ctypes.data_as(P64)
+        return arr
+
+    def query_set_limbs(self, idx_vectors, minus_vectors):
+        """idx_vectors: K*E*2*L separately allocated uint64[N] arrays in [hf][pos][comp][limb] order (what a
+        deserialised OpenFHE query holds), minus_vectors: 2*L of them."""
+        K, b, E = self._dims
+        assert len(idx_vectors) == K * E * 2 * self.L and len(minus_vectors) == 2 * self.L
+        ai, am = self._ptr_array(idx_vectors), self._ptr_array(minus_vectors)
+        check(lib().psi_multi_query_set_limbs(self._h, ai, am))
+
+    def run(self):
+        check(lib().psi_multi_run(self._h))
+
+    def result_get(self, out=None, sync=True):
+        K, b, E = self._dims
+        if out is None:
+            out = np.empty((b, 2, self.L, self.N), dtype=np.uint64)
+        check(lib().psi_multi_result_get(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
+        if sync:
+            check(lib().psi_multi_sync(self._h))
+        return out
+
+    def result_get_ptr(self, out_ptr):
+        check(lib().psi_multi_result_get(self._h, ctypes.cast(out_ptr, ctypes.POINTER(ctypes.c_uint64))))
+
+    def result_get_limbs(self):
+        """b*2*L freshly allocated uint64[N] arrays in [bin][comp][limb] order."""
+        K, b, E = self._dims
+        vecs = [np.empty(self.N, dtype=np.uint64) for _ in range(b * 2 * self.L)]
+        arr = self._ptr_array(vecs)
+        check(lib().psi_multi_result_get_limbs(self._h, arr))
+        return vecs
+
+    def sync(self):
+        check(lib().psi_multi_sync(self._h))
+
+    def run_launch_count(self):
+        n = ctypes.c_uint32()
+        check(lib().psi_multi_run_launch_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().psi_multi_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -355,9 +561,10 @@ class BatchedFHEHIPPIE:
         self.cryptoContext = cryptoContext
         self.pK = pK
         h = ctypes.c_void_p()
+        create = lib().psi_pie_create_multi if isinstance(cryptoContext, MultiContext) else lib().psi_pie_create
         try:
-            check(lib().psi_pie_create(cryptoContext._h, ctypes.byref(cryptoContext.params), hct._h, _seed(shuffleSeed),
-                                       _seed(maskSeed), int(keepSlots), ctypes.byref(h)))
+            check(create(cryptoContext._h, ctypes.byref(cryptoContext.params), hct._h, _seed(shuffleSeed),
+                         _seed(maskSeed), int(keepSlots), ctypes.byref(h)))
         except PsiError as e:
             _raise_like_reference(e)
         self._h = h

@@ -42,6 +42,8 @@ def lib():
         L.orc_pack.argtypes = [ctypes.c_void_p, _i64p, ctypes.c_int, _u64p]
         L.orc_unpack.argtypes = [ctypes.c_void_p, _u64p, _i64p]
         L.orc_encode.argtypes = [ctypes.c_void_p, _i64p, ctypes.c_int, _u64p]
+        L.orc_set_encode_lift.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.orc_set_packing_cofactor.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.orc_keygen.argtypes = [ctypes.c_void_p, ctypes.c_uint64, _u64p, _u64p, _u64p]
         L.orc_encrypt_sk.argtypes = [ctypes.c_void_p, _u64p, _i64p, ctypes.c_int, ctypes.c_uint64, _u64p]
         L.orc_decrypt.argtypes = [ctypes.c_void_p, _u64p, _u64p, ctypes.c_int, _i64p,
@@ -53,6 +55,7 @@ def lib():
         L.orc_relin.argtypes = [ctypes.c_void_p, _u64p, _u64p, _u64p, _u64p]
         L.orc_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _u64p, _u64p, _u64p,
                               _u64p, _u64p, _u64p, _u64p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.orc_run_cold.argtypes = L.orc_run.argtypes
         L.orc_max_threads.restype = ctypes.c_int
         _LIB = L
     return _LIB
@@ -106,6 +109,14 @@ class Oracle:
         out = np.empty(self.N, dtype=np.int64)
         lib().orc_unpack(self._h, _p(np.ascontiguousarray(coeff, dtype=np.uint64)), _pi(out))
         return out
+
+    def set_encode_lift(self, mode):
+        """0 = plain (default), 1 = centred; see orc_encode."""
+        lib().orc_set_encode_lift(self._h, mode)
+
+    def set_packing_cofactor(self, mode):
+        """0 = co-factor 3 (default), 1 = 2N - 1; see orc_set_packing_cofactor."""
+        lib().orc_set_packing_cofactor(self._h, mode)
 
     def encode(self, slots):
         """MakePackedPlaintext + SetFormat(EVALUATION): [L][N]."""
@@ -183,6 +194,17 @@ class Oracle:
         lib().orc_run(self._h, K, b, E, _p(pt), _p(mask), _p(idx), _p(minus), _p(evk_b), _p(evk_a), _p(out),
                       bin_begin, bin_end, nthreads)
         return out
+
+
+def run_cold(o, pt_coeff, mask_coeff, idx, minus, evk_b, evk_a, nthreads=1, out=None):
+    """orc_run_cold: pt_coeff [K][b][E][N], mask_coeff [b][N] packed coefficients mod t (Oracle.pack output); the
+    plaintext lifts and transforms happen inside the call, as in the reference's first run()."""
+    K, b, E = pt_coeff.shape[:3]
+    if out is None:
+        out = np.zeros((b, 2, o.L, o.N), dtype=np.uint64)
+    lib().orc_run_cold(o._h, K, b, E, _p(pt_coeff), _p(mask_coeff), _p(idx), _p(minus), _p(evk_b), _p(evk_a), _p(out), 0, b,
+                       nthreads)
+    return out
 
 
 def max_threads():

@@ -202,12 +202,28 @@ typedef struct orc_ctx {
     u64 QHatInvModq_s[PSI_MAX_LIMBS], negPQHatInvModq_s[PSI_MAX_LIMBS], PHatInvModp_s[PSI_MAX_LIMBS];
     /* client-side (encrypt / decrypt) constants */
     u64 negQModt, tInvModq[PSI_MAX_LIMBS];
+    /* risk-register switches: each selects between two readings of OpenFHE */
+    int encode_lift; /* PSI_ENCODE_LIFT_PLAIN (default) / PSI_ENCODE_LIFT_CENTRED */
 } orc_ctx;
 
 static const modctx* mod_at(const orc_ctx* c, int idx) {
     if (idx < c->L) return &c->mq[idx];
     if (idx < c->L + c->Lp) return &c->mp[idx - c->L];
     return &c->mt;
+}
+
+/* OpenFHE PackedEncoding::SetParams_2n (recalled): slot i <-> exponent 5^i, slot i+N/2 <-> cofactor*5^i with
+ * cofactor 3 (1.0.x line as recalled; default) or 2N-1 (the other reading); the transform output is bit-reversed,
+ * hence the bitrev of (e-1)/2. */
+void orc_set_packing_cofactor(orc_ctx* c, int mode) {
+    int N = c->N, logN = c->mt.logN;
+    u64 m = 2 * (u64)N, cur = 1, cofactor = mode == PSI_PACK_COFACTOR_CONJ ? m - 1 : 3;
+    for (int i = 0; i < N / 2; i++) {
+        c->to_crt[bitrev((cur - 1) / 2, logN)] = (uint32_t)i;
+        u64 cof = (cur * cofactor) % m;
+        c->to_crt[bitrev((cof - 1) / 2, logN)] = (uint32_t)(i + N / 2);
+        cur = (cur * 5) % m;
+    }
 }
 
 orc_ctx* orc_create(const psi_params* p) {
@@ -225,17 +241,8 @@ orc_ctx* orc_create(const psi_params* p) {
         c->negPQHatInvModq_s[i] = shoup(p->negPQHatInvModq[i], p->q[i]);
     }
     for (int j = 0; j < c->Lp; j++) c->PHatInvModp_s[j] = shoup(p->PHatInvModp[j], p->p[j]);
-    /* OpenFHE PackedEncoding::SetParams_2n (recalled): slot i <-> exponent 5^i, slot i+N/2 <->
-     * 3*5^i; the transform output is bit-reversed, hence the bitrev of (e-1)/2. */
-    int N = c->N, logN = c->mt.logN;
-    c->to_crt = malloc(sizeof(uint32_t) * N);
-    u64 m = 2 * (u64)N, cur = 1;
-    for (int i = 0; i < N / 2; i++) {
-        c->to_crt[bitrev((cur - 1) / 2, logN)] = (uint32_t)i;
-        u64 cof = (cur * 3) % m;
-        c->to_crt[bitrev((cof - 1) / 2, logN)] = (uint32_t)(i + N / 2);
-        cur = (cur * 5) % m;
-    }
+    c->to_crt = malloc(sizeof(uint32_t) * c->N);
+    orc_set_packing_cofactor(c, PSI_PACK_COFACTOR_3);
     u64 Qmodt = 1;
     for (int i = 0; i < c->L; i++) Qmodt = mulmod(Qmodt, p->q[i] % p->t, p->t);
     c->negQModt = (p->t - Qmodt) % p->t;
@@ -294,11 +301,23 @@ void orc_unpack(const orc_ctx* c, const u64* coeff, int64_t* slots) {
     }
     free(tmp);
 }
-/* Plaintext operand of EvalMult(ct,pt): packed, lifted to every q_i, EVALUATION. out: [L][N] */
+void orc_set_encode_lift(orc_ctx* c, int mode) { c->encode_lift = mode; }
+
+/* Plaintext operand of EvalMult(ct,pt): packed, lifted to every q_i, EVALUATION. out: [L][N]
+ * Lift of a coefficient c in [0,t):  PLAIN: c in every limb (OpenFHE >= 1.0 as recalled: Encode copies the
+ * coefficients into the first tower, SwitchModulus - centred about q_0 - leaves values < t alone);
+ * CENTRED: c > t/2 -> q_l - (t - c) (SURVEY.md Appendix A's reading). */
 int orc_encode(const orc_ctx* c, const int64_t* slots, int nslots, u64* out) {
     int N = c->N;
+    u64 t = c->P.t;
     if (orc_pack(c, slots, nslots, out)) return -1;
-    for (int l = 1; l < c->L; l++) memcpy(out + (size_t)l * N, out, sizeof(u64) * N);
+    for (int l = c->L - 1; l >= 0; l--) { /* limb 0 last: it is the source */
+        u64 q = c->P.q[l];
+        for (int j = 0; j < N; j++) {
+            u64 v = out[j];
+            out[(size_t)l * N + j] = (c->encode_lift == PSI_ENCODE_LIFT_CENTRED && v > (t >> 1)) ? v + (q - t) : v;
+        }
+    }
     for (int l = 0; l < c->L; l++) ntt_fwd(out + (size_t)l * N, &c->mq[l], N);
     return 0;
 }
@@ -694,6 +713,59 @@ int orc_run(const orc_ctx* c, int K, int b, int E, const u64* pt, const u64* mas
             }
         }
         orc_mul_ctpt(c, prod, mask + (size_t)bin * poly, out + (size_t)bin * ctsz);
+        free(tmp);
+        free(acc);
+        free(prod);
+    }
+    return 0;
+}
+
+/* COLD variant of orc_run: what the reference's first (and, with one query per server process, only) run() pays.
+ * The plaintexts MakePackedPlaintext produced are still in COEFFICIENT form when run() starts; every
+ * EvalMult(ct, pt) first brings its plaintext to EVALUATION (SetFormat inside LeveledSHEBase::EvalMult, recalled:
+ * OpenFHE 1.0.x converts a copy on every call, earlier lines cache it in the plaintext - either way the first
+ * run() does K*b*E + b plaintext transforms of L limbs each).
+ *   pt_coeff:[K][b][E][N]  mask_coeff:[b][N]   packed coefficients mod t (orc_pack output); the rest as orc_run. */
+static void lift_and_transform(const orc_ctx* c, const u64* coeff, u64* out) {
+    const int N = c->N;
+    const u64 t = c->P.t;
+    for (int l = 0; l < c->L; l++) {
+        const u64 q = c->P.q[l];
+        u64* o = out + (size_t)l * N;
+        for (int j = 0; j < N; j++) {
+            u64 v = coeff[j];
+            o[j] = (c->encode_lift == PSI_ENCODE_LIFT_CENTRED && v > (t >> 1)) ? v + (q - t) : v;
+        }
+        ntt_fwd(o, &c->mq[l], N);
+    }
+}
+int orc_run_cold(const orc_ctx* c, int K, int b, int E, const u64* pt_coeff, const u64* mask_coeff, const u64* idx,
+                 const u64* minus, const u64* evk_b, const u64* evk_a, u64* out, int bin_begin, int bin_end, int nthreads) {
+    const int N = c->N, L = c->L;
+    const size_t poly = (size_t)L * N, ctsz = 2 * poly;
+    if (nthreads < 1) nthreads = 1;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+#endif
+    for (int bin = bin_begin; bin < bin_end; bin++) {
+        u64* prod = malloc(sizeof(u64) * ctsz);
+        u64* acc = malloc(sizeof(u64) * ctsz);
+        u64* tmp = malloc(sizeof(u64) * ctsz);
+        u64* pts = malloc(sizeof(u64) * (size_t)E * poly);
+        for (int hf = 0; hf < K; hf++) {
+            for (int pos = 0; pos < E; pos++)
+                lift_and_transform(c, pt_coeff + ((((size_t)hf * b + bin) * E) + pos) * N, pts + (size_t)pos * poly);
+            orc_mac_bin(c, E, idx + (size_t)hf * E * ctsz, pts, minus, acc);
+            if (hf == 0)
+                memcpy(prod, acc, sizeof(u64) * ctsz);
+            else {
+                orc_mul_ctct(c, prod, acc, evk_b, evk_a, tmp);
+                memcpy(prod, tmp, sizeof(u64) * ctsz);
+            }
+        }
+        lift_and_transform(c, mask_coeff + (size_t)bin * N, pts);
+        orc_mul_ctpt(c, prod, pts, out + (size_t)bin * ctsz);
+        free(pts);
         free(tmp);
         free(acc);
         free(prod);

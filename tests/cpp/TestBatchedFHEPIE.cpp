@@ -6,11 +6,15 @@
 // Client-side cryptography (KeyGen, Encrypt with the secret key, Decrypt) is not part of the product: it
 // comes from the ORACLE (oracle/psi_oracle.c), which only tests may link.
 // Expected output: "Test should output matches twice" followed by exactly two lines "Matches".
+// With an argument the evaluator is the single-process multi-device one (psi_multi_*, the server stays one
+// process with one PIE object):  TestBatchedFHEPIE 0,1  runs on devices 0 and 1 (a device may repeat).
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
 #include <random>
+#include <sstream>
+#include <string>
 #include <vector>
 
 #include "BatchedFHEHIPPIE.hpp"
@@ -34,14 +38,23 @@ static void ck(int rc, const char* what) {
     }
 }
 
-int main() {
+int main(int argc, char** argv) {
+    std::vector<int> devices;  // empty: one psi_ctx on device 0
+    if (argc > 1) {
+        std::stringstream ss(argv[1]);
+        for (std::string tok; std::getline(ss, tok, ',');) devices.push_back(std::atoi(tok.c_str()));
+    }
     // Step 1 - crypto context (TestBatchedFHEPIE.cpp:14-31): ring dimension and sizeQ as the library picks
     const uint64_t n = (1ULL << 32) + (1ULL << 20) + (1ULL << 19) + 1;
     psi_params params;
     ck(psi_params_generate(8192, n, /*depth*/ 2, 0, &params), "GenCryptoContext");
     psi_ctx* dev = nullptr;
-    ck(psi_ctx_create(&params, 0, &dev), "psi_ctx_create");
-    CryptoContext cryptoContext{params, dev};
+    psi_multi* multi = nullptr;
+    if (devices.empty())
+        ck(psi_ctx_create(&params, 0, &dev), "psi_ctx_create");
+    else
+        ck(psi_multi_create(&params, devices.data(), (uint32_t)devices.size(), &multi), "psi_multi_create");
+    CryptoContext cryptoContext{params, dev, multi};
     PublicKey publicKey;
     const size_t ctWords = (size_t)2 * params.L * params.N;
 
@@ -49,7 +62,8 @@ int main() {
     orc_ctx* client = orc_create(&params);
     std::vector<uint64_t> sk((size_t)params.L * params.N), evk_b((size_t)params.L * params.L * params.N), evk_a(evk_b.size());
     orc_keygen(client, 2024, sk.data(), evk_b.data(), evk_a.data());
-    ck(psi_set_relin_key(dev, evk_b.data(), evk_a.data()), "InsertEvalMultKey");
+    ck(multi ? psi_multi_set_relin_key(multi, evk_b.data(), evk_a.data()) : psi_set_relin_key(dev, evk_b.data(), evk_a.data()),
+       "InsertEvalMultKey");
 
     // 100 random non-zero elements mod n (:54-70)
     std::mt19937 mt((uint32_t)122333444455555ULL);
@@ -110,5 +124,6 @@ int main() {
     }
     orc_destroy(client);
     psi_ctx_destroy(dev);
+    psi_multi_destroy(multi);
     return matches == 2 ? 0 : 1;
 }

@@ -326,10 +326,15 @@ def test_cpp_known_answer_program():
     import subprocess
     here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp")
     subprocess.check_call(["make", "-C", here, "-s"])
-    out = subprocess.run([os.path.join(here, "TestBatchedFHEPIE")], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stdout + out.stderr
-    assert out.stdout.count("Matches\n") == 2
-    assert "Test should output matches twice" in out.stdout
+    import torch
+    second = 1 if torch.cuda.device_count() > 1 else 0
+    # no argument: one psi_ctx; with a device list: the single-process multi-device evaluator (two distinct GPUs
+    # when the box has them, else two contexts on GPU 0)
+    for extra in ([], ["0"], ["0,%d" % second], ["0,%d,0" % second]):
+        out = subprocess.run([os.path.join(here, "TestBatchedFHEPIE")] + extra, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert out.stdout.count("Matches\n") == 2
+        assert "Test should output matches twice" in out.stdout
 
 
 def test_run_randomised_shapes():
