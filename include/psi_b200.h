@@ -238,6 +238,11 @@ int psi_debug_ntt(psi_ctx* ctx, uint64_t* data, const uint32_t* moduli, uint32_t
                   int inverse);
 int psi_debug_mul_ctct(psi_ctx* ctx, const uint64_t* ct1, const uint64_t* ct2, uint64_t* out);
 
+/* Tuning knobs for measurements (tools/tune_shapes.py): mac_variant 0 = bin-block width of the inner-product kernel
+ * chosen from the resident bins (default), 1 / 2 = force 2 / 4 bins per CTA (process-wide); phase2_groups 0 = number
+ * of concurrent bin groups of the ct x ct chain chosen from the resident bins (default), 1..4 = force; -1 = leave. */
+int psi_debug_set_tuning(psi_ctx* ctx, int mac_variant, int phase2_groups);
+
 /* Integer-pipe peak micro-benchmark (the IMAD roofline
  * denominator is measured, not assumed).  Returns 32x32->64 multiply-adds per
  * second over the whole chip. */
@@ -361,6 +366,9 @@ int psi_multi_run_launch_count(psi_multi* m, uint32_t* out);
 /* BatchedFHEHIPPIE over a psi_multi (same constructor semantics as psi_pie_create) */
 int psi_pie_create_multi(psi_multi* m, const psi_params* params, psi_hct* hct, uint64_t shuffle_seed, uint64_t mask_seed,
                          int keep_slots, psi_pie** out);
+
+/* number of CUDA devices visible to the process (hosts that build their device list without the CUDA headers) */
+int psi_device_count(int* n);
 
 const char* psi_last_error(void);
 const char* psi_version(void);

@@ -80,6 +80,7 @@ SYMBOLS = {
     "psi_result_device_ptr": (_int, [_vp, _vpp, ctypes.POINTER(_sz)]),
     "psi_debug_ntt": (_int, [_vp, _u64p, _u32p, _u32, _int]),
     "psi_debug_mul_ctct": (_int, [_vp, _u64p, _u64p, _u64p]),
+    "psi_debug_set_tuning": (_int, [_vp, _int, _int]),
     "psi_bench_imad_peak": (_int, [_int, ctypes.POINTER(ctypes.c_double)]),
     "psi_bench_pipe_peak": (_int, [_int, _int, ctypes.POINTER(ctypes.c_double)]),
     "psi_hct_create": (_int, [_u64, _u32, _u64, _u32, _u64, _u64, _u64, _int, _int, _u64, _vpp]),
@@ -127,6 +128,7 @@ SYMBOLS = {
     "psi_multi_sync": (_int, [_vp]),
     "psi_multi_run_launch_count": (_int, [_vp, _u32p]),
     "psi_pie_create_multi": (_int, [_vp, _pp, _vp, _u64, _u64, _int, _vpp]),
+    "psi_device_count": (_int, [ctypes.POINTER(_int)]),
     "psi_last_error": (ctypes.c_char_p, []),
     "psi_version": (ctypes.c_char_p, []),
 }
@@ -135,7 +137,8 @@ _LIB = None
 
 
 def lib_path():
-    return os.path.join(_HERE, "libpsi_b200.so")
+    # PSI_B200_LIB selects an experiment build of the same library (Makefile: BUILD= LIB= EXTRA=)
+    return os.environ.get("PSI_B200_LIB") or os.path.join(_HERE, "libpsi_b200.so")
 
 
 def build_library(force=False):

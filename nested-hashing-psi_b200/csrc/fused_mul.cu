@@ -75,10 +75,10 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_tensor(const DevTables* 
     // free by k_cols_scale, whose N^-1 constant is N^-1 * R.  Operands are brought below 2q + 2^32 first
     // so that every 128-bit sum stays below q * 2^64; outputs are in [0, 2q), which the inverse row pass
     // accepts as is.
-    const u64 q = md.q, q2 = 2 * q, qinv = md.qinv;
+    const u64 q = md.q, qinv = md.qinv;
     for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) {
-        const u64 a0 = lazy_sub_hi(arr[sl(j)], q2), a1 = lazy_sub_hi(arr[P + sl(j)], q2);
-        const u64 b0 = lazy_sub_hi(arr[2 * P + sl(j)], q2), b1 = lazy_sub_hi(arr[3 * P + sl(j)], q2);
+        const u64 a0 = lazy_below_2q(arr[sl(j)], q), a1 = lazy_below_2q(arr[P + sl(j)], q);
+        const u64 b0 = lazy_below_2q(arr[2 * P + sl(j)], q), b1 = lazy_below_2q(arr[3 * P + sl(j)], q);
         u64 hi, lo;
         mul128(hi, lo, a0, b0);
         arr[sl(j)] = mont_redc_lazy(hi, lo, q, qinv);
@@ -126,17 +126,17 @@ __global__ void __launch_bounds__((2 + L) * kGroup, L <= 4 ? 2 : 1)
     __syncthreads();  // the key-switch inner product reads all 2 + L arrays
 
     const size_t LN = (size_t)L * N;
-    const u64 q = md.q, q2 = 2 * q, qinv = md.qinv;
+    const u64 q = md.q, qinv = md.qinv;
     for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) {
         const size_t n = (size_t)kk * N + tile_base + j;
         u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
 #pragma unroll
         for (int i = 0; i < L; i++) {
-            const u64 d = lazy_sub_hi(arr[(2 + i) * P + sl(j)], q2);  // < 2q + 2^32: L <= 7 terms, 14 q^2 + small < q * 2^64 for q < 2^60
+            const u64 d = lazy_below_2q(arr[(2 + i) * P + sl(j)], q);  // < 2q + 2^32: L <= 7 terms, 14 q^2 + small < q * 2^64 for q < 2^60
             mac128(h0, l0, d, evk_bR[(size_t)i * LN + n]);
             mac128(h1, l1, d, evk_aR[(size_t)i * LN + n]);
         }
-        // + (c0, c1): forward-transform outputs < 4q + 2^32, reduction outputs < 2q
+        // + (c0, c1): forward-transform outputs < 2 kLazy q + 2^32 <= 8q + 2^32, reduction outputs < 2q
         u64 r0 = mont_redc_lazy(h0, l0, q, qinv) + arr[sl(j)];
         u64 r1 = mont_redc_lazy(h1, l1, q, qinv) + arr[P + sl(j)];
         if (maskR) {
@@ -149,8 +149,8 @@ __global__ void __launch_bounds__((2 + L) * kGroup, L <= 4 ? 2 : 1)
             r0 = r0 >= q ? r0 - q : r0;
             r1 = r1 >= q ? r1 - q : r1;
         } else {
-            r0 = reduce_pow2q<3>(r0, q);
-            r1 = reduce_pow2q<3>(r1, q);
+            r0 = reduce_pow2q<4>(r0, q);
+            r1 = reduce_pow2q<4>(r1, q);
         }
         out[(bin * 2) * LN + n] = r0;
         out[(bin * 2 + 1) * LN + n] = r1;

@@ -48,20 +48,61 @@ __device__ __forceinline__ void group_sync() {
 }
 
 // ---- lazy butterflies ------------------------------------------------------------------------
-// forward (Cooley-Tukey): inputs < 4q + 2^32, outputs < 4q + 2^32
-__device__ __forceinline__ void ct_bf(u64& x, u64& y, const ulonglong2 tw, u64 q2, u64 nq) {
-    const u64 u = lazy_sub_hi(x, q2);
-    const u64 v = mul_shoup_lazy(y, tw.x, tw.y, 0 - nq);
-    x = u + v;
-    y = u - v + q2;
+// ncu shows fmaheavy as the busiest pipe (every IMAD.WIDE occupies it for four cycles), so a variant of the Shoup
+// product with an APPROXIMATE high product was built:
+//   floor(y * w' / 2^64)  ~  y1 w'1 + hi32(y1 w'0) + hi32(y0 w'1)          (three IMAD.WIDE instead of four)
+// which is the exact quotient or up to 2 below it, i.e. the lazy product lands in [0, 4q) instead of [0, 2q).
+// All lazy values of the transforms therefore live below 2 * kLazy * q = 8q (q < 2^60: 8q < 2^63), corrections
+// subtract kLazy * q, and whoever consumes a transform output either reduces exactly (shoup_canon, reduce_pow2q) or
+// brings it below 2q first (lazy_below_2q).  PSI_BF_APPROX = 0 is the exact four-product form (values < 4q).
+// MEASURED (round 2, config B, both builds bit-exact against the oracle): phase 2 takes 1.051 ms with the
+// approximate product and 1.054 ms with the exact one (2 bin groups: 1.014 / 1.012) — the multiplier pipe is NOT
+// what bounds these kernels, so the exact form stays the default and the approximate one an option (make EXTRA=-DPSI_BF_APPROX=1).
+#ifndef PSI_BF_APPROX
+#define PSI_BF_APPROX 0
+#endif
+#if PSI_BF_APPROX
+constexpr u64 kLazy = 4;
+__device__ __forceinline__ u64 bf_mul(u64 y, const ulonglong2 tw, u64 nq) {
+    const uint32_t y0 = lo32(y), y1 = hi32(y), s0 = lo32(tw.y), s1 = hi32(tw.y);
+    const u64 a = madw32(y1, s0, 0), b = madw32(y0, s1, 0);
+    const u64 h = madw32(y1, s1, (u64)hi32(a)) + (u64)hi32(b);
+    // low 64 bits of y * w + h * (2^64 - q): two IMAD.WIDE for the low words, four 32-bit IMADs into the high word
+    const uint32_t w0 = lo32(tw.x), w1 = hi32(tw.x), h0 = lo32(h), h1 = hi32(h), n0 = lo32(nq), n1 = hi32(nq);
+    u64 r = madw32(y0, w0, 0);
+    r = madw32(h0, n0, r);
+    uint32_t top = hi32(r);
+    top += y0 * w1;
+    top += y1 * w0;
+    top += h0 * n1;
+    top += h1 * n0;
+    return ((u64)top << 32) | lo32(r);
 }
-// inverse (Gentleman-Sande): inputs < 2q + e (e grows by at most a factor two per stage from 2^32,
-// far below q after 14 stages), x output < 2q + 2e, y output < 2q
-__device__ __forceinline__ void gs_bf(u64& x, u64& y, const ulonglong2 tw, u64 q2, u64 nq) {
-    const u64 s = lazy_sub_hi(x + y, q2);
-    const u64 d = x - y + 2 * q2;
+#else
+constexpr u64 kLazy = 2;
+__device__ __forceinline__ u64 bf_mul(u64 y, const ulonglong2 tw, u64 nq) { return mul_shoup_lazy(y, tw.x, tw.y, 0 - nq); }
+#endif
+// a transform output (< 2 * kLazy * q + slack) brought below 2q + 2^32
+__device__ __forceinline__ u64 lazy_below_2q(u64 x, u64 q) {
+#if PSI_BF_APPROX
+    x = lazy_sub_hi(x, 4 * q);
+#endif
+    return lazy_sub_hi(x, 2 * q);
+}
+// forward (Cooley-Tukey): inputs < 2 qc + slack, outputs < 2 qc + slack, qc = kLazy * q
+__device__ __forceinline__ void ct_bf(u64& x, u64& y, const ulonglong2 tw, u64 qc, u64 nq) {
+    const u64 u = lazy_sub_hi(x, qc);
+    const u64 v = bf_mul(y, tw, nq);
+    x = u + v;
+    y = u - v + qc;
+}
+// inverse (Gentleman-Sande): inputs < qc + e (e grows by at most a factor two per stage from 2^32,
+// far below q after 14 stages), x output < qc + 2e, y output < qc
+__device__ __forceinline__ void gs_bf(u64& x, u64& y, const ulonglong2 tw, u64 qc, u64 nq) {
+    const u64 s = lazy_sub_hi(x + y, qc);
+    const u64 d = x - y + 2 * qc;
     x = s;
-    y = mul_shoup_lazy(d, tw.x, tw.y, 0 - nq);
+    y = bf_mul(d, tw, nq);
 }
 
 // One stage (local stage sig0 + r) of a radix-2^R register pass.  All loop bounds are template constants
@@ -117,7 +158,7 @@ template <int R, bool INV>
 __device__ __forceinline__ void radix_pass(u64* __restrict__ sm, const ulonglong2* __restrict__ tw, uint32_t m,
                                            uint32_t sig0, uint32_t delta, uint32_t tile_base, u64 q, uint32_t tid) {
     const uint32_t lt = m - sig0 - R;  // log2 of the stride between a thread's coefficients
-    const u64 q2 = 2 * q, nq = 0 - q;
+    const u64 q2 = kLazy * q, nq = 0 - q;  // correction amount of the lazy butterflies
     for (uint32_t blk = tid; blk < ((1u << m) >> R); blk += kGroup) {
         const uint32_t off = blk & ((1u << lt) - 1), grp = blk >> lt;
         const uint32_t base = (grp << (m - sig0)) + off;
@@ -174,7 +215,7 @@ __device__ __forceinline__ void radix_pass_ct(u64* __restrict__ sm, const ulongl
                                               uint32_t tile_base, u64 q, uint32_t tid) {
     constexpr int LT = M - SIG0 - R;
     constexpr uint32_t NBLK = (1u << M) >> R;
-    const u64 q2 = 2 * q, nq = 0 - q;
+    const u64 q2 = kLazy * q, nq = 0 - q;  // correction amount of the lazy butterflies
 #pragma unroll
     for (uint32_t it = 0; it < (NBLK + kGroup - 1) / kGroup; it++) {
         const uint32_t blk = tid + it * kGroup;

@@ -135,6 +135,11 @@ struct psi_ctx {
     size_t pool_in_words = 0, pool_out_words = 0;
     cudaEvent_t ev_pool_in = nullptr;  // last upload that read pool_in
     int host_threads = 8;
+    // phase 2 in bin groups on concurrent streams (tails of one group's kernels overlap the next group's heads);
+    // 0 = choose from the number of resident bins
+    uint32_t p2_groups = 0;
+    cudaStream_t aux[3] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {};
 
     KCtx k(cudaStream_t s) const { return KCtx{d_tab, N, logN, L, Lp, s}; }
 };
@@ -341,50 +346,59 @@ static int alloc_work(psi_ctx* c) {
 // One batched EvalMult(ct,ct) + relinearise over B ciphertext pairs (+ optional mask multiply).
 // a, bb: [B][2][L][N] EVALUATION (a = multipliedResult, bb = innerProductResult; the operand order of
 // BatchedFHEHIPPIE.cpp:123 matters); out: [B][2][L][N].
+// bin0: first bin of the batch inside the context's work buffers — bin groups evaluated concurrently on several
+// streams (psi_run_phases) work in disjoint slices of the scratch arrays.
 static int mul_ctct_batch(psi_ctx* c, cudaStream_t s, uint32_t B, const u64* a, const u64* bb, const u64* mask,
-                          u64* out, uint32_t* launches) {
+                          u64* out, uint32_t* launches, uint32_t bin0 = 0) {
     const KCtx k = c->k(s);
     const uint32_t L = c->L, Lp = c->Lp, LT = L + Lp;
     const size_t N = c->N;
     uint32_t nl = 0;
+    // per-bin sizes of the scratch arrays (alloc_work)
+    u64* const w_coef = c->coef.p + (size_t)bin0 * 4 * L * N;
+    u64* const w_e1 = c->e1.p + (size_t)bin0 * 2 * LT * N;
+    u64* const w_e2 = c->e2.p + (size_t)bin0 * 2 * LT * N;
+    u64* const w_ten = c->ten.p + (size_t)bin0 * 3 * LT * N;
+    u64* const w_res = c->res.p + (size_t)bin0 * 3 * L * N;
+    u64* const w_dig = c->dig.p + (size_t)bin0 * L * L * N;
     if (fused_mul_supported(k)) {
         // the fused relinearisation takes the key and the masks in Montgomery form
         const u64* maskR = mask ? c->maskR.p + (mask - c->mask.p) : nullptr;
-        CK(launch_fused_mul(k, B, a, bb, c->coef.p, c->coef.p + (size_t)B * 2 * L * N, c->e1.p, c->e2.p, c->ten.p,
-                            c->res.p, c->dig.p, c->evk_bR.p, c->evk_aR.p, maskR, out));
+        CK(launch_fused_mul(k, B, a, bb, w_coef, w_coef + (size_t)B * 2 * L * N, w_e1, w_e2, w_ten,
+                            w_res, w_dig, c->evk_bR.p, c->evk_aR.p, maskR, out));
         if (launches) *launches += 5;
         return PSI_OK;
     }
-    u64* coef1 = c->coef.p;                         // [B*2][L][N]
-    u64* coef2 = c->coef.p + (size_t)B * 2 * L * N;  // [B*2][L][N]
+    u64* coef1 = w_coef;                         // [B*2][L][N]
+    u64* coef2 = w_coef + (size_t)B * 2 * L * N;  // [B*2][L][N]
     // (1) both operands to COEFFICIENT
     NttBatch nb{a, coef1, B * 2 * L, L, L * N, N, L * N, 0, L};
     CK(launch_ntt(k, nb, true)); nl++;
     nb = NttBatch{bb, coef2, B * 2 * L, L, L * N, N, L * N, 0, L};
     CK(launch_ntt(k, nb, true)); nl++;
     // (2) first operand: exact Q -> P extension; Q limbs stay as given (EVALUATION)
-    CK(launch_expand_q_to_p(k, B * 2, coef1, c->e1.p)); nl++;
-    nb = NttBatch{c->e1.p + (size_t)L * N, c->e1.p + (size_t)L * N, B * 2 * Lp, Lp, LT * N, N, LT * N, L, Lp};
+    CK(launch_expand_q_to_p(k, B * 2, coef1, w_e1)); nl++;
+    nb = NttBatch{w_e1 + (size_t)L * N, w_e1 + (size_t)L * N, B * 2 * Lp, Lp, LT * N, N, LT * N, L, Lp};
     CK(launch_ntt(k, nb, false)); nl++;
-    CK(cudaMemcpy2DAsync(c->e1.p, LT * N * sizeof(u64), a, L * N * sizeof(u64), L * N * sizeof(u64), (size_t)B * 2,
+    CK(cudaMemcpy2DAsync(w_e1, LT * N * sizeof(u64), a, L * N * sizeof(u64), L * N * sizeof(u64), (size_t)B * 2,
                          cudaMemcpyDeviceToDevice, s));
     // (3) second operand: P-over-Q fast extension, all limbs back to EVALUATION
-    CK(launch_fast_expand_poverq(k, B * 2, coef2, c->e2.p)); nl++;
-    nb = NttBatch{c->e2.p, c->e2.p, B * 2 * LT, LT, LT * N, N, LT * N, 0, LT};
+    CK(launch_fast_expand_poverq(k, B * 2, coef2, w_e2)); nl++;
+    nb = NttBatch{w_e2, w_e2, B * 2 * LT, LT, LT * N, N, LT * N, 0, LT};
     CK(launch_ntt(k, nb, false)); nl++;
     // (4) tensor, (5) COEFFICIENT, (6) scale by t/P and round into Q
-    CK(launch_tensor(k, B, c->e1.p, c->e2.p, c->ten.p)); nl++;
-    nb = NttBatch{c->ten.p, c->ten.p, B * 3 * LT, LT, LT * N, N, LT * N, 0, LT};
+    CK(launch_tensor(k, B, w_e1, w_e2, w_ten)); nl++;
+    nb = NttBatch{w_ten, w_ten, B * 3 * LT, LT, LT * N, N, LT * N, 0, LT};
     CK(launch_ntt(k, nb, true)); nl++;
-    CK(launch_scale_round(k, B * 3, c->ten.p, c->res.p)); nl++;
+    CK(launch_scale_round(k, B * 3, w_ten, w_res)); nl++;
     // (7) relinearise: digits of c2 (BV, digit size 0), everything to EVALUATION, accumulate
-    CK(launch_relin_digits(k, B, c->res.p, c->dig.p)); nl++;
-    nb = NttBatch{c->dig.p, c->dig.p, B * L * L, L, L * N, N, L * N, 0, L};
+    CK(launch_relin_digits(k, B, w_res, w_dig)); nl++;
+    nb = NttBatch{w_dig, w_dig, B * L * L, L, L * N, N, L * N, 0, L};
     CK(launch_ntt(k, nb, false)); nl++;
     // components 0 and 1 only: group = bin, 2L of its 3L limb-polys
-    nb = NttBatch{c->res.p, c->res.p, B * 2 * L, 2 * L, 3 * L * N, N, 3 * L * N, 0, L};
+    nb = NttBatch{w_res, w_res, B * 2 * L, 2 * L, 3 * L * N, N, 3 * L * N, 0, L};
     CK(launch_ntt(k, nb, false)); nl++;
-    CK(launch_relin_accum(k, B, c->res.p, c->dig.p, c->evk_b.p, c->evk_a.p, mask, out)); nl++;
+    CK(launch_relin_accum(k, B, w_res, w_dig, c->evk_b.p, c->evk_a.p, mask, out)); nl++;
     if (launches) *launches += nl;
     return PSI_OK;
 }
@@ -394,7 +408,15 @@ static int mul_ctct_batch(psi_ctx* c, cudaStream_t s, uint32_t B, const u64* a, 
 extern "C" {
 
 const char* psi_last_error(void) { return g_last_error.c_str(); }
-const char* psi_version(void) { return "psi_b200 0.1 (sm_100a)"; }
+const char* psi_version(void) { return "psi_b200 0.2 (sm_100a)"; }
+
+int psi_device_count(int* n) {
+    if (!n) return set_error(PSI_ERR_INVALID, "null argument");
+    *n = 0;
+    cudaError_t e = cudaGetDeviceCount(n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    return PSI_OK;
+}
 
 int psi_ctx_create(const psi_params* p, int device, psi_ctx** out) {
     if (!p || !out) return set_error(PSI_ERR_INVALID, "null argument");
@@ -443,6 +465,11 @@ int psi_ctx_destroy(psi_ctx* c) {
                            &c->coef,     &c->e1,    &c->e2,    &c->ten, &c->res, &c->dig, &c->prod,  &c->out, &c->out2, &c->minus_in};
     for (auto* b : bufs) b->release();
     c->to_crt.release();
+    for (auto& st : c->aux)
+        if (st) cudaStreamDestroy(st);
+    for (auto& e : c->ev_join)
+        if (e) cudaEventDestroy(e);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->pool_in) cudaFreeHost(c->pool_in);
     if (c->pool_out) cudaFreeHost(c->pool_out);
     if (c->ev_pool_in) cudaEventDestroy(c->ev_pool_in);
@@ -886,6 +913,13 @@ int psi_result_get_limbs(psi_ctx* c, uint64_t* const* out_limbs, void* stream) {
     return PSI_OK;
 }
 
+int psi_debug_set_tuning(psi_ctx* c, int mac_variant, int phase2_groups) {
+    if (!c || mac_variant < -1 || mac_variant > 2 || phase2_groups < -1 || phase2_groups > 4) return set_error(PSI_ERR_INVALID, "bad tuning value");
+    if (mac_variant >= 0) mac_force_variant(mac_variant);
+    if (phase2_groups >= 0) c->p2_groups = (uint32_t)phase2_groups;
+    return PSI_OK;
+}
+
 int psi_set_host_threads(psi_ctx* c, int n) {
     if (!c || n < 1 || n > 256) return set_error(PSI_ERR_INVALID, "host thread count must be in [1, 256]");
     c->host_threads = n;
@@ -968,17 +1002,45 @@ int psi_run_phases(psi_ctx* c, uint32_t phases, void* stream) {
         }
         nl++;
     } else {
-        const u64* prod = c->acc.p;  // hf = 0
-        for (uint32_t hf = 1; hf < c->K; hf++) {
-            const bool last = hf + 1 == c->K;
-            u64* dst = last ? result : c->prod.p;
-            if ((rc = mul_ctct_batch(c, s, c->b, prod, c->acc.p + (size_t)hf * c->b * ct, last ? c->mask.p : nullptr,
-                                     dst, &nl))) {
-                c->ran = false;
-                return rc;
+        // Bin groups: the bins are independent, so the multiplication chain of one group can run next to another
+        // group's; with few resident bins (a shard of a multi-GPU query) every kernel is less than one wave and a
+        // second group fills the SMs the first leaves idle at its tails.
+        uint32_t G = c->p2_groups ? c->p2_groups : (c->b >= 4 ? 2u : 1u);  // measured: 2 groups -3 % .. -13 % for b = 5 .. 75
+        if (G > c->b) G = c->b;
+        if (G > 4) G = 4;
+        if (G > 1) {
+            rc = PSI_OK;
+            if (!c->ev_fork) {
+                cudaError_t e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+                for (int i = 0; i < 3 && e == cudaSuccess; i++) {
+                    e = cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking);
+                    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
+                }
+                if (e != cudaSuccess) return cuda_fail(e, "bin-group streams");
             }
-            prod = dst;
+            CK(cudaEventRecord(c->ev_fork, s));
         }
+        for (uint32_t g = 0; g < G; g++) {
+            const uint32_t g0 = (uint32_t)((uint64_t)c->b * g / G), g1 = (uint32_t)((uint64_t)c->b * (g + 1) / G), Bg = g1 - g0;
+            cudaStream_t sg = g == 0 ? s : c->aux[g - 1];
+            if (g > 0) CK(cudaStreamWaitEvent(sg, c->ev_fork, 0));
+            const u64* prod = c->acc.p + (size_t)g0 * ct;  // hf = 0
+            for (uint32_t hf = 1; hf < c->K; hf++) {
+                const bool last = hf + 1 == c->K;
+                u64* dst = (last ? result : c->prod.p) + (size_t)g0 * ct;
+                if ((rc = mul_ctct_batch(c, sg, Bg, prod, c->acc.p + ((size_t)hf * c->b + g0) * ct,
+                                         last ? c->mask.p + (size_t)g0 * c->L * c->N : nullptr, dst, g == 0 ? &nl : nullptr, g0))) {
+                    c->ran = false;
+                    return rc;
+                }
+                prod = dst;
+            }
+            if (g > 0) {
+                CK(cudaEventRecord(c->ev_join[g - 1], sg));
+                CK(cudaStreamWaitEvent(s, c->ev_join[g - 1], 0));
+            }
+        }
+        if (G > 1) nl = 1 + (nl - 1) * G;  // every group launches the same kernels
     }
     c->out_cur = next_out;
     c->launches_per_run = nl;

@@ -41,21 +41,27 @@ __device__ __forceinline__ void fold30(u64& hi, u64& lo, u64 ll, u64 mid, u64 hh
 constexpr int kMacCoeffs = 128;  // coefficients per CTA tile (= one row of one limb)
 
 // The operands are streamed by the copy engine: one producer thread issues cp.async.bulk (SASS UBLKCP)
-// copies of whole position-chunks — 8 positions x 1 KiB per bin, 8 x 2 KiB of index words — into a
-// two-stage shared-memory ring guarded by mbarriers, and 256 consumer threads (128 coefficients x 2
-// bin-lanes x 2 bins) do nothing but LDS + IMAD.WIDE.  Two CTAs per SM; the data in flight per SM (up to
-// 192 KiB) is set by the rings, not by how many loads the compiler keeps in registers.
+// copies of whole position-chunks — CHUNK positions x 1 KiB per bin, CHUNK x 2 KiB of index words — into a
+// STAGES-deep shared-memory ring guarded by mbarriers, and 256 consumer threads (128 coefficients x 2
+// bin-lanes, BT bins each) do nothing but LDS + IMAD.WIDE.  The data in flight per SM is set by the rings, not
+// by how many loads the compiler keeps in registers.
 //
 // Multiplier work is what limits the consumers (IMAD.WIDE issues at a quarter of the FP32 rate), so one
 // 60 x 60-bit product is formed with THREE 32 x 32 products (Karatsuba on the 30-bit halves):
 //   ll += x0*y0,  hh += x1*y1,  kk += (x0+x1)*(y0+y1),  middle = kk - ll - hh.
 // ll and hh stay below 2^63 over 8 positions; kk may wrap, but the middle sum is < 2^64, so the wrapped
 // 64-bit difference is exact.  Hence the fold into the 128-bit running total after every 8 positions.
-constexpr int kMacPosChunk = 8;   // positions per stage == positions between folds
-constexpr int kMacStages = 2;
-constexpr int kMacBT = 2, kMacLanes = 2, kMacBins = kMacBT * kMacLanes;
+//
+// The bin-block width (2 * BT bins per CTA) is chosen from the number of resident bins (launch_mac): a block
+// width that divides b_local wastes no bin-lane, and a wider block re-reads the index slice from L2 fewer
+// times — what matters when a GPU holds 6 of the 47 bins of a sharded query.
+constexpr int kMacFold = 8;  // positions between folds
+constexpr int kMacLanes = 2;
 constexpr int kMacConsumers = kMacCoeffs * kMacLanes;
-constexpr size_t kMacStageWords = (size_t)kMacPosChunk * kMacCoeffs * (2 + kMacBins);  // idx + pt words per stage
+template <int BT, int CHUNK>
+__host__ __device__ constexpr size_t mac_stage_words() {
+    return (size_t)CHUNK * kMacCoeffs * (2 + kMacLanes * BT);  // idx + pt words per stage
+}
 
 // canonical residue of hi * 2^64 + lo: hi through the Shoup pair of 2^64 mod q, lo through floor(2^64 / q)
 __device__ __forceinline__ u64 reduce128(u64 hi, u64 lo, const u64 q, const u64 R, const u64 Rs, const u64 qrecip) {
@@ -73,20 +79,34 @@ __device__ __forceinline__ u64 redc_canonical(u64 hi, u64 lo, const u64 q, const
     return r >= q ? r - q : r;
 }
 
-__global__ void __launch_bounds__(kMacConsumers + 32, 2)
-    k_mac_tma(const DevTables* __restrict__ tab, uint32_t N, uint32_t L, uint32_t b, uint32_t E, const u64* __restrict__ pt,
-              const u64* __restrict__ idx, const u64* __restrict__ minus, u64* __restrict__ acc) {
-    extern __shared__ __align__(128) u64 ring[];  // [stage][ idx: 8 x 2 x 128 | pt: 4 bins x 8 x 128 ]
-    __shared__ __align__(8) uint64_t full_bar[kMacStages], empty_bar[kMacStages];
+// What one launch covers: hash functions [hf0, hf0 + gridDim.y), positions [pos0, pos1) of each.  flags: bit 0 =
+// add the previous contents of acc (a later slice of the same inner product), bit 1 = add minusCompareElement
+// (the last slice).  A whole query is one launch with pos0 = 0, pos1 = E, flags = 2; the streamed single-query
+// path (psi_query_run_streamed) evaluates slices as their index ciphertexts arrive over PCIe.
+struct MacRange {
+    uint32_t hf0, pos0, pos1, flags;
+};
+
+template <int BT, int CHUNK, int STAGES>
+__global__ void __launch_bounds__(kMacConsumers + 32, (BT == 1 ? 3 : 2))
+    k_mac_tma(const DevTables* __restrict__ tab, uint32_t N, uint32_t L, uint32_t b, uint32_t E, MacRange rg,
+              const u64* __restrict__ pt, const u64* __restrict__ idx, const u64* __restrict__ minus, u64* __restrict__ acc) {
+    constexpr int kBins = kMacLanes * BT;
+    constexpr size_t kStageWords = mac_stage_words<BT, CHUNK>();
+    constexpr uint32_t kChunksPerFold = kMacFold / CHUNK;
+    static_assert(kMacFold % CHUNK == 0, "a fold covers whole chunks");
+    extern __shared__ __align__(128) u64 ring[];  // [stage][ idx: CHUNK x 2 x 128 | pt: bins x CHUNK x 128 ]
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
     const size_t LN = (size_t)L * N, T = LN / kMacCoeffs;
     // CTAs that share an index slice (same hf and tile, different bin blocks) are adjacent in launch
     // order, so the slice comes from DRAM once and from L2 for the other bin blocks
-    const uint32_t nbb = (b + kMacBins - 1) / kMacBins;
-    const uint32_t hf = blockIdx.y, tile = blockIdx.x / nbb, bin_blk0 = (blockIdx.x % nbb) * kMacBins;
-    const uint32_t nbins = min((uint32_t)kMacBins, b - bin_blk0);
-    const uint32_t nchunks = (E + kMacPosChunk - 1) / kMacPosChunk;
+    const uint32_t nbb = (b + kBins - 1) / kBins;
+    const uint32_t hf = rg.hf0 + blockIdx.y, tile = blockIdx.x / nbb, bin_blk0 = (blockIdx.x % nbb) * kBins;
+    const uint32_t nbins = min((uint32_t)kBins, b - bin_blk0);
+    const uint32_t npos = rg.pos1 - rg.pos0;
+    const uint32_t nchunks = (npos + CHUNK - 1) / CHUNK;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kMacStages; s++) {
+        for (int s = 0; s < STAGES; s++) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], kMacConsumers);
         }
@@ -100,15 +120,15 @@ __global__ void __launch_bounds__(kMacConsumers + 32, 2)
             const u64* isrc = idx + ((size_t)hf * T + tile) * E * 2 * kMacCoeffs;
             const u64* psrc = pt + ((size_t)hf * b + bin_blk0) * (size_t)E * LN + (size_t)tile * E * kMacCoeffs;
             for (uint32_t ch = 0; ch < nchunks; ch++) {
-                const uint32_t s = ch % kMacStages, round = ch / kMacStages;
+                const uint32_t s = ch % STAGES, round = ch / STAGES;
                 if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
-                const uint32_t p0 = ch * kMacPosChunk, np = min((uint32_t)kMacPosChunk, E - p0);
-                u64* st = ring + (size_t)s * kMacStageWords;
+                const uint32_t p0 = rg.pos0 + ch * CHUNK, np = min((uint32_t)CHUNK, rg.pos1 - p0);
+                u64* st = ring + (size_t)s * kStageWords;
                 const uint32_t ibytes = np * 2 * kMacCoeffs * 8, pbytes = np * kMacCoeffs * 8;
                 mbar_expect_tx(&full_bar[s], ibytes + nbins * pbytes);
                 bulk_g2s(st, isrc + (size_t)p0 * 2 * kMacCoeffs, ibytes, &full_bar[s]);
                 for (uint32_t j = 0; j < nbins; j++)
-                    bulk_g2s(st + (size_t)kMacPosChunk * kMacCoeffs * (2 + j), psrc + (size_t)j * E * LN + (size_t)p0 * kMacCoeffs,
+                    bulk_g2s(st + (size_t)CHUNK * kMacCoeffs * (2 + j), psrc + (size_t)j * E * LN + (size_t)p0 * kMacCoeffs,
                              pbytes, &full_bar[s]);
             }
         }
@@ -118,25 +138,25 @@ __global__ void __launch_bounds__(kMacConsumers + 32, 2)
     // ---- consumers
     const uint32_t w = threadIdx.x & (kMacCoeffs - 1), lane = threadIdx.x / kMacCoeffs;
     const size_t c = (size_t)tile * kMacCoeffs + w;
-    u64 ll[kMacBT][2], kk[kMacBT][2], hh[kMacBT][2], tlo[kMacBT][2], thi[kMacBT][2];
+    u64 ll[BT][2], kk[BT][2], hh[BT][2], tlo[BT][2], thi[BT][2];
 #pragma unroll
-    for (int j = 0; j < kMacBT; j++)
+    for (int j = 0; j < BT; j++)
 #pragma unroll
         for (int k = 0; k < 2; k++) ll[j][k] = kk[j][k] = hh[j][k] = tlo[j][k] = thi[j][k] = 0;
 
     uint32_t folds = 0;
     for (uint32_t ch = 0; ch < nchunks; ch++) {
-        const uint32_t s = ch % kMacStages, round = ch / kMacStages;
-        const uint32_t np = min((uint32_t)kMacPosChunk, E - ch * kMacPosChunk);
+        const uint32_t s = ch % STAGES, round = ch / STAGES;
+        const uint32_t np = min((uint32_t)CHUNK, npos - ch * CHUNK);
         mbar_wait(&full_bar[s], round & 1);
-        const uint2* si = reinterpret_cast<const uint2*>(ring + (size_t)s * kMacStageWords) + w;
-        const uint2* sp = si + (size_t)kMacPosChunk * kMacCoeffs * (2 + lane * kMacBT);
+        const uint2* si = reinterpret_cast<const uint2*>(ring + (size_t)s * kStageWords) + w;
+        const uint2* sp = si + (size_t)CHUNK * kMacCoeffs * (2 + lane * BT);
         auto body = [&](int p) {
             const uint2 i0 = si[p * 2 * kMacCoeffs], i1 = si[p * 2 * kMacCoeffs + kMacCoeffs];
             const uint32_t s0 = i0.x + i0.y, s1 = i1.x + i1.y;
 #pragma unroll
-            for (int j = 0; j < kMacBT; j++) {
-                const uint2 y = sp[(j * kMacPosChunk + p) * kMacCoeffs];
+            for (int j = 0; j < BT; j++) {
+                const uint2 y = sp[(j * CHUNK + p) * kMacCoeffs];
                 const uint32_t sy = y.x + y.y;
                 ll[j][0] = madw(i0.x, y.x, ll[j][0]);
                 hh[j][0] = madw(i0.y, y.y, hh[j][0]);
@@ -146,25 +166,26 @@ __global__ void __launch_bounds__(kMacConsumers + 32, 2)
                 kk[j][1] = madw(s1, sy, kk[j][1]);
             }
         };
-        if (np == kMacPosChunk) {
+        if (np == CHUNK) {
 #pragma unroll
-            for (int p = 0; p < kMacPosChunk; p++) body(p);
+            for (int p = 0; p < CHUNK; p++) body(p);
         } else {
             for (uint32_t p = 0; p < np; p++) body((int)p);
         }
         mbar_arrive(&empty_bar[s]);  // this thread is done reading stage s
+        if ((ch + 1) % kChunksPerFold != 0 && ch + 1 < nchunks) continue;
 #pragma unroll
-        for (int j = 0; j < kMacBT; j++)
+        for (int j = 0; j < BT; j++)
 #pragma unroll
             for (int k = 0; k < 2; k++) {
                 fold30(thi[j][k], tlo[j][k], ll[j][k], kk[j][k] - ll[j][k] - hh[j][k], hh[j][k]);
                 ll[j][k] = kk[j][k] = hh[j][k] = 0;
             }
-        if (++folds == kMacMaxTerms / kMacPosChunk && ch + 1 < nchunks) {  // keep the total within redc_canonical's bound for any E
+        if (++folds == kMacMaxTerms / kMacFold && ch + 1 < nchunks) {  // keep the total within redc_canonical's bound for any E
             folds = 0;
             const ModDev& mdr = tab->mods[c / N];
 #pragma unroll
-            for (int j = 0; j < kMacBT; j++)
+            for (int j = 0; j < BT; j++)
 #pragma unroll
                 for (int k = 0; k < 2; k++) {
                     tlo[j][k] = reduce128(thi[j][k], tlo[j][k], mdr.q, mdr.Rmodq, mdr.Rmodq_s, mdr.mu_hi);
@@ -174,30 +195,72 @@ __global__ void __launch_bounds__(kMacConsumers + 32, 2)
     }
     const ModDev& md = tab->mods[c / N];
     const u64 q = md.q, qinv = md.qinv;
-    const u64 m0 = minus[c], m1 = minus[LN + c];
+    const bool add_old = rg.flags & 1u, add_minus = rg.flags & 2u;
+    const u64 m0 = add_minus ? minus[c] : 0, m1 = add_minus ? minus[LN + c] : 0;
 #pragma unroll
-    for (int j = 0; j < kMacBT; j++) {
-        const uint32_t bin = bin_blk0 + lane * kMacBT + j;
+    for (int j = 0; j < BT; j++) {
+        const uint32_t bin = bin_blk0 + lane * BT + j;
         if (bin < b) {
             u64* o = acc + (((size_t)hf * b + bin) * 2) * LN + c;
-            o[0] = addmod(redc_canonical(thi[j][0], tlo[j][0], q, qinv), m0, q);
-            o[LN] = addmod(redc_canonical(thi[j][1], tlo[j][1], q, qinv), m1, q);
+            u64 r0 = addmod(redc_canonical(thi[j][0], tlo[j][0], q, qinv), m0, q);
+            u64 r1 = addmod(redc_canonical(thi[j][1], tlo[j][1], q, qinv), m1, q);
+            if (add_old) {
+                r0 = addmod(r0, o[0], q);
+                r1 = addmod(r1, o[LN], q);
+            }
+            o[0] = r0;
+            o[LN] = r1;
         }
     }
 }
 
+// The instantiations the launcher chooses from: <bins per lane, positions per stage, stages>
+//   <2, 8, 2>  4 bins per CTA, 96 KiB ring, 2 CTAs / SM: the full-database shape (b = 47: 12 blocks)
+//   <1, 8, 2>  2 bins per CTA, 64 KiB ring, 3 CTAs / SM: few resident bins whose count 4 does not divide (a GPU's
+//              5 or 6 of the 47 bins of a sharded query: 85.6 % of the HBM peak against 78 % with 4-bin blocks)
+// (a 6-bin block, <3, 4, 3>, was measured too: never the fastest, 77-81 % at b = 5, 6, 47; profiles/r02_tune_shapes.md)
+template <int BT, int CHUNK, int STAGES>
+static cudaError_t mac_launch_t(const KCtx& k, uint32_t nhf, uint32_t b, uint32_t E, const MacRange& rg, const u64* pt,
+                                const u64* idx, const u64* minus, u64* acc, bool init_only) {
+    constexpr size_t smem = STAGES * mac_stage_words<BT, CHUNK>() * sizeof(u64);
+    if (init_only)
+        return cudaFuncSetAttribute(k_mac_tma<BT, CHUNK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t LN = (size_t)k.L * k.N;
+    constexpr int kBins = kMacLanes * BT;
+    dim3 grid(cdiv(LN, kMacCoeffs) * ((b + kBins - 1) / kBins), nhf);
+    k_mac_tma<BT, CHUNK, STAGES><<<grid, kMacConsumers + 32, smem, k.s>>>(k.tab, k.N, k.L, b, E, rg, pt, idx, minus, acc);
+    return cudaGetLastError();
+}
+
+static int g_mac_force = 0;  // tuning / tests: 0 = choose by shape, 1 / 2 = force 2 / 4 bins per CTA
+void mac_force_variant(int v) { g_mac_force = v; }
+
+// bin-block width for b resident bins: 2-bin blocks when 4-bin blocks would leave more than a tenth of the
+// bin-lanes idle (measured: b = 5, 6, 14 faster with 2, b = 26, 47, 75 faster with 4)
+static int mac_choose(uint32_t b) {
+    if (g_mac_force) return g_mac_force;
+    const uint32_t slots4 = ((b + 3) / 4) * 4, slots2 = ((b + 1) / 2) * 2;
+    return (slots2 < slots4 && (slots4 - b) * 10 > slots4) ? 1 : 2;
+}
+
 cudaError_t mac_init_device() {
-    return cudaFuncSetAttribute(k_mac_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(kMacStages * kMacStageWords * sizeof(u64)));
+    const KCtx k{};
+    const MacRange rg{};
+    cudaError_t e = mac_launch_t<2, 8, 2>(k, 0, 0, 0, rg, nullptr, nullptr, nullptr, nullptr, true);
+    if (e == cudaSuccess) e = mac_launch_t<1, 8, 2>(k, 0, 0, 0, rg, nullptr, nullptr, nullptr, nullptr, true);
+    return e;
+}
+
+cudaError_t launch_mac_range(const KCtx& k, uint32_t hf0, uint32_t nhf, uint32_t b, uint32_t E, uint32_t pos0, uint32_t pos1,
+                             uint32_t flags, const u64* pt, const u64* idx, const u64* minus, u64* acc) {
+    const MacRange rg{hf0, pos0, pos1, flags};
+    if (mac_choose(b) == 1) return mac_launch_t<1, 8, 2>(k, nhf, b, E, rg, pt, idx, minus, acc, false);
+    return mac_launch_t<2, 8, 2>(k, nhf, b, E, rg, pt, idx, minus, acc, false);
 }
 
 cudaError_t launch_mac(const KCtx& k, uint32_t K, uint32_t b, uint32_t E, const u64* pt, const u64* idx,
                        const u64* minus, u64* acc) {
-    const size_t LN = (size_t)k.L * k.N;
-    dim3 grid(cdiv(LN, kMacCoeffs) * ((b + kMacBins - 1) / kMacBins), K);
-    const size_t smem = kMacStages * kMacStageWords * sizeof(u64);
-    k_mac_tma<<<grid, kMacConsumers + 32, smem, k.s>>>(k.tab, k.N, k.L, b, E, pt, idx, minus, acc);
-    return cudaGetLastError();
+    return launch_mac_range(k, 0, K, b, E, 0, E, 2u, pt, idx, minus, acc);
 }
 
 // Storage formats of the two operands of phase 1.  Words: canonical residue < 2^60 <-> split-30 word

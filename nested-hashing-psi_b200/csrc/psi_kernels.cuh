@@ -72,6 +72,11 @@ cudaError_t launch_retile_pt(cudaStream_t s, u64* flat, u64* tiled, size_t LN, u
 cudaError_t launch_retile_idx(const KCtx& k, const u64* flat, u64* tiled, size_t LN, uint32_t K, uint32_t E);
 cudaError_t launch_mac(const KCtx& k, uint32_t K, uint32_t b, uint32_t E, const u64* pt, const u64* idx,
                        const u64* minus, u64* acc);
+// A slice of the same inner products: hash functions [hf0, hf0 + nhf), positions [pos0, pos1); flags bit 0 = add the
+// previous contents of acc, bit 1 = add minusCompareElement
+cudaError_t launch_mac_range(const KCtx& k, uint32_t hf0, uint32_t nhf, uint32_t b, uint32_t E, uint32_t pos0, uint32_t pos1,
+                             uint32_t flags, const u64* pt, const u64* idx, const u64* minus, u64* acc);
+void mac_force_variant(int v);  // 0 = choose the bin-block width by shape, 1..3 = force 2 * v bins per CTA (tuning, tests)
 
 // EvalMult(ct,ct) building blocks, all batched over B ciphertexts (see psi_api.cu for the sequence)
 cudaError_t launch_expand_q_to_p(const KCtx& k, uint32_t groups, const u64* coef, u64* ext);

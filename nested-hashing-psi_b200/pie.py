@@ -225,6 +225,10 @@ class CryptoContext:
     def set_host_threads(self, n):
         check(lib().psi_set_host_threads(self._h, n))
 
+    def set_tuning(self, mac_variant=-1, phase2_groups=-1):
+        """psi_debug_set_tuning: force the inner-product bin-block width / the number of phase-2 bin groups."""
+        check(lib().psi_debug_set_tuning(self._h, mac_variant, phase2_groups))
+
     def query_landing_ptrs(self, which):
         """(idx_ptr, idx_bytes, minus_ptr, minus_bytes) of device landing buffer `which` (0 or 1)."""
         pi, pm, ni, nm = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_size_t()
