@@ -447,6 +447,17 @@ def main():
         cc.sync(sp)
         m["ms_e2e_serial"] = timed(e2e_serial_step, args.steps) / args.steps
         m["last_result"] = r_host
+        # the same single query with upload slices, evaluation and download groups overlapped inside the query
+        m["ms_e2e_streamed"] = None
+        if world == 1:
+            def e2e_streamed_step():
+                cc.query_run_streamed_ptr(idx_ptr, minus_ptr, r_host2.data_ptr(), sp)
+            for _ in range(3):
+                e2e_streamed_step()
+            cc.sync(sp)
+            m["ms_e2e_streamed"] = timed(e2e_streamed_step, args.steps) / args.steps
+            if not torch.equal(r_host, r_host2):
+                raise SystemExit("bench.py: streamed single-query path returned different results")
 
         def e2e_pipelined(steps, warm):
             """Elapsed ms of `steps` queries through the 3-stream pipeline (upload of query i+1 and download of result
@@ -653,12 +664,15 @@ def main():
             "roofline": roofline, "roofline_int": roofline_int, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "items/s", "ms_per_step": m["ms_e2e"], "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "serial_ms_per_step": m["ms_e2e_serial"],
+                    "serial_streamed_ms_per_step": m["ms_e2e_streamed"],
                     "serial_value": total_items / (m["ms_e2e_serial"] * 1e-3),
                     "limb_vectors": limb_leg,
                     "path": "pinned host query -> psi_query_upload | psi_query_commit -> psi_run -> psi_result_get -> "
                             "pinned host, three streams: upload of query i+1 and download of result i-1 overlap "
                             "run i; the warm-up queries run through the same pipeline, the timed region holds every copy "
-                            "and kernel of exactly `steps` queries (serial_* = one query at a time)"
+                            "and kernel of exactly `steps` queries (serial_* = one query at a time; serial_streamed = one query at a "
+                            "time through psi_query_run_streamed: upload slices, partial inner products, bin groups and their "
+                            "downloads overlapped inside the query)"
                             + ((" (N > 1: NCCL gather to rank 0 over NVLink, then one D2H)" if args.gather == "nccl" else
                                 " (N > 1: every rank downloads its own bins over its own PCIe link)") if world > 1 else ""),
                     "gather": args.gather if world > 1 else None, "rank0_numa_node": numa_node,

@@ -212,6 +212,14 @@ int psi_run(psi_ctx* ctx, void* stream);
 enum { PSI_PHASE_INNER_PRODUCT = 1, PSI_PHASE_MULTIPLY_MASK = 2, PSI_PHASE_ALL = 3 };
 int psi_run_phases(psi_ctx* ctx, uint32_t phases, void* stream);
 
+/* setMinusCompareElement + setIndex + run + getResultList for ONE query with the PCIe transfers overlapped inside
+ * the query (the reference's server evaluates exactly one query per session, BatchedFHEPSIServer.cpp:99-108): the
+ * index ciphertexts are uploaded in slices (hash function, position range) and each slice's share of the inner
+ * products is accumulated as soon as it has landed; the ct x ct chain runs over the bins in groups and the results
+ * of a group are downloaded while the next group is evaluated.  idx [K][E][2][L][N], minus [2][L][N], out
+ * [b][2][L][N] are host buffers (pinned for full speed).  Asynchronous: synchronise `stream` before reading out. */
+int psi_query_run_streamed(psi_ctx* ctx, const uint64_t* idx, const uint64_t* minus, uint64_t* out, void* stream);
+
 /* getResultList (BatchedFHEHIPPIE.hpp:35-38): asynchronous D2H of [b][2][L][N]
  * on `stream`; the caller synchronises the stream before reading `out`.  Results are double-buffered on
  * the device: the call reads the buffer of the most recently ENQUEUED psi_run, and the next psi_run writes

@@ -73,6 +73,7 @@ SYMBOLS = {
     "psi_query_next_landing": (_int, [_vp, _u32p]),
     "psi_query_uploaded": (_int, [_vp, _u32]),
     "psi_run": (_int, [_vp, _vp]),
+    "psi_query_run_streamed": (_int, [_vp, _u64p, _u64p, _u64p, _vp]),
     "psi_run_phases": (_int, [_vp, _u32, _vp]),
     "psi_result_get": (_int, [_vp, _u64p, _vp]),
     "psi_stream_sync": (_int, [_vp]),

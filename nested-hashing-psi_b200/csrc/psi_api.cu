@@ -68,6 +68,7 @@ static uint32_t h_bitrev(uint32_t x, int bits) {
 }
 
 constexpr size_t kDbChunk = 256;  // plaintexts staged per re-tiling / encode step
+constexpr uint32_t kMaxStreamSlices = 32;  // upload slices of psi_query_run_streamed
 
 template <typename T>
 struct DevBuf {
@@ -140,6 +141,9 @@ struct psi_ctx {
     uint32_t p2_groups = 0;
     cudaStream_t aux[3] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {};
+    // psi_query_run_streamed: copy-in / copy-out streams and the events that order slices and bin groups
+    cudaStream_t sq_in = nullptr, sq_out = nullptr;
+    cudaEvent_t ev_slice[kMaxStreamSlices] = {}, ev_group[4] = {}, ev_sq = nullptr;
 
     KCtx k(cudaStream_t s) const { return KCtx{d_tab, N, logN, L, Lp, s}; }
 };
@@ -467,6 +471,13 @@ int psi_ctx_destroy(psi_ctx* c) {
     c->to_crt.release();
     for (auto& st : c->aux)
         if (st) cudaStreamDestroy(st);
+    if (c->sq_in) cudaStreamDestroy(c->sq_in);
+    if (c->sq_out) cudaStreamDestroy(c->sq_out);
+    for (auto& e : c->ev_slice)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_group)
+        if (e) cudaEventDestroy(e);
+    if (c->ev_sq) cudaEventDestroy(c->ev_sq);
     for (auto& e : c->ev_join)
         if (e) cudaEventDestroy(e);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -972,6 +983,51 @@ int psi_query_commit(psi_ctx* c, void* stream) {
 
 int psi_run(psi_ctx* c, void* stream) { return psi_run_phases(c, PSI_PHASE_ALL, stream); }
 
+// The ct x ct chain + mask of bins [g0, g1) into result (the context's [b][2][L][N] buffer), split into G bin
+// groups on concurrent streams forked from / joined into s.  The bins are independent, so one group's kernels fill
+// the SMs another group's tails leave idle (measured: 2 groups -3 % at 47 bins, -13 % at 12).
+static int phase2_bins(psi_ctx* c, cudaStream_t s, uint32_t g0, uint32_t g1, uint32_t G, u64* result, uint32_t* nl) {
+    const size_t ct = (size_t)2 * c->L * c->N;
+    const uint32_t nb = g1 - g0;
+    if (G > nb) G = nb;
+    if (G > 4) G = 4;
+    if (G < 1) G = 1;
+    if (G > 1) {
+        if (!c->ev_fork) {
+            cudaError_t e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+            for (int i = 0; i < 3 && e == cudaSuccess; i++) {
+                e = cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking);
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
+            }
+            if (e != cudaSuccess) return cuda_fail(e, "bin-group streams");
+        }
+        CK(cudaEventRecord(c->ev_fork, s));
+    }
+    for (uint32_t g = 0; g < G; g++) {
+        const uint32_t b0 = g0 + (uint32_t)((uint64_t)nb * g / G), b1 = g0 + (uint32_t)((uint64_t)nb * (g + 1) / G);
+        cudaStream_t sg = g == 0 ? s : c->aux[g - 1];
+        if (g > 0) CK(cudaStreamWaitEvent(sg, c->ev_fork, 0));
+        const u64* prod = c->acc.p + (size_t)b0 * ct;  // hf = 0
+        for (uint32_t hf = 1; hf < c->K; hf++) {
+            const bool last = hf + 1 == c->K;
+            u64* dst = (last ? result : c->prod.p) + (size_t)b0 * ct;
+            int rc = mul_ctct_batch(c, sg, b1 - b0, prod, c->acc.p + ((size_t)hf * c->b + b0) * ct,
+                                    last ? c->mask.p + (size_t)b0 * c->L * c->N : nullptr, dst, nl, b0);
+            if (rc) return rc;
+            prod = dst;
+        }
+        if (g > 0) {
+            CK(cudaEventRecord(c->ev_join[g - 1], sg));
+            CK(cudaStreamWaitEvent(s, c->ev_join[g - 1], 0));
+        }
+    }
+    return PSI_OK;
+}
+
+static uint32_t default_groups(const psi_ctx* c, uint32_t nbins) {
+    return c->p2_groups ? c->p2_groups : (nbins >= 4 ? 2u : 1u);
+}
+
 int psi_run_phases(psi_ctx* c, uint32_t phases, void* stream) {
     if (!c) return set_error(PSI_ERR_INVALID, "null argument");
     if (!(phases & PSI_PHASE_ALL)) return set_error(PSI_ERR_INVALID, "no phase selected");
@@ -981,7 +1037,6 @@ int psi_run_phases(psi_ctx* c, uint32_t phases, void* stream) {
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const KCtx k = c->k(s);
-    const size_t ct = (size_t)2 * c->L * c->N;
     uint32_t nl = 0;
     if (phases & PSI_PHASE_INNER_PRODUCT) {
         CK(launch_mac(k, c->K, c->b, c->E, c->pt.p, c->idx.p, c->minus.p, c->acc.p)); nl++;
@@ -1001,47 +1056,101 @@ int psi_run_phases(psi_ctx* c, uint32_t phases, void* stream) {
             return cuda_fail(e1, "launch_mul_ctpt");
         }
         nl++;
-    } else {
-        // Bin groups: the bins are independent, so the multiplication chain of one group can run next to another
-        // group's; with few resident bins (a shard of a multi-GPU query) every kernel is less than one wave and a
-        // second group fills the SMs the first leaves idle at its tails.
-        uint32_t G = c->p2_groups ? c->p2_groups : (c->b >= 4 ? 2u : 1u);  // measured: 2 groups -3 % .. -13 % for b = 5 .. 75
-        if (G > c->b) G = c->b;
-        if (G > 4) G = 4;
-        if (G > 1) {
-            rc = PSI_OK;
-            if (!c->ev_fork) {
-                cudaError_t e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
-                for (int i = 0; i < 3 && e == cudaSuccess; i++) {
-                    e = cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking);
-                    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
-                }
-                if (e != cudaSuccess) return cuda_fail(e, "bin-group streams");
-            }
-            CK(cudaEventRecord(c->ev_fork, s));
-        }
-        for (uint32_t g = 0; g < G; g++) {
-            const uint32_t g0 = (uint32_t)((uint64_t)c->b * g / G), g1 = (uint32_t)((uint64_t)c->b * (g + 1) / G), Bg = g1 - g0;
-            cudaStream_t sg = g == 0 ? s : c->aux[g - 1];
-            if (g > 0) CK(cudaStreamWaitEvent(sg, c->ev_fork, 0));
-            const u64* prod = c->acc.p + (size_t)g0 * ct;  // hf = 0
-            for (uint32_t hf = 1; hf < c->K; hf++) {
-                const bool last = hf + 1 == c->K;
-                u64* dst = (last ? result : c->prod.p) + (size_t)g0 * ct;
-                if ((rc = mul_ctct_batch(c, sg, Bg, prod, c->acc.p + ((size_t)hf * c->b + g0) * ct,
-                                         last ? c->mask.p + (size_t)g0 * c->L * c->N : nullptr, dst, g == 0 ? &nl : nullptr, g0))) {
-                    c->ran = false;
-                    return rc;
-                }
-                prod = dst;
-            }
-            if (g > 0) {
-                CK(cudaEventRecord(c->ev_join[g - 1], sg));
-                CK(cudaStreamWaitEvent(s, c->ev_join[g - 1], 0));
-            }
-        }
-        if (G > 1) nl = 1 + (nl - 1) * G;  // every group launches the same kernels
+    } else if ((rc = phase2_bins(c, s, 0, c->b, default_groups(c, c->b), result, &nl))) {
+        c->ran = false;
+        return rc;
     }
+    c->out_cur = next_out;
+    c->launches_per_run = nl;
+    c->ran = true;
+    return PSI_OK;
+}
+
+// One query, host memory to host memory, with the transfers overlapped INSIDE the query: what the reference's server
+// does once per session (BatchedFHEPSIServer.cpp:99-108: setMinusCompareElement, setIndex, run, getResultList).
+//   upload     the K*E index ciphertexts cross PCIe in slices (hash function, position range); as soon as a slice
+//              has landed it is re-tiled and its part of the inner products is accumulated (launch_mac_range), so
+//              when the last slice arrives only that slice's share of phase 1 is still to do;
+//   download   the ct x ct chain runs over the bins in kStreamOutGroups groups; the result ciphertexts of a group
+//              go back to the host while the next group is evaluated.
+// idx, minus, out: host buffers (pinned for full speed) laid out as for psi_query_set / psi_result_get.  Everything
+// is enqueued; the caller synchronises `stream` (the last download is ordered into it) before reading out.
+// download groups shrink towards the end: only the LAST group's download is exposed, and a bin downloads faster
+// (18.7 us at 56 GB/s) than it evaluates (22 us), so the copy engine keeps up with the earlier, larger groups
+constexpr uint32_t kStreamSlicesPerHf = 4, kStreamOutGroups = 4;
+static const double kStreamOutCut[kStreamOutGroups + 1] = {0.0, 0.38, 0.72, 0.91, 1.0};
+int psi_query_run_streamed(psi_ctx* c, const uint64_t* idx, const uint64_t* minus, uint64_t* out, void* stream) {
+    if (!c || !idx || !minus || !out) return set_error(PSI_ERR_INVALID, "null argument");
+    if (!c->have_db) return set_error(PSI_ERR_STATE, "run() needs a database");
+    if (c->K > 1 && !c->have_evk) return set_error(PSI_ERR_STATE, "EvalMult(ct,ct) needs the relinearisation key");
+    if (c->n_uploaded != c->n_committed) return set_error(PSI_ERR_STATE, "an uploaded query is waiting for psi_query_commit");
+    int rc = ensure_device(c);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c->sq_in) {
+        CK(cudaStreamCreateWithFlags(&c->sq_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->sq_out, cudaStreamNonBlocking));
+        for (auto& e : c->ev_slice) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : c->ev_group) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_sq, cudaEventDisableTiming));
+    }
+    const KCtx k = c->k(s);
+    const size_t N = c->N, LN = (size_t)c->L * N, ct = 2 * LN;
+    const uint32_t K = c->K, E = c->E, w = c->n_uploaded & 1u;
+    u64* const land = c->idx_in.p + w * c->idx_words();
+    u64* const land_minus = c->minus_in.p + w * 2 * LN;
+    uint32_t nl = 0;
+    // the copy stream starts where the caller's stream is (previous evaluation, previous use of the landing buffer)
+    CK(cudaEventRecord(c->ev_sq, s));
+    CK(cudaStreamWaitEvent(c->sq_in, c->ev_sq, 0));
+    CK(cudaStreamWaitEvent(c->sq_out, c->ev_sq, 0));
+    CK(cudaMemcpyAsync(land_minus, minus, ct * sizeof(u64), cudaMemcpyHostToDevice, c->sq_in));
+    uint32_t n_slices = 0;
+    for (uint32_t hf = 0; hf < K; hf++) {
+        const uint32_t S = E < kStreamSlicesPerHf ? E : kStreamSlicesPerHf;
+        for (uint32_t sl = 0; sl < S; sl++, n_slices++) {
+            if (n_slices >= kMaxStreamSlices) return set_error(PSI_ERR_INVALID, "too many hash functions for the streamed path");
+            const uint32_t p0 = (uint32_t)((uint64_t)E * sl / S), p1 = (uint32_t)((uint64_t)E * (sl + 1) / S);
+            const size_t off = ((size_t)hf * E + p0) * ct;
+            CK(cudaMemcpyAsync(land + off, idx + off, (size_t)(p1 - p0) * ct * sizeof(u64), cudaMemcpyHostToDevice, c->sq_in));
+            CK(cudaEventRecord(c->ev_slice[n_slices], c->sq_in));
+            CK(cudaStreamWaitEvent(s, c->ev_slice[n_slices], 0));
+            if (hf == 0 && sl == 0) CK(cudaMemcpyAsync(c->minus.p, land_minus, ct * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+            CK(launch_retile_idx_range(k, land, c->idx.p, LN, E, hf, p0, p1)); nl++;
+            CK(launch_mac_range(k, hf, 1, c->b, E, p0, p1, (p0 > 0 ? 1u : 0u) | (p1 == E ? 2u : 0u), c->pt.p, c->idx.p, c->minus.p,
+                                c->acc.p)); nl++;
+        }
+    }
+    c->n_uploaded++;
+    c->n_committed++;
+    c->have_query = true;
+    const uint32_t next_out = c->out_cur ^ 1u;
+    u64* const result = c->out_buf(next_out);
+    uint32_t cuts[kStreamOutGroups + 1];
+    for (uint32_t g = 0; g <= kStreamOutGroups; g++) cuts[g] = (uint32_t)(kStreamOutCut[g] * c->b + 0.5);
+    cuts[kStreamOutGroups] = c->b;
+    for (uint32_t g = 0; g < kStreamOutGroups; g++) {
+        const uint32_t g0 = cuts[g], g1 = cuts[g + 1];
+        if (g1 <= g0) continue;
+        if (K == 1) {
+            cudaError_t e1 = launch_mul_ctpt(k, g1 - g0, c->acc.p + (size_t)g0 * ct, c->mask.p + (size_t)g0 * LN, result + (size_t)g0 * ct);
+            if (e1 != cudaSuccess) {
+                c->ran = false;
+                return cuda_fail(e1, "launch_mul_ctpt");
+            }
+            nl++;
+        } else if ((rc = phase2_bins(c, s, g0, g1, default_groups(c, g1 - g0), result, &nl))) {
+            c->ran = false;
+            return rc;
+        }
+        CK(cudaEventRecord(c->ev_group[g], s));
+        CK(cudaStreamWaitEvent(c->sq_out, c->ev_group[g], 0));
+        CK(cudaMemcpyAsync(out + (size_t)g0 * ct, result + (size_t)g0 * ct, (size_t)(g1 - g0) * ct * sizeof(u64), cudaMemcpyDeviceToHost,
+                           c->sq_out));
+    }
+    // join: the caller's stream is done when the last download is
+    CK(cudaEventRecord(c->ev_sq, c->sq_out));
+    CK(cudaStreamWaitEvent(s, c->ev_sq, 0));
     c->out_cur = next_out;
     c->launches_per_run = nl;
     c->ran = true;

@@ -310,6 +310,26 @@ __global__ void __launch_bounds__(256) k_retile_idx(const DevTables* __restrict_
     const ModDev& md = tab->mods[cidx / N];
     tiled[(((hf * T + tile) * E + pos) * 2 + comp) * kMacCoeffs + w] = to_split30(mul_shoup(flat[i], md.Rmodq, md.Rmodq_s, md.q));
 }
+// positions [pos0, pos1) of hash function hf only (the streamed single-query path re-tiles slices as they land)
+__global__ void __launch_bounds__(256) k_retile_idx_range(const DevTables* __restrict__ tab, uint32_t N, const u64* __restrict__ flat,
+                                                          u64* __restrict__ tiled, size_t LN, uint32_t E, uint32_t hf,
+                                                          uint32_t pos0, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t cidx = i % LN, r = i / LN;  // r = (pos - pos0) * 2 + comp
+    const size_t comp = r & 1, pos = pos0 + (r >> 1);
+    const size_t T = LN / kMacCoeffs, tile = cidx / kMacCoeffs, w = cidx % kMacCoeffs;
+    const ModDev& md = tab->mods[cidx / N];
+    const u64 v = flat[(((size_t)hf * E + pos) * 2 + comp) * LN + cidx];
+    tiled[((((size_t)hf * T + tile) * E + pos) * 2 + comp) * kMacCoeffs + w] = to_split30(mul_shoup(v, md.Rmodq, md.Rmodq_s, md.q));
+}
+cudaError_t launch_retile_idx_range(const KCtx& k, const u64* flat, u64* tiled, size_t LN, uint32_t E, uint32_t hf, uint32_t pos0,
+                                    uint32_t pos1) {
+    const size_t total = (size_t)(pos1 - pos0) * 2 * LN;
+    if (total == 0) return cudaSuccess;
+    k_retile_idx_range<<<cdiv(total, 256), 256, 0, k.s>>>(k.tab, k.N, flat, tiled, LN, E, hf, pos0, total);
+    return cudaGetLastError();
+}
 cudaError_t launch_retile_idx(const KCtx& k, const u64* flat, u64* tiled, size_t LN, uint32_t K, uint32_t E) {
     const size_t total = (size_t)K * E * 2 * LN;
     if (total == 0) return cudaSuccess;

@@ -70,6 +70,8 @@ cudaError_t launch_ntt(const KCtx& k, const NttBatch& b, bool inverse);
 cudaError_t launch_retile_pt(cudaStream_t s, u64* flat, u64* tiled, size_t LN, uint32_t E, size_t p0, size_t n,
                              bool to_tiled, const DevTables* range_tab = nullptr, int* bad = nullptr);
 cudaError_t launch_retile_idx(const KCtx& k, const u64* flat, u64* tiled, size_t LN, uint32_t K, uint32_t E);
+cudaError_t launch_retile_idx_range(const KCtx& k, const u64* flat, u64* tiled, size_t LN, uint32_t E, uint32_t hf, uint32_t pos0,
+                                    uint32_t pos1);
 cudaError_t launch_mac(const KCtx& k, uint32_t K, uint32_t b, uint32_t E, const u64* pt, const u64* idx,
                        const u64* minus, u64* acc);
 // A slice of the same inner products: hash functions [hf0, hf0 + nhf), positions [pos0, pos1); flags bit 0 = add the

@@ -246,6 +246,20 @@ class CryptoContext:
         """Declares landing buffer `which` filled by the caller (sharding.QueryDistributor); query_commit follows."""
         check(lib().psi_query_uploaded(self._h, which))
 
+    def query_run_streamed_ptr(self, idx_ptr, minus_ptr, out_ptr, stream=None):
+        """One query host -> host with upload slices / evaluation / download groups overlapped (raw addresses)."""
+        p = ctypes.POINTER(ctypes.c_uint64)
+        check(lib().psi_query_run_streamed(self._h, ctypes.cast(idx_ptr, p), ctypes.cast(minus_ptr, p), ctypes.cast(out_ptr, p), stream))
+
+    def query_run_streamed(self, idx, minus, stream=None):
+        (idx, pi), (minus, pm) = _u64(idx), _u64(minus)
+        K, b, E = self._dims
+        assert idx.shape == (K, E, 2, self.L, self.N) and minus.shape == (2, self.L, self.N)
+        out = np.empty((b, 2, self.L, self.N), dtype=np.uint64)
+        check(lib().psi_query_run_streamed(self._h, pi, pm, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), stream))
+        check(lib().psi_stream_sync(stream))
+        return out
+
     def run(self, stream=None, phases=3):
         """psi_run / psi_run_phases: 1 = inner products only, 2 = ct x ct + mask only, 3 = all."""
         check(lib().psi_run_phases(self._h, phases, stream))

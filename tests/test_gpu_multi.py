@@ -60,7 +60,8 @@ def test_multi_run_matches_oracle(small, devices):
     mc.run()
     got = mc.result_get()
     assert np.array_equal(got, s["want"])
-    assert mc.run_launch_count() == 6 * len(devices)
+    # 1 inner-product launch + 5 fused ct x ct kernels per bin group (two concurrent groups from 4 resident bins on)
+    assert mc.run_launch_count() == sum(1 + 5 * (2 if r1 - r0 >= 4 else 1) for r0, r1 in ranges)
 
 
 @pytest.mark.parametrize("devices", device_lists()[:3] + device_lists()[3:4], ids=lambda d: "dev" + "".join(map(str, d)))
@@ -122,6 +123,31 @@ def test_single_context_limb_vector_ingestion(small):
         cc.run()
         vecs = cc.result_get_limbs()
         assert np.array_equal(np.stack(vecs).reshape(want.shape), want)
+
+
+def test_streamed_single_query_matches_run(small):
+    """psi_query_run_streamed (upload slices -> partial inner products -> bin groups -> downloads, all overlapped inside
+    ONE query) returns the limbs psi_query_set + psi_run + psi_result_get return; also K = 1, K = 3, ragged E and b."""
+    s = small
+    cc = P.CryptoContext(s["params"])
+    cc.InsertEvalMultKey(s["evk_b"], s["evk_a"])
+    cc.db_load_limbs(s["pt"], s["mask"])
+    for rep in range(2):
+        assert np.array_equal(cc.query_run_streamed(s["idx"], s["minus"]), s["want"])
+        assert np.array_equal(cc.query_run_streamed(s["idx2"], s["minus2"]), s["want2"])
+    # interleaved with the two-step path (landing buffers and result buffers alternate in both)
+    cc.query_set(s["idx"], s["minus"])
+    cc.run()
+    assert np.array_equal(cc.result_get(), s["want"])
+    assert np.array_equal(cc.query_run_streamed(s["idx2"], s["minus2"]), s["want2"])
+    rng = np.random.default_rng(77)
+    o, params = s["o"], s["params"]
+    for K, b, E in ((1, 3, 2), (3, 2, 9), (2, 1, 1), (2, 7, 13)):
+        pt, mask = sc.random_pt(rng, params, (K, b, E)), sc.random_pt(rng, params, (b,))
+        idx, minus = sc.random_ct(rng, params, (K, E)), sc.random_ct(rng, params)
+        cc.db_load_limbs(pt, mask)
+        want = o.run(pt, mask, idx, minus, s["evk_b"], s["evk_a"])
+        assert np.array_equal(cc.query_run_streamed(idx, minus), want), (K, b, E)
 
 
 def test_sharded_db_calls_match_unsharded(small):
