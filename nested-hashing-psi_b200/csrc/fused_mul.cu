@@ -5,10 +5,11 @@
 namespace psi {
 
 // ---- (1) rows, inverse: both operands, all 4L limb-polys of a bin --------------------------------
-// grid (R/8, L, B), 4 groups: a.c0, a.c1, b.c0, b.c1 of limb blockIdx.y
+// grid (R/8, L, B), 4 groups: a.c0, a.c1, b.c0, b.c1 of limb blockIdx.y.  ops: bit 0 = operand a, bit 1 = operand b
+// (the streamed single-query path prepares operand a while the index ciphertexts of operand b are still uploading)
 __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_inv(const DevTables* __restrict__ tab, uint32_t logN,
                                                             const u64* __restrict__ a, const u64* __restrict__ b,
-                                                            u64* __restrict__ ha, u64* __restrict__ hb) {
+                                                            u64* __restrict__ ha, u64* __restrict__ hb, uint32_t ops) {
     extern __shared__ __align__(16) u64 smem[];
     const uint32_t N = 1u << logN, L = tab->L;
     const uint32_t m = kLogCols + kRowTileLog, M = 1u << m, P = padded(M);
@@ -25,11 +26,13 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_inv(const DevTables* __r
         mbar_expect_tx(&tw_bar, kRowTwEntries * 16u);
         stage_row_twiddles(tws, tab->mods[l].itw_rows, blockIdx.x, &tw_bar);
     }
-    load_rows(arr + g * P, (g < 2 ? a : b) + off, tid);
+    const bool active = (ops >> (g >> 1)) & 1u;
+    if (active) load_rows(arr + g * P, (g < 2 ? a : b) + off, tid);
     __syncthreads();
     mbar_wait(&tw_bar, 0);
-    transform_rows<true>(tab, arr, P, 4, [l](uint32_t) { return l; }, g, 4, logN, tile_base, tid, tws);
-    store_rows(arr + g * P, (g < 2 ? ha : hb) + off, tid);
+    // an inactive group owns no array (group index 4 = none) and takes part in no group barrier
+    transform_rows<true>(tab, arr, P, 4, [l](uint32_t) { return l; }, active ? g : 4, 4, logN, tile_base, tid, tws);
+    if (active) store_rows(arr + g * P, (g < 2 ? ha : hb) + off, tid);
 }
 
 // ---- (3) rows: forward, tensor, inverse -----------------------------------------------------------
@@ -193,12 +196,12 @@ static cudaError_t dispatch_cols(PSI_COLS_ARGS) {
 cudaError_t fused_mul_init_device(const KCtx& k) {
     if (!fused_mul_supported(k)) return cudaSuccess;
     return launch_fused_mul(k, 0xffffffffu, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                            nullptr, nullptr, nullptr, nullptr);
+                            nullptr, nullptr, nullptr, nullptr, 3);
 }
 
 cudaError_t launch_fused_mul(const KCtx& k, uint32_t B, const u64* a, const u64* b, u64* ha, u64* hb, u64* e1p,
                              u64* e2h, u64* th, u64* rh, u64* dh, const u64* evk_b, const u64* evk_a, const u64* mask,
-                             u64* out) {
+                             u64* out, uint32_t ops) {
     const uint32_t L = k.L, LT = k.L + k.Lp;
     const uint32_t logR = k.logN - kLogCols;
     const uint32_t row_tiles = (1u << logR) >> kRowTileLog;
@@ -219,10 +222,12 @@ cudaError_t launch_fused_mul(const KCtx& k, uint32_t B, const u64* a, const u64*
     }
     if (B == 0) return cudaSuccess;
 
-    k_rows_inv<<<dim3(row_tiles, L, B), 4 * kGroup, 4 * row_arr + tw_bytes, k.s>>>(k.tab, k.logN, a, b, ha, hb);
-    if ((e = dispatch_cols(k, B, ha, hb, e1p, e2h, nullptr, nullptr, nullptr, 0)) != cudaSuccess) return e;
+    // ops: bit 0 = the part that only needs operand a (row-inverse + exact Q -> P extension of a), bit 1 = everything else
+    k_rows_inv<<<dim3(row_tiles, L, B), 4 * kGroup, 4 * row_arr + tw_bytes, k.s>>>(k.tab, k.logN, a, b, ha, hb, ops);
+    if ((e = dispatch_cols(k, B, ha, hb, e1p, e2h, nullptr, nullptr, nullptr, (int)ops - 1)) != cudaSuccess) return e;
+    if (!(ops & 2u)) return cudaGetLastError();
     k_rows_tensor<<<dim3(row_tiles, LT, B), 4 * kGroup, 4 * row_arr + 2 * tw_bytes, k.s>>>(k.tab, k.logN, a, e1p, e2h, th);
-    if ((e = dispatch_cols(k, B, nullptr, nullptr, nullptr, nullptr, th, rh, dh, 1)) != cudaSuccess) return e;
+    if ((e = dispatch_cols(k, B, nullptr, nullptr, nullptr, nullptr, th, rh, dh, 3)) != cudaSuccess) return e;
     const dim3 rg(row_tiles, L, B);
     const size_t rs = (2 + L) * row_arr + tw_bytes;
     switch (L) {

@@ -379,7 +379,7 @@ __device__ __forceinline__ void store_cols(const u64* sm, u64* __restrict__ poly
 template <int L, int LP, int LOGN_CT>
 __global__ void __launch_bounds__(kColGroups* kGroup, 3)
     k_cols_extend(const DevTables* __restrict__ tab, uint32_t logN, const u64* __restrict__ ha, const u64* __restrict__ hb,
-                  u64* __restrict__ e1p, u64* __restrict__ e2h) {
+                  u64* __restrict__ e1p, u64* __restrict__ e2h, uint32_t z0) {
     extern __shared__ __align__(16) u64 smem[];
     constexpr int LT = L + LP;
     const uint32_t N = 1u << logN;
@@ -388,7 +388,8 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 3)
     const uint32_t c0 = blockIdx.x << kColTileLog;
     // longest work first: the CTAs of operand 1 (L + Lp output limbs) are launched before those of operand 0 (Lp),
     // so that the tail of the grid is made of the short ones
-    const uint32_t operand = 1u - (blockIdx.z >> 1), comp = blockIdx.z & 1;
+    // z0: first (operand, comp) slot of this launch (0: both operands or operand 1 only, 2: operand 0 only)
+    const uint32_t zz = blockIdx.z + z0, operand = 1u - (zz >> 1), comp = zz & 1;
     const size_t bin = blockIdx.y;
 
     // column-inverse of the L input limbs
@@ -570,8 +571,13 @@ cudaError_t launch_cols(const KCtx& k, uint32_t B, const u64* ha, const u64* hb,
         if ((e = cudaFuncSetAttribute(k_cols_extend<L, LP, LOGN_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
         return cudaFuncSetAttribute(k_cols_scale<L, LP, LOGN_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     }
-    if (which == 0)
-        k_cols_extend<L, LP, LOGN_CT><<<dim3(col_tiles, B, 4), kColGroups * kGroup, smem, k.s>>>(k.tab, k.logN, ha, hb, e1p, e2h);
+    // which: 0 = extend operand a only, 1 = extend operand b only, 2 = extend both, 3 = scale
+    if (which == 2)
+        k_cols_extend<L, LP, LOGN_CT><<<dim3(col_tiles, B, 4), kColGroups * kGroup, smem, k.s>>>(k.tab, k.logN, ha, hb, e1p, e2h, 0);
+    else if (which == 1)
+        k_cols_extend<L, LP, LOGN_CT><<<dim3(col_tiles, B, 2), kColGroups * kGroup, smem, k.s>>>(k.tab, k.logN, ha, hb, e1p, e2h, 0);
+    else if (which == 0)
+        k_cols_extend<L, LP, LOGN_CT><<<dim3(col_tiles, B, 2), kColGroups * kGroup, smem, k.s>>>(k.tab, k.logN, ha, hb, e1p, e2h, 2);
     else
         k_cols_scale<L, LP, LOGN_CT><<<dim3(col_tiles, B, 3), kColGroups * kGroup, smem, k.s>>>(k.tab, k.logN, th, rh, dh);
     return cudaGetLastError();

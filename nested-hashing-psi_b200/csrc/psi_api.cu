@@ -352,15 +352,21 @@ static int alloc_work(psi_ctx* c) {
 // BatchedFHEHIPPIE.cpp:123 matters); out: [B][2][L][N].
 // bin0: first bin of the batch inside the context's work buffers — bin groups evaluated concurrently on several
 // streams (psi_run_phases) work in disjoint slices of the scratch arrays.
+// ops (fused kernels only): 3 = everything, 1 = the part that needs operand a alone, 2 = the rest (see launch_fused_mul).
 static int mul_ctct_batch(psi_ctx* c, cudaStream_t s, uint32_t B, const u64* a, const u64* bb, const u64* mask,
-                          u64* out, uint32_t* launches, uint32_t bin0 = 0) {
+                          u64* out, uint32_t* launches, uint32_t bin0 = 0, uint32_t ops = 3) {
     const KCtx k = c->k(s);
     const uint32_t L = c->L, Lp = c->Lp, LT = L + Lp;
     const size_t N = c->N;
     uint32_t nl = 0;
     // per-bin sizes of the scratch arrays (alloc_work)
-    u64* const w_coef = c->coef.p + (size_t)bin0 * 4 * L * N;
-    u64* const w_e1 = c->e1.p + (size_t)bin0 * 2 * LT * N;
+    // row-inverse halves of the two operands: two regions of b bins each, so that a bin's slice does not depend on
+    // how the bins are grouped
+    u64* const w_coef = c->coef.p + (size_t)bin0 * 2 * L * N;
+    u64* const w_coef2 = c->coef.p + ((size_t)c->b + bin0) * 2 * L * N;
+    // the fused kernels keep only the P limbs of the extended first operand ([bin][2][Lp][N]); a bin's slice must not
+    // depend on the grouping either (ops = 1 prepares all bins at once, ops = 2 runs per group)
+    u64* const w_e1 = c->e1.p + (size_t)bin0 * 2 * (fused_mul_supported(c->k(s)) ? Lp : LT) * N;
     u64* const w_e2 = c->e2.p + (size_t)bin0 * 2 * LT * N;
     u64* const w_ten = c->ten.p + (size_t)bin0 * 3 * LT * N;
     u64* const w_res = c->res.p + (size_t)bin0 * 3 * L * N;
@@ -368,13 +374,14 @@ static int mul_ctct_batch(psi_ctx* c, cudaStream_t s, uint32_t B, const u64* a, 
     if (fused_mul_supported(k)) {
         // the fused relinearisation takes the key and the masks in Montgomery form
         const u64* maskR = mask ? c->maskR.p + (mask - c->mask.p) : nullptr;
-        CK(launch_fused_mul(k, B, a, bb, w_coef, w_coef + (size_t)B * 2 * L * N, w_e1, w_e2, w_ten,
-                            w_res, w_dig, c->evk_bR.p, c->evk_aR.p, maskR, out));
-        if (launches) *launches += 5;
+        CK(launch_fused_mul(k, B, a, bb, w_coef, w_coef2, w_e1, w_e2, w_ten, w_res, w_dig, c->evk_bR.p, c->evk_aR.p, maskR, out,
+                            ops));
+        if (launches) *launches += ops == 1 ? 2 : 5;
         return PSI_OK;
     }
-    u64* coef1 = w_coef;                         // [B*2][L][N]
-    u64* coef2 = w_coef + (size_t)B * 2 * L * N;  // [B*2][L][N]
+    if (ops == 1) return PSI_OK;  // the unfused path has no split: everything happens in the ops = 2 call
+    u64* coef1 = w_coef;   // [B*2][L][N]
+    u64* coef2 = w_coef2;  // [B*2][L][N]
     // (1) both operands to COEFFICIENT
     NttBatch nb{a, coef1, B * 2 * L, L, L * N, N, L * N, 0, L};
     CK(launch_ntt(k, nb, true)); nl++;
@@ -986,7 +993,8 @@ int psi_run(psi_ctx* c, void* stream) { return psi_run_phases(c, PSI_PHASE_ALL, 
 // The ct x ct chain + mask of bins [g0, g1) into result (the context's [b][2][L][N] buffer), split into G bin
 // groups on concurrent streams forked from / joined into s.  The bins are independent, so one group's kernels fill
 // the SMs another group's tails leave idle (measured: 2 groups -3 % at 47 bins, -13 % at 12).
-static int phase2_bins(psi_ctx* c, cudaStream_t s, uint32_t g0, uint32_t g1, uint32_t G, u64* result, uint32_t* nl) {
+static int phase2_bins(psi_ctx* c, cudaStream_t s, uint32_t g0, uint32_t g1, uint32_t G, u64* result, uint32_t* nl,
+                       uint32_t first_ops = 3) {
     const size_t ct = (size_t)2 * c->L * c->N;
     const uint32_t nb = g1 - g0;
     if (G > nb) G = nb;
@@ -1012,7 +1020,7 @@ static int phase2_bins(psi_ctx* c, cudaStream_t s, uint32_t g0, uint32_t g1, uin
             const bool last = hf + 1 == c->K;
             u64* dst = (last ? result : c->prod.p) + (size_t)b0 * ct;
             int rc = mul_ctct_batch(c, sg, b1 - b0, prod, c->acc.p + ((size_t)hf * c->b + b0) * ct,
-                                    last ? c->mask.p + (size_t)b0 * c->L * c->N : nullptr, dst, nl, b0);
+                                    last ? c->mask.p + (size_t)b0 * c->L * c->N : nullptr, dst, nl, b0, hf == 1 ? first_ops : 3);
             if (rc) return rc;
             prod = dst;
         }
@@ -1097,6 +1105,7 @@ int psi_query_run_streamed(psi_ctx* c, const uint64_t* idx, const uint64_t* minu
     const KCtx k = c->k(s);
     const size_t N = c->N, LN = (size_t)c->L * N, ct = 2 * LN;
     const uint32_t K = c->K, E = c->E, w = c->n_uploaded & 1u;
+    const bool split_a = fused_mul_supported(k);
     u64* const land = c->idx_in.p + w * c->idx_words();
     u64* const land_minus = c->minus_in.p + w * 2 * LN;
     uint32_t nl = 0;
@@ -1120,6 +1129,10 @@ int psi_query_run_streamed(psi_ctx* c, const uint64_t* idx, const uint64_t* minu
             CK(launch_mac_range(k, hf, 1, c->b, E, p0, p1, (p0 > 0 ? 1u : 0u) | (p1 == E ? 2u : 0u), c->pt.p, c->idx.p, c->minus.p,
                                 c->acc.p)); nl++;
         }
+        // the first operand of the first multiplication (the inner products of hash function 0) is complete while the
+        // ciphertexts of hash function 1 are still crossing PCIe: its row-inverse and exact basis extension run now
+        if (hf == 0 && K > 1 && split_a)
+            if ((rc = mul_ctct_batch(c, s, c->b, c->acc.p, c->acc.p + (size_t)c->b * ct, nullptr, nullptr, &nl, 0, 1))) return rc;
     }
     c->n_uploaded++;
     c->n_committed++;
@@ -1139,7 +1152,7 @@ int psi_query_run_streamed(psi_ctx* c, const uint64_t* idx, const uint64_t* minu
                 return cuda_fail(e1, "launch_mul_ctpt");
             }
             nl++;
-        } else if ((rc = phase2_bins(c, s, g0, g1, default_groups(c, g1 - g0), result, &nl))) {
+        } else if ((rc = phase2_bins(c, s, g0, g1, default_groups(c, g1 - g0), result, &nl, split_a ? 2 : 3))) {
             c->ran = false;
             return rc;
         }

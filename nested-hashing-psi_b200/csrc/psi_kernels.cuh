@@ -97,9 +97,11 @@ cudaError_t ntt_init_device();
 cudaError_t mac_init_device();
 // dst[g][l][n] = src[g][l][n] * 2^64 mod q_l  (groups of L limb-polys): Montgomery form of constants
 cudaError_t launch_to_montgomery(const KCtx& k, uint32_t groups, const u64* src, u64* dst);
+// ops: 3 = the whole multiplication; 1 = only the part that needs operand a alone (row-inverse + exact Q -> P
+// extension of a: scratch ha, e1p); 2 = the rest, after an ops = 1 launch on the same scratch
 cudaError_t launch_fused_mul(const KCtx& k, uint32_t B, const u64* a, const u64* b, u64* ha, u64* hb, u64* e1p,
                              u64* e2h, u64* th, u64* rh, u64* dh, const u64* evk_b, const u64* evk_a, const u64* mask,
-                             u64* out);
+                             u64* out, uint32_t ops = 3);
 cudaError_t launch_mul_ctpt(const KCtx& k, uint32_t B, const u64* ct, const u64* pt, u64* out);
 
 // Packed encoding, centred lift: crt [n][N] in [0, t) -> out [n][L][N]
