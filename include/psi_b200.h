@@ -49,9 +49,15 @@ enum psi_status {
     PSI_ERR_STATE = 4      /* call order violated (e.g. run before query_set) */
 };
 
-/* OpenFHE MultiplicationTechnique / KeySwitchTechnique of the BFV context. */
+/* OpenFHE MultiplicationTechnique / KeySwitchTechnique of the BFV context.  HPSPOVERQ + BV (digit size 0) are the
+ * BFVrns defaults of the 1.0.x line as recalled and run through the fused kernels; HPS and HYBRID are the other
+ * variants a context may carry (risk register) and run through the unfused kernels. */
 enum { PSI_MULT_HPS = 0, PSI_MULT_HPSPOVERQ = 1 };
-enum { PSI_KS_BV = 0 };
+enum { PSI_KS_BV = 0, PSI_KS_HYBRID = 1 };
+/* How the host library's compiler evaluates the double sums nu += x * inv of SwitchCRTBasis / ScaleAndRound:
+ * separate multiply and add (x86-64 without -march flags: no FMA available; default) or fused multiply-add
+ * (-march=native builds, aarch64: GCC contracts by default). */
+enum { PSI_FP_SEPARATE = 0, PSI_FP_FMA = 1 };
 
 /*
  * Everything the device needs to know about the BFV-RNS context.  When linked
@@ -93,6 +99,17 @@ typedef struct psi_params {
     /* DCRTPoly::ScaleAndRound by t/P with output basis Q (HPSPOVERQ) */
     uint64_t tQSHatInvModsDivsModq[PSI_MAX_LIMBS][PSI_MAX_LIMBS + 1]; /* [j][i<Lp], [j][Lp] */
     double tQSHatInvModsDivsFrac[PSI_MAX_LIMBS];
+
+    /* ---- appended in 0.2; the layout of everything above is unchanged ---- */
+    uint32_t fp_contract;  /* PSI_FP_* */
+    uint32_t ks_num_parts; /* HYBRID: numPartQ, the number of digits Q is partitioned into (0 for BV) */
+    uint32_t Lk;           /* HYBRID: sizeP of the key-switching basis (0 for BV) */
+    uint32_t reserved2;
+    uint64_t pk[PSI_MAX_LIMBS];     /* HYBRID: special primes of the key-switching basis */
+    uint64_t psi_pk[PSI_MAX_LIMBS]; /* their 2N-th roots */
+    /* DCRTPoly::ScaleAndRound by t/Q with output basis P (PSI_MULT_HPS); S = Q*P */
+    uint64_t tPSHatInvModsDivsModp[PSI_MAX_LIMBS][PSI_MAX_LIMBS + 1]; /* [j][i<L], [j][L] */
+    double tPSHatInvModsDivsFrac[PSI_MAX_LIMBS];
 } psi_params;
 
 typedef struct psi_ctx psi_ctx; /* opaque, one per device */
@@ -102,6 +119,11 @@ typedef struct psi_ctx psi_ctx; /* opaque, one per device */
  * dimension).  L_override = 0 derives sizeQ from the noise estimate. */
 int psi_params_generate(uint32_t N, uint64_t t, uint32_t mult_depth, uint32_t L_override,
                         psi_params* out);
+/* The same with the variant choices of the context: mult_technique PSI_MULT_*, ks_technique PSI_KS_* (HYBRID: the
+ * number of digits follows OpenFHE's rule for the depth, the special primes continue below the other two bases),
+ * fp_contract PSI_FP_*. */
+int psi_params_generate_ex(uint32_t N, uint64_t t, uint32_t mult_depth, uint32_t L_override, uint32_t mult_technique,
+                           uint32_t ks_technique, uint32_t fp_contract, psi_params* out);
 
 /* The same tables for moduli and roots that come from the host library (the OpenFHE adapter reads them from
  * ILDCRTParams: q / psi_q = ciphertext basis Q, p / psi_p = auxiliary basis of EvalMult, psi_t = the packed
@@ -115,8 +137,9 @@ int psi_ctx_create(const psi_params* p, int device, psi_ctx** out);
 int psi_ctx_destroy(psi_ctx* ctx);
 
 /* Replaces cryptoContext->DeserializeEvalMultKey (BatchedFHEPSIServer.cpp:49) as
- * consumed by EvalMult(ct,ct) (BatchedFHEHIPPIE.cpp:123).  evk_b, evk_a:
- * [L][L][N] u64 each, EVALUATION. */
+ * consumed by EvalMult(ct,ct) (BatchedFHEHIPPIE.cpp:123).  evk_b, evk_a, EVALUATION:
+ *   BV      [L][L][N] u64 each (digit i, limb k)
+ *   HYBRID  [ks_num_parts][L + Lk][N] u64 each (digit j, limbs of Q then of the key-switching basis) */
 int psi_set_relin_key(psi_ctx* ctx, const uint64_t* evk_b, const uint64_t* evk_a);
 
 /* Replaces the ctor's vectorizedHCT / preCalcRandomMask members

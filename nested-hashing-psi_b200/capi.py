@@ -46,6 +46,9 @@ class PsiParams(ctypes.Structure):
         ("negPQHatInvModq", _U64x8), ("qInvModp", _U64x8 * MAX_LIMBS), ("PHatInvModp", _U64x8),
         ("PHatModq", _U64x8 * MAX_LIMBS), ("alphaPModq", _U64x8 * (MAX_LIMBS + 1)), ("pInv", _F64x8),
         ("tQSHatInvModsDivsModq", _U64x9 * MAX_LIMBS), ("tQSHatInvModsDivsFrac", _F64x8),
+        ("fp_contract", ctypes.c_uint32), ("ks_num_parts", ctypes.c_uint32), ("Lk", ctypes.c_uint32),
+        ("reserved2", ctypes.c_uint32), ("pk", _U64x8), ("psi_pk", _U64x8),
+        ("tPSHatInvModsDivsModp", _U64x9 * MAX_LIMBS), ("tPSHatInvModsDivsFrac", _F64x8),
     ]
 
 
@@ -60,6 +63,7 @@ _u32, _u64, _int, _sz = ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int, ctypes.c
 # every symbol include/psi_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "psi_params_generate": (_int, [_u32, _u64, _u32, _u32, _pp]),
+    "psi_params_generate_ex": (_int, [_u32, _u64, _u32, _u32, _u32, _u32, _u32, _pp]),
     "psi_ctx_create": (_int, [_pp, _int, _vpp]),
     "psi_ctx_destroy": (_int, [_vp]),
     "psi_set_relin_key": (_int, [_vp, _u64p, _u64p]),
@@ -173,8 +177,13 @@ def check(rc):
         raise PsiError(rc, lib().psi_last_error().decode("utf-8", "replace"))
 
 
-def params_generate(N, t, depth, L_override=0):
-    """psi_params_generate: stand-alone BFV-RNS context tables (host only, no device needed)."""
+MULT_HPS, MULT_HPSPOVERQ = 0, 1
+KS_BV, KS_HYBRID = 0, 1
+FP_SEPARATE, FP_FMA = 0, 1
+
+
+def params_generate(N, t, depth, L_override=0, mult_technique=MULT_HPSPOVERQ, ks_technique=KS_BV, fp_contract=FP_SEPARATE):
+    """psi_params_generate(_ex): stand-alone BFV-RNS context tables (host only, no device needed)."""
     p = PsiParams()
-    check(lib().psi_params_generate(N, t, depth, L_override, ctypes.byref(p)))
+    check(lib().psi_params_generate_ex(N, t, depth, L_override, mult_technique, ks_technique, fp_contract, ctypes.byref(p)))
     return p

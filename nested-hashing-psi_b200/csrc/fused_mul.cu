@@ -181,7 +181,7 @@ cudaError_t launch_to_montgomery(const KCtx& k, uint32_t groups, const u64* src,
 // sizeQ + 1; anything else takes the unfused kernels.  Bounds that hold up to 7 limbs: 8-term split-30 sums
 // (16 products < 2^60 per partial sum), L * (2q + 2^32) < 2^64 for the key-switch Montgomery reduction.
 bool fused_mul_supported(const KCtx& k) {
-    return k.logN >= kLogCols + kRowTileLog && k.L >= 1 && k.L <= 7 && (k.Lp == k.L || (k.Lp == k.L + 1 && k.L <= 6));
+    return k.fused_ok && k.logN >= kLogCols + kRowTileLog && k.L >= 1 && k.L <= 7 && (k.Lp == k.L || (k.Lp == k.L + 1 && k.L <= 6));
 }
 
 static cudaError_t dispatch_cols(PSI_COLS_ARGS) {

@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 3)
 #pragma unroll
             for (int i = 0; i < L; i++) {
                 y[i] = shoup_canon(smem[i * P + sl(j)], tab->QHatInvNinv[i], tab->QHatInvNinv_s[i], tab->mods[i].q);
-                nu = __dadd_rn(nu, __dmul_rn(__ull2double_rn(y[i]), tab->qInv[i]));
+                nu = nu_step(nu, __ull2double_rn(y[i]), tab->qInv[i], tab->fp_fma);
             }
             const unsigned alpha = (unsigned)nu;
             uint32_t y0[L], y1[L];
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 3)
                 pp[jj] = acc3_reduce(acc, mp.q, mp.qinv);
                 // exact P -> Q (DCRTPoly::SwitchCRTBasis)
                 z[jj] = shoup_canon(pp[jj], tab->PHatInvModp[jj], tab->PHatInvModp_s[jj], mp.q);
-                nu = __dadd_rn(nu, __dmul_rn(__ull2double_rn(z[jj]), tab->pInv[jj]));
+                nu = nu_step(nu, __ull2double_rn(z[jj]), tab->pInv[jj], tab->fp_fma);
                 z0[jj] = (uint32_t)z[jj] & 0x3fffffffu;
                 z1[jj] = (uint32_t)(z[jj] >> 30);
             }
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 3)
         for (int i = 0; i < LP; i++) {
             const ModDev& mp = tab->mods[L + i];
             xp[i] = shoup_canon(smem[(L + i) * P + sl(j)], mp.ninvR, mp.ninvR_s, mp.q);
-            nu = __dadd_rn(nu, __dmul_rn(tab->tQSfrac[i], __ull2double_rn(xp[i])));
+            nu = nu_step(nu, tab->tQSfrac[i], __ull2double_rn(xp[i]), tab->fp_fma);
         }
         const u64 alpha = __double2ull_rz(nu);  // < LP * 2^60
         uint32_t xp0[LP], xp1[LP];

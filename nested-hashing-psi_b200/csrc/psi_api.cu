@@ -145,7 +145,9 @@ struct psi_ctx {
     cudaStream_t sq_in = nullptr, sq_out = nullptr;
     cudaEvent_t ev_slice[kMaxStreamSlices] = {}, ev_group[4] = {}, ev_sq = nullptr;
 
-    KCtx k(cudaStream_t s) const { return KCtx{d_tab, N, logN, L, Lp, s}; }
+    uint32_t Lk = 0, ks_parts = 0;  // HYBRID key switching
+    bool hybrid = false, hps = false;
+    KCtx k(cudaStream_t s) const { return KCtx{d_tab, N, logN, L, Lp, s, Lk, !hybrid && !hps}; }
 };
 
 namespace psi {
@@ -177,7 +179,7 @@ static int build_pack_perm(psi_ctx* c, uint32_t mode) {
 
 static int build_tables(psi_ctx* c) {
     const psi_params& P = c->P;
-    const uint32_t N = c->N, L = c->L, Lp = c->Lp, nm = L + Lp + 1;
+    const uint32_t N = c->N, L = c->L, Lp = c->Lp, nm = L + Lp + 1 + c->Lk;
     std::vector<u64> tw((size_t)nm * 4 * N);
     DevTables T;
     std::memset(&T, 0, sizeof(T));
@@ -190,8 +192,8 @@ static int build_tables(psi_ctx* c) {
     CK(c->twiddles2.alloc(tw.size()));
     std::vector<u64> tw2(tw.size());
     for (uint32_t m = 0; m < nm; m++) {
-        const u64 q = m < L ? P.q[m] : (m < L + Lp ? P.p[m - L] : P.t);
-        const u64 psi_root = m < L ? P.psi_q[m] : (m < L + Lp ? P.psi_p[m - L] : P.psi_t);
+        const u64 q = m < L ? P.q[m] : (m < L + Lp ? P.p[m - L] : (m == L + Lp ? P.t : P.pk[m - L - Lp - 1]));
+        const u64 psi_root = m < L ? P.psi_q[m] : (m < L + Lp ? P.psi_p[m - L] : (m == L + Lp ? P.psi_t : P.psi_pk[m - L - Lp - 1]));
         if (q < 2 || q >= (1ull << 60)) return set_error(PSI_ERR_INVALID, "moduli must be below 2^60 (OpenFHE's maximum for BFVrns)");
         if (h_powmod(psi_root, N, q) != q - 1)
             return set_error(PSI_ERR_INVALID, "psi is not a primitive 2N-th root of unity for one of the moduli");
@@ -324,6 +326,49 @@ static int build_tables(psi_ctx* c) {
         for (uint32_t j = 0; j < Lp; j++) T.alphaQModp[a][j] = P.alphaQModp[a][j];
     for (uint32_t a = 0; a <= Lp; a++)
         for (uint32_t i = 0; i < L; i++) T.alphaPModq[a][i] = P.alphaPModq[a][i];
+    // ---- variants
+    T.fp_fma = P.fp_contract == PSI_FP_FMA;
+    T.hps = c->hps;
+    for (uint32_t j = 0; j < Lp; j++)
+        for (uint32_t i = 0; i <= L; i++) T.tPS[j][i] = P.tPSHatInvModsDivsModp[j][i];
+    for (uint32_t i = 0; i < L; i++) T.tPSfrac[i] = P.tPSHatInvModsDivsFrac[i];
+    if (c->hybrid) {
+        // KeySwitchHYBRID tables: all exact integers, derived from the moduli (OpenFHE: PartQlHatInvModq, PartQlHatModp,
+        // PInvModq, PHatInvModp, PHatModq)
+        const uint32_t Lk = c->Lk, parts = c->ks_parts, alpha = (L + parts - 1) / parts;
+        T.ks_parts = parts;
+        T.ks_alpha = alpha;
+        T.Lk = Lk;
+        for (uint32_t i = 0; i < L; i++) {
+            const uint32_t lo = (i / alpha) * alpha, hi = lo + alpha < L ? lo + alpha : L;
+            for (uint32_t m = 0; m < L + Lk; m++) {
+                const u64 mod = m < L ? P.q[m] : P.pk[m - L];
+                u64 r = 1 % mod;
+                for (uint32_t u = lo; u < hi; u++)
+                    if (u != i) r = h_mulmod(r, P.q[u] % mod, mod);
+                T.PartQHatModt[i][m] = r;
+            }
+            T.PartQHatInvModq[i] = h_powmod(T.PartQHatModt[i][i], P.q[i] - 2, P.q[i]);
+            T.PartQHatInvModq_s[i] = h_shoup(T.PartQHatInvModq[i], P.q[i]);
+            u64 pk = 1;
+            for (uint32_t u = 0; u < Lk; u++) pk = h_mulmod(pk, P.pk[u] % P.q[i], P.q[i]);
+            T.PkInvModq[i] = h_powmod(pk, P.q[i] - 2, P.q[i]);
+            T.PkInvModq_s[i] = h_shoup(T.PkInvModq[i], P.q[i]);
+        }
+        for (uint32_t u = 0; u < Lk; u++) {
+            u64 hat = 1;
+            for (uint32_t v = 0; v < Lk; v++)
+                if (v != u) hat = h_mulmod(hat, P.pk[v] % P.pk[u], P.pk[u]);
+            T.PkHatInvModpk[u] = h_powmod(hat, P.pk[u] - 2, P.pk[u]);
+            T.PkHatInvModpk_s[u] = h_shoup(T.PkHatInvModpk[u], P.pk[u]);
+            for (uint32_t i = 0; i < L; i++) {
+                u64 r = 1;
+                for (uint32_t v = 0; v < Lk; v++)
+                    if (v != u) r = h_mulmod(r, P.pk[v] % P.q[i], P.q[i]);
+                T.PkHatModq[u][i] = r;
+            }
+        }
+    }
     CK(cudaMalloc(&c->d_tab, sizeof(DevTables)));
     CK(cudaMemcpy(c->d_tab, &T, sizeof(T), cudaMemcpyHostToDevice));
 
@@ -341,7 +386,10 @@ static int alloc_work(psi_ctx* c) {
         CK(c->e2.alloc(b * 2 * LT * N));
         CK(c->ten.alloc(b * 3 * LT * N));
         CK(c->res.alloc(b * 3 * L * N));
-        CK(c->dig.alloc(b * L * L * N));
+        {
+            const size_t dig_bv = L * L, dig_hy = (size_t)c->ks_parts * (L + c->Lk);
+            CK(c->dig.alloc(b * (dig_bv > dig_hy ? dig_bv : dig_hy) * N));
+        }
         if (K > 2) CK(c->prod.alloc(b * 2 * L * N));
     }
     return PSI_OK;
@@ -370,7 +418,8 @@ static int mul_ctct_batch(psi_ctx* c, cudaStream_t s, uint32_t B, const u64* a, 
     u64* const w_e2 = c->e2.p + (size_t)bin0 * 2 * LT * N;
     u64* const w_ten = c->ten.p + (size_t)bin0 * 3 * LT * N;
     u64* const w_res = c->res.p + (size_t)bin0 * 3 * L * N;
-    u64* const w_dig = c->dig.p + (size_t)bin0 * L * L * N;
+    const size_t dig_per_bin = c->hybrid && (size_t)c->ks_parts * (L + c->Lk) > (size_t)L * L ? (size_t)c->ks_parts * (L + c->Lk) : (size_t)L * L;
+    u64* const w_dig = c->dig.p + (size_t)bin0 * dig_per_bin * N;
     if (fused_mul_supported(k)) {
         // the fused relinearisation takes the key and the masks in Montgomery form
         const u64* maskR = mask ? c->maskR.p + (mask - c->mask.p) : nullptr;
@@ -393,23 +442,57 @@ static int mul_ctct_batch(psi_ctx* c, cudaStream_t s, uint32_t B, const u64* a, 
     CK(launch_ntt(k, nb, false)); nl++;
     CK(cudaMemcpy2DAsync(w_e1, LT * N * sizeof(u64), a, L * N * sizeof(u64), L * N * sizeof(u64), (size_t)B * 2,
                          cudaMemcpyDeviceToDevice, s));
-    // (3) second operand: P-over-Q fast extension, all limbs back to EVALUATION
-    CK(launch_fast_expand_poverq(k, B * 2, coef2, w_e2)); nl++;
-    nb = NttBatch{w_e2, w_e2, B * 2 * LT, LT, LT * N, N, LT * N, 0, LT};
-    CK(launch_ntt(k, nb, false)); nl++;
-    // (4) tensor, (5) COEFFICIENT, (6) scale by t/P and round into Q
+    if (c->hps) {
+        // (3, HPS) second operand: the same exact extension (DCRTPoly::ExpandCRTBasis on both ciphertexts)
+        CK(launch_expand_q_to_p(k, B * 2, coef2, w_e2)); nl++;
+        nb = NttBatch{w_e2 + (size_t)L * N, w_e2 + (size_t)L * N, B * 2 * Lp, Lp, LT * N, N, LT * N, L, Lp};
+        CK(launch_ntt(k, nb, false)); nl++;
+        CK(cudaMemcpy2DAsync(w_e2, LT * N * sizeof(u64), bb, L * N * sizeof(u64), L * N * sizeof(u64), (size_t)B * 2,
+                             cudaMemcpyDeviceToDevice, s));
+    } else {
+        // (3, HPSPOVERQ) second operand: P-over-Q fast extension, all limbs back to EVALUATION
+        CK(launch_fast_expand_poverq(k, B * 2, coef2, w_e2)); nl++;
+        nb = NttBatch{w_e2, w_e2, B * 2 * LT, LT, LT * N, N, LT * N, 0, LT};
+        CK(launch_ntt(k, nb, false)); nl++;
+    }
+    // (4) tensor, (5) COEFFICIENT, (6) scale and round into Q (HPSPOVERQ: by t/P; HPS: by t/Q into P, then P -> Q)
     CK(launch_tensor(k, B, w_e1, w_e2, w_ten)); nl++;
     nb = NttBatch{w_ten, w_ten, B * 3 * LT, LT, LT * N, N, LT * N, 0, LT};
     CK(launch_ntt(k, nb, true)); nl++;
-    CK(launch_scale_round(k, B * 3, w_ten, w_res)); nl++;
-    // (7) relinearise: digits of c2 (BV, digit size 0), everything to EVALUATION, accumulate
-    CK(launch_relin_digits(k, B, w_res, w_dig)); nl++;
-    nb = NttBatch{w_dig, w_dig, B * L * L, L, L * N, N, L * N, 0, L};
-    CK(launch_ntt(k, nb, false)); nl++;
-    // components 0 and 1 only: group = bin, 2L of its 3L limb-polys
-    nb = NttBatch{w_res, w_res, B * 2 * L, 2 * L, 3 * L * N, N, 3 * L * N, 0, L};
-    CK(launch_ntt(k, nb, false)); nl++;
-    CK(launch_relin_accum(k, B, w_res, w_dig, c->evk_b.p, c->evk_a.p, mask, out)); nl++;
+    if (c->hps) {
+        CK(launch_scale_round_hps(k, B * 3, w_ten, w_res)); nl++;
+    } else {
+        CK(launch_scale_round(k, B * 3, w_ten, w_res)); nl++;
+    }
+    // components 0 and 1 to EVALUATION: group = bin, 2L of its 3L limb-polys
+    if (c->hybrid) {
+        // (7, HYBRID) digits of c2 over the extended basis Q + pk, inner products with the key, ApproxModDown
+        const uint32_t Lk = c->Lk, LE = L + Lk, parts = c->ks_parts, pk0 = L + Lp + 1;
+        u64* const ext = w_ten;  // [B][2][LE][N]: the tensor buffer is free again (3 (L + Lp) >= 2 (L + Lk) limbs per bin)
+        u64* const sw = w_e1;    // [B][2][L][N]
+        CK(launch_hybrid_modup(k, B, w_res, w_dig)); nl++;
+        nb = NttBatch{w_dig, w_dig, B * parts * L, L, LE * N, N, LE * N, 0, L};
+        CK(launch_ntt(k, nb, false)); nl++;
+        nb = NttBatch{w_dig + (size_t)L * N, w_dig + (size_t)L * N, B * parts * Lk, Lk, LE * N, N, LE * N, pk0, Lk};
+        CK(launch_ntt(k, nb, false)); nl++;
+        CK(launch_hybrid_inner(k, B, w_dig, c->evk_b.p, c->evk_a.p, ext)); nl++;
+        nb = NttBatch{ext + (size_t)L * N, ext + (size_t)L * N, B * 2 * Lk, Lk, LE * N, N, LE * N, pk0, Lk};
+        CK(launch_ntt(k, nb, true)); nl++;
+        CK(launch_hybrid_moddown(k, B, ext, sw)); nl++;
+        nb = NttBatch{sw, sw, B * 2 * L, L, L * N, N, L * N, 0, L};
+        CK(launch_ntt(k, nb, false)); nl++;
+        nb = NttBatch{w_res, w_res, B * 2 * L, 2 * L, 3 * L * N, N, 3 * L * N, 0, L};
+        CK(launch_ntt(k, nb, false)); nl++;
+        CK(launch_hybrid_finish(k, B, w_res, ext, sw, mask, out)); nl++;
+    } else {
+        // (7, BV) relinearise: digits of c2 (digit size 0), everything to EVALUATION, accumulate
+        CK(launch_relin_digits(k, B, w_res, w_dig)); nl++;
+        nb = NttBatch{w_dig, w_dig, B * L * L, L, L * N, N, L * N, 0, L};
+        CK(launch_ntt(k, nb, false)); nl++;
+        nb = NttBatch{w_res, w_res, B * 2 * L, 2 * L, 3 * L * N, N, 3 * L * N, 0, L};
+        CK(launch_ntt(k, nb, false)); nl++;
+        CK(launch_relin_accum(k, B, w_res, w_dig, c->evk_b.p, c->evk_a.p, mask, out)); nl++;
+    }
     if (launches) *launches += nl;
     return PSI_OK;
 }
@@ -436,9 +519,17 @@ int psi_ctx_create(const psi_params* p, int device, psi_ctx** out) {
     if (N < 8 || (N & (N - 1)) || N > 16384) return set_error(PSI_ERR_INVALID, "ring dimension must be a power of two in [8, 16384]");
     if (p->L < 1 || p->L > PSI_MAX_LIMBS || p->Lp < 1 || p->Lp > PSI_MAX_LIMBS)
         return set_error(PSI_ERR_INVALID, "sizeQ / sizeP out of range");
-    if (p->mult_technique != PSI_MULT_HPSPOVERQ)
-        return set_error(PSI_ERR_INVALID, "only MultiplicationTechnique HPSPOVERQ (the BFVrns default) is implemented");
-    if (p->ks_technique != PSI_KS_BV) return set_error(PSI_ERR_INVALID, "only BV key switching with digit size 0 is implemented");
+    if (p->mult_technique != PSI_MULT_HPSPOVERQ && p->mult_technique != PSI_MULT_HPS)
+        return set_error(PSI_ERR_INVALID, "MultiplicationTechnique must be HPS or HPSPOVERQ (BEHZ and HPSPOVERQLEVELED are not implemented)");
+    if (p->ks_technique != PSI_KS_BV && p->ks_technique != PSI_KS_HYBRID)
+        return set_error(PSI_ERR_INVALID, "KeySwitchTechnique must be BV (digit size 0) or HYBRID");
+    if (p->fp_contract > PSI_FP_FMA) return set_error(PSI_ERR_INVALID, "unknown floating-point contraction mode");
+    if (p->ks_technique == PSI_KS_HYBRID) {
+        if (p->Lk < 1 || p->Lk > PSI_MAX_LIMBS || p->ks_num_parts < 1 || p->ks_num_parts > p->L)
+            return set_error(PSI_ERR_INVALID, "HYBRID key switching: bad number of digits / special primes");
+        const uint32_t alpha = (p->L + p->ks_num_parts - 1) / p->ks_num_parts;
+        if ((p->L + alpha - 1) / alpha != p->ks_num_parts) return set_error(PSI_ERR_INVALID, "HYBRID key switching: empty digit");
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
@@ -451,6 +542,10 @@ int psi_ctx_create(const psi_params* p, int device, psi_ctx** out) {
     c->N = N;
     c->L = p->L;
     c->Lp = p->Lp;
+    c->hps = p->mult_technique == PSI_MULT_HPS;
+    c->hybrid = p->ks_technique == PSI_KS_HYBRID;
+    c->Lk = c->hybrid ? p->Lk : 0;
+    c->ks_parts = c->hybrid ? p->ks_num_parts : 0;
     while ((1u << c->logN) < N) c->logN++;
     int rc = ensure_device(c);
     if (rc == PSI_OK) rc = build_tables(c);
@@ -514,14 +609,15 @@ int psi_set_relin_key(psi_ctx* c, const uint64_t* evk_b, const uint64_t* evk_a) 
     if (!c || !evk_b || !evk_a) return set_error(PSI_ERR_INVALID, "null argument");
     int rc = ensure_device(c);
     if (rc) return rc;
-    const size_t n = (size_t)c->L * c->L * c->N;
+    // BV: [L][L][N]; HYBRID: [parts][L + Lk][N]
+    const size_t n = c->hybrid ? (size_t)c->ks_parts * (c->L + c->Lk) * c->N : (size_t)c->L * c->L * c->N;
     CK(c->evk_b.alloc(n));
     CK(c->evk_a.alloc(n));
     CK(cudaMemcpy(c->evk_b.p, evk_b, n * sizeof(u64), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->evk_a.p, evk_a, n * sizeof(u64), cudaMemcpyHostToDevice));
-    CK(c->evk_bR.alloc(n));
-    CK(c->evk_aR.alloc(n));
-    {
+    if (!c->hybrid) {
+        CK(c->evk_bR.alloc(n));
+        CK(c->evk_aR.alloc(n));
         const KCtx k = c->k(0);
         CK(launch_to_montgomery(k, c->L, c->evk_b.p, c->evk_bR.p));
         CK(launch_to_montgomery(k, c->L, c->evk_a.p, c->evk_aR.p));

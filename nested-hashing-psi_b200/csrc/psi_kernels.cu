@@ -358,7 +358,7 @@ __device__ __forceinline__ void switch_basis(const DevTables* __restrict__ tab, 
             const u64 cs = Q_TO_P ? tab->QHatInvModq_s[i] : tab->PHatInvModp_s[i];
             y[i] = mul_shoup(x[i], c, cs, a);
             const double inv = Q_TO_P ? tab->qInv[i] : tab->pInv[i];
-            nu = __dadd_rn(nu, __dmul_rn(__ull2double_rn(y[i]), inv));
+            nu = nu_step(nu, __ull2double_rn(y[i]), inv, tab->fp_fma);
         }
     }
     const unsigned alpha = (unsigned)nu;
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(256) k_scale_round(const DevTables* __restrict
     for (int i = 0; i < PSI_MAX_LIMBS; i++) {
         if (i < Lp) {
             xp[i] = ten[((size_t)g * LT + L + i) * N + n];
-            nu = __dadd_rn(nu, __dmul_rn(tab->tQSfrac[i], __ull2double_rn(xp[i])));
+            nu = nu_step(nu, tab->tQSfrac[i], __ull2double_rn(xp[i]), tab->fp_fma);
         }
     }
     const u64 alpha = __double2ull_rz(nu);
@@ -575,6 +575,151 @@ __global__ void __launch_bounds__(256) k_slots_to_crt(const DevTables* __restric
     out[tid] = r;
 }
 
+// PSI_MULT_HPS: DCRTPoly::ScaleAndRound by t/Q with output basis P (nu over the Q limbs), then the exact
+// DCRTPoly::SwitchCRTBasis P -> Q.  ten: [groups][LT][N] COEFFICIENT -> res: [groups][L][N] COEFFICIENT.
+__global__ void __launch_bounds__(256) k_scale_round_hps(const DevTables* __restrict__ tab, uint32_t N, uint32_t groups,
+                                                         const u64* __restrict__ ten, u64* __restrict__ res) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)groups * N) return;
+    const uint32_t g = tid / N, n = tid % N;
+    const int L = tab->L, Lp = tab->Lp, LT = L + Lp;
+    u64 xq[PSI_MAX_LIMBS], yp[PSI_MAX_LIMBS], out[PSI_MAX_LIMBS];
+    double nu = 0.5;
+#pragma unroll
+    for (int i = 0; i < PSI_MAX_LIMBS; i++) {
+        if (i < L) {
+            xq[i] = ten[((size_t)g * LT + i) * N + n];
+            nu = nu_step(nu, tab->tPSfrac[i], __ull2double_rn(xq[i]), tab->fp_fma);
+        }
+    }
+    const u64 alpha = __double2ull_rz(nu);
+#pragma unroll
+    for (int j = 0; j < PSI_MAX_LIMBS; j++) {
+        if (j < Lp) {
+            const ModDev& m = tab->mods[L + j];
+            u64 hi = 0, lo = 0;
+#pragma unroll
+            for (int i = 0; i < PSI_MAX_LIMBS; i++)
+                if (i < L) mac128(hi, lo, xq[i], tab->tPS[j][i]);
+            mac128(hi, lo, ten[((size_t)g * LT + L + j) * N + n], tab->tPS[j][L]);
+            const u64 v = barrett128(hi, lo, m.q, m.mu_hi, m.mu_lo);
+            yp[j] = addmod(v, alpha % m.q, m.q);
+        }
+    }
+    switch_basis<false>(tab, Lp, L, yp, out);
+#pragma unroll
+    for (int l = 0; l < PSI_MAX_LIMBS; l++)
+        if (l < L) res[((size_t)g * L + l) * N + n] = out[l];
+}
+
+// ---- HYBRID key switching (OpenFHE KeySwitchHYBRID as recalled; integers only, no floating point) ----------------
+// c2 (COEFFICIENT, [B][3][L][N] component 2) is cut into ks_parts digits of ks_alpha consecutive limbs.  Digit j is
+// lifted to every other limb of the extended basis Q + pk by ApproxSwitchCRTBasis (no rounding correction); its own
+// limbs keep the coefficients.  dig: [B][parts][L+Lk][N] COEFFICIENT (the caller transforms it).
+__global__ void __launch_bounds__(256) k_hybrid_modup(const DevTables* __restrict__ tab, uint32_t N, uint32_t B,
+                                                      const u64* __restrict__ res, u64* __restrict__ dig) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)B * N) return;
+    const size_t bin = tid / N;
+    const uint32_t n = tid % N;
+    const int L = tab->L, Lk = tab->Lk, LE = L + Lk, parts = tab->ks_parts, alpha = tab->ks_alpha;
+    u64 x[PSI_MAX_LIMBS], y[PSI_MAX_LIMBS];
+#pragma unroll
+    for (int i = 0; i < PSI_MAX_LIMBS; i++)
+        if (i < L) {
+            x[i] = res[((bin * 3 + 2) * L + i) * N + n];
+            y[i] = mul_shoup(x[i], tab->PartQHatInvModq[i], tab->PartQHatInvModq_s[i], tab->mods[i].q);
+        }
+    for (int j = 0; j < parts; j++) {
+        const int lo = j * alpha, hi = min(L, lo + alpha);
+        for (int m = 0; m < LE; m++) {
+            u64 v;
+            if (m >= lo && m < hi) {
+                v = x[m];
+            } else {
+                const ModDev& md = tab->mods[m < L ? m : tab->L + tab->Lp + 1 + (m - L)];
+                u64 h = 0, l = 0;
+#pragma unroll
+                for (int i = 0; i < PSI_MAX_LIMBS; i++)
+                    if (i >= lo && i < hi) mac128(h, l, y[i], tab->PartQHatModt[i][m]);
+                v = barrett128(h, l, md.q, md.mu_hi, md.mu_lo);
+            }
+            dig[((bin * parts + j) * LE + m) * N + n] = v;
+        }
+    }
+}
+
+// ext[bin][comp][m][n] = sum_j dig[bin][j][m][n] * evk_comp[j][m][n]  over the extended basis, EVALUATION
+__global__ void __launch_bounds__(256) k_hybrid_inner(const DevTables* __restrict__ tab, uint32_t N, uint32_t B,
+                                                      const u64* __restrict__ dig, const u64* __restrict__ evk_b,
+                                                      const u64* __restrict__ evk_a, u64* __restrict__ ext) {
+    const int L = tab->L, LE = L + tab->Lk, parts = tab->ks_parts;
+    const size_t LEN = (size_t)LE * N;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)B * LEN) return;
+    const size_t bin = tid / LEN, c = tid % LEN;
+    const int m = (int)(c / N);
+    const ModDev& md = tab->mods[m < L ? m : tab->L + tab->Lp + 1 + (m - L)];
+    u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+    for (int j = 0; j < parts; j++) {
+        const u64 d = dig[(bin * parts + j) * LEN + c];
+        mac128(h0, l0, d, evk_b[(size_t)j * LEN + c]);
+        mac128(h1, l1, d, evk_a[(size_t)j * LEN + c]);
+    }
+    ext[(bin * 2) * LEN + c] = barrett128(h0, l0, md.q, md.mu_hi, md.mu_lo);
+    ext[(bin * 2 + 1) * LEN + c] = barrett128(h1, l1, md.q, md.mu_hi, md.mu_lo);
+}
+
+// ApproxModDown, first half: the special-prime limbs of ext (COEFFICIENT after the caller's inverse transform) are
+// switched to Q by ApproxSwitchCRTBasis.  sw: [B][2][L][N] COEFFICIENT.
+__global__ void __launch_bounds__(256) k_hybrid_moddown(const DevTables* __restrict__ tab, uint32_t N, uint32_t B,
+                                                        const u64* __restrict__ ext, u64* __restrict__ sw) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)B * 2 * N) return;
+    const size_t g = tid / N;  // bin * 2 + comp
+    const uint32_t n = tid % N;
+    const int L = tab->L, Lk = tab->Lk, LE = L + Lk;
+    u64 y[PSI_MAX_LIMBS];
+#pragma unroll
+    for (int u = 0; u < PSI_MAX_LIMBS; u++)
+        if (u < Lk)
+            y[u] = mul_shoup(ext[(g * LE + L + u) * N + n], tab->PkHatInvModpk[u], tab->PkHatInvModpk_s[u],
+                             tab->mods[tab->L + tab->Lp + 1 + u].q);
+#pragma unroll
+    for (int i = 0; i < PSI_MAX_LIMBS; i++)
+        if (i < L) {
+            const ModDev& md = tab->mods[i];
+            u64 h = 0, l = 0;
+#pragma unroll
+            for (int u = 0; u < PSI_MAX_LIMBS; u++)
+                if (u < Lk) mac128(h, l, y[u], tab->PkHatModq[u][i]);
+            sw[(g * L + i) * N + n] = barrett128(h, l, md.q, md.mu_hi, md.mu_lo);
+        }
+}
+
+// ApproxModDown, second half, + (c0, c1) + optional mask: out = c + (ext_q - sw) * Pk^-1, all EVALUATION.
+// res_eval: [B][3][L][N] (components 0, 1), ext: [B][2][L+Lk][N], sw: [B][2][L][N], out: [B][2][L][N].
+__global__ void __launch_bounds__(256) k_hybrid_finish(const DevTables* __restrict__ tab, uint32_t N, uint32_t B,
+                                                       const u64* __restrict__ res_eval, const u64* __restrict__ ext,
+                                                       const u64* __restrict__ sw, const u64* __restrict__ mask,
+                                                       u64* __restrict__ out) {
+    const int L = tab->L, LE = L + tab->Lk;
+    const size_t LN = (size_t)L * N;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)B * LN) return;
+    const size_t bin = tid / LN, c = tid % LN;
+    const int i = (int)(c / N);
+    const ModDev& m = tab->mods[i];
+#pragma unroll
+    for (int comp = 0; comp < 2; comp++) {
+        const u64 e = ext[((bin * 2 + comp) * LE) * N + c];
+        const u64 d = submod(e, sw[(bin * 2 + comp) * LN + c], m.q);
+        u64 r = addmod(res_eval[(bin * 3 + comp) * LN + c], mul_shoup(d, tab->PkInvModq[i], tab->PkInvModq_s[i], m.q), m.q);
+        if (mask) r = mulmod(r, mask[bin * LN + c], m);
+        out[(bin * 2 + comp) * LN + c] = r;
+    }
+}
+
 // Centred lift of packed-encoding coefficients: crt [n][N] in [0, t) -> out [n][L][N], limb l holds c for
 // c <= t/2 and q_l - (t - c) otherwise (the signed representative of c mod t, reduced mod q_l).
 __global__ void __launch_bounds__(256) k_centre_lift(const DevTables* __restrict__ tab, uint32_t N, uint32_t n,
@@ -602,6 +747,24 @@ cudaError_t launch_tensor(const KCtx& k, uint32_t B, const u64* e1, const u64* e
 }
 cudaError_t launch_scale_round(const KCtx& k, uint32_t groups, const u64* ten, u64* res) {
     LAUNCH_1D(k_scale_round, (size_t)groups * k.N, groups, ten, res)
+}
+cudaError_t launch_scale_round_hps(const KCtx& k, uint32_t groups, const u64* ten, u64* res) {
+    LAUNCH_1D(k_scale_round_hps, (size_t)groups * k.N, groups, ten, res)
+}
+cudaError_t launch_hybrid_modup(const KCtx& k, uint32_t B, const u64* res, u64* dig) {
+    LAUNCH_1D(k_hybrid_modup, (size_t)B * k.N, B, res, dig)
+}
+cudaError_t launch_hybrid_inner(const KCtx& k, uint32_t B, const u64* dig, const u64* evk_b, const u64* evk_a, u64* ext) {
+    // the extended basis has L + Lk limbs; Lk comes from the tables
+    k_hybrid_inner<<<cdiv((size_t)B * (k.L + k.Lk) * k.N, 256), 256, 0, k.s>>>(k.tab, k.N, B, dig, evk_b, evk_a, ext);
+    return cudaGetLastError();
+}
+cudaError_t launch_hybrid_moddown(const KCtx& k, uint32_t B, const u64* ext, u64* sw) {
+    LAUNCH_1D(k_hybrid_moddown, (size_t)B * 2 * k.N, B, ext, sw)
+}
+cudaError_t launch_hybrid_finish(const KCtx& k, uint32_t B, const u64* res_eval, const u64* ext, const u64* sw, const u64* mask,
+                                 u64* out) {
+    LAUNCH_1D(k_hybrid_finish, (size_t)B * k.L * k.N, B, res_eval, ext, sw, mask, out)
 }
 cudaError_t launch_relin_digits(const KCtx& k, uint32_t B, const u64* res, u64* dig) {
     LAUNCH_1D(k_relin_digits, (size_t)B * k.L * k.N, B, res, dig)

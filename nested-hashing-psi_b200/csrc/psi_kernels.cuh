@@ -9,7 +9,7 @@
 
 namespace psi {
 
-constexpr int kMaxMods = 2 * PSI_MAX_LIMBS + 1;
+constexpr int kMaxMods = 3 * PSI_MAX_LIMBS + 1;  // q, p, t, then the HYBRID special primes
 
 // Device-resident copy of psi_params plus derived constants (Shoup companions, relin lifts).
 struct DevTables {
@@ -42,14 +42,35 @@ struct DevTables {
     u64 qInvModp_m[PSI_MAX_LIMBS][PSI_MAX_LIMBS];
     u64 PHatModq_m[PSI_MAX_LIMBS][PSI_MAX_LIMBS];
     u64 tQS_m[PSI_MAX_LIMBS][PSI_MAX_LIMBS + 1];
-    ModDev mods[kMaxMods];                    // 0..L-1: q, L..L+Lp-1: p, L+Lp: t
+    // ---- variants of the context (risk register)
+    uint32_t fp_fma;       // PSI_FP_FMA: the double sums nu += x * inv are evaluated with fused multiply-adds
+    uint32_t hps;          // PSI_MULT_HPS
+    // HPS: ScaleAndRound by t/Q with output basis P
+    u64 tPS[PSI_MAX_LIMBS][PSI_MAX_LIMBS + 1];
+    double tPSfrac[PSI_MAX_LIMBS];
+    // HYBRID key switching: Q cut into ks_parts digits of ks_alpha consecutive limbs, extended basis Q + Lk special primes
+    uint32_t ks_parts, ks_alpha, Lk, pad_;
+    u64 PartQHatInvModq[PSI_MAX_LIMBS], PartQHatInvModq_s[PSI_MAX_LIMBS];
+    u64 PartQHatModt[PSI_MAX_LIMBS][2 * PSI_MAX_LIMBS];  // [i][m]: (digit modulus / q_i) mod (m < L ? q_m : pk_{m-L})
+    u64 PkInvModq[PSI_MAX_LIMBS], PkInvModq_s[PSI_MAX_LIMBS];
+    u64 PkHatInvModpk[PSI_MAX_LIMBS], PkHatInvModpk_s[PSI_MAX_LIMBS];
+    u64 PkHatModq[PSI_MAX_LIMBS][PSI_MAX_LIMBS];         // [k][i]
+    ModDev mods[kMaxMods];                    // 0..L-1: q, L..L+Lp-1: p, L+Lp: t, L+Lp+1..: pk (HYBRID)
 };
+
+// nu += x * y the way the host library's compiler evaluates it (PSI_FP_SEPARATE / PSI_FP_FMA): explicit
+// round-to-nearest intrinsics, so that nvcc never contracts or splits on its own
+__device__ __forceinline__ double nu_step(double nu, double x, double y, uint32_t fma_mode) {
+    return fma_mode ? __fma_rn(x, y, nu) : __dadd_rn(nu, __dmul_rn(x, y));
+}
 
 // What every launcher needs: device tables + the host copy of the dimensions + the stream.
 struct KCtx {
     const DevTables* tab;
     uint32_t N, logN, L, Lp;
     cudaStream_t s;
+    uint32_t Lk = 0;         // HYBRID: size of the key-switching basis
+    bool fused_ok = true;    // the fused ct x ct kernels implement HPSPOVERQ + BV only
 };
 
 // Batched negacyclic NTT over `n_polys` limb-polynomials of N coefficients.
@@ -85,6 +106,14 @@ cudaError_t launch_expand_q_to_p(const KCtx& k, uint32_t groups, const u64* coef
 cudaError_t launch_fast_expand_poverq(const KCtx& k, uint32_t groups, const u64* coef, u64* ext);
 cudaError_t launch_tensor(const KCtx& k, uint32_t B, const u64* e1, const u64* e2, u64* ten);
 cudaError_t launch_scale_round(const KCtx& k, uint32_t groups, const u64* ten, u64* res);
+// HPS: ScaleAndRound by t/Q into P, then the exact SwitchCRTBasis P -> Q; same buffers as launch_scale_round
+cudaError_t launch_scale_round_hps(const KCtx& k, uint32_t groups, const u64* ten, u64* res);
+// HYBRID key switching (KeySwitchHYBRID, unfused): see psi_kernels.cu
+cudaError_t launch_hybrid_modup(const KCtx& k, uint32_t B, const u64* res, u64* dig);
+cudaError_t launch_hybrid_inner(const KCtx& k, uint32_t B, const u64* dig, const u64* evk_b, const u64* evk_a, u64* ext);
+cudaError_t launch_hybrid_moddown(const KCtx& k, uint32_t B, const u64* ext, u64* sw);
+cudaError_t launch_hybrid_finish(const KCtx& k, uint32_t B, const u64* res_eval, const u64* ext, const u64* sw, const u64* mask,
+                                 u64* out);
 cudaError_t launch_relin_digits(const KCtx& k, uint32_t B, const u64* res, u64* dig);
 cudaError_t launch_relin_accum(const KCtx& k, uint32_t B, const u64* res_eval, const u64* dig, const u64* evk_b,
                                const u64* evk_a, const u64* mask /*nullable*/, u64* out);

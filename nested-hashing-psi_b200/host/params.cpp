@@ -168,10 +168,29 @@ static void fill_tables(psi_params* out) {
         uint64_t shat = mulmod(qhat, prod_mod(p, Lp, -1, q[j]), q[j]);      // (S/q_j) mod q_j
         out->tQSHatInvModsDivsModq[j][Lp] = mulmod(mulmod(t % q[j], qhat, q[j]), invmod_prime(shat, q[j]), q[j]);
     }
+    // HPS: ScaleAndRound by t/Q, output P.  c_i = t*P*[(S/q_i)^-1]_{q_i}: frac_i = (c_i mod q_i)/q_i and
+    // floor(c_i/q_i) = -(c_i mod q_i) * q_i^-1 (mod p_j) because c_i = 0 mod p_j; own P limb: t*(P/p_j)*[(S/p_j)^-1]_{p_j}
+    for (uint32_t i = 0; i < L; ++i) {
+        uint64_t shat = mulmod(prod_mod(q, L, (int)i, q[i]), prod_mod(p, Lp, -1, q[i]), q[i]);  // (S/q_i) mod q_i
+        uint64_t rem = mulmod(mulmod(t % q[i], prod_mod(p, Lp, -1, q[i]), q[i]), invmod_prime(shat, q[i]), q[i]);
+        out->tPSHatInvModsDivsFrac[i] = (double)rem / (double)q[i];
+        for (uint32_t j = 0; j < Lp; ++j) {
+            uint64_t v = mulmod(rem % p[j], invmod_prime(q[i], p[j]), p[j]);
+            out->tPSHatInvModsDivsModp[j][i] = (p[j] - v) % p[j];
+        }
+    }
+    for (uint32_t j = 0; j < Lp; ++j) {
+        uint64_t phat = prod_mod(p, Lp, (int)j, p[j]);                      // (P/p_j) mod p_j
+        uint64_t shat = mulmod(phat, prod_mod(q, L, -1, p[j]), p[j]);       // (S/p_j) mod p_j
+        out->tPSHatInvModsDivsModp[j][L] = mulmod(mulmod(t % p[j], phat, p[j]), invmod_prime(shat, p[j]), p[j]);
+    }
 }
 
 
-int generate_params(uint32_t N, uint64_t t, uint32_t depth, uint32_t L_override, psi_params* out) {
+int generate_params(uint32_t N, uint64_t t, uint32_t depth, uint32_t L_override, psi_params* out, uint32_t mult_technique,
+                    uint32_t ks_technique, uint32_t fp_contract) {
+    if (mult_technique > PSI_MULT_HPSPOVERQ || ks_technique > PSI_KS_HYBRID || fp_contract > PSI_FP_FMA)
+        return set_error(PSI_ERR_INVALID, "unknown multiplication / key-switching technique or fp mode");
     if (!out) return PSI_ERR_INVALID;
     if (N < 8 || (N & (N - 1)) != 0 || N > 65536) return set_error(PSI_ERR_INVALID, "ring dimension must be a power of two");
     const uint64_t m = 2ull * N;
@@ -180,12 +199,15 @@ int generate_params(uint32_t N, uint64_t t, uint32_t depth, uint32_t L_override,
     uint32_t L = L_override ? L_override : derive_size_q(N, t, depth ? depth : 1);
     if (L < 1 || L > PSI_MAX_LIMBS) return set_error(PSI_ERR_INVALID, "sizeQ out of range (1..PSI_MAX_LIMBS)");
     std::memset(out, 0, sizeof(*out));
-    const uint32_t Lp = L;
+    // HPSPOVERQ: sizeP = sizeQ; HPS: one limb more (the tensor of two centred lifts needs Q*P > N * Q^2 / 2)
+    const uint32_t Lp = mult_technique == PSI_MULT_HPS ? L + 1 : L;
+    if (Lp > PSI_MAX_LIMBS) return set_error(PSI_ERR_INVALID, "sizeP out of range (HPS needs sizeQ + 1 <= PSI_MAX_LIMBS)");
     out->N = N;
     out->L = L;
     out->Lp = Lp;
-    out->mult_technique = PSI_MULT_HPSPOVERQ;
-    out->ks_technique = PSI_KS_BV;
+    out->mult_technique = mult_technique;
+    out->ks_technique = ks_technique;
+    out->fp_contract = fp_contract;
     out->t = t;
     uint64_t* q = out->q;
     uint64_t* p = out->p;
@@ -196,6 +218,21 @@ int generate_params(uint32_t N, uint64_t t, uint32_t depth, uint32_t L_override,
     for (uint32_t i = 0; i < L; ++i) out->psi_q[i] = min_primitive_root(m, q[i]);
     for (uint32_t j = 0; j < Lp; ++j) out->psi_p[j] = min_primitive_root(m, p[j]);
     out->psi_t = min_primitive_root(m, t);
+    if (ks_technique == PSI_KS_HYBRID) {
+        // OpenFHE ComputeNumLargeDigits (recalled): 3 digits for depth > 3, 2 for depth > 0, else 1; never more than
+        // sizeQ; sizeP of the key-switching basis = limbs of the largest digit; special primes continue below
+        uint32_t parts = depth > 3 ? 3 : (depth > 0 ? 2 : 1);
+        if (parts > L) parts = L;
+        const uint32_t alpha = (L + parts - 1) / parts;
+        out->ks_num_parts = (L + alpha - 1) / alpha;
+        out->Lk = alpha;
+        uint64_t prev = p[Lp - 1];
+        for (uint32_t i = 0; i < alpha; ++i) {
+            prev = previous_prime(prev, m);
+            out->pk[i] = prev;
+            out->psi_pk[i] = min_primitive_root(m, prev);
+        }
+    }
     fill_tables(out);
     return PSI_OK;
 }
@@ -242,5 +279,9 @@ extern "C" int psi_params_from_moduli(uint32_t N, uint64_t t, uint32_t L, const 
 }
 
 extern "C" int psi_params_generate(uint32_t N, uint64_t t, uint32_t mult_depth, uint32_t L_override, psi_params* out) {
-    return psi::generate_params(N, t, mult_depth, L_override, out);
+    return psi::generate_params(N, t, mult_depth ? mult_depth : 1, L_override, out, PSI_MULT_HPSPOVERQ, PSI_KS_BV, PSI_FP_SEPARATE);
+}
+extern "C" int psi_params_generate_ex(uint32_t N, uint64_t t, uint32_t mult_depth, uint32_t L_override, uint32_t mult_technique,
+                                      uint32_t ks_technique, uint32_t fp_contract, psi_params* out) {
+    return psi::generate_params(N, t, mult_depth ? mult_depth : 1, L_override, out, mult_technique, ks_technique, fp_contract);
 }

@@ -12,6 +12,7 @@ int set_error(int status, const std::string& msg);
 
 bool is_prime_u64(uint64_t n);
 uint64_t min_primitive_root(uint64_t m, uint64_t q);
-int generate_params(uint32_t N, uint64_t t, uint32_t depth, uint32_t L_override, psi_params* out);
+int generate_params(uint32_t N, uint64_t t, uint32_t depth, uint32_t L_override, psi_params* out, uint32_t mult_technique,
+                    uint32_t ks_technique, uint32_t fp_contract);
 
 }  // namespace psi

@@ -51,6 +51,13 @@ class PublicKey:
     """Stored but never used by run() (BatchedFHEHIPPIE.hpp:22); kept for signature parity."""
 
 
+def _evk_shape(params):
+    """psi_set_relin_key layouts: BV [L][L][N] (digit, limb); HYBRID [numPartQ][L + Lk][N]."""
+    if params.ks_technique == capi.KS_HYBRID:
+        return (params.ks_num_parts, params.L + params.Lk, params.N)
+    return (params.L, params.L, params.N)
+
+
 class CryptoContext:
     """What the PIE needs of lbcrypto::CryptoContext<DCRTPoly>: the BFV-RNS parameter tables, the
     relinearisation key (DeserializeEvalMultKey, BatchedFHEPSIServer.cpp:49) and the device evaluator."""
@@ -79,7 +86,7 @@ class CryptoContext:
 
     def InsertEvalMultKey(self, evk_b, evk_a):
         (evk_b, pb), (evk_a, pa) = _u64(evk_b), _u64(evk_a)
-        assert evk_b.shape == (self.L, self.L, self.N) and evk_a.shape == evk_b.shape
+        assert evk_b.shape == _evk_shape(self.params) and evk_a.shape == evk_b.shape
         check(lib().psi_set_relin_key(self._h, pb, pa))
 
     # --- raw C-ABI level (the PIE class sits on top of these) ----------------------------------
@@ -341,7 +348,7 @@ class MultiContext:
 
     def InsertEvalMultKey(self, evk_b, evk_a):
         (evk_b, pb), (evk_a, pa) = _u64(evk_b), _u64(evk_a)
-        assert evk_b.shape == (self.L, self.L, self.N) and evk_a.shape == evk_b.shape
+        assert evk_b.shape == _evk_shape(self.params) and evk_a.shape == evk_b.shape
         check(lib().psi_multi_set_relin_key(self._h, pb, pa))
 
     def db_load_limbs(self, pt, mask):

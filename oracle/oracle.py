@@ -53,6 +53,8 @@ def lib():
         L.orc_mul_ctct.argtypes = [ctypes.c_void_p, _u64p, _u64p, _u64p, _u64p, _u64p]
         L.orc_mul_core.argtypes = [ctypes.c_void_p, _u64p, _u64p, _u64p]
         L.orc_relin.argtypes = [ctypes.c_void_p, _u64p, _u64p, _u64p, _u64p]
+        L.orc_relin_hybrid.argtypes = [ctypes.c_void_p, _u64p, _u64p, _u64p, _u64p]
+        L.orc_keygen_hybrid.argtypes = [ctypes.c_void_p, ctypes.c_uint64, _u64p, _u64p, _u64p]
         L.orc_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _u64p, _u64p, _u64p,
                               _u64p, _u64p, _u64p, _u64p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.orc_run_cold.argtypes = L.orc_run.argtypes
@@ -128,11 +130,21 @@ class Oracle:
         return out
 
     # -- client side --------------------------------------------------------------
+    @property
+    def hybrid(self):
+        return self.params.ks_technique == 1
+
+    def evk_shape(self):
+        """BV: [L][L][N] (digit, limb); HYBRID: [numPartQ][L + Lk][N] (digit, limb of Q then of the special basis)."""
+        if self.hybrid:
+            return (self.params.ks_num_parts, self.L + self.params.Lk, self.N)
+        return (self.L, self.L, self.N)
+
     def keygen(self, seed):
         sk = np.empty((self.L, self.N), dtype=np.uint64)
-        evk_b = np.empty((self.L, self.L, self.N), dtype=np.uint64)
-        evk_a = np.empty((self.L, self.L, self.N), dtype=np.uint64)
-        lib().orc_keygen(self._h, seed, _p(sk), _p(evk_b), _p(evk_a))
+        evk_b = np.empty(self.evk_shape(), dtype=np.uint64)
+        evk_a = np.empty(self.evk_shape(), dtype=np.uint64)
+        (lib().orc_keygen_hybrid if self.hybrid else lib().orc_keygen)(self._h, seed, _p(sk), _p(evk_b), _p(evk_a))
         return sk, evk_b, evk_a
 
     def encrypt(self, sk, slots, seed):
@@ -180,7 +192,9 @@ class Oracle:
 
     def relin(self, res, evk_b, evk_a):
         out = np.empty((2, self.L, self.N), dtype=np.uint64)
-        lib().orc_relin(self._h, _p(np.ascontiguousarray(res)), _p(evk_b), _p(evk_a), _p(out))
+        assert evk_b.shape == self.evk_shape() and evk_a.shape == self.evk_shape()
+        (lib().orc_relin_hybrid if self.hybrid else lib().orc_relin)(self._h, _p(np.ascontiguousarray(res)), _p(evk_b),
+                                                                    _p(evk_a), _p(out))
         return out
 
     def run(self, pt, mask, idx, minus, evk_b, evk_a, bin_begin=0, bin_end=None, nthreads=1, out=None):

@@ -167,13 +167,14 @@ class RefParams:
     """Plain-Python container of every table psi_params carries, computed straight from the
     definitions with unbounded integers."""
 
-    def __init__(self, N, t, depth=None, L=None, dcrt_bits=60, Lp=None):
+    def __init__(self, N, t, depth=None, L=None, dcrt_bits=60, Lp=None, mult_technique=1, ks_technique=0, fp_contract=0):
         assert N & (N - 1) == 0
         assert (t - 1) % (2 * N) == 0, "packed encoding needs t = 1 mod 2N"
         if L is None:
             L = size_q(N, t, depth, dcrt_bits)
         self.N, self.t, self.L = N, t, L
-        self.Lp = L if Lp is None else Lp          # HPSPOVERQ: sizeP = sizeQ (recalled)
+        # HPSPOVERQ: sizeP = sizeQ; HPS: sizeP = sizeQ + 1 (the tensor of two centred lifts needs QP > N Q^2 / 2) (recalled)
+        self.Lp = (L + 1 if mult_technique == 0 else L) if Lp is None else Lp
         m = 2 * N
         q = [previous_prime(first_prime(dcrt_bits, m), m)]
         for _ in range(1, L):
@@ -210,11 +211,46 @@ class RefParams:
             self.tQSHatInvModsDivsFrac.append(float(rem) / float(p[i]))
         for j in range(Lq):
             self.tQSHatInvModsDivsModq[j][Lp_] = (t * (Q // q[j]) * pow(S // q[j], -1, q[j])) % q[j]
+        # HPS: ScaleAndRound by t/Q, output P: inputs = Q limbs then the own P limb
+        self.tPSHatInvModsDivsModp = [[0] * (Lq + 1) for _ in range(Lp_)]
+        self.tPSHatInvModsDivsFrac = []
+        for i in range(Lq):
+            c = t * P * pow(S // q[i], -1, q[i])
+            quo, rem = divmod(c, q[i])
+            for j in range(Lp_):
+                self.tPSHatInvModsDivsModp[j][i] = quo % p[j]
+            self.tPSHatInvModsDivsFrac.append(float(rem) / float(q[i]))
+        for j in range(Lp_):
+            self.tPSHatInvModsDivsModp[j][Lq] = (t * (P // p[j]) * pow(S // p[j], -1, p[j])) % p[j]
+        self.mult_technique, self.ks_technique, self.fp_contract = mult_technique, ks_technique, fp_contract
+        # HYBRID key switching (recalled): numPartQ = 3 for depth > 3, 2 for depth > 0, else 1 (ComputeNumLargeDigits),
+        # never more than sizeQ; sizeP of the key-switching basis = limbs of the largest digit; special primes = the
+        # next primes below the other bases
+        self.ks_num_parts, self.Lk, self.pk, self.psi_pk = 0, 0, [], []
+        if ks_technique == 1:
+            d = depth if depth is not None else 2
+            self.ks_num_parts = min(L, 3 if d > 3 else (2 if d > 0 else 1))
+            alpha = -(-L // self.ks_num_parts)
+            self.ks_num_parts = -(-L // alpha)          # digits actually populated
+            self.Lk = alpha
+            prev = p[-1]
+            for _ in range(self.Lk):
+                prev = previous_prime(prev, m)
+                self.pk.append(prev)
+            self.psi_pk = [root_of_unity_min(m, x) for x in self.pk]
 
     def to_struct(self):
         s = PsiParams()
         s.N, s.L, s.Lp = self.N, self.L, self.Lp
-        s.mult_technique, s.ks_technique, s.reserved = 1, 0, 0
+        s.mult_technique, s.ks_technique, s.reserved = self.mult_technique, self.ks_technique, 0
+        s.fp_contract, s.ks_num_parts, s.Lk, s.reserved2 = self.fp_contract, self.ks_num_parts, self.Lk, 0
+        for i in range(self.Lk):
+            s.pk[i], s.psi_pk[i] = self.pk[i], self.psi_pk[i]
+        for j in range(self.Lp):
+            for i in range(self.L + 1):
+                s.tPSHatInvModsDivsModp[j][i] = self.tPSHatInvModsDivsModp[j][i]
+        for i in range(self.L):
+            s.tPSHatInvModsDivsFrac[i] = self.tPSHatInvModsDivsFrac[i]
         s.t, s.psi_t = self.t, self.psi_t
         for i in range(self.L):
             s.q[i], s.psi_q[i] = self.q[i], self.psi_q[i]
@@ -268,6 +304,9 @@ class PsiParams(ctypes.Structure):
         ("pInv", _F64x8),
         ("tQSHatInvModsDivsModq", _U64x9 * MAX_LIMBS),
         ("tQSHatInvModsDivsFrac", _F64x8),
+        ("fp_contract", ctypes.c_uint32), ("ks_num_parts", ctypes.c_uint32), ("Lk", ctypes.c_uint32),
+        ("reserved2", ctypes.c_uint32), ("pk", _U64x8), ("psi_pk", _U64x8),
+        ("tPSHatInvModsDivsModp", _U64x9 * MAX_LIMBS), ("tPSHatInvModsDivsFrac", _F64x8),
     ]
 
 
@@ -291,4 +330,8 @@ def struct_to_dict(s):
         "pInv": list(s.pInv[:Lp]),
         "tQSHatInvModsDivsModq": [list(s.tQSHatInvModsDivsModq[j][:Lp + 1]) for j in range(L)],
         "tQSHatInvModsDivsFrac": list(s.tQSHatInvModsDivsFrac[:Lp]),
+        "fp_contract": s.fp_contract, "ks_num_parts": s.ks_num_parts, "Lk": s.Lk,
+        "pk": list(s.pk[:s.Lk]), "psi_pk": list(s.psi_pk[:s.Lk]),
+        "tPSHatInvModsDivsModp": [list(s.tPSHatInvModsDivsModp[j][:L + 1]) for j in range(Lp)],
+        "tPSHatInvModsDivsFrac": list(s.tPSHatInvModsDivsFrac[:L]),
     }

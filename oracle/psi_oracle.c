@@ -204,6 +204,16 @@ typedef struct orc_ctx {
     u64 negQModt, tInvModq[PSI_MAX_LIMBS];
     /* risk-register switches: each selects between two readings of OpenFHE */
     int encode_lift; /* PSI_ENCODE_LIFT_PLAIN (default) / PSI_ENCODE_LIFT_CENTRED */
+    /* HYBRID key switching (P.ks_technique == PSI_KS_HYBRID): Q is partitioned into `parts` digits of `alpha`
+     * consecutive limbs; the extended basis is Q followed by the Lk special primes pk */
+    int parts, alpha, Lk;
+    modctx mk[PSI_MAX_LIMBS];
+    u64 PartQHatInvModq[PSI_MAX_LIMBS];                     /* [i]: (Qpart/q_i)^-1 mod q_i, Qpart = the digit of limb i */
+    u64 PartQHatModt[PSI_MAX_LIMBS][2 * PSI_MAX_LIMBS];     /* [i][m]: (Qpart/q_i) mod (m < L ? q_m : pk_{m-L}) */
+    u64 PkInvModq[PSI_MAX_LIMBS];                           /* (prod pk)^-1 mod q_i */
+    u64 PkModq[PSI_MAX_LIMBS];                              /* (prod pk) mod q_i (key generation) */
+    u64 PkHatInvModpk[PSI_MAX_LIMBS];                       /* [(Pk/pk_k)^-1] mod pk_k */
+    u64 PkHatModq[PSI_MAX_LIMBS][PSI_MAX_LIMBS];            /* [k][i]: (Pk/pk_k) mod q_i */
 } orc_ctx;
 
 static const modctx* mod_at(const orc_ctx* c, int idx) {
@@ -243,6 +253,39 @@ orc_ctx* orc_create(const psi_params* p) {
     for (int j = 0; j < c->Lp; j++) c->PHatInvModp_s[j] = shoup(p->PHatInvModp[j], p->p[j]);
     c->to_crt = malloc(sizeof(uint32_t) * c->N);
     orc_set_packing_cofactor(c, PSI_PACK_COFACTOR_3);
+    if (p->ks_technique == PSI_KS_HYBRID) {
+        int L = c->L;
+        c->parts = (int)p->ks_num_parts;
+        c->Lk = (int)p->Lk;
+        c->alpha = (L + c->parts - 1) / c->parts;
+        for (int k = 0; k < c->Lk; k++) modctx_init(&c->mk[k], p->pk[k], p->psi_pk[k], c->N);
+        for (int i = 0; i < L; i++) {
+            int j = i / c->alpha, lo = j * c->alpha, hi = lo + c->alpha < L ? lo + c->alpha : L;
+            for (int m = 0; m < L + c->Lk; m++) {
+                u64 mod = m < L ? p->q[m] : p->pk[m - L], r = 1 % mod;
+                for (int u = lo; u < hi; u++)
+                    if (u != i) r = mulmod(r, p->q[u] % mod, mod);
+                c->PartQHatModt[i][m] = r;
+            }
+            c->PartQHatInvModq[i] = invmod(c->PartQHatModt[i][i], p->q[i]);
+            u64 pk = 1;
+            for (int k = 0; k < c->Lk; k++) pk = mulmod(pk, p->pk[k] % p->q[i], p->q[i]);
+            c->PkModq[i] = pk;
+            c->PkInvModq[i] = invmod(pk, p->q[i]);
+        }
+        for (int k = 0; k < c->Lk; k++) {
+            u64 hat = 1;
+            for (int u = 0; u < c->Lk; u++)
+                if (u != k) hat = mulmod(hat, p->pk[u] % p->pk[k], p->pk[k]);
+            c->PkHatInvModpk[k] = invmod(hat, p->pk[k]);
+            for (int i = 0; i < L; i++) {
+                u64 r = 1;
+                for (int u = 0; u < c->Lk; u++)
+                    if (u != k) r = mulmod(r, p->pk[u] % p->q[i], p->q[i]);
+                c->PkHatModq[k][i] = r;
+            }
+        }
+    }
     u64 Qmodt = 1;
     for (int i = 0; i < c->L; i++) Qmodt = mulmod(Qmodt, p->q[i] % p->t, p->t);
     c->negQModt = (p->t - Qmodt) % p->t;
@@ -253,6 +296,7 @@ void orc_destroy(orc_ctx* c) {
     if (!c) return;
     for (int i = 0; i < c->L; i++) modctx_free(&c->mq[i]);
     for (int j = 0; j < c->Lp; j++) modctx_free(&c->mp[j]);
+    for (int k = 0; k < c->Lk; k++) modctx_free(&c->mk[k]);
     modctx_free(&c->mt);
     free(c->to_crt);
     free(c);
@@ -520,6 +564,14 @@ void orc_mul_ctpt(const orc_ctx* c, const u64* ct, const u64* pt, u64* out) {
         }
 }
 
+/* nu += x * y the way the host library's compiler evaluates it: separate multiply and add (x86-64 without -march
+ * flags, the default) or one fused multiply-add (-march=native builds, aarch64); P.fp_contract selects. */
+static inline double nu_step(double nu, double x, double y, int fma_mode) {
+    if (fma_mode) return fma(x, y, nu);
+    double prod = x * y;
+    return nu + prod;
+}
+
 /* DCRTPoly::SwitchCRTBasis (HPS'18 eq. (3), OpenFHE order recalled): exact conversion of one
  * coefficient from basis A (moduli a[], nA) to basis B.  The number of A-overflows is
  * alpha = (unsigned) (0.5 + sum_i (double)y_i * aInv[i]) accumulated left to right in IEEE
@@ -528,13 +580,12 @@ static inline void switch_crt_basis_coeff(int nA, int nB, const u64* x, const u6
                                           const u64* AHatInvModa_s, const double* aInv,
                                           const u64 (*AHatModb)[PSI_MAX_LIMBS], /* [out j][in i] */
                                           const u64 (*alphaAModb)[PSI_MAX_LIMBS], /* [alpha][j] */
-                                          const modctx* mb, u64* out) {
+                                          const modctx* mb, u64* out, int fma_mode) {
     u64 y[PSI_MAX_LIMBS];
     double nu = 0.5;
     for (int i = 0; i < nA; i++) {
         y[i] = mulshoup(x[i], AHatInvModa[i], AHatInvModa_s[i], aMod[i]);
-        double prod = (double)y[i] * aInv[i];
-        nu = nu + prod;
+        nu = nu_step(nu, (double)y[i], aInv[i], fma_mode);
     }
     unsigned alpha = (unsigned)nu;
     for (int j = 0; j < nB; j++) {
@@ -556,6 +607,7 @@ static inline void switch_crt_basis_coeff(int nA, int nB, const u64* x, const u6
 void orc_mul_core(const orc_ctx* c, const u64* ct1, const u64* ct2, u64* res) {
     const int N = c->N, L = c->L, Lp = c->Lp, LT = L + Lp;
     const psi_params* P = &c->P;
+    const int fm = (int)P->fp_contract, hps = P->mult_technique == PSI_MULT_HPS;
     size_t polyQ = (size_t)L * N, polyT = (size_t)LT * N;
     u64* e1 = malloc(sizeof(u64) * 2 * polyT); /* ct1 in QP, EVAL */
     u64* e2 = malloc(sizeof(u64) * 2 * polyT); /* ct2 in QP, EVAL */
@@ -563,22 +615,26 @@ void orc_mul_core(const orc_ctx* c, const u64* ct1, const u64* ct2, u64* res) {
     u64* ten = malloc(sizeof(u64) * 3 * polyT);
 
     for (int k = 0; k < 2; k++) {
-        /* --- ct1: ExpandCRTBasis, Q limbs kept from the EVALUATION input */
-        u64* o = e1 + k * polyT;
-        memcpy(o, ct1 + k * polyQ, sizeof(u64) * polyQ);
-        memcpy(tmp, ct1 + k * polyQ, sizeof(u64) * polyQ);
-        for (int l = 0; l < L; l++) ntt_inv(tmp + (size_t)l * N, &c->mq[l], N);
-        for (int j = 0; j < N; j++) {
-            u64 x[PSI_MAX_LIMBS], y[PSI_MAX_LIMBS];
-            for (int l = 0; l < L; l++) x[l] = tmp[(size_t)l * N + j];
-            switch_crt_basis_coeff(L, Lp, x, P->q, P->QHatInvModq, c->QHatInvModq_s, P->qInv, P->QHatModp,
-                                   P->alphaQModp, c->mp, y);
-            for (int l = 0; l < Lp; l++) o[(size_t)(L + l) * N + j] = y[l];
+        /* --- ExpandCRTBasis, Q limbs kept from the EVALUATION input: ct1 always, ct2 too under HPS */
+        for (int op = 0; op < (hps ? 2 : 1); op++) {
+            const u64* src = (op ? ct2 : ct1) + k * polyQ;
+            u64* o = (op ? e2 : e1) + k * polyT;
+            memcpy(o, src, sizeof(u64) * polyQ);
+            memcpy(tmp, src, sizeof(u64) * polyQ);
+            for (int l = 0; l < L; l++) ntt_inv(tmp + (size_t)l * N, &c->mq[l], N);
+            for (int j = 0; j < N; j++) {
+                u64 x[PSI_MAX_LIMBS], y[PSI_MAX_LIMBS];
+                for (int l = 0; l < L; l++) x[l] = tmp[(size_t)l * N + j];
+                switch_crt_basis_coeff(L, Lp, x, P->q, P->QHatInvModq, c->QHatInvModq_s, P->qInv, P->QHatModp,
+                                       P->alphaQModp, c->mp, y, fm);
+                for (int l = 0; l < Lp; l++) o[(size_t)(L + l) * N + j] = y[l];
+            }
+            for (int l = 0; l < Lp; l++) ntt_fwd(o + (size_t)(L + l) * N, &c->mp[l], N);
         }
-        for (int l = 0; l < Lp; l++) ntt_fwd(o + (size_t)(L + l) * N, &c->mp[l], N);
+        if (hps) continue;
 
-        /* --- ct2: COEFFICIENT, FastExpandCRTBasisPloverQ (KPZ'21), EVALUATION */
-        o = e2 + k * polyT;
+        /* --- HPSPOVERQ, ct2: COEFFICIENT, FastExpandCRTBasisPloverQ (KPZ'21), EVALUATION */
+        u64* o = e2 + k * polyT;
         memcpy(tmp, ct2 + k * polyQ, sizeof(u64) * polyQ);
         for (int l = 0; l < L; l++) ntt_inv(tmp + (size_t)l * N, &c->mq[l], N);
         for (int j = 0; j < N; j++) {
@@ -591,7 +647,7 @@ void orc_mul_core(const orc_ctx* c, const u64* ct1, const u64* ct2, u64* res) {
                 pp[l] = barrett128(sum, &c->mp[l]);
             }
             switch_crt_basis_coeff(Lp, L, pp, P->p, P->PHatInvModp, c->PHatInvModp_s, P->pInv, P->PHatModq,
-                                   P->alphaPModq, c->mq, qq);
+                                   P->alphaPModq, c->mq, qq, fm);
             for (int l = 0; l < L; l++) o[(size_t)l * N + j] = qq[l];
             for (int l = 0; l < Lp; l++) o[(size_t)(L + l) * N + j] = pp[l];
         }
@@ -610,26 +666,40 @@ void orc_mul_core(const orc_ctx* c, const u64* ct1, const u64* ct2, u64* res) {
             t2[j] = barrett128((u128)a1[j] * b1[j], m);
         }
     }
-    /* --- COEFFICIENT, then DCRTPoly::ScaleAndRound by t/P with output basis Q:
-     * nu = 0.5 + sum_i frac[i] * (double) x_{p_i}  (left to right, no FMA), alpha = (u64) nu */
+    /* --- COEFFICIENT, then DCRTPoly::ScaleAndRound:
+     *   HPSPOVERQ  by t/P with output basis Q:  nu = 0.5 + sum_i frac[i] * (double) x_{p_i}, alpha = (u64) nu
+     *   HPS        by t/Q with output basis P (nu over the Q limbs), then the exact SwitchCRTBasis P -> Q */
     for (int k = 0; k < 3; k++) {
         u64* x = ten + k * polyT;
         for (int l = 0; l < LT; l++) ntt_inv(x + (size_t)l * N, mod_at(c, l), N);
         u64* r = res + k * polyQ;
         for (int j = 0; j < N; j++) {
             double nu = 0.5;
-            for (int i = 0; i < Lp; i++) {
-                double prod = P->tQSHatInvModsDivsFrac[i] * (double)x[(size_t)(L + i) * N + j];
-                nu = nu + prod;
-            }
-            u64 alpha = (u64)nu;
-            for (int l = 0; l < L; l++) {
-                u128 cur = 0;
-                for (int i = 0; i < Lp; i++)
-                    cur += (u128)x[(size_t)(L + i) * N + j] * P->tQSHatInvModsDivsModq[l][i];
-                cur += (u128)x[(size_t)l * N + j] * P->tQSHatInvModsDivsModq[l][Lp];
-                u64 v = barrett128(cur, &c->mq[l]);
-                r[(size_t)l * N + j] = addmod(v, alpha % P->q[l], P->q[l]);
+            if (!hps) {
+                for (int i = 0; i < Lp; i++) nu = nu_step(nu, P->tQSHatInvModsDivsFrac[i], (double)x[(size_t)(L + i) * N + j], fm);
+                u64 alpha = (u64)nu;
+                for (int l = 0; l < L; l++) {
+                    u128 cur = 0;
+                    for (int i = 0; i < Lp; i++)
+                        cur += (u128)x[(size_t)(L + i) * N + j] * P->tQSHatInvModsDivsModq[l][i];
+                    cur += (u128)x[(size_t)l * N + j] * P->tQSHatInvModsDivsModq[l][Lp];
+                    u64 v = barrett128(cur, &c->mq[l]);
+                    r[(size_t)l * N + j] = addmod(v, alpha % P->q[l], P->q[l]);
+                }
+            } else {
+                u64 yp[PSI_MAX_LIMBS], qq[PSI_MAX_LIMBS];
+                for (int i = 0; i < L; i++) nu = nu_step(nu, P->tPSHatInvModsDivsFrac[i], (double)x[(size_t)i * N + j], fm);
+                u64 alpha = (u64)nu;
+                for (int l = 0; l < Lp; l++) {
+                    u128 cur = 0;
+                    for (int i = 0; i < L; i++) cur += (u128)x[(size_t)i * N + j] * P->tPSHatInvModsDivsModp[l][i];
+                    cur += (u128)x[(size_t)(L + l) * N + j] * P->tPSHatInvModsDivsModp[l][L];
+                    u64 v = barrett128(cur, &c->mp[l]);
+                    yp[l] = addmod(v, alpha % P->p[l], P->p[l]);
+                }
+                switch_crt_basis_coeff(Lp, L, yp, P->p, P->PHatInvModp, c->PHatInvModp_s, P->pInv, P->PHatModq,
+                                       P->alphaPModq, c->mq, qq, fm);
+                for (int l = 0; l < L; l++) r[(size_t)l * N + j] = qq[l];
             }
         }
     }
@@ -679,10 +749,127 @@ void orc_relin(const orc_ctx* c, const u64* res, const u64* evk_b, const u64* ev
     free(tmp);
 }
 
+/* RelinearizeCore + KeySwitchHYBRID::KeySwitchCore (recalled): c2 is cut into `parts` digits of alpha consecutive
+ * limbs; each digit is lifted from its own limbs to all other limbs of Q and to the special primes by
+ * ApproxSwitchCRTBasis (no rounding correction, integers only), everything goes to EVALUATION, the inner products with
+ * the key run over the extended basis, and ApproxModDown divides by the special modulus: the P limbs go to
+ * COEFFICIENT, are switched to Q the same approximate way, transformed, subtracted and multiplied by P^-1.
+ * No floating point anywhere: bit-exactness vs the host library is structural.
+ * res: [3][L][N] COEFFICIENT; evk_b / evk_a: [parts][L+Lk][N] EVALUATION; out: [2][L][N] EVALUATION. */
+void orc_relin_hybrid(const orc_ctx* c, const u64* res, const u64* evk_b, const u64* evk_a, u64* out) {
+    const int N = c->N, L = c->L, Lk = c->Lk, LE = L + Lk, parts = c->parts, alpha = c->alpha;
+    const psi_params* P = &c->P;
+    size_t polyQ = (size_t)L * N, polyE = (size_t)LE * N;
+    const u64* c2 = res + 2 * polyQ;
+    u64* dig = malloc(sizeof(u64) * polyE);
+    u64* ext = calloc(2 * polyE, sizeof(u64)); /* (sum_j d_j b_j, sum_j d_j a_j) over Q + pk */
+    for (int j = 0; j < parts; j++) {
+        int lo = j * alpha, hi = lo + alpha < L ? lo + alpha : L;
+        for (int n = 0; n < N; n++) {
+            u64 y[PSI_MAX_LIMBS];
+            for (int i = lo; i < hi; i++) y[i] = mulmod(c2[(size_t)i * N + n], c->PartQHatInvModq[i], P->q[i]);
+            for (int m = 0; m < LE; m++) {
+                if (m >= lo && m < hi) {
+                    dig[(size_t)m * N + n] = c2[(size_t)m * N + n]; /* own limb: the coefficient itself */
+                    continue;
+                }
+                const modctx* mm = m < L ? &c->mq[m] : &c->mk[m - L];
+                u128 sum = 0;
+                for (int i = lo; i < hi; i++) sum += (u128)y[i] * c->PartQHatModt[i][m];
+                dig[(size_t)m * N + n] = barrett128(sum, mm);
+            }
+        }
+        for (int m = 0; m < LE; m++) {
+            const modctx* mm = m < L ? &c->mq[m] : &c->mk[m - L];
+            ntt_fwd(dig + (size_t)m * N, mm, N);
+            const u64* kb = evk_b + ((size_t)j * LE + m) * N;
+            const u64* ka = evk_a + ((size_t)j * LE + m) * N;
+            u64 *o0 = ext + (size_t)m * N, *o1 = ext + polyE + (size_t)m * N;
+            for (int n = 0; n < N; n++) {
+                o0[n] = addmod(o0[n], barrett128((u128)dig[(size_t)m * N + n] * kb[n], mm), mm->q);
+                o1[n] = addmod(o1[n], barrett128((u128)dig[(size_t)m * N + n] * ka[n], mm), mm->q);
+            }
+        }
+    }
+    /* ApproxModDown of both components, then + (c0, c1) */
+    u64* sw = malloc(sizeof(u64) * polyQ);
+    for (int k = 0; k < 2; k++) {
+        u64* e = ext + k * polyE;
+        for (int u = 0; u < Lk; u++) ntt_inv(e + (size_t)(L + u) * N, &c->mk[u], N);
+        for (int n = 0; n < N; n++) {
+            u64 y[PSI_MAX_LIMBS];
+            for (int u = 0; u < Lk; u++) y[u] = mulmod(e[(size_t)(L + u) * N + n], c->PkHatInvModpk[u], P->pk[u]);
+            for (int i = 0; i < L; i++) {
+                u128 sum = 0;
+                for (int u = 0; u < Lk; u++) sum += (u128)y[u] * c->PkHatModq[u][i];
+                sw[(size_t)i * N + n] = barrett128(sum, &c->mq[i]);
+            }
+        }
+        memcpy(out + k * polyQ, res + k * polyQ, sizeof(u64) * polyQ);
+        for (int i = 0; i < L; i++) {
+            u64 q = P->q[i];
+            ntt_fwd(sw + (size_t)i * N, &c->mq[i], N);
+            ntt_fwd(out + k * polyQ + (size_t)i * N, &c->mq[i], N);
+            u64* o = out + k * polyQ + (size_t)i * N;
+            for (int n = 0; n < N; n++)
+                o[n] = addmod(o[n], mulmod(submod(e[(size_t)i * N + n], sw[(size_t)i * N + n], q), c->PkInvModq[i], q), q);
+        }
+    }
+    free(sw);
+    free(ext);
+    free(dig);
+}
+
+/* EvalMultKeyGen under HYBRID (KeySwitchHYBRID::KeySwitchGenInternal, recalled): for digit j, a_j uniform and e_j
+ * Gaussian over the extended basis, b_j = -a_j s + e_j + [P]_{q_i} s^2 on the limbs of digit j only.
+ * sk: [L][N] EVAL (orc_keygen's secret is re-derived from the same seed); evk_b, evk_a: [parts][L+Lk][N]. */
+void orc_keygen_hybrid(const orc_ctx* c, u64 seed, u64* sk, u64* evk_b, u64* evk_a) {
+    int N = c->N, L = c->L, Lk = c->Lk, LE = L + Lk;
+    rng_t r = {seed};
+    int64_t* small = malloc(sizeof(int64_t) * N);
+    int64_t* secret = malloc(sizeof(int64_t) * N);
+    for (int j = 0; j < N; j++) secret[j] = (int64_t)rng_below(&r, 3) - 1;
+    small_to_eval(c, secret, sk);
+    u64* s_ext = malloc(sizeof(u64) * (size_t)LE * N);
+    u64* e_ext = malloc(sizeof(u64) * (size_t)LE * N);
+    for (int m = 0; m < LE; m++) {
+        const modctx* mm = m < L ? &c->mq[m] : &c->mk[m - L];
+        for (int j = 0; j < N; j++) s_ext[(size_t)m * N + j] = secret[j] < 0 ? mm->q - 1 : (u64)secret[j];
+        ntt_fwd(s_ext + (size_t)m * N, mm, N);
+    }
+    for (int part = 0; part < c->parts; part++) {
+        int lo = part * c->alpha, hi = lo + c->alpha < L ? lo + c->alpha : L;
+        for (int j = 0; j < N; j++) small[j] = rng_gauss(&r, 3.19);
+        for (int m = 0; m < LE; m++) {
+            const modctx* mm = m < L ? &c->mq[m] : &c->mk[m - L];
+            u64 q = mm->q;
+            u64* e = e_ext + (size_t)m * N;
+            for (int j = 0; j < N; j++) e[j] = small[j] < 0 ? q - (u64)(-small[j]) : (u64)small[j];
+            ntt_fwd(e, mm, N);
+            u64* a = evk_a + ((size_t)part * LE + m) * N;
+            u64* b = evk_b + ((size_t)part * LE + m) * N;
+            const u64* s = s_ext + (size_t)m * N;
+            for (int j = 0; j < N; j++) {
+                a[j] = rng_below(&r, q);
+                u64 v = submod(e[j], mulmod(a[j], s[j], q), q);
+                if (m >= lo && m < hi) v = addmod(v, mulmod(c->PkModq[m], mulmod(s[j], s[j], q), q), q);
+                b[j] = v;
+            }
+        }
+    }
+    free(e_ext);
+    free(s_ext);
+    free(secret);
+    free(small);
+}
+
 void orc_mul_ctct(const orc_ctx* c, const u64* ct1, const u64* ct2, const u64* evk_b, const u64* evk_a, u64* out) {
     u64* res = malloc(sizeof(u64) * 3 * (size_t)c->L * c->N); /* scaled result in Q, COEFFICIENT */
     orc_mul_core(c, ct1, ct2, res);
-    orc_relin(c, res, evk_b, evk_a, out);
+    if (c->P.ks_technique == PSI_KS_HYBRID)
+        orc_relin_hybrid(c, res, evk_b, evk_a, out);
+    else
+        orc_relin(c, res, evk_b, evk_a, out);
     free(res);
 }
 

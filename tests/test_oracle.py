@@ -23,8 +23,8 @@ import scenario as sc
 T32 = 4296540161  # 2^32 + 2^20 + 2^19 + 1  (BatchedFHEPSIClient.cpp:29, TestBatchedFHEPIE.cpp:16)
 
 
-def small_oracle(N=64, L=2):
-    return Oracle(RefParams(N, T32, L=L).to_struct())
+def small_oracle(N=64, L=2, **variant):
+    return Oracle(RefParams(N, T32, L=L, **variant).to_struct())
 
 
 def test_ntt_matches_definition():
@@ -95,12 +95,18 @@ def test_encrypt_decrypt_roundtrip():
     assert budget >= 60  # fresh ciphertext (the estimate saturates at 64 bits of fixed-point precision)
 
 
-@pytest.mark.parametrize("N,L", [(32, 2), (64, 3)])
-def test_mul_core_against_exact_bfv(N, L):
-    """HPSPOVERQ tensor + scale-and-round vs the exact definition round(t/Q * tensor): the RNS
+VARIANTS = [dict(), dict(mult_technique=0), dict(ks_technique=1), dict(mult_technique=0, ks_technique=1, fp_contract=1),
+            dict(fp_contract=1)]
+
+
+@pytest.mark.parametrize("variant", VARIANTS, ids=lambda v: "-".join("%s%d" % (k[:2], x) for k, x in v.items()) or "default")
+@pytest.mark.parametrize("N,L", [(32, 2), (64, 3), (64, 5)])
+def test_mul_core_against_exact_bfv(N, L, variant):
+    """HPSPOVERQ / HPS tensor + scale-and-round vs the exact definition round(t/Q * tensor): the RNS
     procedure may only add a noise-sized term (bounded by ~ t * N * (L+1), from rounding P/Q * ct2),
-    never a wrap-around; and both decrypt (with s, s^2) to the slot-wise product."""
-    o = small_oracle(N, L)
+    never a wrap-around; and both decrypt (with s, s^2) to the slot-wise product.  Relinearisation (BV or HYBRID)
+    must leave the message alone; separate / fused evaluation of the double sums only moves roundings."""
+    o = small_oracle(N, L, **variant)
     ex = ExactBFV(o)
     rng = np.random.default_rng(4)
     sk, evk_b, evk_a = o.keygen(9)

@@ -17,6 +17,18 @@ def test_generators_agree(N, t, depth):
         assert got[key] == want[key], key
 
 
+@pytest.mark.parametrize("depth,L", [(3, 0), (2, 0), (5, 0), (1, 1), (3, 5)])
+def test_generators_agree_on_variants(depth, L):
+    """HPS tables, HYBRID digit count / special primes, fp mode: C++ generator == exact Python definitions."""
+    got = struct_to_dict(P.params_generate(16384, T32, depth, L, mult_technique=0, ks_technique=1, fp_contract=1))
+    want = struct_to_dict(RefParams(16384, T32, depth, L=L or None, mult_technique=0, ks_technique=1, fp_contract=1).to_struct())
+    assert got == want
+    assert got["mult_technique"] == 0 and got["ks_technique"] == 1 and got["fp_contract"] == 1
+    assert got["ks_num_parts"] * got["Lk"] >= got["L"] > (got["ks_num_parts"] - 1) * got["Lk"]
+    mods = got["q"] + got["p"] + got["pk"]
+    assert len(set(mods)) == len(mods) and mods == sorted(mods, reverse=True)
+
+
 def test_moduli_properties():
     p = P.params_generate(16384, T32, 3)
     mods = list(p.q[:p.L]) + list(p.p[:p.Lp])
