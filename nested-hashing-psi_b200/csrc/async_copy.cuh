@@ -34,4 +34,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
+// per-thread asynchronous copies (SASS LDGSTS): no staging registers, every copy of a tile in flight at once.
+// 8 bytes because the padded tile layout (fused_mul.cuh sl()) only keeps 8-byte alignment.
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 }  // namespace psi

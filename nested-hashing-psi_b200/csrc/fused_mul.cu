@@ -27,12 +27,19 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_inv(const DevTables* __r
         stage_row_twiddles(tws, tab->mods[l].itw_rows, blockIdx.x, &tw_bar);
     }
     const bool active = (ops >> (g >> 1)) & 1u;
-    if (active) load_rows(arr + g * P, (g < 2 ? a : b) + off, tid);
+    // experiment builds (results are garbage): bit 0 = no tile load, bit 1 = no transform, bit 2 = no store.  MEASURED at
+    // config B: 73.0 us as is, 65.4 without load and store, 33.1 without the transform (tools/p2_variants.sh)
+#ifndef PSI_DBG_SKIP
+#define PSI_DBG_SKIP 0
+#endif
+    if (active && !(PSI_DBG_SKIP & 1)) load_rows(arr + g * P, (g < 2 ? a : b) + off, tid);
+    loads_wait();
     __syncthreads();
     mbar_wait(&tw_bar, 0);
     // an inactive group owns no array (group index 4 = none) and takes part in no group barrier
-    transform_rows<true>(tab, arr, P, 4, [l](uint32_t) { return l; }, active ? g : 4, 4, logN, tile_base, tid, tws);
-    if (active) store_rows(arr + g * P, (g < 2 ? ha : hb) + off, tid);
+    if (!(PSI_DBG_SKIP & 2))
+        transform_rows<true>(tab, arr, P, 4, [l](uint32_t) { return l; }, active ? g : 4, 4, logN, tile_base, tid, tws);
+    if (active && !(PSI_DBG_SKIP & 4)) store_rows(arr + g * P, (g < 2 ? ha : hb) + off, tid);
 }
 
 // ---- (3) rows: forward, tensor, inverse -----------------------------------------------------------
@@ -66,6 +73,7 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_tensor(const DevTables* 
         stage_row_twiddles(tws_i, md.itw_rows, blockIdx.x, &tw_bar);
     }
     load_rows(arr + g * P, src + tile_base, tid);
+    loads_wait();
     __syncthreads();
     mbar_wait(&tw_bar, 0);
     // the Q limbs of the first operand are already in EVALUATION form: arrays 0, 1 are skipped for l < L
@@ -123,6 +131,7 @@ __global__ void __launch_bounds__((2 + L) * kGroup, L <= 4 ? 2 : 1)
         stage_row_twiddles(tws, md.ftw_rows, blockIdx.x, &tw_bar);
     }
     load_rows(arr + g * P, src + tile_base, tid);
+    loads_wait();
     __syncthreads();
     mbar_wait(&tw_bar, 0);
     transform_rows<false>(tab, arr, P, 2 + L, [kk](uint32_t) { return kk; }, g, 2 + L, logN, tile_base, tid, tws);

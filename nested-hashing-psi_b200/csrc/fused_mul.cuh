@@ -334,14 +334,36 @@ __device__ __forceinline__ ulonglong2 ld_tile16(const u64* p) {
 
 // ---- tile movers (16-byte global accesses) ------------------------------------------------------
 // row tile: 2^(7+kRowTileLog) contiguous coefficients
+// PSI_ASYNC_LOADS: the tile loads are per-thread cp.async copies (SASS LDGSTS) straight into the padded layout: every
+// copy of a tile in flight at once, no staging registers, one wait before the barrier that publishes the tile.
+// MEASURED (round 2, config B): same kernel times as the register version (LDG.128 + two STS.64, unroll 4) to three
+// digits -- an experiment build of k_rows_inv without any tile load or store runs in 65.4 us against 73.0, i.e. the
+// global traffic is 10 % of that kernel and far less of the others; see DESIGN.md 3.2 "what bounds phase 2".
+#ifndef PSI_ASYNC_LOADS
+#define PSI_ASYNC_LOADS 1
+#endif
 __device__ __forceinline__ void load_rows(u64* sm, const u64* __restrict__ poly_tile, uint32_t tid) {
     const uint32_t M2 = 1u << (kLogCols + kRowTileLog - 1);
+#if PSI_ASYNC_LOADS
+#pragma unroll
+    for (uint32_t j = tid; j < M2; j += kGroup) {
+        cp_async8(sm + sl(2 * j), poly_tile + 2 * j);
+        cp_async8(sm + sl(2 * j) + 1, poly_tile + 2 * j + 1);
+    }
+#else
 #pragma unroll 4
     for (uint32_t j = tid; j < M2; j += kGroup) {
         const ulonglong2 v = ld_tile16(poly_tile + 2 * j);
         sm[sl(2 * j)] = v.x;
         sm[sl(2 * j) + 1] = v.y;
     }
+#endif
+}
+// every thread calls this between its loads and the barrier that publishes the tile
+__device__ __forceinline__ void loads_wait() {
+#if PSI_ASYNC_LOADS
+    cp_async_wait_all();
+#endif
 }
 __device__ __forceinline__ void store_rows(const u64* sm, u64* __restrict__ poly_tile, uint32_t tid) {
     const uint32_t M2 = 1u << (kLogCols + kRowTileLog - 1);
@@ -352,6 +374,15 @@ __device__ __forceinline__ void store_rows(const u64* sm, u64* __restrict__ poly
 // column tile: local j = r * 8 + cc  <->  global n = r * 128 + c0 + cc
 __device__ __forceinline__ void load_cols(u64* sm, const u64* __restrict__ poly, uint32_t logR, uint32_t c0, uint32_t tid) {
     const uint32_t M2 = 1u << (logR + kColTileLog - 1);
+#if PSI_ASYNC_LOADS
+#pragma unroll 8
+    for (uint32_t j = tid; j < M2; j += kGroup) {
+        const uint32_t e = 2 * j;
+        const u64* src = poly + ((e >> kColTileLog) << kLogCols) + c0 + (e & ((1u << kColTileLog) - 1));
+        cp_async8(sm + sl(e), src);
+        cp_async8(sm + sl(e) + 1, src + 1);
+    }
+#else
 #pragma unroll 4
     for (uint32_t j = tid; j < M2; j += kGroup) {
         const uint32_t e = 2 * j;
@@ -359,6 +390,7 @@ __device__ __forceinline__ void load_cols(u64* sm, const u64* __restrict__ poly,
         sm[sl(e)] = v.x;
         sm[sl(e) + 1] = v.y;
     }
+#endif
 }
 __device__ __forceinline__ void store_cols(const u64* sm, u64* __restrict__ poly, uint32_t logR, uint32_t c0, uint32_t tid) {
     const uint32_t M2 = 1u << (logR + kColTileLog - 1);
@@ -395,6 +427,7 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 3)
     // column-inverse of the L input limbs
     const u64* src = (operand ? hb : ha) + ((bin * 2 + comp) * L) * (size_t)N;
     for (uint32_t a = g; a < L; a += kColGroups) load_cols(smem + a * P, src + (size_t)a * N, logR, c0, tid);
+    loads_wait();
     __syncthreads();
     transform_cols<true, LOGN_CT>(tab, smem, P, L, [](uint32_t a) { return a; }, g, kColGroups, logN, tid);
     __syncthreads();  // the extension reads every limb of a coefficient
@@ -493,6 +526,7 @@ __global__ void __launch_bounds__(kColGroups* kGroup, 3)
     const size_t bin = blockIdx.y;
     for (uint32_t a = g; a < LT; a += kColGroups)
         load_cols(smem + a * P, th + ((bin * 3 + comp) * LT + a) * (size_t)N, logR, c0, tid);
+    loads_wait();
     __syncthreads();
     transform_cols<true, LOGN_CT>(tab, smem, P, LT, [](uint32_t a) { return a; }, g, kColGroups, logN, tid);
     __syncthreads();  // scale-and-round reads every limb of a coefficient

@@ -875,7 +875,10 @@ cudaError_t pipe_peak(int device, int kind, double* per_second) {
     if (e != cudaSuccess) return e;
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return e;
-    const unsigned blocks = prop.multiProcessorCount * 8, threads = 256;
+    // kind bits 4..7: resident 256-thread blocks per SM (0 = 8, i.e. 16 warps per scheduler); the fused kernels run at 3
+    const unsigned per_sm = (kind >> 4) & 15 ? (kind >> 4) & 15 : 8;
+    kind &= 15;
+    const unsigned blocks = prop.multiProcessorCount * per_sm, threads = 256;
     const uint32_t iters = kind == 0 ? 4096 : 2048;
     u64* out = nullptr;
     if ((e = cudaMalloc(&out, (size_t)blocks * threads * sizeof(u64))) != cudaSuccess) return e;
