@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -139,12 +140,22 @@ struct psi_ctx {
     // phase 2 in bin groups on concurrent streams (tails of one group's kernels overlap the next group's heads);
     // 0 = choose from the number of resident bins
     uint32_t p2_groups = 0;
-    cudaStream_t aux[3] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join[3] = {};
+    cudaStream_t aux[7] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[7] = {};
     // psi_query_run_streamed: copy-in / copy-out streams and the events that order slices and bin groups
     cudaStream_t sq_in = nullptr, sq_out = nullptr;
     cudaEvent_t ev_slice[kMaxStreamSlices] = {}, ev_group[4] = {}, ev_sq = nullptr;
 
+    // run() as a CUDA graph: the launch set of one evaluation (inner product, bin groups forked over the auxiliary
+    // streams, their joins) is captured once per (phases, result buffer, grouping, buffer addresses) and replayed, so a
+    // query costs one graph launch instead of 11-25 kernel launches and event operations on the host
+    struct RunGraph {
+        uint64_t key = 0;
+        cudaGraphExec_t exec = nullptr;
+        uint32_t launches = 0;
+    };
+    std::vector<RunGraph> graphs;
+    bool use_graph = true;
     uint32_t Lk = 0, ks_parts = 0;  // HYBRID key switching
     bool hybrid = false, hps = false;
     KCtx k(cudaStream_t s) const { return KCtx{d_tab, N, logN, L, Lp, s, Lk, !hybrid && !hps}; }
@@ -559,13 +570,17 @@ int psi_ctx_create(const psi_params* p, int device, psi_ctx** out) {
         psi_ctx_destroy(c);
         return rc;
     }
+    c->use_graph = std::getenv("PSI_NO_GRAPH") == nullptr;  // tuning / debugging: direct launches
     *out = c;
     return PSI_OK;
 }
 
+static void drop_run_graphs(psi_ctx* c);
+
 int psi_ctx_destroy(psi_ctx* c) {
     if (!c) return PSI_OK;
     cudaSetDevice(c->device);
+    drop_run_graphs(c);
     if (c->d_tab) cudaFree(c->d_tab);
     DevBuf<u64>* bufs[] = {&c->twiddles, &c->twiddles2, &c->twiddles_rows, &c->evk_bR, &c->evk_aR, &c->maskR, &c->evk_b, &c->evk_a, &c->pt, &c->mask, &c->idx, &c->idx_in, &c->stage, &c->minus, &c->acc,
                            &c->coef,     &c->e1,    &c->e2,    &c->ten, &c->res, &c->dig, &c->prod,  &c->out, &c->out2, &c->minus_in};
@@ -1028,7 +1043,7 @@ int psi_result_get_limbs(psi_ctx* c, uint64_t* const* out_limbs, void* stream) {
 }
 
 int psi_debug_set_tuning(psi_ctx* c, int mac_variant, int phase2_groups) {
-    if (!c || mac_variant < -1 || mac_variant > 2 || phase2_groups < -1 || phase2_groups > 4) return set_error(PSI_ERR_INVALID, "bad tuning value");
+    if (!c || mac_variant < -1 || mac_variant > 2 || phase2_groups < -1 || phase2_groups > 8) return set_error(PSI_ERR_INVALID, "bad tuning value");
     if (mac_variant >= 0) mac_force_variant(mac_variant);
     if (phase2_groups >= 0) c->p2_groups = (uint32_t)phase2_groups;
     return PSI_OK;
@@ -1086,6 +1101,17 @@ int psi_query_commit(psi_ctx* c, void* stream) {
 
 int psi_run(psi_ctx* c, void* stream) { return psi_run_phases(c, PSI_PHASE_ALL, stream); }
 
+static int phase2_streams(psi_ctx* c) {
+    if (c->ev_fork) return PSI_OK;
+    cudaError_t e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < 7 && e == cudaSuccess; i++) {
+        e = cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "bin-group streams");
+    return PSI_OK;
+}
+
 // The ct x ct chain + mask of bins [g0, g1) into result (the context's [b][2][L][N] buffer), split into G bin
 // groups on concurrent streams forked from / joined into s.  The bins are independent, so one group's kernels fill
 // the SMs another group's tails leave idle (measured: 2 groups -3 % at 47 bins, -13 % at 12).
@@ -1094,17 +1120,11 @@ static int phase2_bins(psi_ctx* c, cudaStream_t s, uint32_t g0, uint32_t g1, uin
     const size_t ct = (size_t)2 * c->L * c->N;
     const uint32_t nb = g1 - g0;
     if (G > nb) G = nb;
-    if (G > 4) G = 4;
+    if (G > 8) G = 8;
     if (G < 1) G = 1;
     if (G > 1) {
-        if (!c->ev_fork) {
-            cudaError_t e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
-            for (int i = 0; i < 3 && e == cudaSuccess; i++) {
-                e = cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking);
-                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
-            }
-            if (e != cudaSuccess) return cuda_fail(e, "bin-group streams");
-        }
+        int rc0 = phase2_streams(c);
+        if (rc0) return rc0;
         CK(cudaEventRecord(c->ev_fork, s));
     }
     for (uint32_t g = 0; g < G; g++) {
@@ -1132,6 +1152,46 @@ static uint32_t default_groups(const psi_ctx* c, uint32_t nbins) {
     return c->p2_groups ? c->p2_groups : (nbins >= 4 ? 2u : 1u);
 }
 
+// Enqueues one evaluation on s (and the auxiliary streams forked from it); result = the buffer this run writes.
+static int enqueue_run(psi_ctx* c, uint32_t phases, cudaStream_t s, u64* result, uint32_t* nl_out) {
+    const KCtx k = c->k(s);
+    uint32_t nl = 0;
+    int rc;
+    if (phases & PSI_PHASE_INNER_PRODUCT) {
+        CK(launch_mac(k, c->K, c->b, c->E, c->pt.p, c->idx.p, c->minus.p, c->acc.p)); nl++;
+    }
+    if (phases & PSI_PHASE_MULTIPLY_MASK) {
+        if (c->K == 1) {
+            cudaError_t e1 = launch_mul_ctpt(k, c->b, c->acc.p, c->mask.p, result);
+            if (e1 != cudaSuccess) return cuda_fail(e1, "launch_mul_ctpt");
+            nl++;
+        } else if ((rc = phase2_bins(c, s, 0, c->b, default_groups(c, c->b), result, &nl))) {
+            return rc;
+        }
+    }
+    *nl_out = nl;
+    return PSI_OK;
+}
+
+// everything a captured launch set depends on: dimensions, tuning, and the address of every buffer a kernel touches
+static uint64_t run_graph_key(const psi_ctx* c, uint32_t phases, uint32_t out_which) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&h](uint64_t v) { h = (h ^ v) * 1099511628211ull; };
+    const void* ptrs[] = {c->pt.p,  c->mask.p, c->maskR.p, c->idx.p, c->minus.p, c->acc.p,   c->coef.p,  c->e1.p,   c->e2.p, c->ten.p,
+                          c->res.p, c->dig.p,  c->prod.p,  c->out.p, c->out2.p,  c->evk_b.p, c->evk_a.p, c->evk_bR.p, c->evk_aR.p, c->d_tab};
+    for (const void* p : ptrs) mix((uint64_t)(uintptr_t)p);
+    for (uint64_t v : {(uint64_t)c->K, (uint64_t)c->b, (uint64_t)c->E, (uint64_t)phases, (uint64_t)out_which, (uint64_t)c->p2_groups,
+                       (uint64_t)mac_forced_variant()})
+        mix(v);
+    return h;
+}
+
+static void drop_run_graphs(psi_ctx* c) {
+    for (auto& g : c->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    c->graphs.clear();
+}
+
 int psi_run_phases(psi_ctx* c, uint32_t phases, void* stream) {
     if (!c) return set_error(PSI_ERR_INVALID, "null argument");
     if (!(phases & PSI_PHASE_ALL)) return set_error(PSI_ERR_INVALID, "no phase selected");
@@ -1140,33 +1200,54 @@ int psi_run_phases(psi_ctx* c, uint32_t phases, void* stream) {
     int rc = ensure_device(c);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    const KCtx k = c->k(s);
-    uint32_t nl = 0;
-    if (phases & PSI_PHASE_INNER_PRODUCT) {
-        CK(launch_mac(k, c->K, c->b, c->E, c->pt.p, c->idx.p, c->minus.p, c->acc.p)); nl++;
-    }
-    if (!(phases & PSI_PHASE_MULTIPLY_MASK)) {
-        c->launches_per_run = nl;
-        return PSI_OK;
-    }
+    const bool writes_result = (phases & PSI_PHASE_MULTIPLY_MASK) != 0;
     // this run writes the OTHER result buffer; out_cur / ran only change once every launch has been enqueued, so a
     // failure part-way never exposes a half-written buffer through psi_result_get
     const uint32_t next_out = c->out_cur ^ 1u;
     u64* const result = c->out_buf(next_out);
-    if (c->K == 1) {
-        cudaError_t e1 = launch_mul_ctpt(k, c->b, c->acc.p, c->mask.p, result);
-        if (e1 != cudaSuccess) {
-            c->ran = false;
-            return cuda_fail(e1, "launch_mul_ctpt");
+    uint32_t nl = 0;
+    // the legacy default stream cannot be captured: it takes the direct launches
+    if (c->use_graph && s != nullptr && s != cudaStreamLegacy) {
+        const uint64_t key = run_graph_key(c, phases, writes_result ? next_out : 2u);
+        psi_ctx::RunGraph* g = nullptr;
+        for (auto& e : c->graphs)
+            if (e.key == key) g = &e;
+        if (!g) {
+            if (c->graphs.size() >= 16) drop_run_graphs(c);  // buffers were re-allocated many times: start over
+            // the bin-group streams and events must exist before the capture starts
+            if ((rc = phase2_streams(c))) return rc;
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            rc = enqueue_run(c, phases, s, result, &nl);
+            const cudaError_t ee = cudaStreamEndCapture(s, &graph);
+            if (rc != PSI_OK || ee != cudaSuccess) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                if (writes_result) c->ran = false;
+                return rc != PSI_OK ? rc : cuda_fail(ee, "cudaStreamEndCapture");
+            }
+            cudaGraphExec_t exec = nullptr;
+            const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ei != cudaSuccess) return cuda_fail(ei, "cudaGraphInstantiate");
+            c->graphs.push_back(psi_ctx::RunGraph{key, exec, nl});
+            g = &c->graphs.back();
         }
-        nl++;
-    } else if ((rc = phase2_bins(c, s, 0, c->b, default_groups(c, c->b), result, &nl))) {
-        c->ran = false;
+        const cudaError_t el = cudaGraphLaunch(g->exec, s);
+        if (el != cudaSuccess) {
+            if (writes_result) c->ran = false;
+            return cuda_fail(el, "cudaGraphLaunch");
+        }
+        nl = g->launches;
+    } else if ((rc = enqueue_run(c, phases, s, result, &nl))) {
+        if (writes_result) c->ran = false;
         return rc;
     }
-    c->out_cur = next_out;
     c->launches_per_run = nl;
-    c->ran = true;
+    if (writes_result) {
+        c->out_cur = next_out;
+        c->ran = true;
+    }
     return PSI_OK;
 }
 

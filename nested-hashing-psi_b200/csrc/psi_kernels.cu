@@ -234,6 +234,7 @@ static cudaError_t mac_launch_t(const KCtx& k, uint32_t nhf, uint32_t b, uint32_
 
 static int g_mac_force = 0;  // tuning / tests: 0 = choose by shape, 1 / 2 = force 2 / 4 bins per CTA
 void mac_force_variant(int v) { g_mac_force = v; }
+int mac_forced_variant() { return g_mac_force; }
 
 // bin-block width for b resident bins: 2-bin blocks when 4-bin blocks would leave more than a tenth of the
 // bin-lanes idle (measured: b = 5, 6, 14 faster with 2, b = 26, 47, 75 faster with 4)

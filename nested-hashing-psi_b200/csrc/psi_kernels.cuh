@@ -99,6 +99,7 @@ cudaError_t launch_mac(const KCtx& k, uint32_t K, uint32_t b, uint32_t E, const 
 // previous contents of acc, bit 1 = add minusCompareElement
 cudaError_t launch_mac_range(const KCtx& k, uint32_t hf0, uint32_t nhf, uint32_t b, uint32_t E, uint32_t pos0, uint32_t pos1,
                              uint32_t flags, const u64* pt, const u64* idx, const u64* minus, u64* acc);
+int mac_forced_variant();
 void mac_force_variant(int v);  // 0 = choose the bin-block width by shape, 1..3 = force 2 * v bins per CTA (tuning, tests)
 
 // EvalMult(ct,ct) building blocks, all batched over B ciphertexts (see psi_api.cu for the sequence)
