@@ -280,6 +280,8 @@ int psi_debug_set_tuning(psi_ctx* ctx, int mac_variant, int phase2_groups);
 int psi_bench_imad_peak(int device, double* mads_per_second);
 /* kind 0: IMAD.WIDE.U32 per second (same as above); kind 1: 64-bit Harvey/Shoup lazy butterflies per
  * second with operands in registers (the NTT's compute ceiling); kinds 2, 3: two other codings of the same butterfly.
+ * kinds 4, 5: the exchange of 16 u64 per thread between two radix passes through padded shared memory / through
+ * __shfl_xor butterflies, in exchanges per second.
  * Bits 4..7 of kind: resident 256-thread blocks per SM (0 = 8), to read the rate against occupancy. */
 int psi_bench_pipe_peak(int device, int kind, double* per_second);
 

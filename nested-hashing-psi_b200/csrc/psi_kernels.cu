@@ -871,6 +871,64 @@ __global__ void __launch_bounds__(256) k_butterfly3_peak(u64* out, uint32_t iter
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x[0] ^ x[1] ^ x[2] ^ x[3] ^ y[0] ^ y[1] ^ y[2] ^ y[3];
 }
 
+// kinds 4 / 5: the data exchange between two radix passes in isolation.  16 lanes hold 16 u64 each (lane l holds
+// elements 16 l .. 16 l + 15 of a 256-element block) and end up with the transpose (lane l holds elements l, l + 16, ...):
+//   kind 4: through padded shared memory, as the fused kernels do it: 16 STS.64, barrier, 16 LDS.64
+//   kind 5: through the register file: four butterfly steps with __shfl_xor, each moving half of the values
+//           (2 x 8 SHFL per step and a select per moved word)
+// A 64-bit add between exchanges keeps the values live.  Returns exchanges (16 values per thread) per second.
+__global__ void __launch_bounds__(256) k_exchange_smem_peak(u64* out, uint32_t iters) {
+    __shared__ u64 sm[256 * 17 + 16];
+    u64 v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = threadIdx.x * 16 + k + blockIdx.x;
+    const uint32_t lane16 = threadIdx.x & 15, grp = threadIdx.x >> 4;
+    u64* base = sm + grp * (16 * 17);
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) base[lane16 * 17 + k] = v[k];   // conflict-free: lane stride 17 words
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] = base[k * 17 + lane16] + i;
+        __syncwarp();
+    }
+    u64 acc = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc ^= v[k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(256) k_exchange_shfl_peak(u64* out, uint32_t iters) {
+    u64 v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = threadIdx.x * 16 + k + blockIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int step = 0; step < 4; step++) {
+            const int m = 8 >> step;  // lane distance and value distance of this step
+            const bool upper = (lane & m) != 0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                if (k & m) continue;
+                // the lower lane keeps v[k] and receives the partner's v[k]; it sends v[k + m]; the upper lane mirrors
+                const u64 send = upper ? v[k] : v[k + m];
+                const u64 got = __shfl_xor_sync(0xffffffffu, send, m);
+                if (upper)
+                    v[k] = got;
+                else
+                    v[k + m] = got;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] += i;
+    }
+    u64 acc = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc ^= v[k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 cudaError_t pipe_peak(int device, int kind, double* per_second) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return e;
@@ -897,6 +955,10 @@ cudaError_t pipe_peak(int device, int kind, double* per_second) {
             k_butterfly_peak<<<blocks, threads>>>(out, iters, q, w, ws);
         else if (kind == 2)
             k_butterfly2_peak<<<blocks, threads>>>(out, iters, q, w, ws);
+        else if (kind == 4)
+            k_exchange_smem_peak<<<blocks, threads>>>(out, iters);
+        else if (kind == 5)
+            k_exchange_shfl_peak<<<blocks, threads>>>(out, iters);
         else
             k_butterfly3_peak<<<blocks, threads>>>(out, iters, q, w, ws);
         cudaEventRecord(t1);
@@ -909,7 +971,7 @@ cudaError_t pipe_peak(int device, int kind, double* per_second) {
     cudaEventDestroy(t1);
     cudaFree(out);
     if (e != cudaSuccess) return e;
-    const double per_thread = kind == 0 ? (double)iters * 64.0 : (double)iters * 4.0;
+    const double per_thread = kind == 0 ? (double)iters * 64.0 : (kind >= 4 ? (double)iters : (double)iters * 4.0);
     *per_second = (double)blocks * threads * per_thread / (best * 1e-3);
     return cudaSuccess;
 }
