@@ -13,7 +13,8 @@ METRICS = [
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM % of peak"),
     ("lts__t_sector_hit_rate.pct", "L2 hit %"), ("l1tex__t_sector_hit_rate.pct", "L1 hit %"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
-    ("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "fmaheavy (IMAD) pipe busy %"),
+    ("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "fmaheavy (IMAD) pipe busy % (of elapsed)"),
+    ("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active", "fmaheavy (IMAD) pipe busy % (of active)"),
     ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu pipe inst %"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe %"),
     ("smsp__inst_executed.sum", "warp instructions"),
@@ -24,13 +25,17 @@ METRICS = [
     ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall wait"),
     ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall barrier"),
     ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall not_selected"),
+    ("smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "stall dispatch"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall short_scoreboard"),
 ]
 
 
-def main(path):
+def main(path, first=0):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
+    if first:
+        data = data[:first]
     ki = hdr.index("Kernel Name")
     names = [r[ki].split("(")[0].replace("void ", "").replace("psi::", "") for r in data]
     print("| metric | unit | " + " | ".join(names) + " |")
@@ -50,4 +55,4 @@ def main(path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 0)

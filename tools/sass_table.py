@@ -1,0 +1,52 @@
+"""Static SASS opcode counts of the hot kernels (cuobjdump -sass of the built objects) as a markdown table.
+usage: python tools/sass_table.py r02 > profiles/r02_sass_evidence.md"""
+import collections
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+B = os.path.join(ROOT, "nested-hashing-psi_b200", "build")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+WANT = [("psi_kernels.o", r"k_mac_tmaILi2ELi8ELi2E"), ("fused_mul.o", r"k_rows_relinILi4E"), ("fused_mul.o", r"k_rows_tensor"),
+        ("fused_mul.o", r"k_rows_inv"), ("fused_cols_a.o|fused_cols_b.o|fused_cols_c.o|fused_cols_d.o", r"k_cols_scaleILi4ELi4ELi14E"),
+        ("fused_cols_a.o|fused_cols_b.o|fused_cols_c.o|fused_cols_d.o", r"k_cols_extendILi4ELi4ELi14E"), ("ntt.o", r"k_nttILb0E")]
+CLS = [("UBLKCP", r"^UBLKCP"), ("LDGSTS", r"^LDGSTS"), ("SYNCS.*", r"^SYNCS"), ("IMAD.WIDE*", r"^IMAD\.WIDE"),
+       ("IMAD / IMAD.HI", r"^IMAD(\.U32|\.HI\.U32|\.HI)?$"), ("IMAD.X/.IADD/.MOV/.SHL (adds and moves on the multiplier pipe)", r"^IMAD\.(X|IADD|MOV|SHL)"),
+       ("IADD3*", r"^IADD3"), ("LDS/STS", r"^(LDS|STS)"), ("LDG/STG", r"^(LDG|STG)"), ("BAR", r"^BAR"), ("SHFL", r"^SHFL"),
+       ("tensor ops (HMMA/UTCMMA/...)", r"^(HMMA|IMMA|UTC|QGMMA|HGMMA)")]
+print("# Round %s — SASS evidence (cuobjdump -sass of the built objects, sm_100a)\n" % tag[1:])
+print("Static counts per kernel. `UBLKCP` = `cp.async.bulk` (TMA bulk copy engine), `LDGSTS` = per-thread `cp.async`, `SYNCS.*` = "
+      "mbarrier operations, `IMAD.WIDE*` = 32x32+64 multiply-add on the fmaheavy pipe. No tensor-core instruction anywhere: the "
+      "path is 64-bit residue arithmetic. No `SHFL` in the transforms: the exchange between radix passes goes through padded "
+      "shared memory, measured 1.67x faster than `__shfl_xor` butterflies (DESIGN.md 3.2).\n")
+print("| kernel | " + " | ".join(c for c, _ in CLS) + " | instructions | regs |")
+print("|---|" + "---|" * (len(CLS) + 2))
+for objs, pat in WANT:
+    for obj in objs.split("|"):
+        path = os.path.join(B, obj)
+        if not os.path.exists(path):
+            continue
+        sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+        res = subprocess.run(["cuobjdump", "-res-usage", path], capture_output=True, text=True).stdout
+        fn, cnt = None, collections.Counter()
+        found = {}
+        for line in sass.splitlines():
+            m = re.search(r"Function : (\S+)", line)
+            if m:
+                fn = m.group(1)
+                continue
+            m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+            if m and fn and re.search(pat, fn):
+                found.setdefault(fn, collections.Counter())[m.group(1)] += 1
+        for fn, c in found.items():
+            regs = "?"
+            m = re.search(re.escape(fn) + r".*?REG:(\d+)", res, re.S)
+            if m:
+                regs = m.group(1)
+            demangled = subprocess.run(["c++filt", fn], capture_output=True, text=True).stdout.split("(")[0].replace("void ", "").replace("psi::", "").strip()
+            row = [str(sum(v for k, v in c.items() if re.search(rx, k))) for _, rx in CLS]
+            print("| %s | %s | %d | %s |" % (demangled, " | ".join(row), sum(c.values()), regs))
+        if found:
+            break
