@@ -144,6 +144,8 @@ struct psi_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join[7] = {};
     // psi_query_run_streamed: copy-in / copy-out streams and the events that order slices and bin groups
     cudaStream_t sq_in = nullptr, sq_out = nullptr;
+    cudaStream_t sq_grp[4] = {};  // bin groups of the streamed query, descending priority
+    cudaEvent_t ev_sq_fork = nullptr;
     cudaEvent_t ev_slice[kMaxStreamSlices] = {}, ev_group[4] = {}, ev_sq = nullptr;
 
     // run() as a CUDA graph: the launch set of one evaluation (inner product, bin groups forked over the auxiliary
@@ -590,6 +592,9 @@ int psi_ctx_destroy(psi_ctx* c) {
         if (st) cudaStreamDestroy(st);
     if (c->sq_in) cudaStreamDestroy(c->sq_in);
     if (c->sq_out) cudaStreamDestroy(c->sq_out);
+    for (auto& st : c->sq_grp)
+        if (st) cudaStreamDestroy(st);
+    if (c->ev_sq_fork) cudaEventDestroy(c->ev_sq_fork);
     for (auto& e : c->ev_slice)
         if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_group)
@@ -1278,14 +1283,47 @@ int psi_query_run_streamed(psi_ctx* c, const uint64_t* idx, const uint64_t* minu
         for (auto& e : c->ev_slice) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : c->ev_group) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_sq, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_sq_fork, cudaEventDisableTiming));
+        // one stream per download group, the earlier group at the higher priority: all groups are enqueued at once,
+        // the block scheduler serves the first group first and fills its partial waves with the next one's CTAs
+        int least = 0, greatest = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        for (int g = 0; g < 4; g++) {
+            int prio = greatest + g;
+            if (prio > least) prio = least;
+            CK(cudaStreamCreateWithPriority(&c->sq_grp[g], cudaStreamNonBlocking, prio));
+        }
     }
     const KCtx k = c->k(s);
     const size_t N = c->N, LN = (size_t)c->L * N, ct = 2 * LN;
     const uint32_t K = c->K, E = c->E, w = c->n_uploaded & 1u;
     const bool split_a = fused_mul_supported(k);
+    // tuning switches (tools/tune_streamed.py): PSI_STREAM_SLICES=n, PSI_STREAM_CUTS="a,b,c"
+    uint32_t slices_per_hf = kStreamSlicesPerHf;
+    double out_cut[kStreamOutGroups + 1];
+    for (uint32_t g = 0; g <= kStreamOutGroups; g++) out_cut[g] = kStreamOutCut[g];
+    if (const char* e = std::getenv("PSI_STREAM_SLICES")) {
+        const int v = std::atoi(e);
+        if (v >= 1 && (uint32_t)v * K <= kMaxStreamSlices) slices_per_hf = (uint32_t)v;
+    }
+    if (const char* e = std::getenv("PSI_STREAM_CUTS")) {
+        double a = 0, b2 = 0, c3 = 0;
+        if (std::sscanf(e, "%lf,%lf,%lf", &a, &b2, &c3) == 3 && 0 <= a && a <= b2 && b2 <= c3 && c3 <= 1) {
+            out_cut[1] = a;
+            out_cut[2] = b2;
+            out_cut[3] = c3;
+        }
+    }
     u64* const land = c->idx_in.p + w * c->idx_words();
     u64* const land_minus = c->minus_in.p + w * 2 * LN;
     uint32_t nl = 0;
+    // PSI_STREAM_TIMELINE: debugging aid -- timing events at the milestones of the query, printed (after a
+    // synchronisation) as one JSON line on stderr
+    const bool timeline = std::getenv("PSI_STREAM_TIMELINE") != nullptr;
+    cudaEvent_t tl[8] = {};
+    if (timeline)
+        for (auto& e : tl) CK(cudaEventCreate(&e));
+    if (timeline) CK(cudaEventRecord(tl[0], s));
     // the copy stream starts where the caller's stream is (previous evaluation, previous use of the landing buffer)
     CK(cudaEventRecord(c->ev_sq, s));
     CK(cudaStreamWaitEvent(c->sq_in, c->ev_sq, 0));
@@ -1293,7 +1331,7 @@ int psi_query_run_streamed(psi_ctx* c, const uint64_t* idx, const uint64_t* minu
     CK(cudaMemcpyAsync(land_minus, minus, ct * sizeof(u64), cudaMemcpyHostToDevice, c->sq_in));
     uint32_t n_slices = 0;
     for (uint32_t hf = 0; hf < K; hf++) {
-        const uint32_t S = E < kStreamSlicesPerHf ? E : kStreamSlicesPerHf;
+        uint32_t S = E < slices_per_hf ? E : slices_per_hf;
         for (uint32_t sl = 0; sl < S; sl++, n_slices++) {
             if (n_slices >= kMaxStreamSlices) return set_error(PSI_ERR_INVALID, "too many hash functions for the streamed path");
             const uint32_t p0 = (uint32_t)((uint64_t)E * sl / S), p1 = (uint32_t)((uint64_t)E * (sl + 1) / S);
@@ -1311,29 +1349,42 @@ int psi_query_run_streamed(psi_ctx* c, const uint64_t* idx, const uint64_t* minu
         if (hf == 0 && K > 1 && split_a)
             if ((rc = mul_ctct_batch(c, s, c->b, c->acc.p, c->acc.p + (size_t)c->b * ct, nullptr, nullptr, &nl, 0, 1))) return rc;
     }
+    if (timeline) {
+        CK(cudaEventRecord(tl[1], c->sq_in));  // upload complete
+        CK(cudaEventRecord(tl[2], s));         // inner products complete
+    }
     c->n_uploaded++;
     c->n_committed++;
     c->have_query = true;
     const uint32_t next_out = c->out_cur ^ 1u;
     u64* const result = c->out_buf(next_out);
     uint32_t cuts[kStreamOutGroups + 1];
-    for (uint32_t g = 0; g <= kStreamOutGroups; g++) cuts[g] = (uint32_t)(kStreamOutCut[g] * c->b + 0.5);
+    for (uint32_t g = 0; g <= kStreamOutGroups; g++) cuts[g] = (uint32_t)(out_cut[g] * c->b + 0.5);
     cuts[kStreamOutGroups] = c->b;
+    // The groups run one after another on the caller's stream.  PSI_STREAM_CONCURRENT=1 enqueues them all at once on
+    // prioritised streams instead -- measured slower (3.21-3.35 ms against 3.19-3.23): the priorities do not stagger the
+    // completions, three of four groups finish together and the downloads bunch up (`profiles/r02_streamed_timeline.md`)
+    const bool concurrent = std::getenv("PSI_STREAM_CONCURRENT") != nullptr;
+    if (concurrent) CK(cudaEventRecord(c->ev_sq_fork, s));
     for (uint32_t g = 0; g < kStreamOutGroups; g++) {
         const uint32_t g0 = cuts[g], g1 = cuts[g + 1];
         if (g1 <= g0) continue;
+        cudaStream_t sg = concurrent ? c->sq_grp[g] : s;
+        if (concurrent) CK(cudaStreamWaitEvent(sg, c->ev_sq_fork, 0));
         if (K == 1) {
-            cudaError_t e1 = launch_mul_ctpt(k, g1 - g0, c->acc.p + (size_t)g0 * ct, c->mask.p + (size_t)g0 * LN, result + (size_t)g0 * ct);
+            const KCtx kg = c->k(sg);
+            cudaError_t e1 = launch_mul_ctpt(kg, g1 - g0, c->acc.p + (size_t)g0 * ct, c->mask.p + (size_t)g0 * LN, result + (size_t)g0 * ct);
             if (e1 != cudaSuccess) {
                 c->ran = false;
                 return cuda_fail(e1, "launch_mul_ctpt");
             }
             nl++;
-        } else if ((rc = phase2_bins(c, s, g0, g1, default_groups(c, g1 - g0), result, &nl, split_a ? 2 : 3))) {
+        } else if ((rc = phase2_bins(c, sg, g0, g1, concurrent ? 1u : default_groups(c, g1 - g0), result, &nl, split_a ? 2 : 3))) {
             c->ran = false;
             return rc;
         }
-        CK(cudaEventRecord(c->ev_group[g], s));
+        CK(cudaEventRecord(c->ev_group[g], sg));
+        if (timeline) CK(cudaEventRecord(tl[3 + g], sg));  // bin group g evaluated
         CK(cudaStreamWaitEvent(c->sq_out, c->ev_group[g], 0));
         CK(cudaMemcpyAsync(out + (size_t)g0 * ct, result + (size_t)g0 * ct, (size_t)(g1 - g0) * ct * sizeof(u64), cudaMemcpyDeviceToHost,
                            c->sq_out));
@@ -1341,6 +1392,15 @@ int psi_query_run_streamed(psi_ctx* c, const uint64_t* idx, const uint64_t* minu
     // join: the caller's stream is done when the last download is
     CK(cudaEventRecord(c->ev_sq, c->sq_out));
     CK(cudaStreamWaitEvent(s, c->ev_sq, 0));
+    if (timeline) {
+        CK(cudaEventRecord(tl[7], c->sq_out));
+        CK(cudaEventSynchronize(tl[7]));
+        float ms[8] = {};
+        for (int i = 1; i < 8; i++) cudaEventElapsedTime(&ms[i], tl[0], tl[i]);
+        std::fprintf(stderr, "{\"streamed_timeline_ms\": {\"upload_done\": %.3f, \"inner_products_done\": %.3f, \"groups_done\": [%.3f, %.3f, %.3f, %.3f], \"last_download_done\": %.3f}}\n",
+                     ms[1], ms[2], ms[3], ms[4], ms[5], ms[6], ms[7]);
+        for (auto& e : tl) cudaEventDestroy(e);
+    }
     c->out_cur = next_out;
     c->launches_per_run = nl;
     c->ran = true;
