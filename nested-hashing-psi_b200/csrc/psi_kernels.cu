@@ -56,6 +56,7 @@ constexpr int kMacCoeffs = 128;  // coefficients per CTA tile (= one row of one 
 // width that divides b_local wastes no bin-lane, and a wider block re-reads the index slice from L2 fewer
 // times — what matters when a GPU holds 6 of the 47 bins of a sharded query.
 constexpr int kMacFold = 8;  // positions between folds
+constexpr uint32_t kMacShortRange = 0;  // position ranges up to this length take the 4 x 4 ring (0: never; set from measurements)
 constexpr int kMacLanes = 2;
 constexpr int kMacConsumers = kMacCoeffs * kMacLanes;
 template <int BT, int CHUNK>
@@ -232,16 +233,21 @@ static cudaError_t mac_launch_t(const KCtx& k, uint32_t nhf, uint32_t b, uint32_
     return cudaGetLastError();
 }
 
-static int g_mac_force = 0;  // tuning / tests: 0 = choose by shape, 1 / 2 = force 2 / 4 bins per CTA
+static int g_mac_force = 0;  // tuning / tests: 0 = choose by shape, 1 / 2 = force 2 / 4 bins per CTA, 3 / 4 = the same with a 4 x 4 ring
 void mac_force_variant(int v) { g_mac_force = v; }
 int mac_forced_variant() { return g_mac_force; }
 
 // bin-block width for b resident bins: 2-bin blocks when 4-bin blocks would leave more than a tenth of the
 // bin-lanes idle (measured: b = 5, 6, 14 faster with 2, b = 26, 47, 75 faster with 4)
-static int mac_choose(uint32_t b) {
+// ring shape for npos positions per launch: a short range (E = 14 of BASELINE configs[1], the 12-position slices of the
+// streamed single query) is two chunks of eight, so a 2 x 8 ring never reaches steady state and the consumers wait for
+// eight positions before the first multiply; four stages of four positions start after four and keep three chunks in
+// flight (measured, tools/tune_shapes.py: see profiles/r02_tune_shapes.md)
+static int mac_choose(uint32_t b, uint32_t npos) {
     if (g_mac_force) return g_mac_force;
     const uint32_t slots4 = ((b + 3) / 4) * 4, slots2 = ((b + 1) / 2) * 2;
-    return (slots2 < slots4 && (slots4 - b) * 10 > slots4) ? 1 : 2;
+    const int bins = (slots2 < slots4 && (slots4 - b) * 10 > slots4) ? 1 : 2;
+    return npos <= kMacShortRange ? bins + 2 : bins;
 }
 
 cudaError_t mac_init_device() {
@@ -249,14 +255,20 @@ cudaError_t mac_init_device() {
     const MacRange rg{};
     cudaError_t e = mac_launch_t<2, 8, 2>(k, 0, 0, 0, rg, nullptr, nullptr, nullptr, nullptr, true);
     if (e == cudaSuccess) e = mac_launch_t<1, 8, 2>(k, 0, 0, 0, rg, nullptr, nullptr, nullptr, nullptr, true);
+    if (e == cudaSuccess) e = mac_launch_t<2, 4, 4>(k, 0, 0, 0, rg, nullptr, nullptr, nullptr, nullptr, true);
+    if (e == cudaSuccess) e = mac_launch_t<1, 4, 4>(k, 0, 0, 0, rg, nullptr, nullptr, nullptr, nullptr, true);
     return e;
 }
 
 cudaError_t launch_mac_range(const KCtx& k, uint32_t hf0, uint32_t nhf, uint32_t b, uint32_t E, uint32_t pos0, uint32_t pos1,
                              uint32_t flags, const u64* pt, const u64* idx, const u64* minus, u64* acc) {
     const MacRange rg{hf0, pos0, pos1, flags};
-    if (mac_choose(b) == 1) return mac_launch_t<1, 8, 2>(k, nhf, b, E, rg, pt, idx, minus, acc, false);
-    return mac_launch_t<2, 8, 2>(k, nhf, b, E, rg, pt, idx, minus, acc, false);
+    switch (mac_choose(b, pos1 - pos0)) {
+        case 1: return mac_launch_t<1, 8, 2>(k, nhf, b, E, rg, pt, idx, minus, acc, false);
+        case 3: return mac_launch_t<1, 4, 4>(k, nhf, b, E, rg, pt, idx, minus, acc, false);
+        case 4: return mac_launch_t<2, 4, 4>(k, nhf, b, E, rg, pt, idx, minus, acc, false);
+        default: return mac_launch_t<2, 8, 2>(k, nhf, b, E, rg, pt, idx, minus, acc, false);
+    }
 }
 
 cudaError_t launch_mac(const KCtx& k, uint32_t K, uint32_t b, uint32_t E, const u64* pt, const u64* idx,
