@@ -495,7 +495,9 @@ def main():
             barrier()
             return max_over_ranks(e0.elapsed_time(e1))
 
-        e2e_pipelined(3, 0)
+        # untimed passes through the same pipeline first: on a fresh box the first pipelined pass runs ~7 % slower
+        # (pinned pages first touched by the copy engines, PCIe link and clocks settling); measured 2.25 vs 2.10 ms
+        e2e_pipelined(max(args.steps, 10), 0)
         m["ms_e2e"] = e2e_pipelined(args.steps, max(args.warmup, 3)) / args.steps
         return m
 
