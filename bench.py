@@ -79,6 +79,7 @@ def parse():
     ap.add_argument("--no-weak", action="store_true", help="N > 1, strong scaling: skip the extra weak-scaling measurement")
     ap.add_argument("--cpu-sample-bins", type=int, default=0, help="bins per CPU-baseline repetition (0 = all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stage-times", action="store_true", help="time upload / run / download of the e2e step separately")
     ap.add_argument("--no-limb-leg", action="store_true", help="skip the e2e leg with separately allocated limb vectors")
     ap.add_argument("--gather", default="host", choices=["host", "nccl"],
                     help="N > 1 response gather inside e2e: 'host' = every rank copies its own result ciphertexts to "
@@ -447,6 +448,16 @@ def main():
         cc.sync(sp)
         m["ms_e2e_serial"] = timed(e2e_serial_step, args.steps) / args.steps
         m["last_result"] = r_host
+        # the stages of the serial step on their own (each on the launching stream): what the pipeline can overlap
+        def query_in():
+            upload_query(stream)
+            cc.query_commit(sp)
+
+        m["stages"] = {
+            "query_in_ms": timed(query_in, args.steps) / args.steps,        # H2D (+ all-gather at N > 1) + re-tiling
+            "run_ms": timed(lambda: cc.run(sp), args.steps) / args.steps,
+            "result_out_ms": timed(lambda: fetch_result(stream, r_host), args.steps) / args.steps,
+        } if args.stage_times else None
         # the same single query with upload slices, evaluation and download groups overlapped inside the query
         m["ms_e2e_streamed"] = None
         if world == 1:
@@ -665,7 +676,7 @@ def main():
             "config": workload_config(args, w, params, world),
             "roofline": roofline, "roofline_int": roofline_int, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "items/s", "ms_per_step": m["ms_e2e"], "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "serial_ms_per_step": m["ms_e2e_serial"],
+                    "d2h_bytes_per_step": d2h, "serial_ms_per_step": m["ms_e2e_serial"], "stages": m.get("stages"),
                     "serial_streamed_ms_per_step": m["ms_e2e_streamed"],
                     "serial_value": total_items / (m["ms_e2e_serial"] * 1e-3),
                     "limb_vectors": limb_leg,
