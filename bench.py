@@ -425,7 +425,7 @@ def main():
             query_dist = "allgather" if world > 1 and (K * E * ct_words) % world == 0 else "host"
         qd = None
         if query_dist == "allgather":
-            qd = P.QueryDistributor.for_context(cc, rank, world)
+            qd = P.QueryDistributor.for_context(cc, rank, world, chunks=int(os.environ.get("PSI_QD_CHUNKS", "2")))
             q_idx_host, q_minus_host = q_host[:K * E * ct_words], q_host[K * E * ct_words:]
         m["qd"] = qd is not None
 

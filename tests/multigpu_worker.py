@@ -43,8 +43,10 @@ def main():
     host_idx = torch.from_numpy(idx.view(np.int64).reshape(-1).copy()).pin_memory()
     host_minus = torch.from_numpy(minus.view(np.int64).reshape(-1).copy()).pin_memory()
     qd = P.QueryDistributor.for_context(cc, rank, world)
-    host_idx[:qd.begin] = -1
-    host_idx[qd.end:] = -1
+    keep = torch.zeros_like(host_idx, dtype=torch.bool)
+    for b0, b1 in qd.own_ranges():
+        keep[b0:b1] = True
+    host_idx[~keep] = -1
     qd.distribute(host_idx, host_minus)
     torch.cuda.current_stream().synchronize()
     cc.query_commit()

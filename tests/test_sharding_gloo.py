@@ -68,12 +68,18 @@ def _worker(rank, world, port, tmpdir):
     idx_flat = torch.from_numpy(idx.view(np.int64).reshape(-1))
     minus_flat = torch.from_numpy(minus.view(np.int64).reshape(-1))
     landing_idx, landing_minus = torch.zeros_like(idx_flat), torch.zeros_like(minus_flat)
-    qd = P.QueryDistributor([(landing_idx, landing_minus)], rank, world)
-    host = idx_flat.clone()
-    host[:qd.begin] = -1
-    host[qd.end:] = -1
-    qd.distribute(host, minus_flat)
-    assert torch.equal(landing_idx, idx_flat) and torch.equal(landing_minus, minus_flat)
+    for chunks in (1, 2):     # one slice per rank / the chunked form whose uploads overlap the collectives on a GPU
+        landing_idx.zero_()
+        landing_minus.zero_()
+        qd = P.QueryDistributor([(landing_idx, landing_minus)], rank, world, chunks=chunks)
+        assert qd.chunks == (chunks if idx_flat.numel() % (chunks * world) == 0 else 1)
+        host = torch.full_like(idx_flat, -1)
+        for b0, b1 in qd.own_ranges():
+            host[b0:b1] = idx_flat[b0:b1]
+        if qd.chunks == 1:
+            assert qd.own_ranges() == [(qd.begin, qd.end)]
+        qd.distribute(host, minus_flat)
+        assert torch.equal(landing_idx, idx_flat) and torch.equal(landing_minus, minus_flat)
     idx = landing_idx.numpy().view(np.uint64).reshape(idx.shape)
     minus = landing_minus.numpy().view(np.uint64).reshape(minus.shape)
 
