@@ -213,9 +213,6 @@ void BatchedFHEHIPPIE::run() {
         for (size_t pos = 0; pos < st.E; pos++) limbs_of(indexMatrix[hf][pos], L, N, &idxLimbs[(hf * st.E + pos) * 2 * L]);
     }
     limbs_of(minusCompareElement, L, N, minusLimbs.data());
-    ck(psi_multi_query_set_limbs(st.multi, idxLimbs.data(), minusLimbs.data()));
-    ck(psi_multi_run(st.multi));
-
     // b result ciphertexts: the library scatters straight into the limb vectors that become the DCRTPolys
     const auto& params = minusCompareElement->GetElements()[0].GetParams();
     std::vector<NativeVector> vecs;
@@ -227,7 +224,9 @@ void BatchedFHEHIPPIE::run() {
                 vecs.emplace_back((usint)N, params->GetParams()[l]->GetModulus());
                 outLimbs[(bin * 2 + c) * L + l] = words_of(vecs.back());
             }
-    ck(psi_multi_result_get_limbs(st.multi, outLimbs.data()));
+    // setIndex + setMinusCompareElement + run + getResultList of the session as one call: on one device the host
+    // gather, the upload slices, the evaluation, the download groups and the scatter overlap inside the query
+    ck(psi_multi_query_run_limbs(st.multi, idxLimbs.data(), minusLimbs.data(), outLimbs.data()));
     for (size_t bin = 0; bin < st.b; bin++) {
         std::vector<FHEEncType> cv;
         for (size_t c = 0; c < 2; c++) {

@@ -542,7 +542,23 @@ def main():
             limb_step()
         ms_limb = (time.perf_counter() - t0) * 1e3 / args.steps
         same = np.array_equal(np.concatenate(ov), m["last_result"].numpy().view(np.uint64))
+        # the same vectors through psi_query_run_streamed_limbs: gather, upload slices, evaluation, download groups and
+        # scatter overlapped inside the one query
+        for v in ov:
+            v[:] = 0
+
+        def limb_streamed_step():
+            cc.query_run_streamed_limbs(ai, am, ao, sp)
+
+        for _ in range(3):
+            limb_streamed_step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            limb_streamed_step()
+        ms_limb_streamed = (time.perf_counter() - t0) * 1e3 / args.steps
+        same = same and np.array_equal(np.concatenate(ov), m["last_result"].numpy().view(np.uint64))
         limb_leg = {"serial_ms_per_step": ms_limb, "vs_pinned_serial": ms_limb / m["ms_e2e_serial"],
+                    "streamed_ms_per_step": ms_limb_streamed,
                     "query_vectors": nvec + 2 * L, "result_vectors": len(ov), "bytes_per_vector": N * 8,
                     "host_threads": min(16, max(1, len(os.sched_getaffinity(0)))),
                     "timing": "host wall clock around upload_limbs -> commit -> run -> result_get_limbs (returns when the "

@@ -242,6 +242,13 @@ int psi_run_phases(psi_ctx* ctx, uint32_t phases, void* stream);
  * of a group are downloaded while the next group is evaluated.  idx [K][E][2][L][N], minus [2][L][N], out
  * [b][2][L][N] are host buffers (pinned for full speed).  Asynchronous: synchronise `stream` before reading out. */
 int psi_query_run_streamed(psi_ctx* ctx, const uint64_t* idx, const uint64_t* minus, uint64_t* out, void* stream);
+/* The same from / into separately allocated limb vectors (layouts of psi_query_upload_limbs / psi_result_get_limbs):
+ * every upload slice is gathered into the pinned pool by the host threads while the copy engine moves the previous
+ * one, every download group is scattered into the result vectors as soon as it has arrived.  Synchronous: the
+ * vectors are filled on return.  Replaces receiveIndexMatrix .. sendResult of one session
+ * (BatchedFHEPSIServer.cpp:99-108,124-152) for a query held the way OpenFHE holds it. */
+int psi_query_run_streamed_limbs(psi_ctx* ctx, const uint64_t* const* idx_limbs, const uint64_t* const* minus_limbs,
+                                 uint64_t* const* out_limbs, void* stream);
 
 /* getResultList (BatchedFHEHIPPIE.hpp:35-38): asynchronous D2H of [b][2][L][N]
  * on `stream`; the caller synchronises the stream before reading `out`.  Results are double-buffered on
@@ -395,6 +402,10 @@ int psi_multi_result_get(psi_multi* m, uint64_t* out);
 /* the same into b*2*L separate limb vectors ([bin][comp][limb] order, N words each; sendResult serialises
  * ciphertext by ciphertext, BatchedFHEPSIServer.cpp:143-152); synchronous: the vectors are filled on return */
 int psi_multi_result_get_limbs(psi_multi* m, uint64_t* const* out_limbs);
+/* setIndex + setMinusCompareElement + run + getResultList of one session in one synchronous call, limb vectors in and
+ * out: one device takes the streamed path (psi_query_run_streamed_limbs), several devices the three calls above. */
+int psi_multi_query_run_limbs(psi_multi* m, const uint64_t* const* idx_limbs, const uint64_t* const* minus_limbs,
+                              uint64_t* const* out_limbs);
 int psi_multi_sync(psi_multi* m);
 int psi_multi_run_launch_count(psi_multi* m, uint32_t* out);
 /* BatchedFHEHIPPIE over a psi_multi (same constructor semantics as psi_pie_create) */

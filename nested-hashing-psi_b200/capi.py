@@ -109,6 +109,7 @@ SYMBOLS = {
     "psi_params_from_moduli": (_int, [_u32, _u64, _u32, _u64p, _u64p, _u32, _u64p, _u64p, _u64, _pp]),
     "psi_query_upload_limbs": (_int, [_vp, ctypes.POINTER(_u64p), ctypes.POINTER(_u64p), _vp]),
     "psi_result_get_limbs": (_int, [_vp, ctypes.POINTER(_u64p), _vp]),
+    "psi_query_run_streamed_limbs": (_int, [_vp, ctypes.POINTER(_u64p), ctypes.POINTER(_u64p), ctypes.POINTER(_u64p), _vp]),
     "psi_set_host_threads": (_int, [_vp, _int]),
     "psi_db_load_limbs_shard": (_int, [_vp, _u32, _u32, _u32, _u32, _u32, _u64p, _u64p]),
     "psi_db_encode_slots_shard": (_int, [_vp, _u32, _u32, _u32, _u32, _u32, _u32, _i64p, _i64p]),
@@ -130,6 +131,7 @@ SYMBOLS = {
     "psi_multi_run": (_int, [_vp]),
     "psi_multi_result_get": (_int, [_vp, _u64p]),
     "psi_multi_result_get_limbs": (_int, [_vp, ctypes.POINTER(_u64p)]),
+    "psi_multi_query_run_limbs": (_int, [_vp, ctypes.POINTER(_u64p), ctypes.POINTER(_u64p), ctypes.POINTER(_u64p)]),
     "psi_multi_sync": (_int, [_vp]),
     "psi_multi_run_launch_count": (_int, [_vp, _u32p]),
     "psi_pie_create_multi": (_int, [_vp, _pp, _vp, _u64, _u64, _int, _vpp]),

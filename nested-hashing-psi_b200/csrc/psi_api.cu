@@ -18,6 +18,7 @@
 
 #include "psi_b200.h"
 #include "psi_kernels.cuh"
+#include "host_copy.hpp"
 #include "../host/hashing.hpp"
 #include "../host/psi_host_internal.hpp"
 
@@ -145,6 +146,7 @@ struct psi_ctx {
     // psi_query_run_streamed: copy-in / copy-out streams and the events that order slices and bin groups
     cudaStream_t sq_in = nullptr, sq_out = nullptr;
     cudaStream_t sq_grp[4] = {};  // bin groups of the streamed query, descending priority
+    cudaEvent_t ev_dl[4] = {};    // download of a group complete (limb-vector form: the host scatters it then)
     cudaEvent_t ev_sq_fork = nullptr;
     cudaEvent_t ev_slice[kMaxStreamSlices] = {}, ev_group[4] = {}, ev_sq = nullptr;
 
@@ -595,6 +597,8 @@ int psi_ctx_destroy(psi_ctx* c) {
     for (auto& st : c->sq_grp)
         if (st) cudaStreamDestroy(st);
     if (c->ev_sq_fork) cudaEventDestroy(c->ev_sq_fork);
+    for (auto& e : c->ev_dl)
+        if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_slice)
         if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_group)
@@ -1002,7 +1006,7 @@ int psi_query_upload_limbs(psi_ctx* c, const uint64_t* const* idx_limbs, const u
         const long v0 = (long)(nvec * piece / kLimbPieces), v1 = (long)(nvec * (piece + 1) / kLimbPieces);
         if (v1 == v0) continue;
 #pragma omp parallel for schedule(static) num_threads(nt) if (v1 - v0 >= 16)
-        for (long v = v0; v < v1; v++) std::memcpy(pool + (size_t)v * N, idx_limbs[v], N * sizeof(u64));
+        for (long v = v0; v < v1; v++) copy_limb_vector(pool + (size_t)v * N, idx_limbs[v], N);
         CK(cudaMemcpyAsync(c->idx_in.p + w * W + (size_t)v0 * N, pool + (size_t)v0 * N, (size_t)(v1 - v0) * N * sizeof(u64),
                            cudaMemcpyHostToDevice, s));
     }
@@ -1042,7 +1046,7 @@ int psi_result_get_limbs(psi_ctx* c, uint64_t* const* out_limbs, void* stream) {
         const long v0 = (long)(nvec * piece / kLimbPieces), v1 = (long)(nvec * (piece + 1) / kLimbPieces);
         CK(cudaEventSynchronize(ev[piece]));
 #pragma omp parallel for schedule(static) num_threads(nt) if (v1 - v0 >= 16)
-        for (long v = v0; v < v1; v++) std::memcpy(out_limbs[v], c->pool_out + (size_t)v * N, N * sizeof(u64));
+        for (long v = v0; v < v1; v++) copy_limb_vector(out_limbs[v], c->pool_out + (size_t)v * N, N);
     }
     return PSI_OK;
 }
@@ -1269,8 +1273,14 @@ int psi_run_phases(psi_ctx* c, uint32_t phases, void* stream) {
 // (18.7 us at 56 GB/s) than it evaluates (22 us), so the copy engine keeps up with the earlier, larger groups
 constexpr uint32_t kStreamSlicesPerHf = 4, kStreamOutGroups = 4;
 static const double kStreamOutCut[kStreamOutGroups + 1] = {0.0, 0.38, 0.72, 0.91, 1.0};
-int psi_query_run_streamed(psi_ctx* c, const uint64_t* idx, const uint64_t* minus, uint64_t* out, void* stream) {
-    if (!c || !idx || !minus || !out) return set_error(PSI_ERR_INVALID, "null argument");
+// idx / minus / out: contiguous (pinned) host buffers, or null with the limb-vector forms given instead: then every
+// upload slice is first gathered into the pinned pool by the host threads (while the copy engine moves the previous
+// slice) and every download group is scattered into the result vectors as soon as it has arrived (the call then
+// returns with the vectors filled).
+static int query_run_streamed_impl(psi_ctx* c, const uint64_t* idx, const uint64_t* minus, uint64_t* out,
+                                   const uint64_t* const* idx_limbs, const uint64_t* const* minus_limbs,
+                                   uint64_t* const* out_limbs, void* stream) {
+    const bool limbs = idx_limbs != nullptr;
     if (!c->have_db) return set_error(PSI_ERR_STATE, "run() needs a database");
     if (c->K > 1 && !c->have_evk) return set_error(PSI_ERR_STATE, "EvalMult(ct,ct) needs the relinearisation key");
     if (c->n_uploaded != c->n_committed) return set_error(PSI_ERR_STATE, "an uploaded query is waiting for psi_query_commit");
@@ -1284,6 +1294,7 @@ int psi_query_run_streamed(psi_ctx* c, const uint64_t* idx, const uint64_t* minu
         for (auto& e : c->ev_group) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_sq, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_sq_fork, cudaEventDisableTiming));
+        for (auto& e : c->ev_dl) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         // one stream per download group, the earlier group at the higher priority: all groups are enqueued at once,
         // the block scheduler serves the first group first and fills its partial waves with the next one's CTAs
         int least = 0, greatest = 0;
@@ -1298,6 +1309,18 @@ int psi_query_run_streamed(psi_ctx* c, const uint64_t* idx, const uint64_t* minu
     const size_t N = c->N, LN = (size_t)c->L * N, ct = 2 * LN;
     const uint32_t K = c->K, E = c->E, w = c->n_uploaded & 1u;
     const bool split_a = fused_mul_supported(k);
+    const int nt = c->host_threads;
+    (void)nt;
+    if (limbs) {
+        if ((rc = ensure_pool(&c->pool_in, &c->pool_in_words, c->idx_words() + 2 * LN))) return rc;
+        if ((rc = ensure_pool(&c->pool_out, &c->pool_out_words, (size_t)c->b * ct))) return rc;
+        if (!c->ev_pool_in) CK(cudaEventCreateWithFlags(&c->ev_pool_in, cudaEventDisableTiming));
+        CK(cudaEventSynchronize(c->ev_pool_in));  // the previous upload has read the pool
+        for (size_t v = 0; v < 2 * (size_t)c->L; v++) std::memcpy(c->pool_in + c->idx_words() + v * N, minus_limbs[v], N * sizeof(u64));
+        minus = reinterpret_cast<const uint64_t*>(c->pool_in + c->idx_words());
+        idx = reinterpret_cast<const uint64_t*>(c->pool_in);
+        out = reinterpret_cast<uint64_t*>(c->pool_out);
+    }
     // tuning switches (tools/tune_streamed.py): PSI_STREAM_SLICES=n, PSI_STREAM_CUTS="a,b,c"
     uint32_t slices_per_hf = kStreamSlicesPerHf;
     double out_cut[kStreamOutGroups + 1];
@@ -1336,6 +1359,11 @@ int psi_query_run_streamed(psi_ctx* c, const uint64_t* idx, const uint64_t* minu
             if (n_slices >= kMaxStreamSlices) return set_error(PSI_ERR_INVALID, "too many hash functions for the streamed path");
             const uint32_t p0 = (uint32_t)((uint64_t)E * sl / S), p1 = (uint32_t)((uint64_t)E * (sl + 1) / S);
             const size_t off = ((size_t)hf * E + p0) * ct;
+            if (limbs) {
+                const long v0 = (long)(off / N), v1 = (long)((off + (size_t)(p1 - p0) * ct) / N);
+#pragma omp parallel for schedule(static) num_threads(nt) if (v1 - v0 >= 16)
+                for (long v = v0; v < v1; v++) copy_limb_vector(c->pool_in + (size_t)v * N, idx_limbs[v], N);
+            }
             CK(cudaMemcpyAsync(land + off, idx + off, (size_t)(p1 - p0) * ct * sizeof(u64), cudaMemcpyHostToDevice, c->sq_in));
             CK(cudaEventRecord(c->ev_slice[n_slices], c->sq_in));
             CK(cudaStreamWaitEvent(s, c->ev_slice[n_slices], 0));
@@ -1349,6 +1377,7 @@ int psi_query_run_streamed(psi_ctx* c, const uint64_t* idx, const uint64_t* minu
         if (hf == 0 && K > 1 && split_a)
             if ((rc = mul_ctct_batch(c, s, c->b, c->acc.p, c->acc.p + (size_t)c->b * ct, nullptr, nullptr, &nl, 0, 1))) return rc;
     }
+    if (limbs) CK(cudaEventRecord(c->ev_pool_in, c->sq_in));
     if (timeline) {
         CK(cudaEventRecord(tl[1], c->sq_in));  // upload complete
         CK(cudaEventRecord(tl[2], s));         // inner products complete
@@ -1388,6 +1417,7 @@ int psi_query_run_streamed(psi_ctx* c, const uint64_t* idx, const uint64_t* minu
         CK(cudaStreamWaitEvent(c->sq_out, c->ev_group[g], 0));
         CK(cudaMemcpyAsync(out + (size_t)g0 * ct, result + (size_t)g0 * ct, (size_t)(g1 - g0) * ct * sizeof(u64), cudaMemcpyDeviceToHost,
                            c->sq_out));
+        if (limbs) CK(cudaEventRecord(c->ev_dl[g], c->sq_out));
     }
     // join: the caller's stream is done when the last download is
     CK(cudaEventRecord(c->ev_sq, c->sq_out));
@@ -1404,7 +1434,30 @@ int psi_query_run_streamed(psi_ctx* c, const uint64_t* idx, const uint64_t* minu
     c->out_cur = next_out;
     c->launches_per_run = nl;
     c->ran = true;
+    if (limbs) {
+        // scatter every group into the caller's vectors as soon as it has arrived
+        for (uint32_t g = 0; g < kStreamOutGroups; g++) {
+            const long v0 = (long)cuts[g] * 2 * c->L, v1 = (long)cuts[g + 1] * 2 * c->L;
+            if (v1 <= v0) continue;
+            CK(cudaEventSynchronize(c->ev_dl[g]));
+#pragma omp parallel for schedule(static) num_threads(nt) if (v1 - v0 >= 16)
+            for (long v = v0; v < v1; v++) copy_limb_vector(out_limbs[v], c->pool_out + (size_t)v * N, N);
+        }
+    }
     return PSI_OK;
+}
+
+int psi_query_run_streamed(psi_ctx* c, const uint64_t* idx, const uint64_t* minus, uint64_t* out, void* stream) {
+    if (!c || !idx || !minus || !out) return set_error(PSI_ERR_INVALID, "null argument");
+    return query_run_streamed_impl(c, idx, minus, out, nullptr, nullptr, nullptr, stream);
+}
+
+// The same from / into separately allocated limb vectors (psi_query_upload_limbs / psi_result_get_limbs layouts).
+// Synchronous: the result vectors are filled on return.
+int psi_query_run_streamed_limbs(psi_ctx* c, const uint64_t* const* idx_limbs, const uint64_t* const* minus_limbs,
+                                 uint64_t* const* out_limbs, void* stream) {
+    if (!c || !idx_limbs || !minus_limbs || !out_limbs) return set_error(PSI_ERR_INVALID, "null argument");
+    return query_run_streamed_impl(c, nullptr, nullptr, nullptr, idx_limbs, minus_limbs, out_limbs, stream);
 }
 
 int psi_result_get(psi_ctx* c, uint64_t* out, void* stream) {

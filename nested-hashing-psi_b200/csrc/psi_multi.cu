@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "psi_b200.h"
+#include "host_copy.hpp"
 #include "../host/hashing.hpp"
 #include "../host/psi_host_internal.hpp"
 
@@ -345,7 +346,7 @@ int psi_multi_query_set_limbs(psi_multi* m, const uint64_t* const* idx_limbs, co
         for (long v = v0; v < v1; v++) {
             const size_t lo = (size_t)v * N < b0 ? b0 : (size_t)v * N;
             const size_t hi = (size_t)(v + 1) * N > b1 ? b1 : (size_t)(v + 1) * N;
-            std::memcpy(pool + lo, idx_limbs[v] + (lo - (size_t)v * N), (hi - lo) * sizeof(uint64_t));
+            psi::copy_limb_vector(pool + lo, idx_limbs[v] + (lo - (size_t)v * N), hi - lo);
         }
     };
     return distribute_query(m, pool, pool + W, fill);
@@ -393,9 +394,36 @@ int psi_multi_result_get_limbs(psi_multi* m, uint64_t* const* out_limbs) {
         const int nt = m->host_threads;
         (void)nt;
 #pragma omp parallel for schedule(static) num_threads(nt) if (v1 - v0 >= 16)
-        for (long v = v0; v < v1; v++) std::memcpy(out_limbs[v], m->stage_out + (size_t)v * N, N * sizeof(uint64_t));
+        for (long v = v0; v < v1; v++) psi::copy_limb_vector(out_limbs[v], m->stage_out + (size_t)v * N, N);
     }
     return PSI_OK;
+}
+
+// One query from limb vectors to limb vectors, synchronous.  On ONE device this is psi_query_run_streamed_limbs (host
+// gather, upload slices, evaluation, download groups and scatter overlapped inside the query); on several devices the
+// three calls above in sequence (every device already moves only its share of the query and of the results).
+int psi_multi_query_run_limbs(psi_multi* m, const uint64_t* const* idx_limbs, const uint64_t* const* minus_limbs,
+                              uint64_t* const* out_limbs) {
+    if (!m || !idx_limbs || !minus_limbs || !out_limbs) return set_error(PSI_ERR_INVALID, "null argument");
+    if (!m->have_db) return set_error(PSI_ERR_STATE, "run() needs a database and a query");
+    if (m->devs.size() == 1) {
+        Dev& D = m->devs[0];
+        MCK(cudaSetDevice(D.device));
+        // earlier asynchronous work of this object (uploads, downloads of a previous query) is ordered before
+        MCK(cudaStreamSynchronize(D.s_in));
+        MCK(cudaStreamSynchronize(D.s_out));
+        PCK(psi_set_host_threads(D.ctx, m->host_threads));
+        PCK(psi_query_run_streamed_limbs(D.ctx, idx_limbs, minus_limbs, out_limbs, D.s_run));
+        MCK(cudaEventRecord(D.ev_done, D.s_run));
+        MCK(cudaStreamSynchronize(D.s_run));
+        m->n_runs++;
+        m->ran = true;
+        return PSI_OK;
+    }
+    PCK(psi_multi_query_set_limbs(m, idx_limbs, minus_limbs));
+    PCK(psi_multi_run(m));
+    PCK(psi_multi_result_get_limbs(m, out_limbs));
+    return psi_multi_sync(m);
 }
 
 int psi_multi_sync(psi_multi* m) {

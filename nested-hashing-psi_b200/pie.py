@@ -229,6 +229,21 @@ class CryptoContext:
         check(lib().psi_result_get_limbs(self._h, out_vectors, stream))
         return vecs
 
+    def query_run_streamed_limbs(self, idx_vectors, minus_vectors, out_vectors=None, stream=None):
+        """One query from K*E*2*L + 2*L separate limb vectors into b*2*L result vectors with gather / upload /
+        evaluation / download / scatter overlapped inside the query (psi_query_run_streamed_limbs); synchronous."""
+        K, b, E = self._dims
+        ai = idx_vectors if isinstance(idx_vectors, ctypes.Array) else MultiContext._ptr_array(idx_vectors)
+        am = minus_vectors if isinstance(minus_vectors, ctypes.Array) else MultiContext._ptr_array(minus_vectors)
+        vecs = None
+        if out_vectors is None:
+            vecs = [np.empty(self.N, dtype=np.uint64) for _ in range(b * 2 * self.L)]
+            out_vectors = MultiContext._ptr_array(vecs)
+        elif not isinstance(out_vectors, ctypes.Array):
+            vecs, out_vectors = out_vectors, MultiContext._ptr_array(out_vectors)
+        check(lib().psi_query_run_streamed_limbs(self._h, ai, am, out_vectors, stream))
+        return vecs
+
     def set_host_threads(self, n):
         check(lib().psi_set_host_threads(self._h, n))
 
@@ -439,6 +454,15 @@ class MultiContext:
         vecs = [np.empty(self.N, dtype=np.uint64) for _ in range(b * 2 * self.L)]
         arr = self._ptr_array(vecs)
         check(lib().psi_multi_result_get_limbs(self._h, arr))
+        return vecs
+
+    def query_run_limbs(self, idx_vectors, minus_vectors):
+        """psi_multi_query_run_limbs: one query, limb vectors in, b*2*L freshly allocated result vectors out."""
+        K, b, E = self._dims
+        assert len(idx_vectors) == K * E * 2 * self.L and len(minus_vectors) == 2 * self.L
+        vecs = [np.empty(self.N, dtype=np.uint64) for _ in range(b * 2 * self.L)]
+        check(lib().psi_multi_query_run_limbs(self._h, self._ptr_array(idx_vectors), self._ptr_array(minus_vectors),
+                                              self._ptr_array(vecs)))
         return vecs
 
     def sync(self):

@@ -106,6 +106,28 @@ def test_multi_limb_vector_ingestion(small, devices):
         assert np.array_equal(np.stack(vecs).reshape(want.shape), want)
 
 
+@pytest.mark.parametrize("devices", [[0], [0, 0]] + device_lists()[3:4], ids=lambda d: "dev" + "".join(map(str, d)))
+def test_multi_query_run_limbs(small, devices):
+    """psi_multi_query_run_limbs (what the adapter's run() calls): one device takes the streamed single-query path, a
+    device list the three-call sequence; two different queries in a row, same object."""
+    s = small
+    L, N = s["params"].L, s["params"].N
+    mc = P.MultiContext(s["params"], devices)
+    mc.InsertEvalMultKey(s["evk_b"], s["evk_a"])
+    mc.db_load_limbs(s["pt"], s["mask"])
+    for idx, minus, want in ((s["idx"], s["minus"], s["want"]), (s["idx2"], s["minus2"], s["want2"])):
+        iv = [idx.reshape(-1, N)[i].copy() for i in range(s["K"] * s["E"] * 2 * L)]
+        mv = [minus.reshape(-1, N)[i].copy() for i in range(2 * L)]
+        vecs = mc.query_run_limbs(iv, mv)
+        del iv, mv
+        assert np.array_equal(np.stack(vecs).reshape(want.shape), want)
+    # the plain calls still work on the same object afterwards
+    mc.query_set(s["idx"], s["minus"])
+    mc.run()
+    assert np.array_equal(mc.result_get(), s["want"])
+    mc.close()
+
+
 def test_single_context_limb_vector_ingestion(small):
     """psi_query_upload_limbs / psi_result_get_limbs on one psi_ctx, two queries in a row (the pinned pool is reused)."""
     s = small
@@ -123,6 +145,26 @@ def test_single_context_limb_vector_ingestion(small):
         cc.run()
         vecs = cc.result_get_limbs()
         assert np.array_equal(np.stack(vecs).reshape(want.shape), want)
+
+
+def test_streamed_single_query_from_limb_vectors(small):
+    """psi_query_run_streamed_limbs: the streamed single query with the host gather / scatter of the limb vectors inside
+    the overlap; two queries in a row (pools and landing buffers are reused), then a plain run() on the same context."""
+    s = small
+    L, N = s["params"].L, s["params"].N
+    cc = P.CryptoContext(s["params"])
+    cc.InsertEvalMultKey(s["evk_b"], s["evk_a"])
+    cc.db_load_limbs(s["pt"], s["mask"])
+    cc.set_host_threads(3)
+    for idx, minus, want in ((s["idx"], s["minus"], s["want"]), (s["idx2"], s["minus2"], s["want2"]), (s["idx"], s["minus"], s["want"])):
+        iv = [idx.reshape(-1, N)[i].copy() for i in range(s["K"] * s["E"] * 2 * L)]
+        mv = [minus.reshape(-1, N)[i].copy() for i in range(2 * L)]
+        vecs = cc.query_run_streamed_limbs(iv, mv)
+        del iv, mv
+        assert np.array_equal(np.stack(vecs).reshape(want.shape), want)
+    cc.query_set(s["idx2"], s["minus2"])
+    cc.run()
+    assert np.array_equal(cc.result_get(), s["want2"])
 
 
 def test_streamed_single_query_matches_run(small):
