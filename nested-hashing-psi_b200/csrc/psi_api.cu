@@ -1352,30 +1352,65 @@ static int query_run_streamed_impl(psi_ctx* c, const uint64_t* idx, const uint64
     CK(cudaStreamWaitEvent(c->sq_in, c->ev_sq, 0));
     CK(cudaStreamWaitEvent(c->sq_out, c->ev_sq, 0));
     CK(cudaMemcpyAsync(land_minus, minus, ct * sizeof(u64), cudaMemcpyHostToDevice, c->sq_in));
-    uint32_t n_slices = 0;
+    struct Slice {
+        uint32_t hf, p0, p1;
+        bool last_of_hf;
+    };
+    std::vector<Slice> slices;
     for (uint32_t hf = 0; hf < K; hf++) {
-        uint32_t S = E < slices_per_hf ? E : slices_per_hf;
-        for (uint32_t sl = 0; sl < S; sl++, n_slices++) {
-            if (n_slices >= kMaxStreamSlices) return set_error(PSI_ERR_INVALID, "too many hash functions for the streamed path");
-            const uint32_t p0 = (uint32_t)((uint64_t)E * sl / S), p1 = (uint32_t)((uint64_t)E * (sl + 1) / S);
-            const size_t off = ((size_t)hf * E + p0) * ct;
-            if (limbs) {
-                const long v0 = (long)(off / N), v1 = (long)((off + (size_t)(p1 - p0) * ct) / N);
-#pragma omp parallel for schedule(static) num_threads(nt) if (v1 - v0 >= 16)
-                for (long v = v0; v < v1; v++) copy_limb_vector(c->pool_in + (size_t)v * N, idx_limbs[v], N);
-            }
-            CK(cudaMemcpyAsync(land + off, idx + off, (size_t)(p1 - p0) * ct * sizeof(u64), cudaMemcpyHostToDevice, c->sq_in));
-            CK(cudaEventRecord(c->ev_slice[n_slices], c->sq_in));
-            CK(cudaStreamWaitEvent(s, c->ev_slice[n_slices], 0));
-            if (hf == 0 && sl == 0) CK(cudaMemcpyAsync(c->minus.p, land_minus, ct * sizeof(u64), cudaMemcpyDeviceToDevice, s));
-            CK(launch_retile_idx_range(k, land, c->idx.p, LN, E, hf, p0, p1)); nl++;
-            CK(launch_mac_range(k, hf, 1, c->b, E, p0, p1, (p0 > 0 ? 1u : 0u) | (p1 == E ? 2u : 0u), c->pt.p, c->idx.p, c->minus.p,
-                                c->acc.p)); nl++;
-        }
+        const uint32_t S = E < slices_per_hf ? E : slices_per_hf;
+        for (uint32_t sl = 0; sl < S; sl++)
+            slices.push_back(Slice{hf, (uint32_t)((uint64_t)E * sl / S), (uint32_t)((uint64_t)E * (sl + 1) / S), sl + 1 == S});
+    }
+    if (slices.size() > kMaxStreamSlices) return set_error(PSI_ERR_INVALID, "too many hash functions for the streamed path");
+    // H2D of slice j, then (ordered by an event) its re-tiling and its share of the inner products on the caller's stream
+    auto enqueue_slice = [&](uint32_t j) -> int {
+        const Slice& sl = slices[j];
+        const size_t off = ((size_t)sl.hf * E + sl.p0) * ct;
+        CK(cudaMemcpyAsync(land + off, idx + off, (size_t)(sl.p1 - sl.p0) * ct * sizeof(u64), cudaMemcpyHostToDevice, c->sq_in));
+        CK(cudaEventRecord(c->ev_slice[j], c->sq_in));
+        CK(cudaStreamWaitEvent(s, c->ev_slice[j], 0));
+        if (j == 0) CK(cudaMemcpyAsync(c->minus.p, land_minus, ct * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+        CK(launch_retile_idx_range(k, land, c->idx.p, LN, E, sl.hf, sl.p0, sl.p1)); nl++;
+        CK(launch_mac_range(k, sl.hf, 1, c->b, E, sl.p0, sl.p1, (sl.p0 > 0 ? 1u : 0u) | (sl.p1 == E ? 2u : 0u), c->pt.p, c->idx.p,
+                            c->minus.p, c->acc.p)); nl++;
         // the first operand of the first multiplication (the inner products of hash function 0) is complete while the
         // ciphertexts of hash function 1 are still crossing PCIe: its row-inverse and exact basis extension run now
-        if (hf == 0 && K > 1 && split_a)
-            if ((rc = mul_ctct_batch(c, s, c->b, c->acc.p, c->acc.p + (size_t)c->b * ct, nullptr, nullptr, &nl, 0, 1))) return rc;
+        if (sl.hf == 0 && sl.last_of_hf && K > 1 && split_a)
+            return mul_ctct_batch(c, s, c->b, c->acc.p, c->acc.p + (size_t)c->b * ct, nullptr, nullptr, &nl, 0, 1);
+        return PSI_OK;
+    };
+    auto slice_vectors = [&](uint32_t j, long* v0, long* v1) {
+        const size_t off = ((size_t)slices[j].hf * E + slices[j].p0) * ct;
+        *v0 = (long)(off / N);
+        *v1 = (long)((off + (size_t)(slices[j].p1 - slices[j].p0) * ct) / N);
+    };
+    if (!limbs) {
+        for (uint32_t j = 0; j < slices.size(); j++)
+            if ((rc = enqueue_slice(j))) return rc;
+    } else {
+        // limb vectors: the host threads gather slice j + 1 into the pinned pool while the calling thread enqueues slice j
+        // and the copy engine moves it
+        long v0, v1;
+        slice_vectors(0, &v0, &v1);
+#pragma omp parallel for schedule(static) num_threads(nt) if (v1 - v0 >= 16)
+        for (long v = v0; v < v1; v++) copy_limb_vector(c->pool_in + (size_t)v * N, idx_limbs[v], N);
+        for (uint32_t j = 0; j < slices.size(); j++) {
+            if (j + 1 == slices.size()) {
+                if ((rc = enqueue_slice(j))) return rc;
+                break;
+            }
+            slice_vectors(j + 1, &v0, &v1);
+            int rc_master = PSI_OK;
+#pragma omp parallel num_threads(nt)
+            {
+#pragma omp master
+                rc_master = enqueue_slice(j);
+#pragma omp for schedule(dynamic, 2) nowait
+                for (long v = v0; v < v1; v++) copy_limb_vector(c->pool_in + (size_t)v * N, idx_limbs[v], N);
+            }
+            if (rc_master) return rc_master;
+        }
     }
     if (limbs) CK(cudaEventRecord(c->ev_pool_in, c->sq_in));
     if (timeline) {
