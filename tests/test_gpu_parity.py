@@ -363,6 +363,41 @@ def test_run_randomised_shapes():
         cc.close()
 
 
+def test_one_context_many_databases_and_streams():
+    """run() is replayed as a CUDA graph captured per (phases, result buffer, grouping, buffer addresses): the same
+    context is re-loaded with databases of other shapes (larger, smaller, K = 1, back to the first), run on
+    different streams, with the phases alone and together -- every result against the oracle."""
+    import torch
+
+    cc, o, params = ctx_and_oracle(1024, 3)
+    rng = np.random.default_rng(77)
+    sk, evk_b, evk_a = o.keygen(6)
+    cc.InsertEvalMultKey(evk_b, evk_a)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    shapes = [(2, 5, 7), (2, 9, 3), (2, 2, 4), (1, 4, 5), (3, 3, 2), (2, 5, 7)]
+    for i, (K, b, E) in enumerate(shapes):
+        pt = sc.random_pt(rng, params, (K, b, E))
+        mask = sc.random_pt(rng, params, (b,))
+        cc.db_load_limbs(pt, mask)
+        for rep in range(3):
+            sp = streams[(i + rep) & 1].cuda_stream
+            idx = sc.random_ct(rng, params, (K, E))
+            minus = sc.random_ct(rng, params)
+            cc.query_set(idx, minus, sp)
+            if rep == 1:           # the two phases as separate calls
+                cc.run(sp, phases=1)
+                cc.run(sp, phases=2)
+            else:
+                cc.run(sp)
+            got = cc.result_get(stream=sp)
+            assert np.array_equal(got, o.run(pt, mask, idx, minus, evk_b, evk_a, nthreads=8)), (K, b, E, rep)
+        if i == 2:
+            cc.set_tuning(phase2_groups=1)
+        if i == 4:
+            cc.set_tuning(phase2_groups=0)
+    cc.close()
+
+
 def test_run_is_repeatable_under_load():
     """Race hunting without a sanitizer (compute-sanitizer is closed on the GPU pool): the full-size ring dimension,
     enough bins to fill the machine several times over, the same query evaluated 150 times back to back - every
