@@ -90,8 +90,5 @@ L.append("Roofline (bench.py, live): k_mac_tma %.0f GB/s of algorithmic traffic 
             d["roofline"]["algorithmic_bytes_per_launch"] / 1e9, d["roofline_int"]["achieved"], 100 * d["roofline_int"]["frac"],
             d["roofline_int"]["peak"]))
 open(os.path.join(P, tag + "_launch_list.md"), "w").write("\n".join(L) + "\n")
-for name in ("bench_ref.json", "bench_2p20.json", "bench_2p22.json", "bench_2p28.json", "bench_n2_allgather.json", "bench_n2_host.json",
-             "bench_n8_weak.json", "bench_n8_strong.json"):
-    if os.path.exists(os.path.join(G, name)):
-        open(os.path.join(P, tag + "_" + name), "w").write(open(os.path.join(G, name)).read().strip().splitlines()[-1] + "\n")
+# other bench lines of the round (other workloads, N > 1) are copied into profiles/ by hand from the gpurun call that made them
 print("\n".join(L))
