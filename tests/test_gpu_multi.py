@@ -11,6 +11,7 @@ import torch
 
 import psi_b200 as P
 from oracle.oracle import Oracle
+from oracle.params_ref import RefParams
 
 import scenario as sc
 
@@ -165,6 +166,24 @@ def test_streamed_single_query_from_limb_vectors(small):
     cc.query_set(s["idx2"], s["minus2"])
     cc.run()
     assert np.array_equal(cc.result_get(), s["want2"])
+    # K = 1 (mask only), K = 3, one bin / one position, ragged; then a HYBRID context (unfused chain, no operand split)
+    rng = np.random.default_rng(78)
+    for variant in (dict(), dict(ks_technique=1)):
+        params = sc.make_params(1024, T32, L=2) if not variant else RefParams(1024, T32, depth=2, L=2, **variant).to_struct()
+        o = Oracle(params)
+        cv = P.CryptoContext(params)
+        sk, evk_b, evk_a = o.keygen(3)
+        cv.InsertEvalMultKey(evk_b, evk_a)
+        for K, b, E in ((1, 3, 2), (3, 2, 9), (2, 1, 1), (2, 7, 13)):
+            pt, mask = sc.random_pt(rng, params, (K, b, E)), sc.random_pt(rng, params, (b,))
+            idx, minus = sc.random_ct(rng, params, (K, E)), sc.random_ct(rng, params)
+            cv.db_load_limbs(pt, mask)
+            want = o.run(pt, mask, idx, minus, evk_b, evk_a)
+            iv = [idx.reshape(-1, N)[i].copy() for i in range(K * E * 2 * L)]
+            mv = [minus.reshape(-1, N)[i].copy() for i in range(2 * L)]
+            vecs = cv.query_run_streamed_limbs(iv, mv)
+            assert np.array_equal(np.stack(vecs).reshape(want.shape), want), (variant, K, b, E)
+        cv.close()
 
 
 def test_streamed_single_query_matches_run(small):
