@@ -1052,7 +1052,7 @@ int psi_result_get_limbs(psi_ctx* c, uint64_t* const* out_limbs, void* stream) {
 }
 
 int psi_debug_set_tuning(psi_ctx* c, int mac_variant, int phase2_groups) {
-    if (!c || mac_variant < -1 || mac_variant > 4 || phase2_groups < -1 || phase2_groups > 8) return set_error(PSI_ERR_INVALID, "bad tuning value");
+    if (!c || mac_variant < -1 || mac_variant > 6 || phase2_groups < -1 || phase2_groups > 8) return set_error(PSI_ERR_INVALID, "bad tuning value");
     if (mac_variant >= 0) mac_force_variant(mac_variant);
     if (phase2_groups >= 0) c->p2_groups = (uint32_t)phase2_groups;
     return PSI_OK;

@@ -56,7 +56,7 @@ constexpr int kMacCoeffs = 128;  // coefficients per CTA tile (= one row of one 
 // width that divides b_local wastes no bin-lane, and a wider block re-reads the index slice from L2 fewer
 // times — what matters when a GPU holds 6 of the 47 bins of a sharded query.
 constexpr int kMacFold = 8;  // positions between folds
-constexpr uint32_t kMacShortRange = 0;  // position ranges up to this length take the 4 x 4 ring (0: never; set from measurements)
+constexpr uint32_t kMacShortRange = 16;  // position ranges up to this length take the persistent kernel (measured below)
 constexpr int kMacLanes = 2;
 constexpr int kMacConsumers = kMacCoeffs * kMacLanes;
 template <int BT, int CHUNK>
@@ -215,6 +215,124 @@ __global__ void __launch_bounds__(kMacConsumers + 32, (BT == 1 ? 3 : 2))
     }
 }
 
+// Persistent form for SHORT position ranges (E = 14 of BASELINE configs[1]: two chunks per work item): every CTA walks
+// over work items (bin block, row, hash function) with a stride of the grid and the producer's ring runs ACROSS items,
+// so the first chunk of item i + 1 is in flight while the consumers reduce and store item i -- the per-item bubble
+// (first-chunk latency, ~1.5 us against ~1 us of multiplies at E = 14) is what held the one-item kernel at 57-60 % of
+// the HBM peak.  Same ring, same arithmetic, same results as k_mac_tma; at E = 47 the one-item kernel is faster.
+template <int BT, int CHUNK, int STAGES>
+__global__ void __launch_bounds__(kMacConsumers + 32, (BT == 1 ? 3 : 2))
+    k_mac_persist(const DevTables* __restrict__ tab, uint32_t N, uint32_t L, uint32_t b, uint32_t E, MacRange rg, uint32_t nhf,
+                  const u64* __restrict__ pt, const u64* __restrict__ idx, const u64* __restrict__ minus, u64* __restrict__ acc) {
+    constexpr int kBins = kMacLanes * BT;
+    constexpr size_t kStageWords = mac_stage_words<BT, CHUNK>();
+    extern __shared__ __align__(128) u64 ring[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
+    const size_t LN = (size_t)L * N, T = LN / kMacCoeffs;
+    const uint32_t nbb = (b + kBins - 1) / kBins;
+    const uint32_t npos = rg.pos1 - rg.pos0;
+    const uint32_t nchunks = (npos + CHUNK - 1) / CHUNK;
+    const uint32_t items_per_hf = (uint32_t)T * nbb, n_items = items_per_hf * nhf;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kMacConsumers);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (threadIdx.x >= kMacConsumers) {
+        if (threadIdx.x == kMacConsumers) {
+            uint32_t g = 0;  // chunks issued so far by this CTA, over all its items
+            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const uint32_t hf = rg.hf0 + item / items_per_hf, r = item % items_per_hf;
+                const uint32_t tile = r / nbb, bin_blk0 = (r % nbb) * kBins;
+                const uint32_t nbins = min((uint32_t)kBins, b - bin_blk0);
+                const u64* isrc = idx + ((size_t)hf * T + tile) * E * 2 * kMacCoeffs;
+                const u64* psrc = pt + ((size_t)hf * b + bin_blk0) * (size_t)E * LN + (size_t)tile * E * kMacCoeffs;
+                for (uint32_t ch = 0; ch < nchunks; ch++, g++) {
+                    const uint32_t s = g % STAGES, round = g / STAGES;
+                    if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+                    const uint32_t p0 = rg.pos0 + ch * CHUNK, np = min((uint32_t)CHUNK, rg.pos1 - p0);
+                    u64* st = ring + (size_t)s * kStageWords;
+                    const uint32_t ibytes = np * 2 * kMacCoeffs * 8, pbytes = np * kMacCoeffs * 8;
+                    mbar_expect_tx(&full_bar[s], ibytes + nbins * pbytes);
+                    bulk_g2s(st, isrc + (size_t)p0 * 2 * kMacCoeffs, ibytes, &full_bar[s]);
+                    for (uint32_t j = 0; j < nbins; j++)
+                        bulk_g2s(st + (size_t)CHUNK * kMacCoeffs * (2 + j), psrc + (size_t)j * E * LN + (size_t)p0 * kMacCoeffs,
+                                 pbytes, &full_bar[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    const uint32_t w = threadIdx.x & (kMacCoeffs - 1), lane = threadIdx.x / kMacCoeffs;
+    const bool add_old = rg.flags & 1u, add_minus = rg.flags & 2u;
+    uint32_t g = 0;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint32_t hf = rg.hf0 + item / items_per_hf, r = item % items_per_hf;
+        const uint32_t tile = r / nbb, bin_blk0 = (r % nbb) * kBins;
+        const size_t c = (size_t)tile * kMacCoeffs + w;
+        u64 ll[BT][2], kk[BT][2], hh[BT][2], tlo[BT][2], thi[BT][2];
+#pragma unroll
+        for (int j = 0; j < BT; j++)
+#pragma unroll
+            for (int k = 0; k < 2; k++) ll[j][k] = kk[j][k] = hh[j][k] = tlo[j][k] = thi[j][k] = 0;
+        for (uint32_t ch = 0; ch < nchunks; ch++, g++) {
+            const uint32_t s = g % STAGES, round = g / STAGES;
+            const uint32_t np = min((uint32_t)CHUNK, npos - ch * CHUNK);
+            mbar_wait(&full_bar[s], round & 1);
+            const uint2* si = reinterpret_cast<const uint2*>(ring + (size_t)s * kStageWords) + w;
+            const uint2* sp = si + (size_t)CHUNK * kMacCoeffs * (2 + lane * BT);
+            for (uint32_t p = 0; p < np; p++) {
+                const uint2 i0 = si[p * 2 * kMacCoeffs], i1 = si[p * 2 * kMacCoeffs + kMacCoeffs];
+                const uint32_t s0 = i0.x + i0.y, s1 = i1.x + i1.y;
+#pragma unroll
+                for (int j = 0; j < BT; j++) {
+                    const uint2 y = sp[(j * CHUNK + p) * kMacCoeffs];
+                    const uint32_t sy = y.x + y.y;
+                    ll[j][0] = madw(i0.x, y.x, ll[j][0]);
+                    hh[j][0] = madw(i0.y, y.y, hh[j][0]);
+                    kk[j][0] = madw(s0, sy, kk[j][0]);
+                    ll[j][1] = madw(i1.x, y.x, ll[j][1]);
+                    hh[j][1] = madw(i1.y, y.y, hh[j][1]);
+                    kk[j][1] = madw(s1, sy, kk[j][1]);
+                }
+            }
+            mbar_arrive(&empty_bar[s]);
+            // CHUNK = kMacFold positions per chunk: fold after every chunk (the launcher only takes this kernel for
+            // ranges of at most kMacMaxTerms positions, so the 128-bit total needs no intermediate reduction)
+#pragma unroll
+            for (int j = 0; j < BT; j++)
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    fold30(thi[j][k], tlo[j][k], ll[j][k], kk[j][k] - ll[j][k] - hh[j][k], hh[j][k]);
+                    ll[j][k] = kk[j][k] = hh[j][k] = 0;
+                }
+        }
+        const ModDev& md = tab->mods[c / N];
+        const u64 q = md.q, qinv = md.qinv;
+        const u64 m0 = add_minus ? minus[c] : 0, m1 = add_minus ? minus[LN + c] : 0;
+#pragma unroll
+        for (int j = 0; j < BT; j++) {
+            const uint32_t bin = bin_blk0 + lane * BT + j;
+            if (bin < b) {
+                u64* o = acc + (((size_t)hf * b + bin) * 2) * LN + c;
+                u64 r0 = addmod(redc_canonical(thi[j][0], tlo[j][0], q, qinv), m0, q);
+                u64 r1 = addmod(redc_canonical(thi[j][1], tlo[j][1], q, qinv), m1, q);
+                if (add_old) {
+                    r0 = addmod(r0, o[0], q);
+                    r1 = addmod(r1, o[LN], q);
+                }
+                o[0] = r0;
+                o[LN] = r1;
+            }
+        }
+    }
+}
+
 // The instantiations the launcher chooses from: <bins per lane, positions per stage, stages>
 //   <2, 8, 2>  4 bins per CTA, 96 KiB ring, 2 CTAs / SM: the full-database shape (b = 47: 12 blocks)
 //   <1, 8, 2>  2 bins per CTA, 64 KiB ring, 3 CTAs / SM: few resident bins whose count 4 does not divide (a GPU's
@@ -233,21 +351,42 @@ static cudaError_t mac_launch_t(const KCtx& k, uint32_t nhf, uint32_t b, uint32_
     return cudaGetLastError();
 }
 
+template <int BT, int CHUNK, int STAGES>
+static cudaError_t mac_launch_persist(const KCtx& k, uint32_t nhf, uint32_t b, uint32_t E, const MacRange& rg, const u64* pt,
+                                      const u64* idx, const u64* minus, u64* acc, bool init_only) {
+    static_assert(CHUNK == kMacFold, "the persistent kernel folds once per chunk");
+    constexpr size_t smem = STAGES * mac_stage_words<BT, CHUNK>() * sizeof(u64);
+    if (init_only)
+        return cudaFuncSetAttribute(k_mac_persist<BT, CHUNK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t LN = (size_t)k.L * k.N;
+    constexpr int kBins = kMacLanes * BT;
+    const size_t n_items = cdiv(LN, kMacCoeffs) * ((b + kBins - 1) / kBins) * nhf;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t slots = (size_t)sms * (BT == 1 ? 3 : 2);
+    const unsigned grid = (unsigned)(n_items < slots ? n_items : slots);
+    k_mac_persist<BT, CHUNK, STAGES><<<grid, kMacConsumers + 32, smem, k.s>>>(k.tab, k.N, k.L, b, E, rg, nhf, pt, idx, minus, acc);
+    return cudaGetLastError();
+}
+
 static int g_mac_force = 0;  // tuning / tests: 0 = choose by shape, 1 / 2 = force 2 / 4 bins per CTA, 3 / 4 = the same with a 4 x 4 ring
 void mac_force_variant(int v) { g_mac_force = v; }
 int mac_forced_variant() { return g_mac_force; }
 
 // bin-block width for b resident bins: 2-bin blocks when 4-bin blocks would leave more than a tenth of the
 // bin-lanes idle (measured: b = 5, 6, 14 faster with 2, b = 26, 47, 75 faster with 4)
-// ring shape for npos positions per launch: a short range (E = 14 of BASELINE configs[1], the 12-position slices of the
-// streamed single query) is two chunks of eight, so a 2 x 8 ring never reaches steady state and the consumers wait for
-// eight positions before the first multiply; four stages of four positions start after four and keep three chunks in
-// flight (measured, tools/tune_shapes.py: see profiles/r02_tune_shapes.md)
+// Kernel for npos positions per launch: a short range (E = 14 of BASELINE configs[1], E = 8 of configs[0], the
+// 12-position slices of the streamed single query) is at most two chunks of eight, so the one-item kernel pays its
+// first-chunk latency for every (bin block, row).  MEASURED (tools/tune_shapes.py, % of the HBM peak, one-item kernel ->
+// persistent kernel with the ring across items): 14 bins x 14 positions 59.5 -> 62.6, 14 x 12 55.3 -> 58.6, 47 x 12
+// 57.1 -> 63.1, 8 x 8 51.3 -> 57.9; from 26 positions on the one-item kernel wins (26 x 26: 73.3 against 71.4, 47 x 47:
+// 88.1 against 83.6, 75 x 75: 92.4 against 85.1).  A ring of four stages of four positions (variants 3 / 4) never won.
 static int mac_choose(uint32_t b, uint32_t npos) {
-    if (g_mac_force) return g_mac_force;
+    if (g_mac_force && !(g_mac_force >= 5 && npos > kMacMaxTerms)) return g_mac_force;
     const uint32_t slots4 = ((b + 3) / 4) * 4, slots2 = ((b + 1) / 2) * 2;
     const int bins = (slots2 < slots4 && (slots4 - b) * 10 > slots4) ? 1 : 2;
-    return npos <= kMacShortRange ? bins + 2 : bins;
+    return npos <= kMacShortRange ? bins + 4 : bins;
 }
 
 cudaError_t mac_init_device() {
@@ -257,6 +396,8 @@ cudaError_t mac_init_device() {
     if (e == cudaSuccess) e = mac_launch_t<1, 8, 2>(k, 0, 0, 0, rg, nullptr, nullptr, nullptr, nullptr, true);
     if (e == cudaSuccess) e = mac_launch_t<2, 4, 4>(k, 0, 0, 0, rg, nullptr, nullptr, nullptr, nullptr, true);
     if (e == cudaSuccess) e = mac_launch_t<1, 4, 4>(k, 0, 0, 0, rg, nullptr, nullptr, nullptr, nullptr, true);
+    if (e == cudaSuccess) e = mac_launch_persist<1, 8, 2>(k, 0, 0, 0, rg, nullptr, nullptr, nullptr, nullptr, true);
+    if (e == cudaSuccess) e = mac_launch_persist<2, 8, 2>(k, 0, 0, 0, rg, nullptr, nullptr, nullptr, nullptr, true);
     return e;
 }
 
@@ -267,6 +408,8 @@ cudaError_t launch_mac_range(const KCtx& k, uint32_t hf0, uint32_t nhf, uint32_t
         case 1: return mac_launch_t<1, 8, 2>(k, nhf, b, E, rg, pt, idx, minus, acc, false);
         case 3: return mac_launch_t<1, 4, 4>(k, nhf, b, E, rg, pt, idx, minus, acc, false);
         case 4: return mac_launch_t<2, 4, 4>(k, nhf, b, E, rg, pt, idx, minus, acc, false);
+        case 5: return mac_launch_persist<1, 8, 2>(k, nhf, b, E, rg, pt, idx, minus, acc, false);
+        case 6: return mac_launch_persist<2, 8, 2>(k, nhf, b, E, rg, pt, idx, minus, acc, false);
         default: return mac_launch_t<2, 8, 2>(k, nhf, b, E, rg, pt, idx, minus, acc, false);
     }
 }

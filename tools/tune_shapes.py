@@ -56,7 +56,7 @@ def main():
         cc.sync(sp)
         bytes1 = 8 * L * N * (K * b * E + 2 * K * E + 2 + 2 * K * b)
         ref = None
-        for v in (2, 1, 4, 3):
+        for v in (2, 1, 6, 5):
             cc.set_tuning(mac_variant=v, phase2_groups=1)
             ms = timed(lambda: cc.run(sp, phases=1))
             cc.run(sp)
@@ -64,7 +64,7 @@ def main():
             if ref is None:
                 ref = got
             assert np.array_equal(ref, got), ("mac variant changes the result", b, E, v)
-            print(json.dumps({"b": b, "E": E, "mac_bins_per_cta": 2 * (v if v < 3 else v - 2), "ring": "2x8" if v < 3 else "4x4", "p1_ms": ms, "hbm_frac": bytes1 / (ms * 1e-3) / 6544e9}), flush=True)
+            print(json.dumps({"b": b, "E": E, "mac_bins_per_cta": 2 * (v if v < 3 else v - 4), "kernel": "one item per CTA" if v < 3 else "persistent, ring across items", "p1_ms": ms, "hbm_frac": bytes1 / (ms * 1e-3) / 6544e9}), flush=True)
         cc.set_tuning(mac_variant=0)
         for g in (2,):
             if g > b:
