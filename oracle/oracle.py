@@ -59,6 +59,16 @@ def lib():
                               _u64p, _u64p, _u64p, _u64p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.orc_run_cold.argtypes = L.orc_run.argtypes
         L.orc_max_threads.restype = ctypes.c_int
+        # non-batched FHEHIPPIE
+        L.orc_automorphism_eval.argtypes = [ctypes.c_void_p, _u64p, ctypes.c_uint64, _u64p]
+        L.orc_automorphism_coeff.argtypes = [ctypes.c_void_p, _u64p, ctypes.c_uint64, ctypes.c_int, _u64p]
+        L.orc_find_automorphism_index.restype = ctypes.c_uint64
+        L.orc_find_automorphism_index.argtypes = [ctypes.c_void_p, ctypes.c_int64]
+        L.orc_eval_sum_indices.argtypes = [ctypes.c_void_p, ctypes.c_int, _u64p]
+        L.orc_auto_keygen.argtypes = [ctypes.c_void_p, _u64p, ctypes.c_uint64, ctypes.c_uint64, _u64p, _u64p]
+        L.orc_eval_automorphism.argtypes = [ctypes.c_void_p, _u64p, ctypes.c_uint64, _u64p, _u64p, _u64p]
+        L.orc_nb_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _u64p, _u64p, _u64p, _u64p, ctypes.c_int,
+                                 _u64p, _u64p, _u64p, _u64p]
         _LIB = L
     return _LIB
 
@@ -207,6 +217,57 @@ class Oracle:
             out = np.zeros((b, 2, self.L, self.N), dtype=np.uint64)
         lib().orc_run(self._h, K, b, E, _p(pt), _p(mask), _p(idx), _p(minus), _p(evk_b), _p(evk_a), _p(out),
                       bin_begin, bin_end, nthreads)
+        return out
+
+    # -- non-batched FHEHIPPIE (FHEHIPPIE.cpp:61-77) -------------------------------
+    def automorphism_eval(self, poly, g):
+        """AutomorphismTransform(g) of an EVALUATION polynomial [L][N]."""
+        poly = np.ascontiguousarray(poly, dtype=np.uint64)
+        out = np.empty_like(poly)
+        lib().orc_automorphism_eval(self._h, _p(poly), g, _p(out))
+        return out
+
+    def automorphism_coeff(self, limb, g, mod_index):
+        """a(X) -> a(X^g) on one COEFFICIENT limb [N] (the definition the EVALUATION permutation is checked against)."""
+        limb = np.ascontiguousarray(limb, dtype=np.uint64)
+        out = np.empty_like(limb)
+        lib().orc_automorphism_coeff(self._h, _p(limb), g, mod_index, _p(out))
+        return out
+
+    def find_automorphism_index(self, i):
+        return int(lib().orc_find_automorphism_index(self._h, i))
+
+    def eval_sum_indices(self, batch_size):
+        buf = np.zeros(32, dtype=np.uint64)
+        n = lib().orc_eval_sum_indices(self._h, batch_size, _p(buf))
+        return [int(v) for v in buf[:n]]
+
+    def auto_keygen(self, sk, seed, indices):
+        """EvalSumKeyGen / EvalRotateKeyGen: one BV key per automorphism index -> (key_b, key_a) [n][L][L][N]."""
+        n = len(indices)
+        kb = np.empty((n, self.L, self.L, self.N), dtype=np.uint64)
+        ka = np.empty_like(kb)
+        for i, g in enumerate(indices):
+            lib().orc_auto_keygen(self._h, _p(sk), seed, int(g), _p(kb[i]), _p(ka[i]))
+        return kb, ka
+
+    def eval_automorphism(self, ct, g, key_b, key_a):
+        ct = np.ascontiguousarray(ct, dtype=np.uint64)
+        out = np.empty_like(ct)
+        lib().orc_eval_automorphism(self._h, _p(ct), int(g), _p(key_b), _p(key_a), _p(out))
+        return out
+
+    def nb_run(self, idx, pt, merge_pt, mask, key_index, key_b, key_a):
+        """FHEHIPPIE::run for one PIE.  idx [K][2][L][N], pt [K][b][L][N], merge_pt [L][N], mask [K][L][N],
+        key_index [n] (automorphism indices), key_b / key_a [n][L][L][N] -> [K][2][L][N] (unpermuted)."""
+        K, b = pt.shape[0], pt.shape[1]
+        out = np.zeros((K, 2, self.L, self.N), dtype=np.uint64)
+        ki = np.ascontiguousarray(key_index, dtype=np.uint64)
+        rc = lib().orc_nb_run(self._h, K, b, _p(np.ascontiguousarray(idx)), _p(np.ascontiguousarray(pt)),
+                              _p(np.ascontiguousarray(merge_pt)), _p(np.ascontiguousarray(mask)), len(ki), _p(ki),
+                              _p(np.ascontiguousarray(key_b)), _p(np.ascontiguousarray(key_a)), _p(out))
+        if rc:
+            raise KeyError("automorphism key missing")
         return out
 
 

@@ -31,6 +31,8 @@
  *   orc_keygen         KeyGen + EvalMultKeyGen                  BatchedFHEPSIClient.cpp:88-91
  *   orc_encrypt_sk     Encrypt(secretKey, plaintext)            BatchedFHEPSIClient.cpp:155-166
  *   orc_decrypt        Decrypt + GetPackedValue                 BatchedFHEPSIClient.cpp:249-265
+ *   orc_nb_run         FHEHIPPIE::run (non-batched PIE)         FHEHIPPIE.cpp:61-77
+ *   orc_auto_keygen    EvalSumKeyGen / EvalRotateKeyGen         SimpleFHEPSIClient.cpp:79-90
  */
 #include <math.h>
 #include <stdint.h>
@@ -959,6 +961,241 @@ int orc_run_cold(const orc_ctx* c, int K, int b, int E, const u64* pt_coeff, con
     }
     return 0;
 }
+
+/* ================================================================== non-batched FHEHIPPIE
+ * Restates FHEHIPPIE::run (FHEHIPPIE.cpp:61-77) and the OpenFHE operations underneath (recalled, 1.0.x line):
+ *   EvalInnerProduct(ct, pt, batchSize) = EvalSum(EvalMult(ct, pt), batchSize)          advancedshe.cpp
+ *   EvalSum, power-of-two ring: for the indices g_0 = 5, g_{i+1} = g_i^2 mod 2N (ceil(log2 batchSize) of them; the last
+ *     one is 2N - 1 instead when 2 batchSize >= 2N):  ct += EvalAutomorphism(ct, g_i)
+ *   EvalMerge(cts) = EvalMult(cts[0], m) + sum_{i>=1} EvalAtIndex(EvalMult(cts[i], m), -i),  m = packed {1, 0, 0, ...}
+ *   EvalAtIndex(ct, i) = EvalAutomorphism(ct, FindAutomorphismIndex2n(i)),  index = 5^i mod 2N (5^-1 for i < 0)
+ *   EvalAutomorphism(ct, g): KeySwitchInPlace(ct, key_g) FIRST (c0 += d0, c1 = d1 with (d0, d1) = KeySwitchBV core of
+ *     c1), then AutomorphismTransform(g) of both components; key_g switches s -> sigma_{g^-1}(s)
+ *     (EvalAutomorphismKeyGen permutes the secret with the inverse index for exactly this order)
+ *   AutomorphismTransform in EVALUATION format: result[bitrev(j)] = x[bitrev(((2j+1) g mod 2N) >> 1)] (PrecomputeAutoMap)
+ * No floating point anywhere on this path: every step yields canonical residues, so limb parity with the host library
+ * depends only on the operation ORDER above (key switch before the permutation, centred digit lift).  What is pinned
+ * on the CPU (tests/test_nonbatched.py): the permutation against the coefficient-domain definition a(X) -> a(X^g),
+ * rotation semantics of the decrypted slots, EvalSum / EvalMerge slot semantics and the reference's decode rule
+ * (SimpleFHEPSIClient.cpp:245-262: the item is in the set iff some decrypted slot < b is 0). */
+
+/* PrecomputeAutoMap (recalled): position p of the bit-reversed transform output reads position automap(p) */
+static uint32_t nb_automap(uint32_t p, u64 g, int logN) {
+    u64 j = bitrev(p, logN);
+    u64 m = 2ull << logN;
+    u64 idx = (((2 * j + 1) * g) % m) >> 1;
+    return (uint32_t)bitrev(idx, logN);
+}
+
+/* AutomorphismTransform of one EVALUATION-format polynomial of L limbs. in/out: [L][N], in != out */
+void orc_automorphism_eval(const orc_ctx* c, const u64* in, u64 g, u64* out) {
+    int N = c->N, L = c->L, logN = c->mq[0].logN;
+    for (int p = 0; p < N; p++) {
+        uint32_t src = nb_automap((uint32_t)p, g, logN);
+        for (int l = 0; l < L; l++) out[(size_t)l * N + p] = in[(size_t)l * N + src];
+    }
+}
+
+/* the same map in COEFFICIENT format (definition: X^j -> X^(j g mod 2N), sign flip past N); one limb, modulus index */
+void orc_automorphism_coeff(const orc_ctx* c, const u64* in, u64 g, int mod_index, u64* out) {
+    int N = c->N;
+    u64 q = mod_at(c, mod_index)->q;
+    for (int j = 0; j < N; j++) {
+        u64 e = ((u64)j * g) % (2ull * N);
+        if (e < (u64)N)
+            out[e] = in[j];
+        else
+            out[e - N] = in[j] ? q - in[j] : 0;
+    }
+}
+
+u64 orc_find_automorphism_index(const orc_ctx* c, int64_t i) { /* FindAutomorphismIndex2n */
+    u64 m = 2ull * c->N, g0 = 5;
+    if (i < 0) { /* 5^-1 mod 2N */
+        g0 = 1;
+        u64 b = 5, e = m / 2 - 1; /* the unit group has exponent dividing N = m/2: 5^(m/2 - 1) = 5^-1 */
+        for (; e; e >>= 1) {
+            if (e & 1) g0 = (g0 * b) % m;
+            b = (b * b) % m;
+        }
+        i = -i;
+    }
+    u64 g = 1;
+    for (int64_t k = 0; k < i; k++) g = (g * g0) % m;
+    return g;
+}
+static u64 nb_inverse_index(const orc_ctx* c, u64 g) { /* g^-1 mod 2N: the unit group has exponent N */
+    u64 m = 2ull * c->N, r = 1, b = g % m, e = (u64)c->N - 1;
+    for (; e; e >>= 1) {
+        if (e & 1) r = (r * b) % m;
+        b = (b * b) % m;
+    }
+    return r;
+}
+
+/* GenerateIndices_2n / EvalSum_2n index sequence for a batch size; returns the count (<= 32) */
+int orc_eval_sum_indices(const orc_ctx* c, int batch_size, u64* out) {
+    u64 m = 2ull * c->N, g = 5;
+    int n = 0;
+    if (batch_size <= 1) return 0;
+    int steps = 0;
+    while ((1 << steps) < batch_size) steps++; /* ceil(log2) */
+    for (int i = 0; i < steps - 1; i++) {
+        out[n++] = g;
+        g = (g * g) % m;
+    }
+    out[n++] = (2ull * batch_size < m) ? g : m - 1;
+    return n;
+}
+
+/* EvalAutomorphismKeyGen for one index g, BV digit size 0 (KeySwitchBV::KeySwitchGenInternal(old = s, new =
+ * sigma_{g^-1}(s)), recalled): a_i uniform, e_i Gaussian, key_b[i] = -(a_i s_new + e_i) + s on limb i only.
+ * sk: [L][N] EVAL; key_b, key_a: [L][L][N] EVAL. */
+void orc_auto_keygen(const orc_ctx* c, const u64* sk, u64 seed, u64 g, u64* key_b, u64* key_a) {
+    int N = c->N, L = c->L;
+    rng_t r = {seed ^ (g * 0x9E3779B97F4A7C15ull)};
+    u64* snew = malloc(sizeof(u64) * (size_t)L * N);
+    orc_automorphism_eval(c, sk, nb_inverse_index(c, g), snew);
+    int64_t* small = malloc(sizeof(int64_t) * N);
+    u64* e = malloc(sizeof(u64) * (size_t)L * N);
+    for (int i = 0; i < L; i++) {
+        for (int j = 0; j < N; j++) small[j] = rng_gauss(&r, 3.19);
+        small_to_eval(c, small, e);
+        for (int k = 0; k < L; k++) {
+            u64 q = c->P.q[k];
+            u64* a = key_a + ((size_t)i * L + k) * N;
+            u64* b = key_b + ((size_t)i * L + k) * N;
+            for (int j = 0; j < N; j++) {
+                a[j] = rng_below(&r, q);
+                u64 v = submod(0, addmod(mulmod(a[j], snew[(size_t)k * N + j], q), e[(size_t)k * N + j], q), q);
+                if (k == i) v = addmod(v, sk[(size_t)k * N + j], q);
+                b[j] = v;
+            }
+        }
+    }
+    free(e);
+    free(small);
+    free(snew);
+}
+
+/* KeySwitchBV::KeySwitchCore of one EVALUATION polynomial (recalled): to COEFFICIENT, CRTDecompose (digit i = limb i,
+ * centred switch to every q_k), to EVALUATION, inner products with the key.  x: [L][N]; d0, d1: [L][N] EVAL. */
+static void nb_keyswitch_core(const orc_ctx* c, const u64* x, const u64* key_b, const u64* key_a, u64* d0, u64* d1) {
+    const int N = c->N, L = c->L;
+    const psi_params* P = &c->P;
+    size_t polyQ = (size_t)L * N;
+    u64* coef = malloc(sizeof(u64) * polyQ);
+    u64* dig = malloc(sizeof(u64) * N);
+    memcpy(coef, x, sizeof(u64) * polyQ);
+    for (int l = 0; l < L; l++) ntt_inv(coef + (size_t)l * N, &c->mq[l], N);
+    memset(d0, 0, sizeof(u64) * polyQ);
+    memset(d1, 0, sizeof(u64) * polyQ);
+    for (int i = 0; i < L; i++) {
+        u64 qi = P->q[i], half = (qi - 1) >> 1;
+        for (int k = 0; k < L; k++) {
+            u64 qk = P->q[k], qi_mod_qk = qi % qk;
+            const modctx* m = &c->mq[k];
+            for (int j = 0; j < N; j++) {
+                u64 v = coef[(size_t)i * N + j];
+                u64 rr = v % qk;
+                if (i != k && v > half) rr = submod(rr, qi_mod_qk, qk); /* NativeVector::SwitchModulus */
+                dig[j] = rr;
+            }
+            ntt_fwd(dig, m, N);
+            const u64* kb = key_b + ((size_t)i * L + k) * N;
+            const u64* ka = key_a + ((size_t)i * L + k) * N;
+            u64 *o0 = d0 + (size_t)k * N, *o1 = d1 + (size_t)k * N;
+            for (int j = 0; j < N; j++) {
+                o0[j] = addmod(o0[j], barrett128((u128)dig[j] * kb[j], m), qk);
+                o1[j] = addmod(o1[j], barrett128((u128)dig[j] * ka[j], m), qk);
+            }
+        }
+    }
+    free(dig);
+    free(coef);
+}
+
+/* EvalAutomorphism(ct, g) with its key.  ct, out: [2][L][N] EVAL (out != ct) */
+void orc_eval_automorphism(const orc_ctx* c, const u64* ct, u64 g, const u64* key_b, const u64* key_a, u64* out) {
+    const int N = c->N, L = c->L;
+    size_t polyQ = (size_t)L * N;
+    u64* t0 = malloc(sizeof(u64) * 2 * polyQ);
+    u64* t1 = t0 + polyQ;
+    nb_keyswitch_core(c, ct + polyQ, key_b, key_a, t0, t1);
+    for (int l = 0; l < L; l++)
+        for (int j = 0; j < N; j++)
+            t0[(size_t)l * N + j] = addmod(t0[(size_t)l * N + j], ct[(size_t)l * N + j], c->P.q[l]);
+    orc_automorphism_eval(c, t0, g, out);
+    orc_automorphism_eval(c, t1, g, out + polyQ);
+    free(t0);
+}
+
+static void nb_add_ct(const orc_ctx* c, u64* acc, const u64* x) {
+    const int N = c->N, L = c->L;
+    for (int k = 0; k < 2; k++)
+        for (int l = 0; l < L; l++) {
+            u64 q = c->P.q[l];
+            size_t o = ((size_t)k * L + l) * N;
+            for (int j = 0; j < N; j++) acc[o + j] = addmod(acc[o + j], x[o + j], q);
+        }
+}
+
+/* keys: n_keys automorphism keys, key_index[n] = its index g, key_b / key_a: [n_keys][L][L][N] */
+static int nb_find_key(int n_keys, const u64* key_index, u64 g) {
+    for (int i = 0; i < n_keys; i++)
+        if (key_index[i] == g) return i;
+    return -1;
+}
+
+/* FHEHIPPIE::run for one PIE, FHEHIPPIE.cpp:61-77.
+ *   idx:[K][2][L][N] (indexMatrix)  pt:[K][b][L][N] (vectorizedCT)  merge_pt:[L][N] (EvalMerge's packed {1,0,..})
+ *   mask:[K][L][N] (preCalcRandomMask)  out:[K][2][L][N], out[hf] = result of hash function hf (the caller applies
+ *   permutationVector, FHEHIPPIE.cpp:74).  Returns -1 when a needed automorphism key is missing (OpenFHE throws). */
+int orc_nb_run(const orc_ctx* c, int K, int b, const u64* idx, const u64* pt, const u64* merge_pt, const u64* mask,
+               int n_keys, const u64* key_index, const u64* key_b, const u64* key_a, u64* out) {
+    const int N = c->N, L = c->L;
+    const size_t poly = (size_t)L * N, ctsz = 2 * poly, keysz = (size_t)L * poly;
+    u64 sum_idx[32];
+    const int n_sum = orc_eval_sum_indices(c, b, sum_idx); /* EvalInnerProduct(.., vectorizedCT[hfInd].size()) */
+    u64* cur = malloc(sizeof(u64) * ctsz);
+    u64* rot = malloc(sizeof(u64) * ctsz);
+    u64* merged = malloc(sizeof(u64) * ctsz);
+    int rc = 0;
+    for (int hf = 0; hf < K && !rc; hf++) {
+        for (int bin = 0; bin < b && !rc; bin++) {
+            orc_mul_ctpt(c, idx + (size_t)hf * ctsz, pt + ((size_t)hf * b + bin) * poly, cur);
+            for (int s = 0; s < n_sum; s++) {
+                int ki = nb_find_key(n_keys, key_index, sum_idx[s]);
+                if (ki < 0) {
+                    rc = -1;
+                    break;
+                }
+                orc_eval_automorphism(c, cur, sum_idx[s], key_b + ki * keysz, key_a + ki * keysz, rot);
+                nb_add_ct(c, cur, rot);
+            }
+            if (rc) break;
+            orc_mul_ctpt(c, cur, merge_pt, rot); /* EvalMerge: keep slot 0 ... */
+            if (bin == 0)
+                memcpy(merged, rot, sizeof(u64) * ctsz);
+            else { /* ... and move it to slot `bin` */
+                u64 g = orc_find_automorphism_index(c, -(int64_t)bin);
+                int ki = nb_find_key(n_keys, key_index, g);
+                if (ki < 0) {
+                    rc = -1;
+                    break;
+                }
+                orc_eval_automorphism(c, rot, g, key_b + ki * keysz, key_a + ki * keysz, cur);
+                nb_add_ct(c, merged, cur);
+            }
+        }
+        if (!rc) orc_mul_ctpt(c, merged, mask + (size_t)hf * poly, out + (size_t)hf * ctsz);
+    }
+    free(merged);
+    free(rot);
+    free(cur);
+    return rc;
+}
+
 
 int orc_max_threads(void) {
 #ifdef _OPENMP
