@@ -412,6 +412,36 @@ int psi_multi_run_launch_count(psi_multi* m, uint32_t* out);
 int psi_pie_create_multi(psi_multi* m, const psi_params* params, psi_hct* hct, uint64_t shuffle_seed, uint64_t mask_seed,
                          int keep_slots, psi_pie** out);
 
+/* ------------------------------------------------------------------------------------------
+ * Non-batched FHEHIPPIE: one private indexed equality check per outer cell of the server's nested
+ * cuckoo table.  Replaces FHEHIPPIE (FHEHIPPIE.hpp:18-50; ctor FHEHIPPIE.cpp:9-59, run :61-77) and the loop
+ * FHEHIPPIECollection::runAll makes over it (SimpleFHEPSIServer.cpp:126-160): the whole collection of PIEs is one
+ * database and psi_nb_run evaluates a contiguous range of them in lock step.  BFV, BV key switching (digit size 0).
+ * Per PIE: K hash functions, b bins of b positions (the ctor demands a square inner table, FHEHIPPIE.cpp:13-16).
+ * Results come back per hash function in natural order; permutationVector (FHEHIPPIE.cpp:74) is the caller's.
+ * ------------------------------------------------------------------------------------------ */
+/* the automorphism indices run() needs: EvalSum of `batch_size` slots (EvalSum_2n), and EvalAtIndex(i)
+ * (FindAutomorphismIndex2n).  Pure host arithmetic, no device. */
+int psi_nb_eval_sum_indices(uint32_t N, uint32_t batch_size, uint64_t* out /*[<= 32]*/, uint32_t* n);
+int psi_nb_rotation_index(uint32_t N, int64_t i, uint64_t* out);
+/* DeserializeEvalSumKey + DeserializeEvalAutomorphismKey (SimpleFHEPSIServer.cpp:45-62): one BV key per automorphism
+ * index, key_b / key_a [n_keys][L][L][N] EVALUATION ((*evalKey->GetBVector())[digit] / GetAVector, limb by limb). */
+int psi_nb_set_automorphism_keys(psi_ctx* c, uint32_t n_keys, const uint64_t* auto_index, const uint64_t* key_b,
+                                 const uint64_t* key_a);
+/* the ctor's vectorizedCT / preCalcRandomMask of n_pie PIEs (FHEHIPPIE.cpp:25-58) as EVALUATION limbs:
+ * pt [n_pie][K][b][L][N], mask [n_pie][K][L][N]; merge [L][N] = MakePackedPlaintext({1, 0, ...}) of EvalMerge */
+int psi_nb_db_load_limbs(psi_ctx* c, uint32_t n_pie, uint32_t K, uint32_t b, const uint64_t* pt_limbs,
+                         const uint64_t* mask_limbs, const uint64_t* merge_limbs);
+/* the same from slot values, encoded on the device (MakePackedPlaintext, FHEHIPPIE.cpp:52,57):
+ * slots [n_pie][K][b][nslots] (plainVec: the b positions of a bin, then 1; nslots = b + 1), mask_slots [n_pie][K][b] */
+int psi_nb_db_encode_slots(psi_ctx* c, uint32_t n_pie, uint32_t K, uint32_t b, uint32_t nslots, const int64_t* slots,
+                           const int64_t* mask_slots);
+int psi_nb_db_get_limbs(psi_ctx* c, uint64_t* pt_limbs, uint64_t* mask_limbs, uint64_t* merge_limbs); /* any may be null */
+/* setIndex + run + getResultList (FHEHIPPIE.hpp:39-49, FHEHIPPIE.cpp:61-77) of PIEs [pie_begin, pie_end):
+ * idx, out: HOST [pie_end - pie_begin][K][2][L][N]; synchronous.  A missing key is PSI_ERR_STATE (OpenFHE throws). */
+int psi_nb_run(psi_ctx* c, uint32_t pie_begin, uint32_t pie_end, const uint64_t* idx, uint64_t* out, void* stream);
+int psi_nb_launch_count(psi_ctx* c, uint32_t* out); /* kernels launched by the last psi_nb_run */
+
 /* number of CUDA devices visible to the process (hosts that build their device list without the CUDA headers) */
 int psi_device_count(int* n);
 

@@ -11,12 +11,13 @@ CUDA device is missing the calls raise.
 from .capi import (PsiError, PsiParams, lib, lib_path, build_library, params_generate, PLAINTEXT_MODULUS,
                    depth_for_E, MAX_LIMBS)
 from .pie import (CryptoContext, MultiContext, PublicKey, TabulationHashing, HierarchicalCuckooHashTable, BatchedFHEHIPPIE,
-                  RandomDataInput, client_table, hash_index)
+                  RandomDataInput, client_table, hash_index, FHEHIPPIE, FHEHIPPIECollection,
+                  eval_sum_indices, rotation_index)
 from .sharding import bin_shard, ShardedPIE, QueryDistributor, query_slice
 from .client_query import build_query_slots, extract_intersection
 
 __all__ = [
     "PsiError", "PsiParams", "lib", "lib_path", "build_library", "params_generate", "PLAINTEXT_MODULUS",
     "depth_for_E", "MAX_LIMBS", "CryptoContext", "MultiContext", "PublicKey", "TabulationHashing", "HierarchicalCuckooHashTable",
-    "BatchedFHEHIPPIE", "RandomDataInput", "client_table", "hash_index", "bin_shard", "ShardedPIE", "QueryDistributor", "query_slice", "build_query_slots", "extract_intersection",
+    "BatchedFHEHIPPIE", "FHEHIPPIE", "FHEHIPPIECollection", "eval_sum_indices", "rotation_index", "RandomDataInput", "client_table", "hash_index", "bin_shard", "ShardedPIE", "QueryDistributor", "query_slice", "build_query_slots", "extract_intersection",
 ]

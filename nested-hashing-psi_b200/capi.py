@@ -135,6 +135,14 @@ SYMBOLS = {
     "psi_multi_sync": (_int, [_vp]),
     "psi_multi_run_launch_count": (_int, [_vp, _u32p]),
     "psi_pie_create_multi": (_int, [_vp, _pp, _vp, _u64, _u64, _int, _vpp]),
+    "psi_nb_eval_sum_indices": (_int, [_u32, _u32, _u64p, _u32p]),
+    "psi_nb_rotation_index": (_int, [_u32, ctypes.c_int64, _u64p]),
+    "psi_nb_set_automorphism_keys": (_int, [_vp, _u32, _u64p, _u64p, _u64p]),
+    "psi_nb_db_load_limbs": (_int, [_vp, _u32, _u32, _u32, _u64p, _u64p, _u64p]),
+    "psi_nb_db_encode_slots": (_int, [_vp, _u32, _u32, _u32, _u32, _i64p, _i64p]),
+    "psi_nb_db_get_limbs": (_int, [_vp, _u64p, _u64p, _u64p]),
+    "psi_nb_run": (_int, [_vp, _u32, _u32, _u64p, _u64p, _vp]),
+    "psi_nb_launch_count": (_int, [_vp, _u32p]),
     "psi_device_count": (_int, [ctypes.POINTER(_int)]),
     "psi_last_error": (ctypes.c_char_p, []),
     "psi_version": (ctypes.c_char_p, []),

@@ -18,6 +18,7 @@
 
 #include "psi_b200.h"
 #include "psi_kernels.cuh"
+#include "psi_ctx.cuh"
 #include "host_copy.hpp"
 #include "../host/hashing.hpp"
 #include "../host/psi_host_internal.hpp"
@@ -31,19 +32,13 @@ int set_error(int status, const std::string& msg) {
     return status;
 }
 
-static int cuda_fail(cudaError_t e, const char* what) {
+int cuda_fail(cudaError_t e, const char* what) {
     if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInitializationError ||
         e == cudaErrorSystemDriverMismatch || e == cudaErrorNotSupported)
         return set_error(PSI_ERR_NO_DEVICE, std::string(what) + ": no usable CUDA device (" + cudaGetErrorString(e) +
                                                 "); this library has no CPU path");
     return set_error(PSI_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
-
-#define CK(call)                                        \
-    do {                                                \
-        cudaError_t e__ = (call);                       \
-        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
-    } while (0)
 
 typedef unsigned __int128 u128h;
 
@@ -69,105 +64,13 @@ static uint32_t h_bitrev(uint32_t x, int bits) {
     return r;
 }
 
-constexpr size_t kDbChunk = 256;  // plaintexts staged per re-tiling / encode step
-constexpr uint32_t kMaxStreamSlices = 32;  // upload slices of psi_query_run_streamed
-
-template <typename T>
-struct DevBuf {
-    T* p = nullptr;
-    size_t n = 0;
-    cudaError_t alloc(size_t count) {
-        if (count <= n && p) return cudaSuccess;
-        release();
-        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
-        if (e == cudaSuccess) n = count;
-        return e;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        n = 0;
-    }
-    DevBuf() = default;
-    DevBuf(const DevBuf&) = delete;
-    DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { release(); }  // locals are freed on every exit path (CK returns early)
-};
-
 }  // namespace psi
 
 using namespace psi;
 
-struct psi_ctx {
-    int device = 0;
-    psi_params P{};
-    uint32_t N = 0, logN = 0, L = 0, Lp = 0;
-    DevTables* d_tab = nullptr;
-    DevBuf<u64> twiddles;       // [(L+Lp+1)][4][N]
-    DevBuf<u64> twiddles2;      // [(L+Lp+1)][2][N][2]: {w, ws} and {iw, iws} interleaved
-    DevBuf<u64> twiddles_rows;  // [(L+Lp)][2][N/1024][1016][2]: row-stage twiddles packed per row tile
-    DevBuf<uint32_t> to_crt;    // packed-encoding permutation
-    DevBuf<u64> evk_b, evk_a;   // [L][L][N]
-    DevBuf<u64> evk_bR, evk_aR; // the same times R = 2^64 mod q_k (Montgomery form for the fused relinearisation)
-    DevBuf<u64> maskR;          // masks times R
-    bool have_evk = false;
-    // database
-    uint32_t K = 0, b = 0, E = 0;
-    DevBuf<u64> pt, mask;
-    bool have_db = false;
-    uint32_t encode_lift = PSI_ENCODE_LIFT_PLAIN;
-    // query
-    DevBuf<u64> idx, idx_in, minus;  // idx: tiled split-30; idx_in: two H2D landing buffers [2][K][E][2][L][N]
-    DevBuf<u64> stage;               // chunk staging for the DB re-tiling
-    bool have_query = false;
-    // work
-    DevBuf<u64> acc, coef, e1, e2, ten, res, dig, prod, out, out2;
-    DevBuf<u64> minus_in;  // two H2D landing buffers of minusCompareElement [2][2][L][N]
-    // results are double-buffered: run() i writes out[i & 1], so the D2H of query i can overlap run() i+1
-    uint32_t out_cur = 0;
-    // landing buffer n & 1 receives the n-th uploaded query; commits consume them in the same order, so the upload
-    // of query i+1 never has to wait for the commit of query i
-    uint32_t n_uploaded = 0, n_committed = 0;
-    size_t idx_words() const { return (size_t)K * E * 2 * L * N; }
-    u64* out_buf(uint32_t which) { return which ? out2.p : out.p; }
-    bool ran = false;
-    uint32_t launches_per_run = 0;
-    // pinned staging pools of the *_limbs entry points (separate limb vectors <-> one DMA-able buffer)
-    u64* pool_in = nullptr;
-    u64* pool_out = nullptr;
-    size_t pool_in_words = 0, pool_out_words = 0;
-    cudaEvent_t ev_pool_in = nullptr;  // last upload that read pool_in
-    int host_threads = 8;
-    // phase 2 in bin groups on concurrent streams (tails of one group's kernels overlap the next group's heads);
-    // 0 = choose from the number of resident bins
-    uint32_t p2_groups = 0;
-    cudaStream_t aux[7] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join[7] = {};
-    // psi_query_run_streamed: copy-in / copy-out streams and the events that order slices and bin groups
-    cudaStream_t sq_in = nullptr, sq_out = nullptr;
-    cudaStream_t sq_grp[4] = {};  // bin groups of the streamed query, descending priority
-    cudaEvent_t ev_dl[4] = {};    // download of a group complete (limb-vector form: the host scatters it then)
-    cudaEvent_t ev_sq_fork = nullptr;
-    cudaEvent_t ev_slice[kMaxStreamSlices] = {}, ev_group[4] = {}, ev_sq = nullptr;
-
-    // run() as a CUDA graph: the launch set of one evaluation (inner product, bin groups forked over the auxiliary
-    // streams, their joins) is captured once per (phases, result buffer, grouping, buffer addresses) and replayed, so a
-    // query costs one graph launch instead of 11-25 kernel launches and event operations on the host
-    struct RunGraph {
-        uint64_t key = 0;
-        cudaGraphExec_t exec = nullptr;
-        uint32_t launches = 0;
-    };
-    std::vector<RunGraph> graphs;
-    bool use_graph = true;
-    uint32_t Lk = 0, ks_parts = 0;  // HYBRID key switching
-    bool hybrid = false, hps = false;
-    KCtx k(cudaStream_t s) const { return KCtx{d_tab, N, logN, L, Lp, s, Lk, !hybrid && !hps}; }
-};
-
 namespace psi {
 
-static int ensure_device(psi_ctx* c) {
+int ensure_device(psi_ctx* c) {
     CK(cudaSetDevice(c->device));
     return PSI_OK;
 }
@@ -585,6 +488,7 @@ int psi_ctx_destroy(psi_ctx* c) {
     if (!c) return PSI_OK;
     cudaSetDevice(c->device);
     drop_run_graphs(c);
+    nb_release(c);
     if (c->d_tab) cudaFree(c->d_tab);
     DevBuf<u64>* bufs[] = {&c->twiddles, &c->twiddles2, &c->twiddles_rows, &c->evk_bR, &c->evk_aR, &c->maskR, &c->evk_b, &c->evk_a, &c->pt, &c->mask, &c->idx, &c->idx_in, &c->stage, &c->minus, &c->acc,
                            &c->coef,     &c->e1,    &c->e2,    &c->ten, &c->res, &c->dig, &c->prod,  &c->out, &c->out2, &c->minus_in};
@@ -742,8 +646,8 @@ static cudaError_t lift_and_ntt(psi_ctx* c, const KCtx& k, uint32_t n, const u64
 // buffers stay small next to the DB itself.
 // tiled_E != 0: dst is the tiled plaintext DB (positions per bin = tiled_E) and the plaintexts are numbers
 // p_base .. p_base + n_pt - 1 of it; else dst is flat [n_pt][L][N].
-static int encode_into(psi_ctx* c, size_t n_pt, uint32_t nslots, const int64_t* slots, u64* dst, uint32_t tiled_E,
-                       size_t p_base = 0) {
+static int encode_into_impl(psi_ctx* c, size_t n_pt, uint32_t nslots, const int64_t* slots, u64* dst, uint32_t tiled_E,
+                            size_t p_base = 0) {
     const size_t N = c->N, L = c->L;
     const size_t chunk = n_pt < kDbChunk ? n_pt : kDbChunk;
     if (tiled_E) CK(c->stage.alloc(chunk * L * N));
@@ -793,10 +697,10 @@ int psi_db_encode_slots_shard(psi_ctx* c, uint32_t K, uint32_t b_total, uint32_t
     if ((rc = ensure_device(c))) return rc;
     if ((rc = db_dims(c, K, b, E))) return rc;
     for (uint32_t hf = 0; hf < K; hf++)
-        if ((rc = encode_into(c, (size_t)b * E, nslots, slots + (((size_t)hf * b_total + bin_begin) * E) * nslots, c->pt.p, E,
+        if ((rc = encode_into_impl(c, (size_t)b * E, nslots, slots + (((size_t)hf * b_total + bin_begin) * E) * nslots, c->pt.p, E,
                               (size_t)hf * b * E)))
             return rc;
-    if ((rc = encode_into(c, b, nslots, mv, c->mask.p, 0))) return rc;
+    if ((rc = encode_into_impl(c, b, nslots, mv, c->mask.p, 0))) return rc;
     CK(launch_to_montgomery(c->k(0), b, c->mask.p, c->maskR.p));
     CK(cudaStreamSynchronize(0));
     c->have_db = true;
@@ -888,7 +792,7 @@ int psi_db_build_from_items_shard(psi_ctx* c, uint64_t hash_seed, uint32_t k, ui
             CK(cudaStreamSynchronize(0));
         }
     }
-    if ((rc = encode_into(c, bl, (uint32_t)nslots, mask_slots.data() + (size_t)bin_begin * nslots, c->mask.p, 0))) return rc;
+    if ((rc = encode_into_impl(c, bl, (uint32_t)nslots, mask_slots.data() + (size_t)bin_begin * nslots, c->mask.p, 0))) return rc;
     CK(launch_to_montgomery(c->k(0), bl, c->mask.p, c->maskR.p));
     CK(cudaStreamSynchronize(0));
     c->have_db = true;
@@ -1603,3 +1507,9 @@ int psi_bench_pipe_peak(int device, int kind, double* per_second) {
 }
 
 }  // extern "C"
+
+namespace psi {
+int encode_into(psi_ctx* c, size_t n_pt, uint32_t nslots, const int64_t* slots, u64* dst, uint32_t tiled_E, size_t p_base) {
+    return encode_into_impl(c, n_pt, nslots, slots, dst, tiled_E, p_base);
+}
+}  // namespace psi

@@ -1,0 +1,429 @@
+// Non-batched FHEHIPPIE on the device: one private indexed equality check per outer cell of the
+// server's nested cuckoo table, reference FHEHIPPIE.cpp:9-77 (ctor :9-59, run :61-77), FHEHIPPIE.hpp:18-50, run by
+// SimpleFHEPSIServer.cpp:126-160 through FHEHIPPIECollection (PIECollection.hpp).
+//
+// What run() does per PIE, in OpenFHE calls:   for hf, bin:  EvalInnerProduct(indexMatrix[hf], vectorizedCT[hf][bin], b)
+//                                               EvalMerge over the bins, EvalMult by preCalcRandomMask[hf]
+// What the device does instead: every (pie, hf, bin) triple is one ITEM and the whole collection advances in lock step,
+//   (1) item = idx[pie][hf] (.) pt[item]                                        k_nb_mul_ctpt
+//   (2) ceil(log2 b) EvalSum steps, all items with the same automorphism key:   INTT(c1) -> BV digits -> NTT -> k_nb_ks_apply<ADD>
+//   (3) item (.) packed {1, 0, ...}; rotation by -bin with the key of that bin:  k_nb_mul_ctpt, ... k_nb_ks_apply<SET>
+//   (4) sum over the bins of a (pie, hf) and (.) mask:                           k_nb_sum_mask
+// so a collection of P PIEs costs the same ~4 (steps + 1) + 3 launches as one PIE.  The key switch follows OpenFHE's
+// EvalAutomorphism order (recalled, see oracle/psi_oracle.c): KeySwitchInPlace first, the EVALUATION-format
+// permutation after it - fused here as a scatter: the thread that forms the key-switched value at position j stores
+// it at the position the inverse index maps j to.  No floating point on this path: all residues are canonical.
+#include <algorithm>
+#include <cstring>
+
+#include "psi_ctx.cuh"
+
+namespace psi {
+
+struct NbState {
+    // automorphism keys (EvalSumKeyGen + EvalRotateKeyGen, SimpleFHEPSIClient.cpp:79-90)
+    std::vector<uint64_t> key_index;
+    DevBuf<u64> key_b, key_a;  // [n_keys][L][L][N]
+    // database: vectorizedCT / preCalcRandomMask of every PIE, EvalMerge's plaintext
+    uint32_t n_pie = 0, K = 0, b = 0;
+    DevBuf<u64> pt, mask, merge_pt;  // [n_pie][K][b][L][N], [n_pie][K][L][N], [L][N]
+    bool have_db = false;
+    // work buffers for one chunk of PIEs
+    uint32_t chunk_pies = 0;
+    DevBuf<u64> idx, cur, nxt, coef, dig, out;
+    DevBuf<int> sel_key;        // [steps + b]: key slot per EvalSum step, then per bin (-1 = identity, bin 0)
+    DevBuf<uint32_t> sel_ginv;  // inverse automorphism index of the same entries
+    uint32_t n_sum = 0;
+    uint32_t launches = 0;
+};
+
+void nb_release(psi_ctx* c) {
+    delete c->nb;
+    c->nb = nullptr;
+}
+
+static uint64_t pow_mod_2n(uint64_t g, uint64_t e, uint64_t m) {
+    uint64_t r = 1;
+    g %= m;
+    for (; e; e >>= 1) {
+        if (e & 1) r = (r * g) % m;
+        g = (g * g) % m;
+    }
+    return r;
+}
+// EvalSum_2n / GenerateIndices_2n (OpenFHE advancedshe, recalled): squares of 5, the last one 2N - 1 for a full row
+static uint32_t eval_sum_indices(uint32_t N, uint32_t batch, uint64_t* out) {
+    if (batch <= 1) return 0;
+    const uint64_t m = 2ull * N;
+    uint32_t steps = 0, n = 0;
+    while ((1u << steps) < batch) steps++;
+    uint64_t g = 5;
+    for (uint32_t i = 0; i + 1 < steps; i++) {
+        out[n++] = g;
+        g = (g * g) % m;
+    }
+    out[n++] = (2ull * batch < m) ? g : m - 1;
+    return n;
+}
+// FindAutomorphismIndex2n: 5^i mod 2N, with 5^-1 for negative i (the unit group of Z_2N has exponent N/2)
+static uint64_t rotation_index(uint32_t N, int64_t i) {
+    const uint64_t m = 2ull * N;
+    const uint64_t g0 = i < 0 ? pow_mod_2n(5, N - 1, m) : 5;
+    return pow_mod_2n(g0, (uint64_t)(i < 0 ? -i : i), m);
+}
+
+// PrecomputeAutoMap (recalled): output position p of the bit-reversed EVALUATION vector reads input position automap(p, g)
+__device__ __forceinline__ uint32_t automap(uint32_t p, uint32_t g, uint32_t logN) {
+    const uint32_t j = __brev(p) >> (32 - logN);
+    const uint32_t idx = (((2 * j + 1) * g) & ((2u << logN) - 1)) >> 1;
+    return __brev(idx) >> (32 - logN);
+}
+
+// EvalMult(ct, pt) over items: out[item] = ct[item / ct_div] (.) pt[item * pt_stride]   (pt_stride 0: one plaintext for all)
+__global__ void __launch_bounds__(256) k_nb_mul_ctpt(const DevTables* __restrict__ tab, uint32_t N, uint32_t B,
+                                                     const u64* __restrict__ ct, uint32_t ct_div, const u64* __restrict__ pt,
+                                                     size_t pt_stride, u64* __restrict__ out) {
+    const size_t LN = (size_t)tab->L * N;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)B * LN) return;
+    const size_t item = tid / LN, c = tid % LN;
+    const ModDev& m = tab->mods[c / N];
+    const u64 pv = pt[item * pt_stride + c];
+    const u64* src = ct + (item / ct_div) * 2 * LN;
+    out[(item * 2) * LN + c] = mulmod(src[c], pv, m);
+    out[(item * 2 + 1) * LN + c] = mulmod(src[LN + c], pv, m);
+}
+
+// DCRTPoly::CRTDecompose (BV, digit size 0) of the c1 component: digit i = limb i (COEFFICIENT), switched to every q_k
+// with the centred lift of NativeVector::SwitchModulus.  coef: [B][L][N], dig: [B][L(i)][L(k)][N]
+__global__ void __launch_bounds__(256) k_nb_digits(const DevTables* __restrict__ tab, uint32_t N, uint32_t B,
+                                                   const u64* __restrict__ coef, u64* __restrict__ dig) {
+    const int L = tab->L;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)B * L * N) return;
+    const uint32_t n = tid % N, i = (tid / N) % L;
+    const size_t item = tid / ((size_t)N * L);
+    const u64 v = coef[tid];
+    const u64 qi = tab->mods[i].q;
+    const bool neg = v > ((qi - 1) >> 1);
+#pragma unroll
+    for (int k = 0; k < PSI_MAX_LIMBS; k++) {
+        if (k < L) {
+            const u64 qk = tab->mods[k].q;
+            u64 r = v;
+            if (k != (int)i) {
+                r = (v < qk) ? v : ((v - qk < qk) ? v - qk : v % qk);
+                if (neg) r = submod(r, tab->qModq[i][k], qk);
+            }
+            dig[((item * L + i) * L + k) * N + n] = r;
+        }
+    }
+}
+
+// KeySwitchBV core + KeySwitchInPlace + AutomorphismTransform, and the EvalAdd of EvalSum when ADD.
+//   cur: [B][2][L][N] EVAL, dig: [B][L][L][N] EVAL, keys: [n_keys][L][L][N]
+//   the item's key slot and inverse index come from sel_key / sel_ginv[sel_mod ? item % sel_mod : 0]; slot -1 = the
+//   identity (bin 0 of EvalMerge is not rotated)
+//   ADD: out[item] = cur[item] + sigma_g(keyswitched cur[item]);  else out[item] = sigma_g(keyswitched cur[item])
+template <bool ADD>
+__global__ void __launch_bounds__(256) k_nb_ks_apply(const DevTables* __restrict__ tab, uint32_t N, uint32_t logN, uint32_t B,
+                                                     const u64* __restrict__ cur, const u64* __restrict__ dig,
+                                                     const u64* __restrict__ key_b, const u64* __restrict__ key_a,
+                                                     const int* __restrict__ sel_key, const uint32_t* __restrict__ sel_ginv,
+                                                     uint32_t sel_mod, u64* __restrict__ out) {
+    const int L = tab->L;
+    const size_t LN = (size_t)L * N;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)B * LN) return;
+    const size_t item = tid / LN, c = tid % LN;  // c = k*N + j
+    const uint32_t sel = sel_mod ? (uint32_t)(item % sel_mod) : 0;
+    const int slot = sel_key[sel];
+    const u64* ct = cur + item * 2 * LN;
+    u64* o = out + item * 2 * LN;
+    if (slot < 0) {
+        o[c] = ct[c];
+        o[LN + c] = ct[LN + c];
+        return;
+    }
+    const ModDev& m = tab->mods[c / N];
+    const u64* kb = key_b + (size_t)slot * L * LN;
+    const u64* ka = key_a + (size_t)slot * L * LN;
+    u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+#pragma unroll
+    for (int i = 0; i < PSI_MAX_LIMBS; i++) {
+        if (i < L) {
+            const u64 d = dig[(item * L + i) * LN + c];
+            mac128(h0, l0, d, kb[(size_t)i * LN + c]);
+            mac128(h1, l1, d, ka[(size_t)i * LN + c]);
+        }
+    }
+    u64 v0 = addmod(barrett128(h0, l0, m.q, m.mu_hi, m.mu_lo), ct[c], m.q);
+    u64 v1 = barrett128(h1, l1, m.q, m.mu_hi, m.mu_lo);
+    const uint32_t j = (uint32_t)(c % N);
+    const size_t dst = (c - j) + automap(j, sel_ginv[sel], logN);
+    if (ADD) {
+        v0 = addmod(v0, ct[dst], m.q);
+        v1 = addmod(v1, ct[LN + dst], m.q);
+    }
+    o[dst] = v0;
+    o[LN + dst] = v1;
+}
+
+// EvalMerge's EvalAdd chain over the b bins of a (pie, hf) group + EvalMult by the random mask (FHEHIPPIE.cpp:73)
+__global__ void __launch_bounds__(256) k_nb_sum_mask(const DevTables* __restrict__ tab, uint32_t N, uint32_t G, uint32_t b,
+                                                     const u64* __restrict__ items, const u64* __restrict__ mask,
+                                                     u64* __restrict__ out) {
+    const size_t LN = (size_t)tab->L * N;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)G * LN) return;
+    const size_t grp = tid / LN, c = tid % LN;
+    const ModDev& m = tab->mods[c / N];
+    u64 s0 = 0, s1 = 0;
+    for (uint32_t bin = 0; bin < b; bin++) {
+        const u64* ct = items + (grp * b + bin) * 2 * LN;
+        s0 = addmod(s0, ct[c], m.q);
+        s1 = addmod(s1, ct[LN + c], m.q);
+    }
+    const u64 mv = mask[grp * LN + c];
+    out[(grp * 2) * LN + c] = mulmod(s0, mv, m);
+    out[(grp * 2 + 1) * LN + c] = mulmod(s1, mv, m);
+}
+
+static inline unsigned blocks_for(size_t total) { return (unsigned)((total + 255) / 256); }
+
+static NbState* nb_state(psi_ctx* c) {
+    if (!c->nb) c->nb = new (std::nothrow) NbState();
+    return c->nb;
+}
+
+static int nb_check_ctx(psi_ctx* c) {
+    if (!c) return set_error(PSI_ERR_INVALID, "null argument");
+    if (c->hybrid)
+        return set_error(PSI_ERR_INVALID, "the non-batched PIE implements BV key switching only (ks_technique = PSI_KS_BV)");
+    return ensure_device(c);
+}
+
+static int nb_db_dims(psi_ctx* c, NbState* s, uint32_t n_pie, uint32_t K, uint32_t b) {
+    if (n_pie < 1 || K < 1 || b < 1) return set_error(PSI_ERR_INVALID, "n_pie, K and b must be positive");
+    if ((uint64_t)b + 1 > c->N / 2) return set_error(PSI_ERR_INVALID, "b + 1 slots must fit one row of the packing (N/2)");
+    const size_t LN = (size_t)c->L * c->N;
+    s->have_db = false;
+    s->n_pie = n_pie;
+    s->K = K;
+    s->b = b;
+    CK(s->pt.alloc((size_t)n_pie * K * b * LN));
+    CK(s->mask.alloc((size_t)n_pie * K * LN));
+    CK(s->merge_pt.alloc(LN));
+    s->chunk_pies = 0;
+    return PSI_OK;
+}
+
+// work buffers + selection tables for chunks of up to `pies` PIEs
+static int nb_prepare(psi_ctx* c, NbState* s, uint32_t pies) {
+    if (s->chunk_pies >= pies) return PSI_OK;
+    const uint32_t L = c->L, N = c->N, K = s->K, b = s->b;
+    const size_t LN = (size_t)L * N, items = (size_t)pies * K * b;
+    // key slots: EvalSum steps with batch size b (EvalInnerProduct(.., vectorizedCT[hfInd].size()), FHEHIPPIE.cpp:70),
+    // then the rotation by -bin of EvalMerge
+    uint64_t sum_idx[32];
+    s->n_sum = eval_sum_indices(N, b, sum_idx);
+    std::vector<int> sel_key(s->n_sum + b);
+    std::vector<uint32_t> sel_ginv(s->n_sum + b);
+    auto find = [&](uint64_t g) -> int {
+        for (size_t i = 0; i < s->key_index.size(); i++)
+            if (s->key_index[i] == g) return (int)i;
+        return -1;
+    };
+    for (uint32_t i = 0; i < s->n_sum + b; i++) {
+        if (i == s->n_sum) {  // bin 0 stays where it is
+            sel_key[i] = -1;
+            sel_ginv[i] = 1;
+            continue;
+        }
+        const uint64_t g = i < s->n_sum ? sum_idx[i] : rotation_index(N, -(int64_t)(i - s->n_sum));
+        sel_key[i] = find(g);
+        if (sel_key[i] < 0)  // OpenFHE: "Could not find an EvalKey for index ..."
+            return set_error(PSI_ERR_STATE, "automorphism key for index " + std::to_string(g) + " has not been set");
+        sel_ginv[i] = (uint32_t)pow_mod_2n(g, N - 1, 2ull * N);
+    }
+    CK(s->sel_key.alloc(sel_key.size()));
+    CK(s->sel_ginv.alloc(sel_ginv.size()));
+    CK(cudaMemcpy(s->sel_key.p, sel_key.data(), sel_key.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->sel_ginv.p, sel_ginv.data(), sel_ginv.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CK(s->idx.alloc((size_t)pies * K * 2 * LN));
+    CK(s->out.alloc((size_t)pies * K * 2 * LN));
+    CK(s->cur.alloc(items * 2 * LN));
+    CK(s->nxt.alloc(items * 2 * LN));
+    CK(s->coef.alloc(items * LN));
+    CK(s->dig.alloc(items * L * LN));
+    s->chunk_pies = pies;
+    return PSI_OK;
+}
+
+// the key switch + automorphism of every item: cur -> nxt
+template <bool ADD>
+static int nb_ks_step(psi_ctx* c, NbState* s, const KCtx& k, uint32_t B, uint32_t sel0, uint32_t sel_mod) {
+    const uint32_t L = c->L, N = c->N;
+    const size_t LN = (size_t)L * N;
+    NttBatch nb{s->cur.p + LN, s->coef.p, B * L, L, 2 * LN, N, LN, 0, L};  // c1 of every item to COEFFICIENT
+    CK(launch_ntt(k, nb, true));
+    k_nb_digits<<<blocks_for((size_t)B * LN), 256, 0, k.s>>>(k.tab, N, B, s->coef.p, s->dig.p);
+    CK(cudaGetLastError());
+    nb = NttBatch{s->dig.p, s->dig.p, B * L * L, L, LN, N, LN, 0, L};
+    CK(launch_ntt(k, nb, false));
+    k_nb_ks_apply<ADD><<<blocks_for((size_t)B * LN), 256, 0, k.s>>>(k.tab, N, c->logN, B, s->cur.p, s->dig.p, s->key_b.p, s->key_a.p,
+                                                                   s->sel_key.p + sel0, s->sel_ginv.p + sel0, sel_mod, s->nxt.p);
+    CK(cudaGetLastError());
+    std::swap(s->cur.p, s->nxt.p);
+    std::swap(s->cur.n, s->nxt.n);
+    s->launches += 4;
+    return PSI_OK;
+}
+
+}  // namespace psi
+
+using namespace psi;
+
+extern "C" {
+
+int psi_nb_eval_sum_indices(uint32_t N, uint32_t batch_size, uint64_t* out, uint32_t* n) {
+    if (!out || !n || N < 4 || (N & (N - 1))) return set_error(PSI_ERR_INVALID, "bad argument");
+    *n = eval_sum_indices(N, batch_size, out);
+    return PSI_OK;
+}
+
+int psi_nb_rotation_index(uint32_t N, int64_t i, uint64_t* out) {
+    if (!out || N < 4 || (N & (N - 1))) return set_error(PSI_ERR_INVALID, "bad argument");
+    *out = rotation_index(N, i);
+    return PSI_OK;
+}
+
+int psi_nb_set_automorphism_keys(psi_ctx* c, uint32_t n_keys, const uint64_t* auto_index, const uint64_t* key_b,
+                                 const uint64_t* key_a) {
+    int rc = nb_check_ctx(c);
+    if (rc) return rc;
+    if (!n_keys || !auto_index || !key_b || !key_a) return set_error(PSI_ERR_INVALID, "null argument");
+    NbState* s = nb_state(c);
+    if (!s) return set_error(PSI_ERR_CUDA, "out of host memory");
+    const uint64_t m = 2ull * c->N;
+    for (uint32_t i = 0; i < n_keys; i++)
+        if (!(auto_index[i] & 1) || auto_index[i] >= m)
+            return set_error(PSI_ERR_INVALID, "an automorphism index must be odd and below 2N");
+    const size_t words = (size_t)n_keys * c->L * c->L * c->N;
+    CK(s->key_b.alloc(words));
+    CK(s->key_a.alloc(words));
+    CK(cudaMemcpy(s->key_b.p, key_b, words * sizeof(u64), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->key_a.p, key_a, words * sizeof(u64), cudaMemcpyHostToDevice));
+    s->key_index.assign(auto_index, auto_index + n_keys);
+    s->chunk_pies = 0;  // the key slots of the selection tables are re-derived
+    return PSI_OK;
+}
+
+int psi_nb_db_load_limbs(psi_ctx* c, uint32_t n_pie, uint32_t K, uint32_t b, const uint64_t* pt_limbs,
+                         const uint64_t* mask_limbs, const uint64_t* merge_limbs) {
+    int rc = nb_check_ctx(c);
+    if (rc) return rc;
+    if (!pt_limbs || !mask_limbs || !merge_limbs) return set_error(PSI_ERR_INVALID, "null argument");
+    NbState* s = nb_state(c);
+    if (!s) return set_error(PSI_ERR_CUDA, "out of host memory");
+    if ((rc = nb_db_dims(c, s, n_pie, K, b))) return rc;
+    const size_t LN = (size_t)c->L * c->N;
+    CK(cudaMemcpy(s->pt.p, pt_limbs, (size_t)n_pie * K * b * LN * sizeof(u64), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->mask.p, mask_limbs, (size_t)n_pie * K * LN * sizeof(u64), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->merge_pt.p, merge_limbs, LN * sizeof(u64), cudaMemcpyHostToDevice));
+    s->have_db = true;
+    return PSI_OK;
+}
+
+int psi_nb_db_encode_slots(psi_ctx* c, uint32_t n_pie, uint32_t K, uint32_t b, uint32_t nslots, const int64_t* slots,
+                           const int64_t* mask_slots) {
+    int rc = nb_check_ctx(c);
+    if (rc) return rc;
+    if (!slots || !mask_slots) return set_error(PSI_ERR_INVALID, "null argument");
+    if (nslots < 1 || nslots > c->N) return set_error(PSI_ERR_INVALID, "batch size must be in [1, N]");
+    const uint64_t t = c->P.t;
+    const size_t n_pt = (size_t)n_pie * K * b, n_mask = (size_t)n_pie * K;
+    for (size_t i = 0; i < n_pt * nslots; i++)
+        if ((uint64_t)(slots[i] < 0 ? -slots[i] : slots[i]) >= t)
+            return set_error(PSI_ERR_INVALID, "slot value out of range of the plaintext modulus");
+    for (size_t i = 0; i < n_mask * b; i++)
+        if ((uint64_t)(mask_slots[i] < 0 ? -mask_slots[i] : mask_slots[i]) >= t)
+            return set_error(PSI_ERR_INVALID, "mask value out of range of the plaintext modulus");
+    NbState* s = nb_state(c);
+    if (!s) return set_error(PSI_ERR_CUDA, "out of host memory");
+    if ((rc = nb_db_dims(c, s, n_pie, K, b))) return rc;
+    if ((rc = encode_into(c, n_pt, nslots, slots, s->pt.p, 0))) return rc;
+    if ((rc = encode_into(c, n_mask, b, mask_slots, s->mask.p, 0))) return rc;
+    const int64_t one = 1;  // EvalMerge: MakePackedPlaintext({1, 0, 0, ...})
+    if ((rc = encode_into(c, 1, 1, &one, s->merge_pt.p, 0))) return rc;
+    s->have_db = true;
+    return PSI_OK;
+}
+
+int psi_nb_db_get_limbs(psi_ctx* c, uint64_t* pt_limbs, uint64_t* mask_limbs, uint64_t* merge_limbs) {
+    int rc = nb_check_ctx(c);
+    if (rc) return rc;
+    NbState* s = c->nb;
+    if (!s || !s->have_db) return set_error(PSI_ERR_STATE, "no non-batched database loaded");
+    const size_t LN = (size_t)c->L * c->N;
+    if (pt_limbs) CK(cudaMemcpy(pt_limbs, s->pt.p, (size_t)s->n_pie * s->K * s->b * LN * sizeof(u64), cudaMemcpyDeviceToHost));
+    if (mask_limbs) CK(cudaMemcpy(mask_limbs, s->mask.p, (size_t)s->n_pie * s->K * LN * sizeof(u64), cudaMemcpyDeviceToHost));
+    if (merge_limbs) CK(cudaMemcpy(merge_limbs, s->merge_pt.p, LN * sizeof(u64), cudaMemcpyDeviceToHost));
+    return PSI_OK;
+}
+
+int psi_nb_run(psi_ctx* c, uint32_t pie_begin, uint32_t pie_end, const uint64_t* idx, uint64_t* out, void* stream) {
+    int rc = nb_check_ctx(c);
+    if (rc) return rc;
+    NbState* s = c->nb;
+    if (!s || !s->have_db) return set_error(PSI_ERR_STATE, "no non-batched database loaded");
+    if (s->key_index.empty()) return set_error(PSI_ERR_STATE, "no automorphism keys set");
+    if (!idx || !out) return set_error(PSI_ERR_INVALID, "null argument");
+    if (pie_begin >= pie_end || pie_end > s->n_pie) return set_error(PSI_ERR_INVALID, "bad PIE range");
+    const uint32_t L = c->L, N = c->N, K = s->K, b = s->b;
+    const size_t LN = (size_t)L * N;
+    // chunk size: work buffers of one item are (2 + 2 + 1 + L) polynomials; keep a chunk below ~6 GB
+    const size_t per_pie = (size_t)K * b * (5 + L) * LN * sizeof(u64);
+    const uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(pie_end - pie_begin, (6ull << 30) / per_pie));
+    if ((rc = nb_prepare(c, s, chunk))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const KCtx k = c->k(st);
+    s->launches = 0;
+    for (uint32_t p0 = pie_begin; p0 < pie_end; p0 += chunk) {
+        const uint32_t np = std::min(chunk, pie_end - p0), G = np * K, B = G * b;
+        const size_t off = (size_t)(p0 - pie_begin) * K * 2 * LN;
+        CK(cudaMemcpyAsync(s->idx.p, idx + off, (size_t)G * 2 * LN * sizeof(u64), cudaMemcpyHostToDevice, st));
+        // (1) EvalMult(indexMatrix[hf], vectorizedCT[hf][bin])
+        k_nb_mul_ctpt<<<blocks_for((size_t)B * LN), 256, 0, st>>>(k.tab, N, B, s->idx.p, b, s->pt.p + (size_t)p0 * K * b * LN, LN,
+                                                                  s->cur.p);
+        CK(cudaGetLastError());
+        s->launches++;
+        // (2) EvalSum
+        for (uint32_t step = 0; step < s->n_sum; step++)
+            if ((rc = nb_ks_step<true>(c, s, k, B, step, 0))) return rc;
+        // (3) EvalMerge: keep slot 0, move it to slot `bin`
+        k_nb_mul_ctpt<<<blocks_for((size_t)B * LN), 256, 0, st>>>(k.tab, N, B, s->cur.p, 1, s->merge_pt.p, 0, s->nxt.p);
+        CK(cudaGetLastError());
+        s->launches++;
+        std::swap(s->cur.p, s->nxt.p);
+        std::swap(s->cur.n, s->nxt.n);
+        if (b > 1) {
+            if ((rc = nb_ks_step<false>(c, s, k, B, s->n_sum, b))) return rc;
+        }
+        // (4) sum over the bins, EvalMult by preCalcRandomMask[hf]
+        k_nb_sum_mask<<<blocks_for((size_t)G * LN), 256, 0, st>>>(k.tab, N, G, b, s->cur.p, s->mask.p + (size_t)p0 * K * LN, s->out.p);
+        CK(cudaGetLastError());
+        s->launches++;
+        CK(cudaMemcpyAsync(out + off, s->out.p, (size_t)G * 2 * LN * sizeof(u64), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));  // the chunk buffers are reused
+    }
+    return PSI_OK;
+}
+
+int psi_nb_launch_count(psi_ctx* c, uint32_t* out) {
+    if (!c || !out) return set_error(PSI_ERR_INVALID, "null argument");
+    *out = c->nb ? c->nb->launches : 0;
+    return PSI_OK;
+}
+
+}  // extern "C"

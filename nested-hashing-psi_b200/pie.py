@@ -326,6 +326,61 @@ class CryptoContext:
         check(lib().psi_debug_mul_ctct(self._h, p1, p2, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
         return out
 
+    # --- non-batched FHEHIPPIE (FHEHIPPIE.cpp, SimpleFHEPSIServer.cpp) ---------------------------
+    def InsertEvalAutomorphismKeys(self, indices, key_b, key_a):
+        """DeserializeEvalSumKey + DeserializeEvalAutomorphismKey (SimpleFHEPSIServer.cpp:45-62):
+        indices [n] automorphism indices, key_b / key_a [n][L][L][N]."""
+        idx = np.ascontiguousarray(indices, dtype=np.uint64)
+        (key_b, pb), (key_a, pa) = _u64(key_b), _u64(key_a)
+        assert key_b.shape == (len(idx), self.L, self.L, self.N) and key_a.shape == key_b.shape
+        check(lib().psi_nb_set_automorphism_keys(self._h, len(idx), idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), pb, pa))
+
+    def nb_db_load_limbs(self, pt, mask, merge_pt):
+        (pt, pp), (mask, pm), (merge_pt, pg) = _u64(pt), _u64(mask), _u64(merge_pt)
+        n_pie, K, b = pt.shape[:3]
+        assert pt.shape == (n_pie, K, b, self.L, self.N) and mask.shape == (n_pie, K, self.L, self.N)
+        assert merge_pt.shape == (self.L, self.N)
+        try:
+            check(lib().psi_nb_db_load_limbs(self._h, n_pie, K, b, pp, pm, pg))
+        except PsiError as e:
+            _raise_like_reference(e)
+        self._nb_dims = (n_pie, K, b)
+
+    def nb_db_encode_slots(self, slots, mask_slots):
+        """slots [n_pie][K][b][nslots] (plainVec of FHEHIPPIE.cpp:44-50), mask_slots [n_pie][K][b]."""
+        (slots, ps), (mask_slots, pm) = _i64(slots), _i64(mask_slots)
+        n_pie, K, b, n = slots.shape
+        assert mask_slots.shape == (n_pie, K, b)
+        try:
+            check(lib().psi_nb_db_encode_slots(self._h, n_pie, K, b, n, ps, pm))
+        except PsiError as e:
+            _raise_like_reference(e)
+        self._nb_dims = (n_pie, K, b)
+
+    def nb_db_get_limbs(self):
+        n_pie, K, b = self._nb_dims
+        pt = np.empty((n_pie, K, b, self.L, self.N), dtype=np.uint64)
+        mask = np.empty((n_pie, K, self.L, self.N), dtype=np.uint64)
+        merge = np.empty((self.L, self.N), dtype=np.uint64)
+        p = ctypes.POINTER(ctypes.c_uint64)
+        check(lib().psi_nb_db_get_limbs(self._h, pt.ctypes.data_as(p), mask.ctypes.data_as(p), merge.ctypes.data_as(p)))
+        return pt, mask, merge
+
+    def nb_run(self, idx, pie_begin=0, pie_end=None, stream=None):
+        """idx [n][K][2][L][N] for PIEs pie_begin .. pie_end-1 -> results [n][K][2][L][N] (natural hf order)."""
+        n_pie, K, b = self._nb_dims
+        pie_end = n_pie if pie_end is None else pie_end
+        idx, pi = _u64(idx)
+        assert idx.shape == (pie_end - pie_begin, K, 2, self.L, self.N)
+        out = np.empty_like(idx)
+        check(lib().psi_nb_run(self._h, pie_begin, pie_end, pi, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), stream))
+        return out
+
+    def nb_launch_count(self):
+        n = ctypes.c_uint32()
+        check(lib().psi_nb_launch_count(self._h, ctypes.byref(n)))
+        return n.value
+
     def close(self):
         if getattr(self, "_h", None):
             lib().psi_ctx_destroy(self._h)
@@ -708,3 +763,107 @@ class BatchedFHEHIPPIE:
                 self._h = None
         except Exception:
             pass
+
+
+def eval_sum_indices(N, batch_size):
+    """Automorphism indices of EvalSum(ct, batch_size) (EvalSum_2n): what EvalSumKeyGen must have produced."""
+    buf = np.zeros(32, dtype=np.uint64)
+    n = ctypes.c_uint32()
+    check(lib().psi_nb_eval_sum_indices(N, batch_size, buf.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), ctypes.byref(n)))
+    return [int(v) for v in buf[:n.value]]
+
+
+def rotation_index(N, i):
+    """FindAutomorphismIndex2n(i): the automorphism index of EvalAtIndex(ct, i)."""
+    g = ctypes.c_uint64()
+    check(lib().psi_nb_rotation_index(N, i, ctypes.byref(g)))
+    return g.value
+
+
+class FHEHIPPIE:
+    """The reference's non-batched operator (FHEHIPPIE.hpp:18-50): one PIE over one inner cuckoo table, entry points
+    setIndex / run / getResultList.  PIEs live in a FHEHIPPIECollection, whose database is ONE device array and whose
+    runAll() evaluates every PIE in lock step; run() on a single PIE evaluates just that one."""
+
+    def __init__(self, collection, number):
+        self._c, self._n = collection, number
+        self.indexMatrix = None
+
+    def setIndex(self, indexMatrix):
+        """K ciphertexts [2][L][N] (one per cuckoo hash function, SimpleFHEPSIServer.cpp:162-176)."""
+        self.indexMatrix = indexMatrix
+        self._c._results[self._n] = None
+
+    def run(self):
+        self._c._run_range(self._n, self._n + 1)
+
+    def getResultList(self):
+        r = self._c._results[self._n]
+        if r is None:
+            raise ValueError("run() has not been called")
+        return r
+
+
+class FHEHIPPIECollection:
+    """PIECollection.hpp FHEHIPPIECollection: addPIE(inner cuckoo table) ..., runAll().
+    The per-PIE constructor work (FHEHIPPIE.cpp:9-59: checks, bin permutation, plainVec with the trailing 1, random
+    non-zero masks, result permutation) happens in addPIE; the encoding happens on the device at the first run."""
+
+    def __init__(self, cryptoContext, pK, seed=None):
+        self.cryptoContext, self.pK = cryptoContext, pK
+        self._rng = np.random.default_rng(seed)   # None: OS entropy, like the reference's std::random_device
+        self.myPIEs = []
+        self._slots, self._masks, self._perm = [], [], []
+        self._results = []
+        self._encoded = False
+
+    def addPIE(self, table, stash_size=0):
+        """table: the cells [K][b][E] of one inner CuckooHashTable (HierarchicalCuckooHashTable.cells()[i][j])."""
+        table = np.asarray(table)
+        K, b, E = table.shape
+        if b != E:
+            raise ValueError("Error, for FHE PIE the size of a cuckoo bin has to be equal than the number of bins per hash function.")
+        if stash_size != 0:
+            raise ValueError("Error, FHE PIE does not support a stash (yet).")
+        if self._slots and self._slots[0].shape != (K, b, E + 1):
+            raise ValueError("all PIEs of a collection must have the same table shape")
+        t = int(self.cryptoContext.t)
+        perm2 = self._rng.permutation(b)          # permVec2: hides the bin index (FHEHIPPIE.cpp:29)
+        slots = np.zeros((K, b, E + 1), dtype=np.int64)
+        slots[:, perm2, :E] = table.astype(np.int64)
+        slots[:, :, E] = 1                        # exponent slot of the "minus client" element (:49)
+        self._slots.append(slots)
+        self._masks.append(self._rng.integers(1, t, size=(K, b), dtype=np.int64))   # without 0 (:54)
+        self._perm.append(self._rng.permutation(K))                                  # permutationVector
+        self._results.append(None)
+        self._encoded = False
+        pie = FHEHIPPIE(self, len(self.myPIEs))
+        self.myPIEs.append(pie)
+        return pie
+
+    def _encode(self):
+        if not self._encoded:
+            self.cryptoContext.nb_db_encode_slots(np.stack(self._slots), np.stack(self._masks))
+            self._encoded = True
+
+    def _run_range(self, p0, p1):
+        self._encode()
+        cc = self.cryptoContext
+        K = self._slots[0].shape[0]
+        idx = np.empty((p1 - p0, K, 2, cc.L, cc.N), dtype=np.uint64)
+        for p in range(p0, p1):
+            im = self.myPIEs[p].indexMatrix
+            if im is None:
+                raise ValueError("setIndex must be called before run()")
+            idx[p - p0] = np.asarray(im, dtype=np.uint64)
+        try:
+            out = cc.nb_run(idx, p0, p1)
+        except PsiError as e:
+            _raise_like_reference(e)
+        for p in range(p0, p1):
+            shuffled = np.empty_like(out[p - p0])
+            shuffled[self._perm[p]] = out[p - p0]   # shuffledResultList[permutationVector[hf]] = result (:74)
+            self._results[p] = shuffled
+
+    def runAll(self):
+        self._run_range(0, len(self.myPIEs))

@@ -1,0 +1,131 @@
+"""Non-batched FHEHIPPIE on the GPU (psi_nb_*; reference FHEHIPPIE.cpp:9-77, SimpleFHEPSIServer.cpp:126-160) against
+the oracle's restatement (orc_nb_run), bit-exact, through the C ABI; and the reference-shaped collection end to end
+with the client's decode rule (SimpleFHEPSIClient.cpp:245-262)."""
+import numpy as np
+import pytest
+
+import psi_b200 as P
+from oracle.oracle import Oracle
+from oracle.params_ref import RefParams
+
+import scenario as sc
+
+pytestmark = pytest.mark.gpu
+T32 = 4296540161
+
+
+def make(N, L, depth=None):
+    params = RefParams(N, T32, depth=depth, L=L).to_struct()
+    return P.CryptoContext(params), Oracle(params), params
+
+
+def keys_for(o, sk, b, seed=77):
+    """The client's key set (SimpleFHEPSIClient.cpp:79-90): EvalSumKeyGen for batch size E + 1, rotations -1 .. -E."""
+    idx = list(dict.fromkeys(o.eval_sum_indices(b + 1) + [o.find_automorphism_index(-(i + 1)) for i in range(b)]))
+    kb, ka = o.auto_keygen(sk, seed, idx)
+    return idx, kb, ka
+
+
+@pytest.mark.parametrize("N,L,n_pie,K,b", [(1024, 2, 3, 2, 3), (2048, 3, 2, 3, 5), (4096, 4, 1, 1, 7), (16384, 4, 2, 2, 6),
+                                           (1024, 2, 2, 2, 1), (8192, 3, 1, 2, 9)])
+def test_nb_run_random_limbs(N, L, n_pie, K, b):
+    """Uniformly random residues everywhere (worst case for every reduction and digit lift)."""
+    cc, o, params = make(N, L)
+    rng = np.random.default_rng(N + b)
+    pt = sc.random_pt(rng, params, (n_pie, K, b))
+    mask = sc.random_pt(rng, params, (n_pie, K))
+    merge = sc.random_pt(rng, params)
+    idx = sc.random_ct(rng, params, (n_pie, K))
+    key_index = list(dict.fromkeys(o.eval_sum_indices(b) + [o.find_automorphism_index(-i) for i in range(1, b)])) or [5]
+    key_b = sc.random_pt(rng, params, (len(key_index), L))
+    key_a = sc.random_pt(rng, params, (len(key_index), L))
+    cc.InsertEvalAutomorphismKeys(key_index, key_b, key_a)
+    cc.nb_db_load_limbs(pt, mask, merge)
+    got = cc.nb_run(idx)
+    for p in range(n_pie):
+        want = o.nb_run(idx[p], pt[p], merge, mask[p], key_index, key_b, key_a)
+        assert np.array_equal(got[p], want), p
+    # a sub-range of the collection gives the same ciphertexts
+    if n_pie > 1:
+        assert np.array_equal(cc.nb_run(idx[1:], 1, n_pie), got[1:])
+    assert cc.nb_launch_count() > 0
+
+
+def test_nb_device_encode_matches_oracle():
+    cc, o, params = make(2048, 3)
+    rng = np.random.default_rng(4)
+    n_pie, K, b = 2, 2, 4
+    t = int(params.t)
+    slots = rng.integers(-(t // 2), t // 2, (n_pie, K, b, b + 1), dtype=np.int64)
+    masks = rng.integers(1, t, (n_pie, K, b), dtype=np.int64)
+    cc.nb_db_encode_slots(slots, masks)
+    pt, mask, merge = cc.nb_db_get_limbs()
+    for p in range(n_pie):
+        for hf in range(K):
+            assert np.array_equal(mask[p, hf], o.encode(masks[p, hf]))
+            for bin_ in range(b):
+                assert np.array_equal(pt[p, hf, bin_], o.encode(slots[p, hf, bin_]))
+    assert np.array_equal(merge, o.encode(np.array([1], dtype=np.int64)))
+
+
+def test_nb_collection_end_to_end():
+    """Real keys and ciphertexts; the reference-shaped collection; decode like the reference client."""
+    cc, o, params = make(4096, 3)
+    rng = np.random.default_rng(9)
+    n_pie, K, b = 3, 2, 5
+    E, t = b, int(params.t)
+    sk, _, _ = o.keygen(3)
+    key_index, key_b, key_a = keys_for(o, sk, b)
+    cc.InsertEvalAutomorphismKeys(key_index, key_b, key_a)
+    tables = rng.integers(2, 2 ** 32, size=(n_pie, K, b, E), dtype=np.int64)
+    tables[0, 1, 3, 2] = 0                      # an empty cell
+    xs = [int(rng.integers(2, 2 ** 32)) for _ in range(n_pie)]
+    pos = rng.integers(0, E, size=(n_pie, K))
+    tables[1, 0, 4, pos[1, 0]] = xs[1]          # PIE 1 holds its client's element; PIEs 0 and 2 do not
+    coll = P.FHEHIPPIECollection(cc, P.PublicKey(), seed=5)
+    for p in range(n_pie):
+        pie = coll.addPIE(tables[p])
+        ims = []
+        for hf in range(K):
+            v = np.zeros(E + 1, dtype=np.int64)
+            v[pos[p, hf]] = 1
+            v[E] = -xs[p]
+            ims.append(o.encrypt(sk, v, 100 + p * K + hf))
+        pie.setIndex(ims)
+    coll.runAll()
+    # bit-exact against the oracle on the database the device encoded
+    pt, mask, merge = cc.nb_db_get_limbs()
+    found = []
+    for p in range(n_pie):
+        res = coll.myPIEs[p].getResultList()
+        want = o.nb_run(np.stack(coll.myPIEs[p].indexMatrix), pt[p], merge, mask[p], key_index, key_b, key_a)
+        assert np.array_equal(res[coll._perm[p]], want)
+        hit = False
+        for hf in range(K):
+            dec, amb, budget = o.decrypt(sk, res[hf])
+            assert amb == 0 and budget > 5
+            hit = hit or bool((dec[:b] == 0).any())   # receiveResult: SetLength(maxItemsPerPosition), any 0
+        found.append(hit)
+    assert found == [False, True, False]
+    # one PIE on its own gives the same ciphertexts as inside runAll
+    before = coll.myPIEs[2].getResultList().copy()
+    coll.myPIEs[2].run()
+    assert np.array_equal(coll.myPIEs[2].getResultList(), before)
+
+
+def test_nb_errors_like_the_reference():
+    cc, o, params = make(1024, 2)
+    coll = P.FHEHIPPIECollection(cc, P.PublicKey(), seed=1)
+    with pytest.raises(ValueError, match="size of a cuckoo bin"):
+        coll.addPIE(np.ones((2, 3, 4), dtype=np.int64))
+    with pytest.raises(ValueError, match="stash"):
+        coll.addPIE(np.ones((2, 3, 3), dtype=np.int64), stash_size=1)
+    rng = np.random.default_rng(0)
+    pt = sc.random_pt(rng, params, (1, 1, 3))
+    cc.nb_db_load_limbs(pt, sc.random_pt(rng, params, (1, 1)), sc.random_pt(rng, params))
+    idx = sc.random_ct(rng, params, (1, 1))
+    with pytest.raises(P.PsiError):             # no keys at all
+        cc.nb_run(idx)
+    cc.InsertEvalAutomorphismKeys([5], sc.random_pt(rng, params, (1, 2)), sc.random_pt(rng, params, (1, 2)))
+    with pytest.raises(P.PsiError, match="automorphism key for index"):   # OpenFHE throws on a missing key
+        cc.nb_run(idx)
