@@ -70,8 +70,8 @@ def test_nb_device_encode_matches_oracle():
 
 def test_nb_collection_end_to_end():
     """Real keys and ciphertexts; the reference-shaped collection; decode like the reference client."""
-    cc, o, params = make(4096, 3)
-    rng = np.random.default_rng(9)
+    cc, o, params = make(4096, 4)   # the client asks for depth 3 (SimpleFHEPSIClient.cpp:65): 4 limbs; BV key switching
+    rng = np.random.default_rng(9)  # with 60-bit digits and three plaintext products leave no budget at 3 limbs
     n_pie, K, b = 3, 2, 5
     E, t = b, int(params.t)
     sk, _, _ = o.keygen(3)
