@@ -129,3 +129,17 @@ def test_nb_errors_like_the_reference():
     cc.InsertEvalAutomorphismKeys([5], sc.random_pt(rng, params, (1, 2)), sc.random_pt(rng, params, (1, 2)))
     with pytest.raises(P.PsiError, match="automorphism key for index"):   # OpenFHE throws on a missing key
         cc.nb_run(idx)
+
+
+def test_cpp_known_answer_program_nonbatched():
+    """tests/cpp/TestFHEPIE.cpp: the reference's own non-batched test program (tests/TestFHEPIE.cpp: 15000 elements,
+    3 hash functions, 100 x 100 table, depth 3) re-targeted at the C++ drop-in class psi::FHEHIPPIE; "Matches" exactly
+    once, healthy noise budget, and limbs identical to the oracle's FHEHIPPIE::run on the device-encoded database."""
+    import os
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp")
+    subprocess.check_call(["make", "-C", here, "-s"])
+    out = subprocess.run([os.path.join(here, "TestFHEPIE"), "check"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("Matches\n") == 1
+    assert "noise budget ok: yes" in out.stdout and "limb parity with the oracle: identical" in out.stdout
