@@ -24,17 +24,13 @@
 #include <sstream>
 #include <unordered_map>
 
+#include "adapter_common.hpp"
 #include "psi_b200.h"
 
 using namespace lbcrypto;
+using namespace psi_adapter;
 
 namespace {
-
-void ck(int rc) {
-    if (rc == PSI_OK) return;
-    if (rc == PSI_ERR_INVALID) throw std::invalid_argument(psi_last_error());
-    throw std::runtime_error(psi_last_error());
-}
 
 struct State {
     psi_multi* multi = nullptr;
@@ -51,52 +47,6 @@ State& state_of(const BatchedFHEHIPPIE* self) {
     return *it->second;
 }
 
-// NativeVector stores N machine words back to back (NativeInteger is one uint64_t): the limb vector itself is what
-// the GPU library reads / fills, no per-coefficient ConvertToInt() loop
-const uint64_t* words_of(const NativeVector& v) { return reinterpret_cast<const uint64_t*>(&v[0]); }
-uint64_t* words_of(NativeVector& v) { return reinterpret_cast<uint64_t*>(&v[0]); }
-
-// psi_params of the context.  Moduli and roots are read from the element parameters; the integer tables are a
-// function of the moduli (psi_params_from_moduli); the three double tables are copied from OpenFHE's own (so that
-// they are bit-identical to what the host library rounds with) unless PSI_B200_TABLES=derived.
-psi_params params_from(const CryptoContext<FHEEncType>& cc) {
-    const auto cp = std::dynamic_pointer_cast<CryptoParametersBFVRNS>(cc->GetCryptoParameters());
-    if (!cp) throw std::invalid_argument("BatchedFHEHIPPIE (B200): the context is not BFVrns");
-    if (cp->GetMultiplicationTechnique() != HPSPOVERQ)
-        throw std::invalid_argument("BatchedFHEHIPPIE (B200): only MultiplicationTechnique HPSPOVERQ is implemented");
-    if (cp->GetKeySwitchTechnique() != BV || cp->GetDigitSize() != 0)
-        throw std::invalid_argument("BatchedFHEHIPPIE (B200): only BV key switching with digit size 0 is implemented");
-    const auto& tq = cp->GetElementParams()->GetParams();
-    const auto& tp = cp->GetParamsRl(0)->GetParams();
-    if (tq.size() > PSI_MAX_LIMBS || tp.size() > PSI_MAX_LIMBS) throw std::invalid_argument("BatchedFHEHIPPIE (B200): too many RNS limbs");
-    uint64_t q[PSI_MAX_LIMBS], psiq[PSI_MAX_LIMBS], p[PSI_MAX_LIMBS], psip[PSI_MAX_LIMBS];
-    for (size_t i = 0; i < tq.size(); i++) {
-        q[i] = tq[i]->GetModulus().ConvertToInt();
-        psiq[i] = tq[i]->GetRootOfUnity().ConvertToInt();
-    }
-    for (size_t j = 0; j < tp.size(); j++) {
-        p[j] = tp[j]->GetModulus().ConvertToInt();
-        psip[j] = tp[j]->GetRootOfUnity().ConvertToInt();
-    }
-    psi_params P;
-    ck(psi_params_from_moduli(cc->GetRingDimension(), cp->GetPlaintextModulus(), (uint32_t)tq.size(), q, psiq, (uint32_t)tp.size(), p,
-                              psip, cp->GetEncodingParams()->GetPlaintextRootOfUnity(), &P));
-    const char* mode = std::getenv("PSI_B200_TABLES");
-    if (!mode || std::strcmp(mode, "derived") != 0) {
-        const auto& qInv = cp->GetqInv();
-        const auto& rInv = cp->GetrInv();
-        const auto& frac = cp->GettQlSlHatInvModsDivsFrac(0);
-        if (qInv.size() < tq.size() || rInv.size() < tp.size() || frac.size() < tp.size())
-            throw std::runtime_error("BatchedFHEHIPPIE (B200): HPS double tables missing in the context");
-        for (size_t i = 0; i < tq.size(); i++) P.qInv[i] = qInv[i];
-        for (size_t j = 0; j < tp.size(); j++) {
-            P.pInv[j] = rInv[j];
-            P.tQSHatInvModsDivsFrac[j] = frac[j];
-        }
-    }
-    return P;
-}
-
 std::vector<int> device_list(size_t max_devices) {
     std::vector<int> devs;
     if (const char* env = std::getenv("PSI_B200_DEVICES")) {
@@ -111,22 +61,6 @@ std::vector<int> device_list(size_t max_devices) {
     if (devs.empty()) throw std::runtime_error("BatchedFHEHIPPIE (B200): no CUDA device; the library has no CPU path");
     if (devs.size() > max_devices) devs.resize(max_devices);  // bins are the shard axis: at most one device per bin
     return devs;
-}
-
-// limb pointers of one ciphertext in [comp][limb] order; checks what run() relies on
-void limbs_of(const Ciphertext<FHEEncType>& ct, size_t L, size_t N, const uint64_t** out) {
-    if (!ct) throw std::invalid_argument("BatchedFHEHIPPIE (B200): null ciphertext in the query");
-    const auto& cv = ct->GetElements();
-    if (cv.size() != 2) throw std::invalid_argument("BatchedFHEHIPPIE (B200): query ciphertexts must have two components");
-    for (size_t c = 0; c < 2; c++) {
-        if (cv[c].GetFormat() != Format::EVALUATION || cv[c].GetNumOfElements() != L)
-            throw std::invalid_argument("BatchedFHEHIPPIE (B200): query ciphertexts must be fresh (EVALUATION, all limbs)");
-        for (size_t l = 0; l < L; l++) {
-            const NativeVector& v = cv[c].GetElementAtIndex((usint)l).GetValues();
-            if (v.GetLength() != N) throw std::invalid_argument("BatchedFHEHIPPIE (B200): limb length differs from the ring dimension");
-            out[c * L + l] = words_of(v);
-        }
-    }
 }
 
 }  // namespace

@@ -239,6 +239,22 @@ class CryptoContextImpl {
         return it->second;
     }
     static void InsertEvalMultKey(const std::vector<EvalKey<Element>>& keys, const std::string& keyTag) { keyMap()[keyTag] = keys; }
+    // EvalSum and rotation keys share one process-wide map in OpenFHE: automorphism index -> key, per key tag
+    // (filled by DeserializeEvalSumKey / DeserializeEvalAutomorphismKey, SimpleFHEPSIServer.cpp:45-62)
+    static std::map<usint, EvalKey<Element>>& GetEvalAutomorphismKeyMap(const std::string& keyTag) {
+        auto it = autoKeyMap().find(keyTag);
+        if (it == autoKeyMap().end()) throw std::runtime_error("no automorphism keys for this key tag");
+        return *it->second;
+    }
+    static void InsertEvalAutomorphismKey(std::shared_ptr<std::map<usint, EvalKey<Element>>> keys, const std::string& keyTag) {
+        autoKeyMap()[keyTag] = std::move(keys);
+    }
+
+   private:
+    static std::map<std::string, std::shared_ptr<std::map<usint, EvalKey<Element>>>>& autoKeyMap() {
+        static std::map<std::string, std::shared_ptr<std::map<usint, EvalKey<Element>>>> m;
+        return m;
+    }
 };
 
 }  // namespace lbcrypto

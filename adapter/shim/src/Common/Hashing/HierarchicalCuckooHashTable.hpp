@@ -9,17 +9,7 @@
 #include <stdexcept>
 #include <vector>
 
-#include "hashing.hpp"  // psi::HierarchicalCuckooHashTable (nested-hashing-psi_b200/host)
-
-using namespace std;  // the reference's headers rely on it (libscapi does the same)
-
-typedef unsigned long long biginteger;  // libscapi: boost::multiprecision::cpp_int; the PIE only casts cells to int64_t
-typedef psi::TabulationHashing TabulationHashing;
-
-class CuckooHashTable {
-   public:
-    vector<vector<vector<biginteger>>> cuckooTable;  // [hfInd] x [binIndex] x [index]
-};
+#include "CuckooHashTable.hpp"  // the shim of the inner table (cuckooTable [hfInd][binIndex][index]), biginteger, TabulationHashing
 
 class HierarchicalCuckooHashTable {
     psi::HierarchicalCuckooHashTable impl;
