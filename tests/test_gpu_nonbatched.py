@@ -143,3 +143,36 @@ def test_cpp_known_answer_program_nonbatched():
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("Matches\n") == 1
     assert "noise budget ok: yes" in out.stdout and "limb parity with the oracle: identical" in out.stdout
+
+
+def test_nb_randomised_shapes():
+    """Seeded sweep over ring dimensions, limb counts and table shapes (incl. b a power of two, b = 2, K = 1, extreme
+    residues 0 / q-1 in the operands): every draw is a whole collection compared limb for limb with the oracle."""
+    rng = np.random.default_rng(20261019)
+    for trial in range(12):
+        N = int(rng.choice([256, 512, 1024, 2048, 4096]))
+        L = int(rng.integers(1, 7))
+        n_pie, K, b = int(rng.integers(1, 4)), int(rng.integers(1, 4)), int(rng.choice([2, 3, 4, 6, 8, 11]))
+        cc, o, params = make(N, L)
+        pt = sc.random_pt(rng, params, (n_pie, K, b))
+        mask = sc.random_pt(rng, params, (n_pie, K))
+        merge = sc.random_pt(rng, params)
+        idx = sc.random_ct(rng, params, (n_pie, K))
+        if trial % 3 == 0:   # extreme residues: the digit lift's centring threshold and the reductions' upper ends
+            for l in range(L):
+                q = int(params.q[l])
+                idx[..., l, ::2] = q - 1
+                idx[..., l, 1::4] = 0
+                idx[..., l, 3::8] = (q - 1) // 2
+                idx[..., l, 7::8] = (q - 1) // 2 + 1
+                pt[..., l, ::3] = q - 1
+        key_index = list(dict.fromkeys(o.eval_sum_indices(b) + [o.find_automorphism_index(-i) for i in range(1, b)]))
+        key_b = sc.random_pt(rng, params, (len(key_index), L))
+        key_a = sc.random_pt(rng, params, (len(key_index), L))
+        cc.InsertEvalAutomorphismKeys(key_index, key_b, key_a)
+        cc.nb_db_load_limbs(pt, mask, merge)
+        got = cc.nb_run(idx)
+        for p in range(n_pie):
+            want = o.nb_run(idx[p], pt[p], merge, mask[p], key_index, key_b, key_a)
+            assert np.array_equal(got[p], want), (trial, N, L, n_pie, K, b, p)
+        cc.close()
