@@ -81,6 +81,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stage-times", action="store_true", help="time upload / run / download of the e2e step separately")
     ap.add_argument("--no-limb-leg", action="store_true", help="skip the e2e leg with separately allocated limb vectors")
+    ap.add_argument("--no-nb-leg", action="store_true", help="skip the non-batched FHEHIPPIE leg (SURVEY 8f #4)")
     ap.add_argument("--gather", default="host", choices=["host", "nccl"],
                     help="N > 1 response gather inside e2e: 'host' = every rank copies its own result ciphertexts to "
                          "pinned host memory over its own PCIe link (what a one-process server does with one pinned "
@@ -154,6 +155,52 @@ class ClockSampler(threading.Thread):
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+
+def nonbatched_leg(cc, params, steps, with_cpu):
+    """SURVEY 8f #4 beside the headline path: a collection of non-batched PIEs (FHEHIPPIE.cpp:61-77) on the same context,
+    host -> host through psi_nb_run, one PIE re-computed by the CPU port (parity + the CPU figure).  Shape: BASELINE
+    configs[1]'s inner tables (K = 2, b = E = 14), 8 PIEs of the k*e = 9898 the reference's server would hold."""
+    import psi_b200 as P
+    from oracle.oracle import Oracle
+    n_pie, K, b = 8, 2, 14
+    L, N = params.L, params.N
+    rng = np.random.default_rng(2026)
+    o = Oracle(params)
+    key_index = list(dict.fromkeys(o.eval_sum_indices(b) + [o.find_automorphism_index(-i) for i in range(1, b)]))
+    pt = random_limbs(rng, params, (n_pie, K, b)).reshape(n_pie, K, b, L, N)
+    mask = random_limbs(rng, params, (n_pie, K)).reshape(n_pie, K, L, N)
+    merge = random_limbs(rng, params, (1,)).reshape(L, N)
+    idx = random_limbs(rng, params, (n_pie, K, 2)).reshape(n_pie, K, 2, L, N)
+    key_b = random_limbs(rng, params, (len(key_index), L)).reshape(len(key_index), L, L, N)
+    key_a = random_limbs(rng, params, (len(key_index), L)).reshape(len(key_index), L, L, N)
+    cc.InsertEvalAutomorphismKeys(key_index, key_b, key_a)
+    cc.nb_db_load_limbs(pt, mask, merge)
+    got = cc.nb_run(idx)   # warm-up: work buffers
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        got = cc.nb_run(idx)
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    n_sum = len(o.eval_sum_indices(b))
+    ks = n_pie * K * (b * n_sum + b - 1)
+    leg = {"workload": "non-batched FHEHIPPIE collection: %d PIEs, K=%d, b=E=%d, N=%d, sizeQ=%d" % (n_pie, K, b, N, L),
+           "ms_per_collection": ms, "ms_per_pie": ms / n_pie, "gpu_launches_per_collection": cc.nb_launch_count(),
+           "key_switches": ks, "key_switches_per_s": ks / (ms * 1e-3), "limb_ntts_per_collection": ks * (L + L * L),
+           "timing": "host wall clock around psi_nb_run: pageable host index ciphertexts in, result ciphertexts out",
+           "cpu_port": None, "parity_checked_pies": 0, "parity_ok": None}
+    if with_cpu:
+        t0 = time.perf_counter()
+        want = o.nb_run(idx[0], pt[0], merge, mask[0], key_index, key_b, key_a)
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        ok = bool(np.array_equal(got[0], want))
+        leg.update({"cpu_port": {"ms_per_pie": cpu_ms, "cores": 1, "kind": "port",
+                                 "sample": "1 of %d PIEs (the reference pins its non-batched server to one OpenMP thread, "
+                                           "SimpleFHEPSIServer.cpp:17)" % n_pie},
+                    "parity_checked_pies": 1, "parity_ok": ok})
+        if not ok:
+            raise SystemExit("bench.py: non-batched leg: GPU result limbs differ from the oracle")
+    return leg
 
 
 def host_threads():
@@ -684,6 +731,10 @@ def main():
         cpu["cold"] = {"value": ratec, "unit": "items/s", "cores": threads, "sample": "%d of %d bins x 1" % (nbc, w["b"]),
                        "ms_per_query_extrapolated": dtc * 1e3 * w["b"] / nbc}
 
+    nb_leg = None
+    if rank == 0 and world == 1 and not args.no_nb_leg:
+        nb_leg = nonbatched_leg(cc, params, min(args.steps, 5), not args.no_cpu_baseline)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "items/s", "n_gpus": world, "steps": args.steps,
@@ -709,7 +760,7 @@ def main():
                                    if m["qd"] else "whole query over every GPU's own PCIe link") if world > 1 else None},
             "gpu_launches": m["launches_per_run"] * args.steps,
             "parity_checked_bins": len(checked), "parity_checked_bin_ids": checked, "parity_ok": not bad,
-            "weak": weak,
+            "weak": weak, "nonbatched": nb_leg,
             "phases": phases, "clocks": sampler.summary(), "offline_build_s": offline_s,
         }
         print(json.dumps(line), flush=True)

@@ -3,7 +3,7 @@
 # command, one full-set capture of the kernels of one run(), one of the encode path's k_ntt.  usage: tools/capture_round.sh r02
 tag=${1:-r02}
 G=gpurun_out
-CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-limb-leg"
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-limb-leg --no-nb-leg"
 $CMD > $G/${tag}_bench_short.json 2> $G/${tag}_bench_short.err || { echo "bench failed"; tail -5 $G/${tag}_bench_short.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $G/${tag}_launches.csv $CMD > $G/${tag}_ncu_list.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'k_mac|k_rows|k_cols' -s 22 -c 11 -f -o $G/${tag}_run $CMD > $G/${tag}_ncu_full.log 2>&1
