@@ -133,6 +133,12 @@ cudaError_t launch_fused_mul(const KCtx& k, uint32_t B, const u64* a, const u64*
                              u64* e2h, u64* th, u64* rh, u64* dh, const u64* evk_b, const u64* evk_a, const u64* mask,
                              u64* out, uint32_t ops = 3);
 cudaError_t launch_mul_ctpt(const KCtx& k, uint32_t B, const u64* ct, const u64* pt, u64* out);
+// Fused automorphism key switch of the non-batched path (fused_nb.cu): cur [B][2][L][N] -> out, scratch h [B][L][N],
+// dh [B][L][L][N]; keys in Montgomery form [n_keys][L][L][N]; per-item key slot / inverse index through sel_*
+bool nb_fused_supported(const KCtx& k);
+cudaError_t nb_fused_init_device(const KCtx& k);
+cudaError_t launch_nb_keyswitch(const KCtx& k, uint32_t B, const u64* cur, u64* h, u64* dh, const u64* key_bR, const u64* key_aR,
+                                const int* sel_key, const uint32_t* sel_ginv, uint32_t sel_mod, bool add, u64* out);
 
 // Packed encoding, centred lift: crt [n][N] in [0, t) -> out [n][L][N]
 cudaError_t launch_centre_lift(const KCtx& k, uint32_t n, const u64* crt, u64* out);

@@ -14,6 +14,7 @@
 // permutation after it - fused here as a scatter: the thread that forms the key-switched value at position j stores
 // it at the position the inverse index maps j to.  No floating point on this path: all residues are canonical.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "psi_ctx.cuh"
@@ -24,6 +25,8 @@ struct NbState {
     // automorphism keys (EvalSumKeyGen + EvalRotateKeyGen, SimpleFHEPSIClient.cpp:79-90)
     std::vector<uint64_t> key_index;
     DevBuf<u64> key_b, key_a;  // [n_keys][L][L][N]
+    DevBuf<u64> key_bR, key_aR;  // the same times 2^64 mod q_k (Montgomery form for the fused key switch)
+    bool fused = false;          // fused_nb.cu covers this context (N >= 1024, L <= 7); PSI_NB_UNFUSED=1 forces the generic kernels
     // database: vectorizedCT / preCalcRandomMask of every PIE, EvalMerge's plaintext
     uint32_t n_pie = 0, K = 0, b = 0;
     DevBuf<u64> pt, mask, merge_pt;  // [n_pie][K][b][L][N], [n_pie][K][L][N], [L][N]
@@ -265,6 +268,14 @@ template <bool ADD>
 static int nb_ks_step(psi_ctx* c, NbState* s, const KCtx& k, uint32_t B, uint32_t sel0, uint32_t sel_mod) {
     const uint32_t L = c->L, N = c->N;
     const size_t LN = (size_t)L * N;
+    if (s->fused) {  // three fused kernels (fused_nb.cu)
+        CK(launch_nb_keyswitch(k, B, s->cur.p, s->coef.p, s->dig.p, s->key_bR.p, s->key_aR.p, s->sel_key.p + sel0, s->sel_ginv.p + sel0,
+                               sel_mod, ADD, s->nxt.p));
+        std::swap(s->cur.p, s->nxt.p);
+        std::swap(s->cur.n, s->nxt.n);
+        s->launches += 3;
+        return PSI_OK;
+    }
     NttBatch nb{s->cur.p + LN, s->coef.p, B * L, L, 2 * LN, N, LN, 0, L};  // c1 of every item to COEFFICIENT
     CK(launch_ntt(k, nb, true));
     k_nb_digits<<<blocks_for((size_t)B * LN), 256, 0, k.s>>>(k.tab, N, B, s->coef.p, s->dig.p);
@@ -315,6 +326,16 @@ int psi_nb_set_automorphism_keys(psi_ctx* c, uint32_t n_keys, const uint64_t* au
     CK(cudaMemcpy(s->key_b.p, key_b, words * sizeof(u64), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s->key_a.p, key_a, words * sizeof(u64), cudaMemcpyHostToDevice));
     s->key_index.assign(auto_index, auto_index + n_keys);
+    const KCtx k = c->k(0);
+    s->fused = nb_fused_supported(k) && std::getenv("PSI_NB_UNFUSED") == nullptr;
+    if (s->fused) {
+        CK(nb_fused_init_device(k));
+        CK(s->key_bR.alloc(words));
+        CK(s->key_aR.alloc(words));
+        CK(launch_to_montgomery(k, n_keys * c->L, s->key_b.p, s->key_bR.p));
+        CK(launch_to_montgomery(k, n_keys * c->L, s->key_a.p, s->key_aR.p));
+        CK(cudaStreamSynchronize(0));
+    }
     s->chunk_pies = 0;  // the key slots of the selection tables are re-derived
     return PSI_OK;
 }
