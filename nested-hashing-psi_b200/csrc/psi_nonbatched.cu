@@ -6,10 +6,12 @@
 //                                               EvalMerge over the bins, EvalMult by preCalcRandomMask[hf]
 // What the device does instead: every (pie, hf, bin) triple is one ITEM and the whole collection advances in lock step,
 //   (1) item = idx[pie][hf] (.) pt[item]                                        k_nb_mul_ctpt
-//   (2) ceil(log2 b) EvalSum steps, all items with the same automorphism key:   INTT(c1) -> BV digits -> NTT -> k_nb_ks_apply<ADD>
-//   (3) item (.) packed {1, 0, ...}; rotation by -bin with the key of that bin:  k_nb_mul_ctpt, ... k_nb_ks_apply<SET>
+//   (2) ceil(log2 b) EvalSum steps, all items with the same automorphism key:   the fused key switch of fused_nb.cu
+//       (k_nb_rows_inv -> k_nb_cols_digits -> k_nb_rows_ks<ADD>); contexts it does not cover (N < 1024) take the generic
+//       kernels below: INTT(c1) -> k_nb_digits -> NTT -> k_nb_ks_apply<ADD>
+//   (3) item (.) packed {1, 0, ...}; rotation by -bin with the key of that bin:  k_nb_mul_ctpt, the same key switch <SET>
 //   (4) sum over the bins of a (pie, hf) and (.) mask:                           k_nb_sum_mask
-// so a collection of P PIEs costs the same ~4 (steps + 1) + 3 launches as one PIE.  The key switch follows OpenFHE's
+// so a collection of P PIEs costs the same 3 (steps + 1) + 3 launches as one PIE.  The key switch follows OpenFHE's
 // EvalAutomorphism order (recalled, see oracle/psi_oracle.c): KeySwitchInPlace first, the EVALUATION-format
 // permutation after it - fused here as a scatter: the thread that forms the key-switched value at position j stores
 // it at the position the inverse index maps j to.  No floating point on this path: all residues are canonical.
