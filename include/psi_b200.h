@@ -441,6 +441,17 @@ int psi_nb_db_get_limbs(psi_ctx* c, uint64_t* pt_limbs, uint64_t* mask_limbs, ui
  * idx, out: HOST [pie_end - pie_begin][K][2][L][N]; synchronous.  A missing key is PSI_ERR_STATE (OpenFHE throws). */
 int psi_nb_run(psi_ctx* c, uint32_t pie_begin, uint32_t pie_end, const uint64_t* idx, uint64_t* out, void* stream);
 int psi_nb_launch_count(psi_ctx* c, uint32_t* out); /* kernels launched by the last psi_nb_run */
+/* The same collection over the devices of a psi_multi: PIEs sharded in contiguous blocks (the reference runs its
+ * FHEHIPPIECollections on parallel threads, SimpleFHEPSIServer.cpp:126-160), keys replicated, one host thread per
+ * device inside psi_multi_nb_run; idx / out cover ALL PIEs, [n_pie][K][2][L][N]. */
+int psi_multi_nb_set_automorphism_keys(psi_multi* m, uint32_t n_keys, const uint64_t* auto_index, const uint64_t* key_b,
+                                       const uint64_t* key_a);
+int psi_multi_nb_db_encode_slots(psi_multi* m, uint32_t n_pie, uint32_t K, uint32_t b, uint32_t nslots, const int64_t* slots,
+                                 const int64_t* mask_slots);
+int psi_multi_nb_db_load_limbs(psi_multi* m, uint32_t n_pie, uint32_t K, uint32_t b, const uint64_t* pt_limbs,
+                               const uint64_t* mask_limbs, const uint64_t* merge_limbs);
+int psi_multi_nb_pie_range(psi_multi* m, uint32_t index, uint32_t* pie_begin, uint32_t* pie_end);
+int psi_multi_nb_run(psi_multi* m, const uint64_t* idx, uint64_t* out);
 
 /* number of CUDA devices visible to the process (hosts that build their device list without the CUDA headers) */
 int psi_device_count(int* n);

@@ -143,6 +143,11 @@ SYMBOLS = {
     "psi_nb_db_get_limbs": (_int, [_vp, _u64p, _u64p, _u64p]),
     "psi_nb_run": (_int, [_vp, _u32, _u32, _u64p, _u64p, _vp]),
     "psi_nb_launch_count": (_int, [_vp, _u32p]),
+    "psi_multi_nb_set_automorphism_keys": (_int, [_vp, _u32, _u64p, _u64p, _u64p]),
+    "psi_multi_nb_db_encode_slots": (_int, [_vp, _u32, _u32, _u32, _u32, _i64p, _i64p]),
+    "psi_multi_nb_db_load_limbs": (_int, [_vp, _u32, _u32, _u32, _u64p, _u64p, _u64p]),
+    "psi_multi_nb_pie_range": (_int, [_vp, _u32, _u32p, _u32p]),
+    "psi_multi_nb_run": (_int, [_vp, _u64p, _u64p]),
     "psi_device_count": (_int, [ctypes.POINTER(_int)]),
     "psi_last_error": (ctypes.c_char_p, []),
     "psi_version": (ctypes.c_char_p, []),

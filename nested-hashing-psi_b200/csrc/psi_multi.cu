@@ -19,6 +19,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "psi_b200.h"
@@ -73,6 +74,9 @@ struct psi_multi {
     size_t stage_in_words = 0;
     uint64_t* stage_out = nullptr;
     size_t stage_out_words = 0;
+    // non-batched collection (psi_multi_nb_*): PIEs [nb_begin[d], nb_begin[d + 1]) live on device d
+    std::vector<uint32_t> nb_begin;
+    uint32_t nb_K = 0, nb_b = 0;
     size_t ct_words() const { return (size_t)2 * P.L * P.N; }
     size_t idx_words() const { return (size_t)K * E * ct_words(); }
 };
@@ -441,6 +445,77 @@ int psi_multi_sync(psi_multi* m) {
 int psi_multi_set_host_threads(psi_multi* m, int n) {
     if (!m || n < 1 || n > 256) return set_error(PSI_ERR_INVALID, "host thread count must be in [1, 256]");
     m->host_threads = n;
+    return PSI_OK;
+}
+
+// ---- non-batched FHEHIPPIE collection over the devices (FHEHIPPIE.cpp; the reference runs its collections on
+// parallel threads, SimpleFHEPSIServer.cpp:126-160 - here the PIEs are sharded over the devices in contiguous blocks,
+// the automorphism keys are replicated, and psi_multi_nb_run drives every device from its own host thread) ----------
+int psi_multi_nb_set_automorphism_keys(psi_multi* m, uint32_t n_keys, const uint64_t* auto_index, const uint64_t* key_b,
+                                       const uint64_t* key_a) {
+    if (!m) return set_error(PSI_ERR_INVALID, "null argument");
+    for (Dev& D : m->devs) PCK(psi_nb_set_automorphism_keys(D.ctx, n_keys, auto_index, key_b, key_a));
+    return PSI_OK;
+}
+
+static int nb_shard(psi_multi* m, uint32_t n_pie, uint32_t K, uint32_t b) {
+    const uint32_t n = (uint32_t)m->devs.size();
+    if (n_pie < n) return set_error(PSI_ERR_INVALID, "fewer PIEs than devices: create the psi_multi with at most n_pie devices");
+    m->nb_begin.resize(n + 1);
+    for (uint32_t d = 0; d <= n; d++) m->nb_begin[d] = (uint32_t)(((uint64_t)d * n_pie) / n);
+    m->nb_K = K;
+    m->nb_b = b;
+    return PSI_OK;
+}
+
+int psi_multi_nb_db_encode_slots(psi_multi* m, uint32_t n_pie, uint32_t K, uint32_t b, uint32_t nslots, const int64_t* slots,
+                                 const int64_t* mask_slots) {
+    if (!m || !slots || !mask_slots) return set_error(PSI_ERR_INVALID, "null argument");
+    PCK(nb_shard(m, n_pie, K, b));
+    for (size_t d = 0; d < m->devs.size(); d++) {
+        const uint32_t p0 = m->nb_begin[d], p1 = m->nb_begin[d + 1];
+        PCK(psi_nb_db_encode_slots(m->devs[d].ctx, p1 - p0, K, b, nslots, slots + (size_t)p0 * K * b * nslots,
+                                   mask_slots + (size_t)p0 * K * b));
+    }
+    return PSI_OK;
+}
+
+int psi_multi_nb_db_load_limbs(psi_multi* m, uint32_t n_pie, uint32_t K, uint32_t b, const uint64_t* pt_limbs,
+                               const uint64_t* mask_limbs, const uint64_t* merge_limbs) {
+    if (!m || !pt_limbs || !mask_limbs || !merge_limbs) return set_error(PSI_ERR_INVALID, "null argument");
+    PCK(nb_shard(m, n_pie, K, b));
+    const size_t LN = (size_t)m->P.L * m->P.N;
+    for (size_t d = 0; d < m->devs.size(); d++) {
+        const uint32_t p0 = m->nb_begin[d], p1 = m->nb_begin[d + 1];
+        PCK(psi_nb_db_load_limbs(m->devs[d].ctx, p1 - p0, K, b, pt_limbs + (size_t)p0 * K * b * LN, mask_limbs + (size_t)p0 * K * LN,
+                                 merge_limbs));
+    }
+    return PSI_OK;
+}
+
+int psi_multi_nb_pie_range(psi_multi* m, uint32_t index, uint32_t* pie_begin, uint32_t* pie_end) {
+    if (!m || !pie_begin || !pie_end || index + 1 >= m->nb_begin.size()) return set_error(PSI_ERR_INVALID, "bad argument");
+    *pie_begin = m->nb_begin[index];
+    *pie_end = m->nb_begin[index + 1];
+    return PSI_OK;
+}
+
+int psi_multi_nb_run(psi_multi* m, const uint64_t* idx, uint64_t* out) {
+    if (!m || !idx || !out) return set_error(PSI_ERR_INVALID, "null argument");
+    if (m->nb_begin.size() != m->devs.size() + 1) return set_error(PSI_ERR_STATE, "no non-batched database loaded");
+    const size_t n = m->devs.size(), per_pie = (size_t)m->nb_K * m->ct_words();
+    std::vector<int> rc(n, PSI_OK);
+    std::vector<std::string> msg(n);
+    std::vector<std::thread> workers;
+    for (size_t d = 0; d < n; d++)
+        workers.emplace_back([&, d] {  // psi_nb_run is synchronous: one host thread per device keeps them all busy
+            const uint32_t p0 = m->nb_begin[d], p1 = m->nb_begin[d + 1];
+            rc[d] = psi_nb_run(m->devs[d].ctx, 0, p1 - p0, idx + p0 * per_pie, out + p0 * per_pie, m->devs[d].s_run);
+            if (rc[d] != PSI_OK) msg[d] = psi_last_error();  // the message is thread-local
+        });
+    for (auto& w : workers) w.join();
+    for (size_t d = 0; d < n; d++)
+        if (rc[d] != PSI_OK) return set_error(rc[d], msg[d]);
     return PSI_OK;
 }
 

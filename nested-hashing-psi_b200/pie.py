@@ -528,6 +528,44 @@ class MultiContext:
         check(lib().psi_multi_run_launch_count(self._h, ctypes.byref(n)))
         return n.value
 
+    # --- non-batched FHEHIPPIE collection over the devices -----------------------------------------
+    def InsertEvalAutomorphismKeys(self, indices, key_b, key_a):
+        idx = np.ascontiguousarray(indices, dtype=np.uint64)
+        (key_b, pb), (key_a, pa) = _u64(key_b), _u64(key_a)
+        check(lib().psi_multi_nb_set_automorphism_keys(self._h, len(idx), idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), pb, pa))
+
+    def nb_db_load_limbs(self, pt, mask, merge_pt):
+        (pt, pp), (mask, pm), (merge_pt, pg) = _u64(pt), _u64(mask), _u64(merge_pt)
+        n_pie, K, b = pt.shape[:3]
+        check(lib().psi_multi_nb_db_load_limbs(self._h, n_pie, K, b, pp, pm, pg))
+        self._nb_dims = (n_pie, K, b)
+
+    def nb_db_encode_slots(self, slots, mask_slots):
+        (slots, ps), (mask_slots, pm) = _i64(slots), _i64(mask_slots)
+        n_pie, K, b, n = slots.shape
+        try:
+            check(lib().psi_multi_nb_db_encode_slots(self._h, n_pie, K, b, n, ps, pm))
+        except PsiError as e:
+            _raise_like_reference(e)
+        self._nb_dims = (n_pie, K, b)
+
+    def nb_pie_ranges(self):
+        out = []
+        for i in range(len(self.devices)):
+            a, b = ctypes.c_uint32(), ctypes.c_uint32()
+            check(lib().psi_multi_nb_pie_range(self._h, i, ctypes.byref(a), ctypes.byref(b)))
+            out.append((a.value, b.value))
+        return out
+
+    def nb_run(self, idx, pie_begin=0, pie_end=None):
+        n_pie, K, b = self._nb_dims
+        assert pie_begin == 0 and pie_end in (None, n_pie), "the multi-device collection runs as a whole"
+        idx, pi = _u64(idx)
+        assert idx.shape == (n_pie, K, 2, self.L, self.N)
+        out = np.empty_like(idx)
+        check(lib().psi_multi_nb_run(self._h, pi, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
+        return out
+
     def close(self):
         if getattr(self, "_h", None):
             lib().psi_multi_destroy(self._h)

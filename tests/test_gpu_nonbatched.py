@@ -176,3 +176,40 @@ def test_nb_randomised_shapes():
             want = o.nb_run(idx[p], pt[p], merge, mask[p], key_index, key_b, key_a)
             assert np.array_equal(got[p], want), (trial, N, L, n_pie, K, b, p)
         cc.close()
+
+
+@pytest.mark.parametrize("devices", [(0, 0), (0, 1, 0)])
+def test_nb_collection_over_several_devices(devices):
+    """psi_multi_nb_*: the PIEs of a collection sharded over a device list (a device may repeat: two contexts on one
+    GPU; distinct GPUs when the box has them), one host thread per device; same ciphertexts as one context."""
+    import torch
+    devices = tuple(d if d < torch.cuda.device_count() else 0 for d in devices)
+    params = RefParams(2048, T32, L=3).to_struct()
+    o = Oracle(params)
+    rng = np.random.default_rng(31)
+    n_pie, K, b = 5, 2, 4
+    t = int(params.t)
+    slots = rng.integers(-(t // 2), t // 2, (n_pie, K, b, b + 1), dtype=np.int64)
+    masks = rng.integers(1, t, (n_pie, K, b), dtype=np.int64)
+    idx = sc.random_ct(rng, params, (n_pie, K))
+    key_index = list(dict.fromkeys(o.eval_sum_indices(b) + [o.find_automorphism_index(-i) for i in range(1, b)]))
+    key_b = sc.random_pt(rng, params, (len(key_index), 3))
+    key_a = sc.random_pt(rng, params, (len(key_index), 3))
+    one = P.CryptoContext(params)
+    one.InsertEvalAutomorphismKeys(key_index, key_b, key_a)
+    one.nb_db_encode_slots(slots, masks)
+    want = one.nb_run(idx)
+    pt, mask, merge = one.nb_db_get_limbs()
+    assert np.array_equal(want[3], o.nb_run(idx[3], pt[3], merge, mask[3], key_index, key_b, key_a))
+    mc = P.MultiContext(params, devices)
+    mc.InsertEvalAutomorphismKeys(key_index, key_b, key_a)
+    mc.nb_db_encode_slots(slots, masks)
+    ranges = mc.nb_pie_ranges()
+    assert ranges[0][0] == 0 and ranges[-1][1] == n_pie and all(a < b_ for a, b_ in ranges)
+    assert np.array_equal(mc.nb_run(idx), want)
+    mc.nb_db_load_limbs(pt, mask, merge)          # the limb form shards the same way
+    assert np.array_equal(mc.nb_run(idx), want)
+    with pytest.raises(ValueError):
+        P.MultiContext(params, (0,) * 6).nb_db_encode_slots(slots, masks)   # more devices than PIEs
+    mc.close()
+    one.close()
