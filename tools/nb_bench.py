@@ -1,6 +1,6 @@
 """Timing of the non-batched FHEHIPPIE collection on one GPU next to the CPU port (oracle) — SURVEY 8f #4.
 One step = psi_nb_run over a collection of P PIEs (K hash functions, b x b inner tables), host -> host.
-Usage: python tools/nb_bench.py [--N 16384] [--L 4] [--pies 8] [--K 2] [--b 14] [--steps 5] [--cpu-pies 1]
+Usage: python tools/nb_bench.py [--N 16384] [--L 4] [--pies 8] [--K 2] [--b 14] [--steps 5] [--cpu-pies 1] [--devices 0,1]
 Prints one JSON line (also the per-PIE figures)."""
 import argparse
 import json
@@ -29,9 +29,12 @@ def main():
     ap.add_argument("--b", type=int, default=14)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--cpu-pies", type=int, default=1)
+    ap.add_argument("--devices", default="", help="comma-separated device list: the collection sharded over them (psi_multi_nb_*)")
     a = ap.parse_args()
     params = RefParams(a.N, 4296540161, L=a.L).to_struct()
-    cc, o = P.CryptoContext(params), Oracle(params)
+    devices = [int(d) for d in a.devices.split(",") if d != ""]
+    cc = P.MultiContext(params, devices) if devices else P.CryptoContext(params)
+    o = Oracle(params)
     rng = np.random.default_rng(1)
     pt = sc.random_pt(rng, params, (a.pies, a.K, a.b))
     mask = sc.random_pt(rng, params, (a.pies, a.K))
@@ -57,7 +60,8 @@ def main():
     keyswitches = a.pies * a.K * (a.b * n_sum + a.b - 1)
     print(json.dumps({
         "workload": "non-batched FHEHIPPIE collection: %d PIEs, K=%d, b=E=%d, N=%d, L=%d" % (a.pies, a.K, a.b, a.N, a.L),
-        "gpu_ms_per_collection": gpu_ms, "gpu_ms_per_pie": gpu_ms / a.pies, "launches": cc.nb_launch_count(),
+        "devices": devices or [0], "gpu_ms_per_collection": gpu_ms, "gpu_ms_per_pie": gpu_ms / a.pies,
+        "launches": None if devices else cc.nb_launch_count(),
         "key_switches": keyswitches, "gpu_key_switches_per_s": keyswitches / (gpu_ms * 1e-3),
         "limb_ntts": keyswitches * (a.L + a.L * a.L),
         "cpu_port_ms_per_pie_1_thread": cpu_ms_per_pie, "speedup_per_pie": cpu_ms_per_pie / (gpu_ms / a.pies),
