@@ -40,6 +40,18 @@ struct NbState {
     DevBuf<uint32_t> sel_ginv;  // inverse automorphism index of the same entries
     uint32_t n_sum = 0;
     uint32_t launches = 0;
+    // copy streams and the events that order uploads, evaluations and downloads of consecutive chunks
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {}, ev_eval[2] = {}, ev_out[2] = {};
+    ~NbState() {
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_out) cudaStreamDestroy(s_out);
+        for (int i = 0; i < 2; i++) {
+            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+            if (ev_eval[i]) cudaEventDestroy(ev_eval[i]);
+            if (ev_out[i]) cudaEventDestroy(ev_out[i]);
+        }
+    }
 };
 
 void nb_release(psi_ctx* c) {
@@ -255,8 +267,17 @@ static int nb_prepare(psi_ctx* c, NbState* s, uint32_t pies) {
     CK(s->sel_ginv.alloc(sel_ginv.size()));
     CK(cudaMemcpy(s->sel_key.p, sel_key.data(), sel_key.size() * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s->sel_ginv.p, sel_ginv.data(), sel_ginv.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    CK(s->idx.alloc((size_t)pies * K * 2 * LN));
-    CK(s->out.alloc((size_t)pies * K * 2 * LN));
+    CK(s->idx.alloc((size_t)2 * pies * K * 2 * LN));  // double-buffered: chunk i + 1 uploads while chunk i is evaluated
+    CK(s->out.alloc((size_t)2 * pies * K * 2 * LN));
+    if (!s->s_in) {
+        CK(cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CK(cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s->ev_eval[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming));
+        }
+    }
     CK(s->cur.alloc(items * 2 * LN));
     CK(s->nxt.alloc(items * 2 * LN));
     CK(s->coef.alloc(items * LN));
@@ -405,41 +426,75 @@ int psi_nb_run(psi_ctx* c, uint32_t pie_begin, uint32_t pie_end, const uint64_t*
     if (pie_begin >= pie_end || pie_end > s->n_pie) return set_error(PSI_ERR_INVALID, "bad PIE range");
     const uint32_t L = c->L, N = c->N, K = s->K, b = s->b;
     const size_t LN = (size_t)L * N;
-    // chunk size: work buffers of one item are (2 + 2 + 1 + L) polynomials; keep a chunk below ~6 GB
+    // Chunks of PIEs: the index ciphertexts of chunk i + 1 go up and the results of chunk i - 1 come down while chunk i
+    // is evaluated (copy streams beside the caller's; index and result buffers are double-buffered, the work buffers
+    // are shared because the evaluations are ordered on one stream).  A chunk is at least ~128 items (enough CTAs for
+    // every launch), at most a quarter of the range, and its work buffers - (2 + 2 + 1 + L) polynomials per item - stay
+    // below ~6 GB.
+    const uint32_t n_range = pie_end - pie_begin;
     const size_t per_pie = (size_t)K * b * (5 + L) * LN * sizeof(u64);
-    const uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(pie_end - pie_begin, (6ull << 30) / per_pie));
+    const uint32_t min_pies = (uint32_t)((128 + (size_t)K * b - 1) / ((size_t)K * b));
+    uint32_t chunk = std::max<uint32_t>(min_pies, (n_range + 3) / 4);
+    chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(std::min<uint32_t>(chunk, n_range), (6ull << 30) / per_pie));
     if ((rc = nb_prepare(c, s, chunk))) return rc;
+    chunk = std::min(chunk, s->chunk_pies);
     cudaStream_t st = (cudaStream_t)stream;
     const KCtx k = c->k(st);
     s->launches = 0;
-    for (uint32_t p0 = pie_begin; p0 < pie_end; p0 += chunk) {
-        const uint32_t np = std::min(chunk, pie_end - p0), G = np * K, B = G * b;
-        const size_t off = (size_t)(p0 - pie_begin) * K * 2 * LN;
-        CK(cudaMemcpyAsync(s->idx.p, idx + off, (size_t)G * 2 * LN * sizeof(u64), cudaMemcpyHostToDevice, st));
+    const uint32_t n_chunks = (n_range + chunk - 1) / chunk;
+    const size_t ct_chunk = (size_t)s->chunk_pies * K * 2 * LN;  // words of one index / result buffer
+    auto upload = [&](uint32_t ci) -> int {
+        const uint32_t p0 = pie_begin + ci * chunk, np = std::min(chunk, pie_end - p0), w = ci & 1;
+        if (ci >= 2) CK(cudaStreamWaitEvent(s->s_in, s->ev_eval[w], 0));  // the evaluation of chunk ci - 2 has read this buffer
+        CK(cudaMemcpyAsync(s->idx.p + w * ct_chunk, idx + (size_t)(p0 - pie_begin) * K * 2 * LN, (size_t)np * K * 2 * LN * sizeof(u64),
+                           cudaMemcpyHostToDevice, s->s_in));
+        CK(cudaEventRecord(s->ev_in[w], s->s_in));
+        return PSI_OK;
+    };
+    auto evaluate = [&](uint32_t ci) -> int {
+        const uint32_t p0 = pie_begin + ci * chunk, np = std::min(chunk, pie_end - p0), G = np * K, B = G * b, w = ci & 1;
+        const u64* d_idx = s->idx.p + w * ct_chunk;
+        u64* d_out = s->out.p + w * ct_chunk;
+        CK(cudaStreamWaitEvent(st, s->ev_in[w], 0));
+        if (ci >= 2) CK(cudaStreamWaitEvent(st, s->ev_out[w], 0));  // the results of chunk ci - 2 have left this buffer
         // (1) EvalMult(indexMatrix[hf], vectorizedCT[hf][bin])
-        k_nb_mul_ctpt<<<blocks_for((size_t)B * LN), 256, 0, st>>>(k.tab, N, B, s->idx.p, b, s->pt.p + (size_t)p0 * K * b * LN, LN,
-                                                                  s->cur.p);
+        k_nb_mul_ctpt<<<blocks_for((size_t)B * LN), 256, 0, st>>>(k.tab, N, B, d_idx, b, s->pt.p + (size_t)p0 * K * b * LN, LN, s->cur.p);
         CK(cudaGetLastError());
         s->launches++;
         // (2) EvalSum
+        int r;
         for (uint32_t step = 0; step < s->n_sum; step++)
-            if ((rc = nb_ks_step<true>(c, s, k, B, step, 0))) return rc;
+            if ((r = nb_ks_step<true>(c, s, k, B, step, 0))) return r;
         // (3) EvalMerge: keep slot 0, move it to slot `bin`
         k_nb_mul_ctpt<<<blocks_for((size_t)B * LN), 256, 0, st>>>(k.tab, N, B, s->cur.p, 1, s->merge_pt.p, 0, s->nxt.p);
         CK(cudaGetLastError());
         s->launches++;
         std::swap(s->cur.p, s->nxt.p);
         std::swap(s->cur.n, s->nxt.n);
-        if (b > 1) {
-            if ((rc = nb_ks_step<false>(c, s, k, B, s->n_sum, b))) return rc;
-        }
+        if (b > 1 && (r = nb_ks_step<false>(c, s, k, B, s->n_sum, b))) return r;
         // (4) sum over the bins, EvalMult by preCalcRandomMask[hf]
-        k_nb_sum_mask<<<blocks_for((size_t)G * LN), 256, 0, st>>>(k.tab, N, G, b, s->cur.p, s->mask.p + (size_t)p0 * K * LN, s->out.p);
+        k_nb_sum_mask<<<blocks_for((size_t)G * LN), 256, 0, st>>>(k.tab, N, G, b, s->cur.p, s->mask.p + (size_t)p0 * K * LN, d_out);
         CK(cudaGetLastError());
         s->launches++;
-        CK(cudaMemcpyAsync(out + off, s->out.p, (size_t)G * 2 * LN * sizeof(u64), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));  // the chunk buffers are reused
+        CK(cudaEventRecord(s->ev_eval[w], st));
+        return PSI_OK;
+    };
+    auto download = [&](uint32_t ci) -> int {
+        const uint32_t p0 = pie_begin + ci * chunk, np = std::min(chunk, pie_end - p0), w = ci & 1;
+        CK(cudaStreamWaitEvent(s->s_out, s->ev_eval[w], 0));
+        CK(cudaMemcpyAsync(out + (size_t)(p0 - pie_begin) * K * 2 * LN, s->out.p + w * ct_chunk, (size_t)np * K * 2 * LN * sizeof(u64),
+                           cudaMemcpyDeviceToHost, s->s_out));
+        CK(cudaEventRecord(s->ev_out[w], s->s_out));
+        return PSI_OK;
+    };
+    if ((rc = upload(0)) || (rc = evaluate(0))) return rc;
+    for (uint32_t ci = 0; ci < n_chunks; ci++) {
+        if (ci + 1 < n_chunks && ((rc = upload(ci + 1)) || (rc = evaluate(ci + 1)))) return rc;  // queued behind chunk ci
+        if ((rc = download(ci))) return rc;
     }
+    CK(cudaStreamSynchronize(s->s_out));
+    CK(cudaStreamSynchronize(st));
+    s->launches /= n_chunks;  // per chunk: what one collection-sized launch set costs
     return PSI_OK;
 }
 
