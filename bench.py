@@ -344,6 +344,8 @@ def main():
     numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL logs (its version line under NCCL_DEBUG=VERSION / INFO) belong on stderr: stdout carries ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sampler = ClockSampler(local_rank)
     sampler.start()
