@@ -1,5 +1,7 @@
 // Row kernels, launcher and dispatch of the fused EvalMult(ct,ct) pipeline; the device code shared with the
 // column-kernel translation units lives in fused_mul.cuh (see the design notes at its top).
+#include <cstdlib>
+
 #include "fused_mul.cuh"
 
 namespace psi {
@@ -120,7 +122,8 @@ __global__ void __launch_bounds__((2 + L) * kGroup, L <= 4 ? 2 : 1)
     const uint32_t kk = blockIdx.y, tile_base = blockIdx.x * M;
     const size_t bin = blockIdx.z;
     const ModDev& md = tab->mods[kk];
-    const u64* src = g < 2 ? rh + ((bin * 2 + g) * L + kk) * (size_t)N : dh + ((bin * L + (g - 2)) * L + kk) * (size_t)N;
+    // groups per CTA: 2 + L (one array each) or fewer (arrays dealt round-robin; see relin_groups() below)
+    const uint32_t ng = blockDim.x / kGroup;
     __shared__ __align__(8) uint64_t tw_bar;
     ulonglong2* tws = reinterpret_cast<ulonglong2*>(smem);  // forward twiddles of this row tile
     u64* arr = smem + kRowTwWords;
@@ -130,11 +133,14 @@ __global__ void __launch_bounds__((2 + L) * kGroup, L <= 4 ? 2 : 1)
         mbar_expect_tx(&tw_bar, kRowTwEntries * 16u);
         stage_row_twiddles(tws, md.ftw_rows, blockIdx.x, &tw_bar);
     }
-    load_rows(arr + g * P, src + tile_base, tid);
+    for (uint32_t a = g; a < 2 + L; a += ng) {
+        const u64* src = a < 2 ? rh + ((bin * 2 + a) * L + kk) * (size_t)N : dh + ((bin * L + (a - 2)) * L + kk) * (size_t)N;
+        load_rows(arr + a * P, src + tile_base, tid);
+    }
     loads_wait();
     __syncthreads();
     mbar_wait(&tw_bar, 0);
-    transform_rows<false>(tab, arr, P, 2 + L, [kk](uint32_t) { return kk; }, g, 2 + L, logN, tile_base, tid, tws);
+    transform_rows<false>(tab, arr, P, 2 + L, [kk](uint32_t) { return kk; }, g, ng, logN, tile_base, tid, tws);
     __syncthreads();  // the key-switch inner product reads all 2 + L arrays
 
     const size_t LN = (size_t)L * N;
@@ -182,6 +188,20 @@ cudaError_t launch_to_montgomery(const KCtx& k, uint32_t groups, const u64* src,
     if (total == 0) return cudaSuccess;
     k_to_montgomery<<<(unsigned)((total + 255) / 256), 256, 0, k.s>>>(k.tab, k.N, total, src, dst);
     return cudaGetLastError();
+}
+
+// Groups per k_rows_relin CTA.  One group per array (2 + L) is the natural shape; with L = 4 and at least 16 bins in the
+// launch, FOUR groups that take the six arrays round-robin (256 threads, three CTAs per SM instead of two 384-thread
+// ones) are faster: MEASURED at config B, bit-identical results, phase 2 1.0408 -> 1.0246 ms at 47 bins (three
+// alternating repetitions each, +-0.0005), 0.5402 -> 0.5331 at 24, no change at 12, 0.182 -> 0.187 at 6 (there the
+// longer CTAs lengthen the single partial wave); 3 groups 1.027, 5 groups 1.064.  PSI_RELIN_GROUPS=n forces n (tuning).
+static uint32_t relin_groups(uint32_t L, uint32_t B) {
+    static const int forced = [] {
+        const char* e = std::getenv("PSI_RELIN_GROUPS");
+        return e ? std::atoi(e) : 0;
+    }();
+    if (forced >= 1 && (uint32_t)forced <= 2 + L) return (uint32_t)forced;
+    return (L == 4 && B >= 16) ? 4 : 2 + L;
 }
 
 // ---- launcher --------------------------------------------------------------------------------------
@@ -239,14 +259,15 @@ cudaError_t launch_fused_mul(const KCtx& k, uint32_t B, const u64* a, const u64*
     if ((e = dispatch_cols(k, B, nullptr, nullptr, nullptr, nullptr, th, rh, dh, 3)) != cudaSuccess) return e;
     const dim3 rg(row_tiles, L, B);
     const size_t rs = (2 + L) * row_arr + tw_bytes;
+    const uint32_t rt = relin_groups(L, B) * kGroup;
     switch (L) {
-        case 1: k_rows_relin<1><<<rg, 3 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
-        case 2: k_rows_relin<2><<<rg, 4 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
-        case 3: k_rows_relin<3><<<rg, 5 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
-        case 4: k_rows_relin<4><<<rg, 6 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
-        case 5: k_rows_relin<5><<<rg, 7 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
-        case 6: k_rows_relin<6><<<rg, 8 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
-        default: k_rows_relin<7><<<rg, 9 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
+        case 1: k_rows_relin<1><<<rg, rt, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
+        case 2: k_rows_relin<2><<<rg, rt, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
+        case 3: k_rows_relin<3><<<rg, rt, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
+        case 4: k_rows_relin<4><<<rg, rt, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
+        case 5: k_rows_relin<5><<<rg, rt, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
+        case 6: k_rows_relin<6><<<rg, rt, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
+        default: k_rows_relin<7><<<rg, rt, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
     }
     return cudaGetLastError();
 }
