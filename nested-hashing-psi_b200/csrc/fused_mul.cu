@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_inv(const DevTables* __r
 // grid (R/8, LT, B), 4 groups (a0, a1, b0, b1 of limb blockIdx.y); a: [B][2][L][N] EVALUATION (Q limbs
 // are used as given), e1p/e2h from (2); th: [B][3][LT][N] row-inverse halves
 __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_tensor(const DevTables* __restrict__ tab, uint32_t logN,
-                                                               const u64* __restrict__ a, const u64* __restrict__ e1p,
+                                                               const u64* __restrict__ a_, const u64* __restrict__ e1p,
                                                                const u64* __restrict__ e2h, u64* __restrict__ th) {
     extern __shared__ __align__(16) u64 smem[];
     const uint32_t N = 1u << logN, L = tab->L, Lp = tab->Lp, LT = L + Lp;
@@ -57,12 +57,8 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_tensor(const DevTables* 
     const uint32_t l = blockIdx.y, tile_base = blockIdx.x * M;
     const size_t bin = blockIdx.z;
     const ModDev& md = tab->mods[l];
-    const uint32_t comp = g & 1;
-    const u64* src;
-    if (g < 2)
-        src = l < L ? a + ((bin * 2 + comp) * L + l) * (size_t)N : e1p + ((bin * 2 + comp) * Lp + (l - L)) * (size_t)N;
-    else
-        src = e2h + ((bin * 2 + comp) * LT + l) * (size_t)N;
+    // groups per CTA: 4 (one array each) or fewer, arrays dealt round-robin (tensor_groups() below)
+    const uint32_t ng = blockDim.x / kGroup;
     __shared__ __align__(8) uint64_t tw_bar;
     ulonglong2* tws_f = reinterpret_cast<ulonglong2*>(smem);                  // forward twiddles of this row tile
     ulonglong2* tws_i = reinterpret_cast<ulonglong2*>(smem + kRowTwWords);    // inverse twiddles
@@ -74,14 +70,25 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_tensor(const DevTables* 
         stage_row_twiddles(tws_f, md.ftw_rows, blockIdx.x, &tw_bar);
         stage_row_twiddles(tws_i, md.itw_rows, blockIdx.x, &tw_bar);
     }
-    load_rows(arr + g * P, src + tile_base, tid);
+    for (uint32_t a = g; a < 4; a += ng) {
+        const uint32_t comp = a & 1;
+        const u64* src;
+        if (a < 2)
+            src = l < L ? a_ + ((bin * 2 + comp) * L + l) * (size_t)N : e1p + ((bin * 2 + comp) * Lp + (l - L)) * (size_t)N;
+        else
+            src = e2h + ((bin * 2 + comp) * LT + l) * (size_t)N;
+        load_rows(arr + a * P, src + tile_base, tid);
+    }
     loads_wait();
     __syncthreads();
     mbar_wait(&tw_bar, 0);
     // the Q limbs of the first operand are already in EVALUATION form: arrays 0, 1 are skipped for l < L
     const uint32_t first = l < L ? 2 : 0;
-    transform_rows<false>(tab, arr + first * P, P, 4 - first, [l](uint32_t) { return l; }, g >= first ? g - first : 4,
-                          4 - first, logN, tile_base, tid, tws_f);
+    if (ng == 4)  // one group per array: groups 0, 1 idle for l < L
+        transform_rows<false>(tab, arr + first * P, P, 4 - first, [l](uint32_t) { return l; }, g >= first ? g - first : 4,
+                              4 - first, logN, tile_base, tid, tws_f);
+    else
+        transform_rows<false>(tab, arr + first * P, P, 4 - first, [l](uint32_t) { return l; }, g, ng, logN, tile_base, tid, tws_f);
     __syncthreads();  // the tensor product reads all four arrays
 
     // Tensor product with ONE Montgomery reduction per output: the factor R^-1 it leaves is undone for
@@ -102,8 +109,8 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_tensor(const DevTables* 
         arr[2 * P + sl(j)] = mont_redc_lazy(hi, lo, q, qinv);
     }
     __syncthreads();
-    transform_rows<true>(tab, arr, P, 3, [l](uint32_t) { return l; }, g, 4, logN, tile_base, tid, tws_i);
-    if (g < 3) store_rows(arr + g * P, th + ((bin * 3 + g) * LT + l) * (size_t)N + tile_base, tid);
+    transform_rows<true>(tab, arr, P, 3, [l](uint32_t) { return l; }, g, ng, logN, tile_base, tid, tws_i);
+    for (uint32_t a = g; a < 3; a += ng) store_rows(arr + a * P, th + ((bin * 3 + a) * LT + l) * (size_t)N + tile_base, tid);
 }
 
 // ---- (5) rows: forward, key-switch inner product, add (c0, c1), mask ------------------------------
@@ -204,6 +211,15 @@ static uint32_t relin_groups(uint32_t L, uint32_t B) {
     return (L == 4 && B >= 16) ? 4 : 2 + L;
 }
 
+// groups per k_rows_tensor CTA (PSI_TENSOR_GROUPS=n: experiment switch; 4 = one group per array)
+static uint32_t tensor_groups() {
+    static const int forced = [] {
+        const char* e = std::getenv("PSI_TENSOR_GROUPS");
+        return e ? std::atoi(e) : 0;
+    }();
+    return (forced >= 1 && forced <= 4) ? (uint32_t)forced : 4;
+}
+
 // ---- launcher --------------------------------------------------------------------------------------
 // The column kernels are instantiated for the limb counts BFVrns produces for this path: sizeQ 1..7 (depth 3
 // gives 4, depth 5 — E >= 500, BatchedFHEPSIClient.cpp:50-53 — gives 6 at N = 16384), sizeP = sizeQ or
@@ -255,7 +271,7 @@ cudaError_t launch_fused_mul(const KCtx& k, uint32_t B, const u64* a, const u64*
     k_rows_inv<<<dim3(row_tiles, L, B), 4 * kGroup, 4 * row_arr + tw_bytes, k.s>>>(k.tab, k.logN, a, b, ha, hb, ops);
     if ((e = dispatch_cols(k, B, ha, hb, e1p, e2h, nullptr, nullptr, nullptr, (int)ops - 1)) != cudaSuccess) return e;
     if (!(ops & 2u)) return cudaGetLastError();
-    k_rows_tensor<<<dim3(row_tiles, LT, B), 4 * kGroup, 4 * row_arr + 2 * tw_bytes, k.s>>>(k.tab, k.logN, a, e1p, e2h, th);
+    k_rows_tensor<<<dim3(row_tiles, LT, B), tensor_groups() * kGroup, 4 * row_arr + 2 * tw_bytes, k.s>>>(k.tab, k.logN, a, e1p, e2h, th);
     if ((e = dispatch_cols(k, B, nullptr, nullptr, nullptr, nullptr, th, rh, dh, 3)) != cudaSuccess) return e;
     const dim3 rg(row_tiles, L, B);
     const size_t rs = (2 + L) * row_arr + tw_bytes;
