@@ -67,6 +67,8 @@ def main():
                 print(json.dumps({"MISMATCH": "mul_ctct", "N": N, "L": L, "variant": v, "modes": [m1, m2]}), flush=True)
         # one small run() with the same context
         K, b_, E = int(rng.choice([2, 2, 3])), int(rng.integers(1, 6)), int(rng.integers(1, 10))
+        if L == 4 and N <= 4096 and rng.integers(2) == 0:
+            b_, E = int(rng.integers(16, 27)), int(rng.integers(1, 4))  # >= 16 bins per launch: the four-group k_rows_relin shape
         pt, mask = sc.random_pt(rng, params, (K, b_, E)), sc.random_pt(rng, params, (b_,))
         idx, minus = sc.random_ct(rng, params, (K, E)), sc.random_ct(rng, params)
         cc.db_load_limbs(pt, mask)
@@ -76,6 +78,23 @@ def main():
         if not np.array_equal(cc.result_get(), o.run(pt, mask, idx, minus, evk_b, evk_a, nthreads=8)):
             bad += 1
             print(json.dumps({"MISMATCH": "run", "N": N, "L": L, "variant": v, "shape": [K, b_, E]}), flush=True)
+        # one non-batched collection (BV contexts only): fused key switch for N >= 1024, generic kernels below
+        if not v.get("ks_technique"):
+            n_pie, Kn, bn = int(rng.integers(1, 3)), int(rng.integers(1, 3)), int(rng.choice([2, 3, 4, 5, 8]))
+            key_index = list(dict.fromkeys(o.eval_sum_indices(bn) + [o.find_automorphism_index(-i) for i in range(1, bn)]))
+            kb, ka = sc.random_pt(rng, params, (len(key_index), L)), sc.random_pt(rng, params, (len(key_index), L))
+            ptn, maskn, merge = sc.random_pt(rng, params, (n_pie, Kn, bn)), sc.random_pt(rng, params, (n_pie, Kn)), sc.random_pt(rng, params)
+            idxn = sc.random_ct(rng, params, (n_pie, Kn))
+            m1 = int(rng.integers(6))
+            if m1 < 5:
+                idxn[0, 0] = extreme_ct(rng, params, m1)
+            cc.InsertEvalAutomorphismKeys(key_index, kb, ka)
+            cc.nb_db_load_limbs(ptn, maskn, merge)
+            got = cc.nb_run(idxn)
+            trials += 1
+            if not all(np.array_equal(got[p], o.nb_run(idxn[p], ptn[p], merge, maskn[p], key_index, kb, ka)) for p in range(n_pie)):
+                bad += 1
+                print(json.dumps({"MISMATCH": "nb_run", "N": N, "L": L, "shape": [n_pie, Kn, bn]}), flush=True)
         cc.close()
     print(json.dumps({"fuzz_trials": trials, "mismatches": bad, "seconds": budget}), flush=True)
     sys.exit(1 if bad else 0)
