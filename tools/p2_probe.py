@@ -29,7 +29,7 @@ def main():
     b = int(args[0]) if args else 47
     groups = int(args[1]) if len(args) > 1 else 0
     E, K = 2, 2
-    params = P.params_generate(16384, T32, 3)
+    params = P.params_generate(16384, T32, 3, int(os.environ.get("P2_L", "0")))  # P2_L: override sizeQ (0 = depth 3's)
     L = params.L
     rng = np.random.default_rng(5)
     cc = P.CryptoContext(params)
