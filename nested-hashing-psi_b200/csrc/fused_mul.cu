@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_inv(const DevTables* __r
 // grid (R/8, LT, B), 4 groups (a0, a1, b0, b1 of limb blockIdx.y); a: [B][2][L][N] EVALUATION (Q limbs
 // are used as given), e1p/e2h from (2); th: [B][3][LT][N] row-inverse halves
 __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_tensor(const DevTables* __restrict__ tab, uint32_t logN,
-                                                               const u64* __restrict__ a_, const u64* __restrict__ e1p,
+                                                               const u64* __restrict__ a, const u64* __restrict__ e1p,
                                                                const u64* __restrict__ e2h, u64* __restrict__ th) {
     extern __shared__ __align__(16) u64 smem[];
     const uint32_t N = 1u << logN, L = tab->L, Lp = tab->Lp, LT = L + Lp;
@@ -57,8 +57,12 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_tensor(const DevTables* 
     const uint32_t l = blockIdx.y, tile_base = blockIdx.x * M;
     const size_t bin = blockIdx.z;
     const ModDev& md = tab->mods[l];
-    // groups per CTA: 4 (one array each) or fewer, arrays dealt round-robin (tensor_groups() below)
-    const uint32_t ng = blockDim.x / kGroup;
+    const uint32_t comp = g & 1;
+    const u64* src;
+    if (g < 2)
+        src = l < L ? a + ((bin * 2 + comp) * L + l) * (size_t)N : e1p + ((bin * 2 + comp) * Lp + (l - L)) * (size_t)N;
+    else
+        src = e2h + ((bin * 2 + comp) * LT + l) * (size_t)N;
     __shared__ __align__(8) uint64_t tw_bar;
     ulonglong2* tws_f = reinterpret_cast<ulonglong2*>(smem);                  // forward twiddles of this row tile
     ulonglong2* tws_i = reinterpret_cast<ulonglong2*>(smem + kRowTwWords);    // inverse twiddles
@@ -70,25 +74,14 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_tensor(const DevTables* 
         stage_row_twiddles(tws_f, md.ftw_rows, blockIdx.x, &tw_bar);
         stage_row_twiddles(tws_i, md.itw_rows, blockIdx.x, &tw_bar);
     }
-    for (uint32_t a = g; a < 4; a += ng) {
-        const uint32_t comp = a & 1;
-        const u64* src;
-        if (a < 2)
-            src = l < L ? a_ + ((bin * 2 + comp) * L + l) * (size_t)N : e1p + ((bin * 2 + comp) * Lp + (l - L)) * (size_t)N;
-        else
-            src = e2h + ((bin * 2 + comp) * LT + l) * (size_t)N;
-        load_rows(arr + a * P, src + tile_base, tid);
-    }
+    load_rows(arr + g * P, src + tile_base, tid);
     loads_wait();
     __syncthreads();
     mbar_wait(&tw_bar, 0);
     // the Q limbs of the first operand are already in EVALUATION form: arrays 0, 1 are skipped for l < L
     const uint32_t first = l < L ? 2 : 0;
-    if (ng == 4)  // one group per array: groups 0, 1 idle for l < L
-        transform_rows<false>(tab, arr + first * P, P, 4 - first, [l](uint32_t) { return l; }, g >= first ? g - first : 4,
-                              4 - first, logN, tile_base, tid, tws_f);
-    else
-        transform_rows<false>(tab, arr + first * P, P, 4 - first, [l](uint32_t) { return l; }, g, ng, logN, tile_base, tid, tws_f);
+    transform_rows<false>(tab, arr + first * P, P, 4 - first, [l](uint32_t) { return l; }, g >= first ? g - first : 4,
+                          4 - first, logN, tile_base, tid, tws_f);
     __syncthreads();  // the tensor product reads all four arrays
 
     // Tensor product with ONE Montgomery reduction per output: the factor R^-1 it leaves is undone for
@@ -109,16 +102,18 @@ __global__ void __launch_bounds__(4 * kGroup, 3) k_rows_tensor(const DevTables* 
         arr[2 * P + sl(j)] = mont_redc_lazy(hi, lo, q, qinv);
     }
     __syncthreads();
-    transform_rows<true>(tab, arr, P, 3, [l](uint32_t) { return l; }, g, ng, logN, tile_base, tid, tws_i);
-    for (uint32_t a = g; a < 3; a += ng) store_rows(arr + a * P, th + ((bin * 3 + a) * LT + l) * (size_t)N + tile_base, tid);
+    transform_rows<true>(tab, arr, P, 3, [l](uint32_t) { return l; }, g, 4, logN, tile_base, tid, tws_i);
+    if (g < 3) store_rows(arr + g * P, th + ((bin * 3 + g) * LT + l) * (size_t)N + tile_base, tid);
 }
 
 // ---- (5) rows: forward, key-switch inner product, add (c0, c1), mask ------------------------------
 // grid (R/8, L, B), 2 + L groups (c0, c1, digit 0..L-1 of limb blockIdx.y).  evk_bR / evk_aR / maskR are
 // in Montgomery form (times R = 2^64), so each modular product is one 128-bit multiply-accumulate plus a
 // Montgomery reduction that leaves no stray factor:  REDC(sum_i d_i * evkR_i) = sum_i d_i * evk_i.
-template <int L>
-__global__ void __launch_bounds__((2 + L) * kGroup, L <= 4 ? 2 : 1)
+// NG = groups per CTA: 2 + L (one array each) or 4 (arrays dealt round-robin); a template constant, because a run-time group
+// count keeps a real loop around the unrolled register passes (measured: +2.6 % of phase 2 at the same shape)
+template <int L, int NG>
+__global__ void __launch_bounds__(NG * kGroup, NG * kGroup <= 256 ? 3 : (NG * kGroup <= 384 ? 2 : 1))
     k_rows_relin(const DevTables* __restrict__ tab, uint32_t logN, const u64* __restrict__ rh, const u64* __restrict__ dh,
                  const u64* __restrict__ evk_bR, const u64* __restrict__ evk_aR, const u64* __restrict__ maskR,
                  u64* __restrict__ out) {
@@ -129,8 +124,7 @@ __global__ void __launch_bounds__((2 + L) * kGroup, L <= 4 ? 2 : 1)
     const uint32_t kk = blockIdx.y, tile_base = blockIdx.x * M;
     const size_t bin = blockIdx.z;
     const ModDev& md = tab->mods[kk];
-    // groups per CTA: 2 + L (one array each) or fewer (arrays dealt round-robin; see relin_groups() below)
-    const uint32_t ng = blockDim.x / kGroup;
+    constexpr uint32_t ng = NG;
     __shared__ __align__(8) uint64_t tw_bar;
     ulonglong2* tws = reinterpret_cast<ulonglong2*>(smem);  // forward twiddles of this row tile
     u64* arr = smem + kRowTwWords;
@@ -140,6 +134,7 @@ __global__ void __launch_bounds__((2 + L) * kGroup, L <= 4 ? 2 : 1)
         mbar_expect_tx(&tw_bar, kRowTwEntries * 16u);
         stage_row_twiddles(tws, md.ftw_rows, blockIdx.x, &tw_bar);
     }
+#pragma unroll
     for (uint32_t a = g; a < 2 + L; a += ng) {
         const u64* src = a < 2 ? rh + ((bin * 2 + a) * L + kk) * (size_t)N : dh + ((bin * L + (a - 2)) * L + kk) * (size_t)N;
         load_rows(arr + a * P, src + tile_base, tid);
@@ -197,30 +192,26 @@ cudaError_t launch_to_montgomery(const KCtx& k, uint32_t groups, const u64* src,
     return cudaGetLastError();
 }
 
-// Groups per k_rows_relin CTA.  One group per array (2 + L) is the natural shape; with L = 4 and at least 16 bins in the
-// launch, FOUR groups that take the six arrays round-robin (256 threads, three CTAs per SM instead of two 384-thread
-// ones) are faster: MEASURED at config B, bit-identical results, phase 2 1.0408 -> 1.0246 ms at 47 bins (three
-// alternating repetitions each, +-0.0005), 0.5402 -> 0.5331 at 24, no change at 12, 0.182 -> 0.187 at 6 (there the
-// longer CTAs lengthen the single partial wave); 3 groups 1.027, 5 groups 1.064.  PSI_RELIN_GROUPS=n forces n (tuning).
+template <int L>
+static cudaError_t relin_attr(int bytes) {
+    cudaError_t e = cudaFuncSetAttribute(k_rows_relin<L, 2 + L>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess || L <= 2) return e;
+    return cudaFuncSetAttribute(k_rows_relin<L, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+// Groups per k_rows_relin CTA: one per array (2 + L), or four that take the arrays round-robin (PSI_RELIN_GROUPS=4,
+// or the policy below).  See profiles/r02_phase2_experiments.md 8 for the measurements.
 static uint32_t relin_groups(uint32_t L, uint32_t B) {
     static const int forced = [] {
         const char* e = std::getenv("PSI_RELIN_GROUPS");
         return e ? std::atoi(e) : 0;
     }();
-    if (forced >= 1 && (uint32_t)forced <= 2 + L) return (uint32_t)forced;
-    // L = 5, 6, 7 (448 - 576 threads, one CTA per SM): four groups are faster at every bin count measured (24 bins: -5.5 %,
-    // -4.7 %, -3.6 % of phase 2; 6 and 12 bins: -1 % ... -5 %); L <= 3: the one-group-per-array shape wins (L = 3: +2 %)
-    if (L >= 5) return 4;
-    return (L == 4 && B >= 16) ? 4 : 2 + L;
-}
-
-// groups per k_rows_tensor CTA (PSI_TENSOR_GROUPS=n: experiment switch; 4 = one group per array)
-static uint32_t tensor_groups() {
-    static const int forced = [] {
-        const char* e = std::getenv("PSI_TENSOR_GROUPS");
-        return e ? std::atoi(e) : 0;
-    }();
-    return (forced >= 1 && forced <= 4) ? (uint32_t)forced : 4;
+    (void)B;
+    if (forced == 4) return 4;
+    if (forced > 0) return 2 + L;
+    // L = 4 (the BASELINE contexts): one group per array is faster at every bin count (47 bins: 1.0154 against 1.0227 ms).
+    // L >= 5 (448 - 576 threads, one CTA per SM): four groups, phase 2 -1.3 % ... -1.8 % at 6 and 24 bins.
+    return L >= 5 ? 4 : 2 + L;
 }
 
 // ---- launcher --------------------------------------------------------------------------------------
@@ -260,13 +251,13 @@ cudaError_t launch_fused_mul(const KCtx& k, uint32_t B, const u64* a, const u64*
         if ((e = dispatch_cols(k, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, -1)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(k_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(k_rows_tensor, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(k_rows_relin<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(k_rows_relin<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(k_rows_relin<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(k_rows_relin<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(k_rows_relin<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(k_rows_relin<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
-        return cudaFuncSetAttribute(k_rows_relin<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if ((e = relin_attr<1>(80 * 1024)) != cudaSuccess) return e;
+        if ((e = relin_attr<2>(80 * 1024)) != cudaSuccess) return e;
+        if ((e = relin_attr<3>(80 * 1024)) != cudaSuccess) return e;
+        if ((e = relin_attr<4>(80 * 1024)) != cudaSuccess) return e;
+        if ((e = relin_attr<5>(100 * 1024)) != cudaSuccess) return e;
+        if ((e = relin_attr<6>(100 * 1024)) != cudaSuccess) return e;
+        return relin_attr<7>(100 * 1024);
     }
     if (B == 0) return cudaSuccess;
 
@@ -274,20 +265,33 @@ cudaError_t launch_fused_mul(const KCtx& k, uint32_t B, const u64* a, const u64*
     k_rows_inv<<<dim3(row_tiles, L, B), 4 * kGroup, 4 * row_arr + tw_bytes, k.s>>>(k.tab, k.logN, a, b, ha, hb, ops);
     if ((e = dispatch_cols(k, B, ha, hb, e1p, e2h, nullptr, nullptr, nullptr, (int)ops - 1)) != cudaSuccess) return e;
     if (!(ops & 2u)) return cudaGetLastError();
-    k_rows_tensor<<<dim3(row_tiles, LT, B), tensor_groups() * kGroup, 4 * row_arr + 2 * tw_bytes, k.s>>>(k.tab, k.logN, a, e1p, e2h, th);
+    k_rows_tensor<<<dim3(row_tiles, LT, B), 4 * kGroup, 4 * row_arr + 2 * tw_bytes, k.s>>>(k.tab, k.logN, a, e1p, e2h, th);
     if ((e = dispatch_cols(k, B, nullptr, nullptr, nullptr, nullptr, th, rh, dh, 3)) != cudaSuccess) return e;
     const dim3 rg(row_tiles, L, B);
     const size_t rs = (2 + L) * row_arr + tw_bytes;
-    const uint32_t rt = relin_groups(L, B) * kGroup;
+    const bool four = relin_groups(L, B) == 4 && L > 2;
+#define PSI_RELIN_CASE(l)                                                                                              \
+    case l:                                                                                                            \
+        if (four)                                                                                                      \
+            k_rows_relin<l, 4><<<rg, 4 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out);           \
+        else                                                                                                           \
+            k_rows_relin<l, 2 + l><<<rg, (2 + l) * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); \
+        break;
     switch (L) {
-        case 1: k_rows_relin<1><<<rg, rt, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
-        case 2: k_rows_relin<2><<<rg, rt, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
-        case 3: k_rows_relin<3><<<rg, rt, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
-        case 4: k_rows_relin<4><<<rg, rt, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
-        case 5: k_rows_relin<5><<<rg, rt, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
-        case 6: k_rows_relin<6><<<rg, rt, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
-        default: k_rows_relin<7><<<rg, rt, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out); break;
+        PSI_RELIN_CASE(1)
+        PSI_RELIN_CASE(2)
+        PSI_RELIN_CASE(3)
+        PSI_RELIN_CASE(4)
+        PSI_RELIN_CASE(5)
+        PSI_RELIN_CASE(6)
+        default:
+            if (four)
+                k_rows_relin<7, 4><<<rg, 4 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out);
+            else
+                k_rows_relin<7, 9><<<rg, 9 * kGroup, rs, k.s>>>(k.tab, k.logN, rh, dh, evk_b, evk_a, mask, out);
+            break;
     }
+#undef PSI_RELIN_CASE
     return cudaGetLastError();
 }
 
