@@ -9,9 +9,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 B = os.path.join(ROOT, "nested-hashing-psi_b200", "build")
 tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
-WANT = [("psi_kernels.o", r"k_mac_tmaILi2ELi8ELi2E"), ("fused_mul.o", r"k_rows_relinILi4E"), ("fused_mul.o", r"k_rows_tensor"),
+WANT = [("psi_kernels.o", r"k_mac_tmaILi2ELi8ELi2E"), ("fused_mul.o", r"k_rows_relinILi4ELi6E"), ("fused_mul.o", r"k_rows_tensor"),
         ("fused_mul.o", r"k_rows_inv"), ("fused_cols_a.o|fused_cols_b.o|fused_cols_c.o|fused_cols_d.o", r"k_cols_scaleILi4ELi4ELi14E"),
-        ("fused_cols_a.o|fused_cols_b.o|fused_cols_c.o|fused_cols_d.o", r"k_cols_extendILi4ELi4ELi14E"), ("ntt.o", r"k_nttILb0E")]
+        ("fused_cols_a.o|fused_cols_b.o|fused_cols_c.o|fused_cols_d.o", r"k_cols_extendILi4ELi4ELi14E"), ("ntt.o", r"k_nttILb0E"),
+        ("fused_nb.o", r"k_nb_rows_inv"), ("fused_nb.o", r"k_nb_cols_digitsILi4ELi14E"), ("fused_nb.o", r"k_nb_rows_ksILi4ELb1E")]
 CLS = [("UBLKCP", r"^UBLKCP"), ("LDGSTS", r"^LDGSTS"), ("SYNCS.*", r"^SYNCS"), ("IMAD.WIDE*", r"^IMAD\.WIDE"),
        ("IMAD / IMAD.HI", r"^IMAD(\.U32|\.HI\.U32|\.HI)?$"), ("IMAD.X/.IADD/.MOV/.SHL (adds and moves on the multiplier pipe)", r"^IMAD\.(X|IADD|MOV|SHL)"),
        ("IADD3*", r"^IADD3"), ("LDS/STS", r"^(LDS|STS)"), ("LDG/STG", r"^(LDG|STG)"), ("BAR", r"^BAR"), ("SHFL", r"^SHFL"),
