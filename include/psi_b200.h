@@ -416,7 +416,8 @@ int psi_pie_create_multi(psi_multi* m, const psi_params* params, psi_hct* hct, u
  * Non-batched FHEHIPPIE: one private indexed equality check per outer cell of the server's nested
  * cuckoo table.  Replaces FHEHIPPIE (FHEHIPPIE.hpp:18-50; ctor FHEHIPPIE.cpp:9-59, run :61-77) and the loop
  * FHEHIPPIECollection::runAll makes over it (SimpleFHEPSIServer.cpp:126-160): the whole collection of PIEs is one
- * database and psi_nb_run evaluates a contiguous range of them in lock step.  BFV, BV key switching (digit size 0).
+ * database and psi_nb_run evaluates a contiguous range of them in lock step.  BFV; key switching as the context says:
+ * BV with digit size 0 (fused kernels) or HYBRID (one kernel per operation).
  * Per PIE: K hash functions, b bins of b positions (the ctor demands a square inner table, FHEHIPPIE.cpp:13-16).
  * Results come back per hash function in natural order; permutationVector (FHEHIPPIE.cpp:74) is the caller's.
  * ------------------------------------------------------------------------------------------ */
@@ -425,7 +426,8 @@ int psi_pie_create_multi(psi_multi* m, const psi_params* params, psi_hct* hct, u
 int psi_nb_eval_sum_indices(uint32_t N, uint32_t batch_size, uint64_t* out /*[<= 32]*/, uint32_t* n);
 int psi_nb_rotation_index(uint32_t N, int64_t i, uint64_t* out);
 /* DeserializeEvalSumKey + DeserializeEvalAutomorphismKey (SimpleFHEPSIServer.cpp:45-62): one BV key per automorphism
- * index, key_b / key_a [n_keys][L][L][N] EVALUATION ((*evalKey->GetBVector())[digit] / GetAVector, limb by limb). */
+ * index, key_b / key_a [n_keys][L][L][N] EVALUATION ((*evalKey->GetBVector())[digit] / GetAVector, limb by limb);
+ * HYBRID contexts: [n_keys][numPartQ][L + Lk][N], the layout of psi_set_relin_key. */
 int psi_nb_set_automorphism_keys(psi_ctx* c, uint32_t n_keys, const uint64_t* auto_index, const uint64_t* key_b,
                                  const uint64_t* key_a);
 /* the ctor's vectorizedCT / preCalcRandomMask of n_pie PIEs (FHEHIPPIE.cpp:25-58) as EVALUATION limbs:

@@ -36,6 +36,8 @@ struct NbState {
     // work buffers for one chunk of PIEs
     uint32_t chunk_pies = 0;
     DevBuf<u64> idx, cur, nxt, coef, dig, out;
+    DevBuf<u64> ext, sw;         // HYBRID key switching: inner products over Q + pk, ApproxModDown scratch
+    size_t key_words = 0;        // words of one key component: L*L*N (BV) or numPartQ*(L+Lk)*N (HYBRID)
     DevBuf<int> sel_key;        // [steps + b]: key slot per EvalSum step, then per bin (-1 = identity, bin 0)
     DevBuf<uint32_t> sel_ginv;  // inverse automorphism index of the same entries
     uint32_t n_sum = 0;
@@ -186,6 +188,104 @@ __global__ void __launch_bounds__(256) k_nb_ks_apply(const DevTables* __restrict
     o[LN + dst] = v1;
 }
 
+// ---- HYBRID key switching (KeySwitchHYBRID, recalled; the relinearisation form lives in psi_kernels.cu) ------------
+// c1 (COEFFICIENT, [B][L][N]) is cut into ks_parts digits of ks_alpha consecutive limbs; digit j is lifted to every other
+// limb of Q + pk by ApproxSwitchCRTBasis, its own limbs keep the coefficients.  dig: [B][parts][L+Lk][N] COEFFICIENT.
+__global__ void __launch_bounds__(256) k_nb_hybrid_modup(const DevTables* __restrict__ tab, uint32_t N, uint32_t B,
+                                                         const u64* __restrict__ coef, u64* __restrict__ dig) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)B * N) return;
+    const size_t item = tid / N;
+    const uint32_t n = tid % N;
+    const int L = tab->L, Lk = tab->Lk, LE = L + Lk, parts = tab->ks_parts, alpha = tab->ks_alpha;
+    u64 x[PSI_MAX_LIMBS], y[PSI_MAX_LIMBS];
+#pragma unroll
+    for (int i = 0; i < PSI_MAX_LIMBS; i++)
+        if (i < L) {
+            x[i] = coef[(item * L + i) * N + n];
+            y[i] = mul_shoup(x[i], tab->PartQHatInvModq[i], tab->PartQHatInvModq_s[i], tab->mods[i].q);
+        }
+    for (int j = 0; j < parts; j++) {
+        const int lo = j * alpha, hi = min(L, lo + alpha);
+        for (int m = 0; m < LE; m++) {
+            u64 v;
+            if (m >= lo && m < hi) {
+                v = x[m];
+            } else {
+                const ModDev& md = tab->mods[m < L ? m : tab->L + tab->Lp + 1 + (m - L)];
+                u64 h = 0, l = 0;
+#pragma unroll
+                for (int i = 0; i < PSI_MAX_LIMBS; i++)
+                    if (i >= lo && i < hi) mac128(h, l, y[i], tab->PartQHatModt[i][m]);
+                v = barrett128(h, l, md.q, md.mu_hi, md.mu_lo);
+            }
+            dig[((item * parts + j) * LE + m) * N + n] = v;
+        }
+    }
+}
+
+// ext[item][comp][m][n] = sum_j dig[item][j][m][n] * key_comp[slot(item)][j][m][n] over the extended basis, EVALUATION
+__global__ void __launch_bounds__(256) k_nb_hybrid_inner(const DevTables* __restrict__ tab, uint32_t N, uint32_t B,
+                                                         const u64* __restrict__ dig, const u64* __restrict__ key_b,
+                                                         const u64* __restrict__ key_a, const int* __restrict__ sel_key,
+                                                         uint32_t sel_mod, u64* __restrict__ ext) {
+    const int L = tab->L, LE = L + tab->Lk, parts = tab->ks_parts;
+    const size_t LEN = (size_t)LE * N;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)B * LEN) return;
+    const size_t item = tid / LEN, c = tid % LEN;
+    const int slot = sel_key[sel_mod ? (uint32_t)(item % sel_mod) : 0];
+    if (slot < 0) return;  // identity item: k_nb_hybrid_finish copies it
+    const int m = (int)(c / N);
+    const ModDev& md = tab->mods[m < L ? m : tab->L + tab->Lp + 1 + (m - L)];
+    const u64* kb = key_b + (size_t)slot * parts * LEN;
+    const u64* ka = key_a + (size_t)slot * parts * LEN;
+    u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+    for (int j = 0; j < parts; j++) {
+        const u64 d = dig[(item * parts + j) * LEN + c];
+        mac128(h0, l0, d, kb[(size_t)j * LEN + c]);
+        mac128(h1, l1, d, ka[(size_t)j * LEN + c]);
+    }
+    ext[(item * 2) * LEN + c] = barrett128(h0, l0, md.q, md.mu_hi, md.mu_lo);
+    ext[(item * 2 + 1) * LEN + c] = barrett128(h1, l1, md.q, md.mu_hi, md.mu_lo);
+}
+
+// ApproxModDown, second half, + KeySwitchInPlace (c0 += d0, c1 = d1) + AutomorphismTransform (+ the EvalAdd of EvalSum)
+//   cur: [B][2][L][N] EVAL, ext: [B][2][L+Lk][N] (Q limbs EVAL), sw: [B][2][L][N] EVAL
+template <bool ADD>
+__global__ void __launch_bounds__(256) k_nb_hybrid_finish(const DevTables* __restrict__ tab, uint32_t N, uint32_t logN, uint32_t B,
+                                                          const u64* __restrict__ cur, const u64* __restrict__ ext,
+                                                          const u64* __restrict__ sw, const int* __restrict__ sel_key,
+                                                          const uint32_t* __restrict__ sel_ginv, uint32_t sel_mod,
+                                                          u64* __restrict__ out) {
+    const int L = tab->L, LE = L + tab->Lk;
+    const size_t LN = (size_t)L * N;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)B * LN) return;
+    const size_t item = tid / LN, c = tid % LN;
+    const uint32_t sel = sel_mod ? (uint32_t)(item % sel_mod) : 0;
+    const u64* ct = cur + item * 2 * LN;
+    u64* o = out + item * 2 * LN;
+    if (sel_key[sel] < 0) {
+        o[c] = ct[c];
+        o[LN + c] = ct[LN + c];
+        return;
+    }
+    const int i = (int)(c / N);
+    const ModDev& m = tab->mods[i];
+    const uint32_t j = (uint32_t)(c % N);
+    const size_t dst = (c - j) + automap(j, sel_ginv[sel], logN);
+#pragma unroll
+    for (int comp = 0; comp < 2; comp++) {
+        const u64 e = ext[((item * 2 + comp) * LE) * N + c];
+        const u64 d = submod(e, sw[(item * 2 + comp) * LN + c], m.q);
+        u64 r = mul_shoup(d, tab->PkInvModq[i], tab->PkInvModq_s[i], m.q);
+        if (comp == 0) r = addmod(r, ct[c], m.q);
+        if (ADD) r = addmod(r, ct[comp * LN + dst], m.q);
+        o[comp * LN + dst] = r;
+    }
+}
+
 // EvalMerge's EvalAdd chain over the b bins of a (pie, hf) group + EvalMult by the random mask (FHEHIPPIE.cpp:73)
 __global__ void __launch_bounds__(256) k_nb_sum_mask(const DevTables* __restrict__ tab, uint32_t N, uint32_t G, uint32_t b,
                                                      const u64* __restrict__ items, const u64* __restrict__ mask,
@@ -215,8 +315,6 @@ static NbState* nb_state(psi_ctx* c) {
 
 static int nb_check_ctx(psi_ctx* c) {
     if (!c) return set_error(PSI_ERR_INVALID, "null argument");
-    if (c->hybrid)
-        return set_error(PSI_ERR_INVALID, "the non-batched PIE implements BV key switching only (ks_technique = PSI_KS_BV)");
     return ensure_device(c);
 }
 
@@ -281,7 +379,12 @@ static int nb_prepare(psi_ctx* c, NbState* s, uint32_t pies) {
     CK(s->cur.alloc(items * 2 * LN));
     CK(s->nxt.alloc(items * 2 * LN));
     CK(s->coef.alloc(items * LN));
-    CK(s->dig.alloc(items * L * LN));
+    const size_t dig_polys = c->hybrid ? std::max<size_t>((size_t)L * L, (size_t)c->ks_parts * (L + c->Lk)) : (size_t)L * L;
+    CK(s->dig.alloc(items * dig_polys * N));
+    if (c->hybrid) {
+        CK(s->ext.alloc(items * 2 * (L + c->Lk) * N));
+        CK(s->sw.alloc(items * 2 * LN));
+    }
     s->chunk_pies = pies;
     return PSI_OK;
 }
@@ -297,6 +400,32 @@ static int nb_ks_step(psi_ctx* c, NbState* s, const KCtx& k, uint32_t B, uint32_
         std::swap(s->cur.p, s->nxt.p);
         std::swap(s->cur.n, s->nxt.n);
         s->launches += 3;
+        return PSI_OK;
+    }
+    if (c->hybrid) {  // KeySwitchHYBRID, one kernel per operation
+        const uint32_t Lk = c->Lk, LE = L + Lk, parts = c->ks_parts, pk0 = L + c->Lp + 1;
+        NttBatch hb{s->cur.p + LN, s->coef.p, B * L, L, 2 * LN, N, LN, 0, L};
+        CK(launch_ntt(k, hb, true));
+        k_nb_hybrid_modup<<<blocks_for((size_t)B * N), 256, 0, k.s>>>(k.tab, N, B, s->coef.p, s->dig.p);
+        CK(cudaGetLastError());
+        hb = NttBatch{s->dig.p, s->dig.p, B * parts * L, L, (size_t)LE * N, N, (size_t)LE * N, 0, L};
+        CK(launch_ntt(k, hb, false));
+        hb = NttBatch{s->dig.p + LN, s->dig.p + LN, B * parts * Lk, Lk, (size_t)LE * N, N, (size_t)LE * N, pk0, Lk};
+        CK(launch_ntt(k, hb, false));
+        k_nb_hybrid_inner<<<blocks_for((size_t)B * LE * N), 256, 0, k.s>>>(k.tab, N, B, s->dig.p, s->key_b.p, s->key_a.p, s->sel_key.p + sel0,
+                                                                        sel_mod, s->ext.p);
+        CK(cudaGetLastError());
+        hb = NttBatch{s->ext.p + LN, s->ext.p + LN, B * 2 * Lk, Lk, (size_t)LE * N, N, (size_t)LE * N, pk0, Lk};
+        CK(launch_ntt(k, hb, true));
+        CK(launch_hybrid_moddown(k, B, s->ext.p, s->sw.p));
+        hb = NttBatch{s->sw.p, s->sw.p, B * 2 * L, L, LN, N, LN, 0, L};
+        CK(launch_ntt(k, hb, false));
+        k_nb_hybrid_finish<ADD><<<blocks_for((size_t)B * LN), 256, 0, k.s>>>(k.tab, N, c->logN, B, s->cur.p, s->ext.p, s->sw.p,
+                                                                          s->sel_key.p + sel0, s->sel_ginv.p + sel0, sel_mod, s->nxt.p);
+        CK(cudaGetLastError());
+        std::swap(s->cur.p, s->nxt.p);
+        std::swap(s->cur.n, s->nxt.n);
+        s->launches += 9;
         return PSI_OK;
     }
     NttBatch nb{s->cur.p + LN, s->coef.p, B * L, L, 2 * LN, N, LN, 0, L};  // c1 of every item to COEFFICIENT
@@ -343,7 +472,8 @@ int psi_nb_set_automorphism_keys(psi_ctx* c, uint32_t n_keys, const uint64_t* au
     for (uint32_t i = 0; i < n_keys; i++)
         if (!(auto_index[i] & 1) || auto_index[i] >= m)
             return set_error(PSI_ERR_INVALID, "an automorphism index must be odd and below 2N");
-    const size_t words = (size_t)n_keys * c->L * c->L * c->N;
+    s->key_words = c->hybrid ? (size_t)c->ks_parts * (c->L + c->Lk) * c->N : (size_t)c->L * c->L * c->N;
+    const size_t words = (size_t)n_keys * s->key_words;
     CK(s->key_b.alloc(words));
     CK(s->key_a.alloc(words));
     CK(cudaMemcpy(s->key_b.p, key_b, words * sizeof(u64), cudaMemcpyHostToDevice));
@@ -429,10 +559,12 @@ int psi_nb_run(psi_ctx* c, uint32_t pie_begin, uint32_t pie_end, const uint64_t*
     // Chunks of PIEs: the index ciphertexts of chunk i + 1 go up and the results of chunk i - 1 come down while chunk i
     // is evaluated (copy streams beside the caller's; index and result buffers are double-buffered, the work buffers
     // are shared because the evaluations are ordered on one stream).  A chunk is at least ~128 items (enough CTAs for
-    // every launch), at most a quarter of the range, and its work buffers - (2 + 2 + 1 + L) polynomials per item - stay
-    // below ~6 GB.
+    // every launch), at most a quarter of the range, and its work buffers - (2 + 2 + 1 + L) polynomials per item with BV keys
+    // - stay below ~6 GB.
     const uint32_t n_range = pie_end - pie_begin;
-    const size_t per_pie = (size_t)K * b * (5 + L) * LN * sizeof(u64);
+    const size_t limbs_per_item = 5 * (size_t)L + (c->hybrid ? std::max<size_t>((size_t)L * L, (size_t)c->ks_parts * (L + c->Lk)) + 2 * (L + c->Lk) + 2 * L
+                                                             : (size_t)L * L);
+    const size_t per_pie = (size_t)K * b * limbs_per_item * N * sizeof(u64);
     const uint32_t min_pies = (uint32_t)((128 + (size_t)K * b - 1) / ((size_t)K * b));
     uint32_t chunk = std::max<uint32_t>(min_pies, (n_range + 3) / 4);
     chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(std::min<uint32_t>(chunk, n_range), (6ull << 30) / per_pie));

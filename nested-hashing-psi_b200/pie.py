@@ -329,10 +329,10 @@ class CryptoContext:
     # --- non-batched FHEHIPPIE (FHEHIPPIE.cpp, SimpleFHEPSIServer.cpp) ---------------------------
     def InsertEvalAutomorphismKeys(self, indices, key_b, key_a):
         """DeserializeEvalSumKey + DeserializeEvalAutomorphismKey (SimpleFHEPSIServer.cpp:45-62):
-        indices [n] automorphism indices, key_b / key_a [n][L][L][N]."""
+        indices [n] automorphism indices, key_b / key_a [n][L][L][N] (BV) or [n][numPartQ][L + Lk][N] (HYBRID)."""
         idx = np.ascontiguousarray(indices, dtype=np.uint64)
         (key_b, pb), (key_a, pa) = _u64(key_b), _u64(key_a)
-        assert key_b.shape == (len(idx), self.L, self.L, self.N) and key_a.shape == key_b.shape
+        assert key_b.shape == (len(idx),) + _evk_shape(self.params) and key_a.shape == key_b.shape
         check(lib().psi_nb_set_automorphism_keys(self._h, len(idx), idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), pb, pa))
 
     def nb_db_load_limbs(self, pt, mask, merge_pt):

@@ -66,6 +66,7 @@ def lib():
         L.orc_find_automorphism_index.argtypes = [ctypes.c_void_p, ctypes.c_int64]
         L.orc_eval_sum_indices.argtypes = [ctypes.c_void_p, ctypes.c_int, _u64p]
         L.orc_auto_keygen.argtypes = [ctypes.c_void_p, _u64p, ctypes.c_uint64, ctypes.c_uint64, _u64p, _u64p]
+        L.orc_auto_keygen_hybrid.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, _u64p, _u64p]
         L.orc_eval_automorphism.argtypes = [ctypes.c_void_p, _u64p, ctypes.c_uint64, _u64p, _u64p, _u64p]
         L.orc_nb_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _u64p, _u64p, _u64p, _u64p, ctypes.c_int,
                                  _u64p, _u64p, _u64p, _u64p]
@@ -242,13 +243,18 @@ class Oracle:
         n = lib().orc_eval_sum_indices(self._h, batch_size, _p(buf))
         return [int(v) for v in buf[:n]]
 
-    def auto_keygen(self, sk, seed, indices):
-        """EvalSumKeyGen / EvalRotateKeyGen: one BV key per automorphism index -> (key_b, key_a) [n][L][L][N]."""
+    def auto_keygen(self, sk, seed, indices, key_seed=None):
+        """EvalSumKeyGen / EvalRotateKeyGen: one key per automorphism index -> (key_b, key_a), [n] + evk_shape().
+        HYBRID contexts need key_seed (the seed keygen() was called with): the secret is re-derived over the special primes."""
         n = len(indices)
-        kb = np.empty((n, self.L, self.L, self.N), dtype=np.uint64)
+        kb = np.empty((n,) + self.evk_shape(), dtype=np.uint64)
         ka = np.empty_like(kb)
         for i, g in enumerate(indices):
-            lib().orc_auto_keygen(self._h, _p(sk), seed, int(g), _p(kb[i]), _p(ka[i]))
+            if self.hybrid:
+                assert key_seed is not None
+                lib().orc_auto_keygen_hybrid(self._h, key_seed, seed, int(g), _p(kb[i]), _p(ka[i]))
+            else:
+                lib().orc_auto_keygen(self._h, _p(sk), seed, int(g), _p(kb[i]), _p(ka[i]))
         return kb, ka
 
     def eval_automorphism(self, ct, g, key_b, key_a):

@@ -1115,13 +1115,130 @@ static void nb_keyswitch_core(const orc_ctx* c, const u64* x, const u64* key_b, 
     free(coef);
 }
 
+/* KeySwitchHYBRID::KeySwitchCore of one EVALUATION polynomial (recalled; the relinearisation form is orc_relin_hybrid):
+ * to COEFFICIENT, digits of alpha limbs lifted to Q + pk by ApproxSwitchCRTBasis, to EVALUATION, inner products with
+ * the key over the extended basis, ApproxModDown.  x: [L][N]; key_b / key_a: [parts][L+Lk][N]; d0, d1: [L][N] EVAL. */
+static void nb_keyswitch_core_hybrid(const orc_ctx* c, const u64* x, const u64* key_b, const u64* key_a, u64* d0, u64* d1) {
+    const int N = c->N, L = c->L, Lk = c->Lk, LE = L + Lk, parts = c->parts, alpha = c->alpha;
+    const psi_params* P = &c->P;
+    size_t polyQ = (size_t)L * N, polyE = (size_t)LE * N;
+    u64* coef = malloc(sizeof(u64) * polyQ);
+    u64* dig = malloc(sizeof(u64) * polyE);
+    u64* ext = calloc(2 * polyE, sizeof(u64));
+    u64* sw = malloc(sizeof(u64) * polyQ);
+    memcpy(coef, x, sizeof(u64) * polyQ);
+    for (int l = 0; l < L; l++) ntt_inv(coef + (size_t)l * N, &c->mq[l], N);
+    for (int j = 0; j < parts; j++) {
+        int lo = j * alpha, hi = lo + alpha < L ? lo + alpha : L;
+        for (int n = 0; n < N; n++) {
+            u64 y[PSI_MAX_LIMBS];
+            for (int i = lo; i < hi; i++) y[i] = mulmod(coef[(size_t)i * N + n], c->PartQHatInvModq[i], P->q[i]);
+            for (int m = 0; m < LE; m++) {
+                if (m >= lo && m < hi) {
+                    dig[(size_t)m * N + n] = coef[(size_t)m * N + n];
+                    continue;
+                }
+                const modctx* mm = m < L ? &c->mq[m] : &c->mk[m - L];
+                u128 sum = 0;
+                for (int i = lo; i < hi; i++) sum += (u128)y[i] * c->PartQHatModt[i][m];
+                dig[(size_t)m * N + n] = barrett128(sum, mm);
+            }
+        }
+        for (int m = 0; m < LE; m++) {
+            const modctx* mm = m < L ? &c->mq[m] : &c->mk[m - L];
+            ntt_fwd(dig + (size_t)m * N, mm, N);
+            const u64* kb = key_b + ((size_t)j * LE + m) * N;
+            const u64* ka = key_a + ((size_t)j * LE + m) * N;
+            u64 *o0 = ext + (size_t)m * N, *o1 = ext + polyE + (size_t)m * N;
+            for (int n = 0; n < N; n++) {
+                o0[n] = addmod(o0[n], barrett128((u128)dig[(size_t)m * N + n] * kb[n], mm), mm->q);
+                o1[n] = addmod(o1[n], barrett128((u128)dig[(size_t)m * N + n] * ka[n], mm), mm->q);
+            }
+        }
+    }
+    for (int k = 0; k < 2; k++) { /* ApproxModDown */
+        u64* e = ext + k * polyE;
+        u64* d = k ? d1 : d0;
+        for (int u = 0; u < Lk; u++) ntt_inv(e + (size_t)(L + u) * N, &c->mk[u], N);
+        for (int n = 0; n < N; n++) {
+            u64 y[PSI_MAX_LIMBS];
+            for (int u = 0; u < Lk; u++) y[u] = mulmod(e[(size_t)(L + u) * N + n], c->PkHatInvModpk[u], P->pk[u]);
+            for (int i = 0; i < L; i++) {
+                u128 sum = 0;
+                for (int u = 0; u < Lk; u++) sum += (u128)y[u] * c->PkHatModq[u][i];
+                sw[(size_t)i * N + n] = barrett128(sum, &c->mq[i]);
+            }
+        }
+        for (int i = 0; i < L; i++) {
+            u64 q = P->q[i];
+            ntt_fwd(sw + (size_t)i * N, &c->mq[i], N);
+            for (int n = 0; n < N; n++)
+                d[(size_t)i * N + n] = mulmod(submod(e[(size_t)i * N + n], sw[(size_t)i * N + n], q), c->PkInvModq[i], q);
+        }
+    }
+    free(sw);
+    free(ext);
+    free(dig);
+    free(coef);
+}
+
+/* EvalAutomorphismKeyGen under HYBRID (KeySwitchHYBRID::KeySwitchGenInternal(old = s, new = sigma_{g^-1}(s)), recalled):
+ * for digit j, a_j uniform and e_j Gaussian over Q + pk, b_j = -a_j s_new + e_j + [P]_{q_i} s on the limbs of digit j.
+ * The small secret is re-derived from key_seed (the seed orc_keygen / orc_keygen_hybrid was called with): the special
+ * primes need it outside Q.  key_b, key_a: [parts][L+Lk][N]. */
+void orc_auto_keygen_hybrid(const orc_ctx* c, u64 key_seed, u64 seed, u64 g, u64* key_b, u64* key_a) {
+    int N = c->N, L = c->L, Lk = c->Lk, LE = L + Lk, logN = c->mq[0].logN;
+    rng_t rs = {key_seed};
+    int64_t* secret = malloc(sizeof(int64_t) * N);
+    int64_t* small = malloc(sizeof(int64_t) * N);
+    for (int j = 0; j < N; j++) secret[j] = (int64_t)rng_below(&rs, 3) - 1;
+    u64* s_old = malloc(sizeof(u64) * (size_t)LE * N);
+    u64* s_new = malloc(sizeof(u64) * (size_t)LE * N);
+    u64* e = malloc(sizeof(u64) * N);
+    const u64 ginv = nb_inverse_index(c, g);
+    for (int m = 0; m < LE; m++) {
+        const modctx* mm = m < L ? &c->mq[m] : &c->mk[m - L];
+        u64* so = s_old + (size_t)m * N;
+        for (int j = 0; j < N; j++) so[j] = secret[j] < 0 ? mm->q - 1 : (u64)secret[j];
+        ntt_fwd(so, mm, N);
+        for (int p = 0; p < N; p++) s_new[(size_t)m * N + p] = so[nb_automap((uint32_t)p, ginv, logN)];
+    }
+    rng_t r = {seed ^ (g * 0x9E3779B97F4A7C15ull)};
+    for (int part = 0; part < c->parts; part++) {
+        int lo = part * c->alpha, hi = lo + c->alpha < L ? lo + c->alpha : L;
+        for (int j = 0; j < N; j++) small[j] = rng_gauss(&r, 3.19);
+        for (int m = 0; m < LE; m++) {
+            const modctx* mm = m < L ? &c->mq[m] : &c->mk[m - L];
+            u64 q = mm->q;
+            for (int j = 0; j < N; j++) e[j] = small[j] < 0 ? q - (u64)(-small[j]) : (u64)small[j];
+            ntt_fwd(e, mm, N);
+            u64* a = key_a + ((size_t)part * LE + m) * N;
+            u64* b = key_b + ((size_t)part * LE + m) * N;
+            for (int j = 0; j < N; j++) {
+                a[j] = rng_below(&r, q);
+                u64 v = submod(e[j], mulmod(a[j], s_new[(size_t)m * N + j], q), q);
+                if (m >= lo && m < hi) v = addmod(v, mulmod(c->PkModq[m], s_old[(size_t)m * N + j], q), q);
+                b[j] = v;
+            }
+        }
+    }
+    free(e);
+    free(s_new);
+    free(s_old);
+    free(small);
+    free(secret);
+}
+
 /* EvalAutomorphism(ct, g) with its key.  ct, out: [2][L][N] EVAL (out != ct) */
 void orc_eval_automorphism(const orc_ctx* c, const u64* ct, u64 g, const u64* key_b, const u64* key_a, u64* out) {
     const int N = c->N, L = c->L;
     size_t polyQ = (size_t)L * N;
     u64* t0 = malloc(sizeof(u64) * 2 * polyQ);
     u64* t1 = t0 + polyQ;
-    nb_keyswitch_core(c, ct + polyQ, key_b, key_a, t0, t1);
+    if (c->P.ks_technique == PSI_KS_HYBRID)
+        nb_keyswitch_core_hybrid(c, ct + polyQ, key_b, key_a, t0, t1);
+    else
+        nb_keyswitch_core(c, ct + polyQ, key_b, key_a, t0, t1);
     for (int l = 0; l < L; l++)
         for (int j = 0; j < N; j++)
             t0[(size_t)l * N + j] = addmod(t0[(size_t)l * N + j], ct[(size_t)l * N + j], c->P.q[l]);
@@ -1154,7 +1271,8 @@ static int nb_find_key(int n_keys, const u64* key_index, u64 g) {
 int orc_nb_run(const orc_ctx* c, int K, int b, const u64* idx, const u64* pt, const u64* merge_pt, const u64* mask,
                int n_keys, const u64* key_index, const u64* key_b, const u64* key_a, u64* out) {
     const int N = c->N, L = c->L;
-    const size_t poly = (size_t)L * N, ctsz = 2 * poly, keysz = (size_t)L * poly;
+    const size_t poly = (size_t)L * N, ctsz = 2 * poly;
+    const size_t keysz = c->P.ks_technique == PSI_KS_HYBRID ? (size_t)c->parts * (L + c->Lk) * N : (size_t)L * poly;
     u64 sum_idx[32];
     const int n_sum = orc_eval_sum_indices(c, b, sum_idx); /* EvalInnerProduct(.., vectorizedCT[hfInd].size()) */
     u64* cur = malloc(sizeof(u64) * ctsz);

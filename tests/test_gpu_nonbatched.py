@@ -213,3 +213,30 @@ def test_nb_collection_over_several_devices(devices):
         P.MultiContext(params, (0,) * 6).nb_db_encode_slots(slots, masks)   # more devices than PIEs
     mc.close()
     one.close()
+
+
+@pytest.mark.parametrize("N,L,n_pie,K,b", [(1024, 3, 2, 2, 3), (2048, 4, 1, 2, 5), (16384, 4, 1, 1, 4), (512, 2, 2, 1, 2)])
+def test_nb_run_hybrid_key_switching(N, L, n_pie, K, b):
+    """KeySwitchTechnique HYBRID on the non-batched path (risk register): digits of alpha limbs over Q + pk,
+    ApproxModDown; bit-exact against the oracle's restatement on uniformly random limbs, and a real rotation decrypts."""
+    params = RefParams(N, T32, L=L, ks_technique=1).to_struct()
+    cc, o = P.CryptoContext(params), Oracle(params)
+    rng = np.random.default_rng(N + L)
+    pt = sc.random_pt(rng, params, (n_pie, K, b))
+    mask = sc.random_pt(rng, params, (n_pie, K))
+    merge = sc.random_pt(rng, params)
+    idx = sc.random_ct(rng, params, (n_pie, K))
+    key_index = list(dict.fromkeys(o.eval_sum_indices(b) + [o.find_automorphism_index(-i) for i in range(1, b)]))
+    shape = o.evk_shape()
+    LE = shape[1]
+    mods = [int(params.q[i]) for i in range(L)] + [int(params.pk[i]) for i in range(LE - L)]
+    key_b = np.empty((len(key_index),) + shape, dtype=np.uint64)
+    key_a = np.empty_like(key_b)
+    for m, q in enumerate(mods):    # uniform residues of every limb of the extended basis
+        key_b[:, :, m, :] = rng.integers(0, q, size=(len(key_index), shape[0], N), dtype=np.uint64)
+        key_a[:, :, m, :] = rng.integers(0, q, size=(len(key_index), shape[0], N), dtype=np.uint64)
+    cc.InsertEvalAutomorphismKeys(key_index, key_b, key_a)
+    cc.nb_db_load_limbs(pt, mask, merge)
+    got = cc.nb_run(idx)
+    for p in range(n_pie):
+        assert np.array_equal(got[p], o.nb_run(idx[p], pt[p], merge, mask[p], key_index, key_b, key_a)), p

@@ -128,3 +128,47 @@ def test_nb_run_reports_missing_key():
     idx = query_for(o, sk, K, b, 5, [0])
     with pytest.raises(KeyError):
         o.nb_run(idx, pt, merge_pt, mask, key_index[:1], key_b[:1], key_a[:1])
+
+
+def test_hybrid_rotation_semantics():
+    """The same rotation semantics with KeySwitchTechnique HYBRID (digits of alpha limbs, special primes, ApproxModDown)."""
+    o = Oracle(RefParams(128, T32, L=3, ks_technique=1).to_struct())
+    sk, _, _ = o.keygen(5)
+    half = o.N // 2
+    v = np.arange(1, o.N + 1, dtype=np.int64)
+    ct = o.encrypt(sk, v, 77)
+    for i in (1, -2):
+        g = o.find_automorphism_index(i)
+        kb, ka = o.auto_keygen(sk, 9, [g], key_seed=5)
+        assert kb.shape == (1,) + o.evk_shape()
+        rot = o.eval_automorphism(ct, g, kb[0], ka[0])
+        dec, amb, budget = o.decrypt(sk, rot)
+        assert amb == 0 and budget > 5
+        want = np.concatenate([np.roll(v[:half], -i), np.roll(v[half:], -i)])
+        assert np.array_equal(dec, want), i
+
+
+def test_nb_run_hybrid_decodes():
+    o = Oracle(RefParams(256, T32, L=3, ks_technique=1).to_struct())
+    rng = np.random.default_rng(8)
+    K, b = 2, 3
+    E, t = b, int(o.t)
+    items = rng.integers(2, 2 ** 32, size=(K, b, E), dtype=np.int64)
+    x, positions = 987654321, [2, 0]
+    items[0, 1, positions[0]] = x
+    sk, _, _ = o.keygen(3)
+    pt = np.stack([np.stack([o.encode(np.concatenate([items[hf, bin_], [1]]).astype(np.int64)) for bin_ in range(b)]) for hf in range(K)])
+    mask_slots = rng.integers(1, t, size=(K, b), dtype=np.int64)
+    mask = np.stack([o.encode(mask_slots[hf]) for hf in range(K)])
+    merge_pt = o.encode(np.array([1], dtype=np.int64))
+    key_index = list(dict.fromkeys(o.eval_sum_indices(E + 1) + [o.find_automorphism_index(-(i + 1)) for i in range(E)]))
+    key_b, key_a = o.auto_keygen(sk, 1234, key_index, key_seed=3)
+    idx = query_for(o, sk, K, E, x, positions)
+    out = o.nb_run(idx, pt, merge_pt, mask, key_index, key_b, key_a)
+    for hf in range(K):
+        dec, amb, budget = o.decrypt(sk, out[hf])
+        assert amb == 0 and budget > 5
+        for bin_ in range(b):
+            want = (int(items[hf, bin_, positions[hf]]) - x) * int(mask_slots[hf, bin_]) % t
+            assert int(dec[bin_]) == (want - t if want > t // 2 else want)
+        assert [bin_ for bin_ in range(b) if dec[bin_] == 0] == ([1] if hf == 0 else [])
