@@ -1,4 +1,4 @@
-"""Writes tests/golden/oracle_digests.json and tests/golden/small_case.npz.
+"""Writes tests/golden/oracle_digests.json, tests/golden/small_case.npz and tests/golden/nonbatched_case.npz.
 
 The reference holds no golden ciphertext vectors for this path (keys, noise, shuffle and masks are
 random per run), and OpenFHE is not available to generate any.  These fixtures are therefore
@@ -45,6 +45,30 @@ def small_case():
                 evk_a=evk_a, out=out)
 
 
+def nonbatched_case():
+    """Non-batched FHEHIPPIE (orc_nb_run): 2 PIEs, K=2, b=E=3, N=256, L=2, BV keys for EvalSum(3) and rotations -1, -2."""
+    from oracle.oracle import Oracle
+    from oracle.params_ref import RefParams
+    import scenario as sc
+    params = RefParams(256, T32, L=2).to_struct()
+    o = Oracle(params)
+    rng = np.random.default_rng(20261019)
+    n_pie, K, b = 2, 2, 3
+    sk, _, _ = o.keygen(4)
+    slots = rng.integers(-(T32 // 2), T32 // 2, (n_pie, K, b, b + 1), dtype=np.int64)
+    mask_slots = rng.integers(1, T32, (n_pie, K, b), dtype=np.int64)
+    pt = np.stack([[[o.encode(slots[p, hf, bin_]) for bin_ in range(b)] for hf in range(K)] for p in range(n_pie)])
+    mask = np.stack([[o.encode(mask_slots[p, hf]) for hf in range(K)] for p in range(n_pie)])
+    merge = o.encode(np.array([1], dtype=np.int64))
+    key_index = np.array(list(dict.fromkeys(o.eval_sum_indices(b) + [o.find_automorphism_index(-i) for i in range(1, b)])),
+                         dtype=np.uint64)
+    key_b, key_a = o.auto_keygen(sk, 99, [int(g) for g in key_index])
+    idx = sc.random_ct(rng, params, (n_pie, K))
+    out = np.stack([o.nb_run(idx[p], pt[p], merge, mask[p], key_index, key_b, key_a) for p in range(n_pie)])
+    return dict(slots=slots, mask_slots=mask_slots, pt=pt, mask=mask, merge=merge, key_index=key_index, key_b=key_b, key_a=key_a,
+                idx=idx, out=out)
+
+
 def compute_digests():
     from oracle.oracle import Oracle
     from oracle.params_ref import RefParams
@@ -66,6 +90,7 @@ def compute_digests():
         d[tag + "_mul_core"] = _digest(o.mul_core(ct1, ct2))
         d[tag + "_mul_ctct"] = _digest(o.mul_ctct(ct1, ct2, evk_b, evk_a))
     d["small_case_out"] = _digest(small_case()["out"])
+    d["nonbatched_case_out"] = _digest(nonbatched_case()["out"])
     return d
 
 
@@ -73,4 +98,5 @@ if __name__ == "__main__":
     with open(os.path.join(HERE, "oracle_digests.json"), "w") as f:
         json.dump(compute_digests(), f, indent=1, sort_keys=True)
     np.savez_compressed(os.path.join(HERE, "small_case.npz"), **small_case())
+    np.savez_compressed(os.path.join(HERE, "nonbatched_case.npz"), **nonbatched_case())
     print("written")

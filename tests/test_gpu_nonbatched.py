@@ -240,3 +240,15 @@ def test_nb_run_hybrid_key_switching(N, L, n_pie, K, b):
     got = cc.nb_run(idx)
     for p in range(n_pie):
         assert np.array_equal(got[p], o.nb_run(idx[p], pt[p], merge, mask[p], key_index, key_b, key_a)), p
+
+
+def test_golden_nonbatched_case_on_the_gpu():
+    """The committed fixture through the C ABI: device-encoded database == fixture plaintexts, results == fixture results."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nonbatched_case.npz"))
+    cc, o, params = make(256, 2)
+    cc.InsertEvalAutomorphismKeys(z["key_index"], z["key_b"], z["key_a"])
+    cc.nb_db_encode_slots(z["slots"], z["mask_slots"])
+    pt, mask, merge = cc.nb_db_get_limbs()
+    assert np.array_equal(pt, z["pt"]) and np.array_equal(mask, z["mask"]) and np.array_equal(merge, z["merge"])
+    assert np.array_equal(cc.nb_run(z["idx"]), z["out"])

@@ -172,3 +172,14 @@ def test_nb_run_hybrid_decodes():
             want = (int(items[hf, bin_, positions[hf]]) - x) * int(mask_slots[hf, bin_]) % t
             assert int(dec[bin_]) == (want - t if want > t // 2 else want)
         assert [bin_ for bin_ in range(b) if dec[bin_] == 0] == ([1] if hf == 0 else [])
+
+
+def test_golden_nonbatched_case():
+    """Committed fixture (tests/golden/nonbatched_case.npz, written by make_golden.py): the checker cannot drift silently."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "nonbatched_case.npz"))
+    o = Oracle(RefParams(256, T32, L=2).to_struct())
+    for p in range(z["idx"].shape[0]):
+        assert np.array_equal(o.encode(z["slots"][p, 0, 0]), z["pt"][p, 0, 0])
+        got = o.nb_run(z["idx"][p], z["pt"][p], z["merge"], z["mask"][p], z["key_index"], z["key_b"], z["key_a"])
+        assert np.array_equal(got, z["out"][p])
