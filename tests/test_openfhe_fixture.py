@@ -40,8 +40,41 @@ def load_fixture(path=FIXTURE):
     fx["idx"], fx["minus"] = take((K, E, 2, L, N)), take((2, L, N))
     fx["result"] = take((b, 2, L, N))
     fx["slots"], fx["mask_slots"] = take((K, b, E, nslots), "<i8"), take((b, nslots), "<i8")
+    if off < len(raw):   # optional section of the non-batched path (layout: tools/dump_openfhe_limbs.cpp)
+        assert raw[off:off + 8] == b"PSINB001", "trailing bytes in the fixture"
+        off += 8
+        n_keys, batch, n_rot = (int(v) for v in np.frombuffer(raw, dtype="<u8", count=3, offset=off))
+        off += 24
+        nb = dict(batch=batch, key_index=take((n_keys,)))
+        nb["key_b"], nb["key_a"] = take((n_keys, L, L, N)), take((n_keys, L, L, N))
+        nb["ct_in"] = take((2, L, N))
+        nb["rotations"] = []
+        for _ in range(n_rot):
+            rot = int(take((1,), "<i8")[0])
+            nb["rotations"].append((rot, int(take((1,))[0]), take((2, L, N))))
+        nb["sum_index"] = take((int(take((1,))[0]),))
+        nb["sum_result"] = take((2, L, N))
+        fx["nonbatched"] = nb
     assert off == len(raw), "trailing bytes in the fixture"
     return fx
+
+
+def check_oracle_nonbatched_against(fx):
+    """The recalled details of the non-batched path against what the host library did: FindAutomorphismIndex2n, the
+    EvalSum index sequence, and the limbs of EvalAtIndex / EvalSum (key switch first, permutation after)."""
+    from oracle.oracle import Oracle
+    nb, o = fx["nonbatched"], Oracle(fx["params"])
+    slot_of = {int(g): i for i, g in enumerate(nb["key_index"])}
+    for rot, g, want in nb["rotations"]:
+        assert o.find_automorphism_index(rot) == g
+        assert np.array_equal(o.eval_automorphism(nb["ct_in"], g, nb["key_b"][slot_of[g]], nb["key_a"][slot_of[g]]), want), rot
+    assert sorted(o.eval_sum_indices(nb["batch"])) == sorted(int(g) for g in nb["sum_index"])
+    q = np.array([int(fx["params"].q[l]) for l in range(fx["params"].L)], dtype=np.uint64)[None, :, None]
+    ct = nb["ct_in"]
+    for g in o.eval_sum_indices(nb["batch"]):
+        rot = o.eval_automorphism(ct, g, nb["key_b"][slot_of[g]], nb["key_a"][slot_of[g]])
+        ct = (ct + rot) % q    # residues < 2^60: the sum does not wrap
+    assert np.array_equal(ct, nb["sum_result"])
 
 
 def check_oracle_against(fx):
@@ -59,7 +92,10 @@ def check_oracle_against(fx):
 
 @needs_fixture
 def test_oracle_matches_openfhe_limbs():
-    check_oracle_against(load_fixture())
+    fx = load_fixture()
+    check_oracle_against(fx)
+    if "nonbatched" in fx:
+        check_oracle_nonbatched_against(fx)
 
 
 def test_fixture_format_round_trip(tmp_path):
@@ -90,9 +126,34 @@ def test_fixture_format_round_trip(tmp_path):
             f.write(np.ascontiguousarray(a, dtype="<u8").tobytes())
         for a in (slots, mask_slots):
             f.write(np.ascontiguousarray(a, dtype="<i8").tobytes())
+        # the optional non-batched section, from oracle data as well
+        batch, rotations = 5, [-1, -2, -3]
+        sum_index = o.eval_sum_indices(batch)
+        key_index = sorted(set(sum_index + [o.find_automorphism_index(r) for r in rotations]))
+        key_b, key_a = o.auto_keygen(sk, 77, key_index)
+        ct_in = o.encrypt(sk, np.arange(1, nslots + 1, dtype=np.int64), 5)
+        f.write(b"PSINB001")
+        f.write(np.array([len(key_index), batch, len(rotations)], dtype="<u8").tobytes())
+        f.write(np.array(key_index, dtype="<u8").tobytes())
+        for a in (key_b, key_a, ct_in):
+            f.write(np.ascontiguousarray(a, dtype="<u8").tobytes())
+        q = np.array([int(params.q[l]) for l in range(params.L)], dtype=np.uint64)[None, :, None]
+        for r in rotations:
+            g = o.find_automorphism_index(r)
+            f.write(np.int64(r).tobytes())
+            f.write(np.uint64(g).tobytes())
+            f.write(o.eval_automorphism(ct_in, g, key_b[key_index.index(g)], key_a[key_index.index(g)]).tobytes())
+        f.write(np.uint64(len(sum_index)).tobytes())
+        f.write(np.array(sum_index, dtype="<u8").tobytes())
+        ct = ct_in
+        for g in sum_index:
+            ct = (ct + o.eval_automorphism(ct, g, key_b[key_index.index(g)], key_a[key_index.index(g)])) % q
+        f.write(np.ascontiguousarray(ct, dtype="<u8").tobytes())
     fx = load_fixture(str(path))
     assert (fx["K"], fx["b"], fx["E"], fx["nslots"]) == (K, b, E, nslots)
     check_oracle_against(fx)
+    assert len(fx["nonbatched"]["rotations"]) == 3
+    check_oracle_nonbatched_against(fx)
 
 
 @needs_fixture

@@ -17,6 +17,11 @@
 // File layout (little endian): "PSIOFHE1", u64 sizeof(psi_params), psi_params, u64 K, b, E, nslots, then u64
 // arrays evk_b[L][L][N], evk_a[L][L][N], pt[K][b][E][L][N], mask[b][L][N], idx[K][E][2][L][N], minus[2][L][N],
 // result[b][2][L][N], then int64 arrays slots[K][b][E][nslots], mask_slots[b][nslots].
+// Optional trailing section for the NON-batched path (FHEHIPPIE.cpp:61-77; pins the order inside EvalAutomorphism, the
+// EvalSum index sequence and FindAutomorphismIndex2n): "PSINB001", u64 n_keys, u64 batch, u64 n_rot, u64
+// key_index[n_keys], key_b[n_keys][L][L][N], key_a[n_keys][L][L][N] (every automorphism key of the context, BV),
+// ct_in[2][L][N], then per rotation: i64 rotation, u64 automorphism index, ct EvalAtIndex(ct_in, rotation)[2][L][N];
+// finally u64 n_sum, u64 sum_index[n_sum] (what EvalSumKeyGen(batch) generated) and ct EvalSum(ct_in, batch)[2][L][N].
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -186,6 +191,37 @@ int main(int argc, char** argv) {
         for (uint32_t bin = 0; bin < b; bin++)
             for (uint32_t pos = 0; pos < E; pos++) put(f, slots[hf][bin][pos].data(), 8 * nslots);
     for (uint32_t bin = 0; bin < b; bin++) put(f, mask_slots[bin].data(), 8 * nslots);
+    // ---- non-batched section: EvalSum keys for `batch` slots, rotation keys -1 .. -3 (SimpleFHEPSIClient.cpp:79-90) ----
+    {
+        const uint32_t batch = 5;
+        const std::vector<int32_t> rotations = {-1, -2, -3};
+        // the indices EvalSumKeyGen adds are read off the key map: taken before the rotation keys are generated
+        cc->EvalSumKeyGen(kp.secretKey, kp.publicKey);
+        std::vector<usint> sumIndex;
+        for (const auto& kv : cc->GetEvalAutomorphismKeyMap(kp.secretKey->GetKeyTag())) sumIndex.push_back(kv.first);
+        cc->EvalRotateKeyGen(kp.secretKey, rotations, kp.publicKey);
+        const auto& keyMap = cc->GetEvalAutomorphismKeyMap(kp.secretKey->GetKeyTag());
+        std::vector<int64_t> v(nslots);
+        for (uint32_t i = 0; i < nslots; i++) v[i] = (int64_t)(i + 1);
+        auto ctIn = cc->Encrypt(kp.secretKey, cc->MakePackedPlaintext(v));
+        put(f, "PSINB001", 8);
+        put_u64(f, keyMap.size()); put_u64(f, batch); put_u64(f, rotations.size());
+        for (const auto& kv : keyMap) put_u64(f, kv.first);
+        for (const auto& kv : keyMap)
+            for (const auto& d : kv.second->GetBVector()) put_poly(f, d);
+        for (const auto& kv : keyMap)
+            for (const auto& d : kv.second->GetAVector()) put_poly(f, d);
+        put_ct(f, ctIn);
+        for (int32_t r : rotations) {
+            int64_t r64 = r;
+            put(f, &r64, 8);
+            put_u64(f, FindAutomorphismIndex2n(r, 2 * P.N));  // core/math/nbtheory.h
+            put_ct(f, cc->EvalAtIndex(ctIn, r));
+        }
+        put_u64(f, sumIndex.size());
+        for (usint g : sumIndex) put_u64(f, g);
+        put_ct(f, cc->EvalSum(ctIn, batch));
+    }
     fclose(f);
     printf("wrote %s: N=%u L=%u Lp=%u K=%u b=%u E=%u nslots=%u\n", argv[1], P.N, P.L, P.Lp, K, b, E, nslots);
     return 0;
