@@ -282,7 +282,7 @@ def run_reference(args, w, rank, world):
         "e2e": {"value": rate, "unit": "items/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def bind_to_gpu_numa_node(index):
@@ -323,7 +323,23 @@ def workload_config(args, w, params, world):
                          % (8.0 * params.L * params.N * w["K"] * w["b"] * w["E"] / 1e9)}
 
 
+# stdout carries exactly ONE JSON line: the real stdout is kept aside and file descriptor 1 is pointed at stderr for the
+# rest of the run, so whatever a library prints there (NCCL's version line under NCCL_DEBUG=VERSION) cannot precede it
+_JSON_OUT = None
+
+
+def emit(line):
+    print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
+    if _JSON_OUT is not None:   # the line is out: hand file descriptor 1 back
+        sys.stdout.flush()
+        os.dup2(_JSON_OUT.fileno(), 1)
+
+
 def main():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -765,7 +781,7 @@ def main():
             "weak": weak, "nonbatched": nb_leg,
             "phases": phases, "clocks": sampler.summary(), "offline_build_s": offline_s,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
