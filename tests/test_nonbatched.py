@@ -183,3 +183,29 @@ def test_golden_nonbatched_case():
         assert np.array_equal(o.encode(z["slots"][p, 0, 0]), z["pt"][p, 0, 0])
         got = o.nb_run(z["idx"][p], z["pt"][p], z["merge"], z["mask"][p], z["key_index"], z["key_b"], z["key_a"])
         assert np.array_equal(got, z["out"][p])
+
+
+def test_collection_constructor_logic_without_a_device():
+    """FHEHIPPIE ctor bookkeeping of the Python mirror (FHEHIPPIE.cpp:9-59): errors, bin permutation, trailing 1, masks."""
+    import types
+    import psi_b200 as P
+    coll = P.FHEHIPPIECollection(types.SimpleNamespace(t=T32), P.PublicKey(), seed=7)
+    with pytest.raises(ValueError, match="size of a cuckoo bin"):
+        coll.addPIE(np.ones((2, 3, 4), dtype=np.int64))
+    with pytest.raises(ValueError, match="stash"):
+        coll.addPIE(np.ones((2, 3, 3), dtype=np.int64), stash_size=2)
+    rng = np.random.default_rng(0)
+    table = rng.integers(1, 2 ** 32, size=(2, 5, 5), dtype=np.int64)
+    pie = coll.addPIE(table)
+    slots, masks, perm = coll._slots[0], coll._masks[0], coll._perm[0]
+    assert slots.shape == (2, 5, 6) and (slots[:, :, 5] == 1).all()
+    for hf in range(2):   # the bins are permuted as whole rows, the same permutation for every hash function
+        assert sorted(map(tuple, slots[hf, :, :5])) == sorted(map(tuple, table[hf]))
+    order = [next(j for j in range(5) if (slots[0, j, :5] == table[0, i]).all()) for i in range(5)]
+    assert [next(j for j in range(5) if (slots[1, j, :5] == table[1, i]).all()) for i in range(5)] == order
+    assert masks.shape == (2, 5) and (masks >= 1).all() and (masks < T32).all()
+    assert sorted(perm) == [0, 1]
+    with pytest.raises(ValueError, match="same table shape"):
+        coll.addPIE(np.ones((2, 4, 4), dtype=np.int64))
+    with pytest.raises(ValueError, match="run\\(\\) has not been called"):
+        pie.getResultList()
