@@ -252,3 +252,24 @@ def test_golden_nonbatched_case_on_the_gpu():
     pt, mask, merge = cc.nb_db_get_limbs()
     assert np.array_equal(pt, z["pt"]) and np.array_equal(mask, z["mask"]) and np.array_equal(merge, z["merge"])
     assert np.array_equal(cc.nb_run(z["idx"]), z["out"])
+
+
+def test_nb_run_many_pies_exercises_the_chunk_pipeline():
+    """200 PIEs -> four chunks: index / result buffers are reused (double-buffered) while uploads, evaluations and
+    downloads of consecutive chunks overlap; every PIE against the oracle."""
+    cc, o, params = make(1024, 2)
+    rng = np.random.default_rng(77)
+    n_pie, K, b = 200, 1, 3
+    pt = sc.random_pt(rng, params, (n_pie, K, b))
+    mask = sc.random_pt(rng, params, (n_pie, K))
+    merge = sc.random_pt(rng, params)
+    idx = sc.random_ct(rng, params, (n_pie, K))
+    key_index = list(dict.fromkeys(o.eval_sum_indices(b) + [o.find_automorphism_index(-i) for i in range(1, b)]))
+    key_b = sc.random_pt(rng, params, (len(key_index), 2))
+    key_a = sc.random_pt(rng, params, (len(key_index), 2))
+    cc.InsertEvalAutomorphismKeys(key_index, key_b, key_a)
+    cc.nb_db_load_limbs(pt, mask, merge)
+    got = cc.nb_run(idx)
+    for p in range(n_pie):
+        assert np.array_equal(got[p], o.nb_run(idx[p], pt[p], merge, mask[p], key_index, key_b, key_a)), p
+    assert np.array_equal(cc.nb_run(idx[37:151], 37, 151), got[37:151])   # a range that starts and ends inside chunks
