@@ -209,3 +209,15 @@ def test_collection_constructor_logic_without_a_device():
         coll.addPIE(np.ones((2, 4, 4), dtype=np.int64))
     with pytest.raises(ValueError, match="run\\(\\) has not been called"):
         pie.getResultList()
+
+
+def test_cpp_constructor_bookkeeping_without_a_device():
+    """tests/cpp/TestFHEPIECtor.cpp: the C++ mirror's constructor (host/FHEHIPPIE.hpp) - the reference's two
+    invalid_argument cases, bin permutation, trailing 1, mask range, seeded reproducibility; no device involved."""
+    import os
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp")
+    subprocess.check_call(["make", "-C", here, "-s", "TestFHEPIECtor"])
+    r = subprocess.run([os.path.join(here, "TestFHEPIECtor")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "constructor bookkeeping ok" in r.stdout
