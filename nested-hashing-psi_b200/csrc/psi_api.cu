@@ -420,7 +420,7 @@ static int mul_ctct_batch(psi_ctx* c, cudaStream_t s, uint32_t B, const u64* a, 
 extern "C" {
 
 const char* psi_last_error(void) { return g_last_error.c_str(); }
-const char* psi_version(void) { return "psi_b200 0.2 (sm_100a)"; }
+const char* psi_version(void) { return "psi_b200 0.3 (sm_100a)"; }
 
 int psi_device_count(int* n) {
     if (!n) return set_error(PSI_ERR_INVALID, "null argument");
