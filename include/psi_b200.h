@@ -289,6 +289,8 @@ int psi_bench_imad_peak(int device, double* mads_per_second);
  * second with operands in registers (the NTT's compute ceiling); kinds 2, 3: two other codings of the same butterfly.
  * kinds 4, 5: the exchange of 16 u64 per thread between two radix passes through padded shared memory / through
  * __shfl_xor butterflies, in exchanges per second.
+ * kind 6: the same butterfly with the Shoup quotient formed on the FP64 pipe (a probe: measured slower);
+ * kind 7: its exactness pass, per_second then holds the number of lazy products outside [0, 4q) (must be 0).
  * Bits 4..7 of kind: resident 256-thread blocks per SM (0 = 8), to read the rate against occupancy. */
 int psi_bench_pipe_peak(int device, int kind, double* per_second);
 

@@ -1500,7 +1500,7 @@ int psi_bench_imad_peak(int device, double* mads_per_second) { return psi_bench_
 
 int psi_bench_pipe_peak(int device, int kind, double* per_second) {
     if (!per_second) return set_error(PSI_ERR_INVALID, "null argument");
-    if (kind < 0 || (kind & 15) > 5 || kind > 255) return set_error(PSI_ERR_INVALID, "unknown micro-benchmark kind");
+    if (kind < 0 || (kind & 15) > 7 || kind > 255) return set_error(PSI_ERR_INVALID, "unknown micro-benchmark kind");
     cudaError_t e = pipe_peak(device, kind, per_second);
     if (e != cudaSuccess) return cuda_fail(e, "psi_bench_pipe_peak");
     return PSI_OK;

@@ -5,6 +5,7 @@
 #include "async_copy.cuh"
 
 #include <type_traits>
+#include <vector>
 
 namespace psi {
 
@@ -1032,6 +1033,62 @@ __global__ void __launch_bounds__(256) k_butterfly3_peak(u64* out, uint32_t iter
 //   kind 5: through the register file: four butterfly steps with __shfl_xor, each moving half of the values
 //           (2 x 8 SHFL per step and a select per moved word)
 // A 64-bit add between exchanges keeps the values live.  Returns exchanges (16 values per thread) per second.
+// kind 6: the Shoup QUOTIENT on the FP64 pipe (idea 1b) - a throughput and exactness probe, not used by any
+// product kernel.  floor(y * w / q) is formed from an error-free double product instead of the 4-product mulhi64:
+//   y = y1 * 2^31 + y0 (both halves exact doubles through the 2^52 bit trick), rho = w / q as a double-double scaled by 2^31:
+//   P = y1 * floor(w 2^31 / q) (one exact 32 x 32 integer product), s = fma(d0, rho, d1 * a_lo) < 2^32 in doubles,
+//   h = P + floor(s) - 1, the floor taken by a round-down add of 2^52 (the first version converted with F2I and ran at
+//   5.0e11/s: the conversions sit on the quarter-rate XU pipe)
+// The estimate is never above the true quotient and at most 2 below it, so the lazy product y w - h q lies in [0, 4q)
+// (checked for every butterfly when `check` is set; violations are counted into out[0]).  What remains on the multiplier
+// pipe are the two low 64-bit products.
+__device__ __forceinline__ double u31_to_double(uint32_t v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
+__global__ void __launch_bounds__(256) k_butterfly_fp64_peak(u64* out, uint32_t iters, u64 q, u64 w_in, uint32_t check) {
+    const u64 q2 = 2 * q, q4 = 4 * q;
+    const u64 w = (w_in + threadIdx.x) % q;
+    // rho * 2^31 as a double-double, rho as a double (host-side constants in a product kernel; computed here once)
+    const double qd = (double)q;  // q < 2^60 is not exact in a double: refine rho with one exact remainder step below
+    const double rho = (double)w / qd;
+    // exact double-double of w * 2^31 / q: hi = fl(.), lo from the integer remainder
+    const unsigned __int128 num = (unsigned __int128)w << 31;
+    const u64 ihi = (u64)(num / q);
+    const u64 rem = (u64)(num % q);
+    const uint32_t ihi32 = (uint32_t)ihi;                             // ihi < 2^31 * (w / q) < 2^31
+    const double a_lo = (double)rem / qd;                             // in [0, 1): the fractional part of w 2^31 / q
+    unsigned long long bad = 0;
+    u64 x[4], y[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        x[k] = (threadIdx.x * 2654435761ull + k * 977 + blockIdx.x) % q;
+        y[k] = (threadIdx.x * 40503ull + k * 131 + 7 * blockIdx.x) % q;
+    }
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            u64 u = x[k];
+            if (u >= q4) u -= q4;
+            if (u >= q2) u -= q2;
+            const u64 yy = y[k];  // < 2^62
+            const uint32_t y1 = (uint32_t)(yy >> 31), y0 = (uint32_t)yy & 0x7fffffffu;
+            // y * rho = y1 * (ihi + rem / q) + y0 * rho: the big part y1 * ihi is ONE exact 32 x 32 integer product, the
+            // rest (< 2^32) is formed in doubles and floored by a round-down add of 2^52 (no F2I: the XU pipe is slow)
+            const u64 P = (u64)y1 * ihi32;
+            const double d1 = u31_to_double(y1), d0 = u31_to_double(y0);
+            const double sfrac = __fma_rn(d0, rho, __dmul_rn(d1, a_lo));
+            const u64 S = (u64)__double_as_longlong(__dadd_rd(sfrac, 4503599627370496.0)) & 0xfffffffffffffull;
+            const u64 h = P + S - 1;
+            const u64 v = yy * w - h * q;  // in [0, 4q) when h is the quotient or up to 2 below it
+            if (check && v >= q4) bad++;
+            x[k] = u + v;
+            y[k] = u - v + q4;
+            if (y[k] >= q4) y[k] -= q4;  // keep y below 2^62 for the split (the product kernels track this bound statically)
+        }
+    }
+    u64 r = x[0] ^ x[1] ^ x[2] ^ x[3] ^ y[0] ^ y[1] ^ y[2] ^ y[3];
+    if (check) r = bad;
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 __global__ void __launch_bounds__(256) k_exchange_smem_peak(u64* out, uint32_t iters) {
     __shared__ u64 sm[256 * 17 + 16];
     u64 v[16];
@@ -1114,6 +1171,8 @@ cudaError_t pipe_peak(int device, int kind, double* per_second) {
             k_exchange_smem_peak<<<blocks, threads>>>(out, iters);
         else if (kind == 5)
             k_exchange_shfl_peak<<<blocks, threads>>>(out, iters);
+        else if (kind == 6 || kind == 7)  // 7: exactness check pass (per_second then holds the number of violations)
+            k_butterfly_fp64_peak<<<blocks, threads>>>(out, iters, q, w, kind == 7);
         else
             k_butterfly3_peak<<<blocks, threads>>>(out, iters, q, w, ws);
         cudaEventRecord(t1);
@@ -1122,11 +1181,22 @@ cudaError_t pipe_peak(int device, int kind, double* per_second) {
         cudaEventElapsedTime(&ms, t0, t1);
         if (rep > 0 && ms < best) best = ms;
     }
+    if (kind == 7 && e == cudaSuccess) {  // sum the violation counters
+        std::vector<u64> host((size_t)blocks * threads);
+        e = cudaMemcpy(host.data(), out, host.size() * sizeof(u64), cudaMemcpyDeviceToHost);
+        double total = 0;
+        for (u64 v : host) total += (double)v;
+        cudaEventDestroy(t0);
+        cudaEventDestroy(t1);
+        cudaFree(out);
+        *per_second = total;
+        return e;
+    }
     cudaEventDestroy(t0);
     cudaEventDestroy(t1);
     cudaFree(out);
     if (e != cudaSuccess) return e;
-    const double per_thread = kind == 0 ? (double)iters * 64.0 : (kind >= 4 ? (double)iters : (double)iters * 4.0);
+    const double per_thread = kind == 0 ? (double)iters * 64.0 : ((kind == 4 || kind == 5) ? (double)iters : (double)iters * 4.0);
     *per_second = (double)blocks * threads * per_thread / (best * 1e-3);
     return cudaSuccess;
 }
